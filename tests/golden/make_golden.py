@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""Record golden traces from the UNMODIFIED reference (authoring container only).
+
+    python tests/golden/make_golden.py
+
+Imports /root/reference/gridworld through oracle/ref_harness.py (gym stub, pandas
+copy-on-write shim, synthetic exogenous table), builds the reference's own
+``MultiAgentEnv`` / ``CoordinatedMultiBuildingControlEnv`` for each scenario of
+tests/scenarios.py with this repo's CPU power-flow oracle plugged in through the
+reference's ``pf_config["cls"]`` hook (gridworld/multiagent_env.py:80; the real
+OpenDSS engine is not installable here), steps one full episode under seeded
+actions and stores inputs and outputs as ``tests/golden/<scenario>.npz``:
+
+  actions[T, act_dim]   flat, agent-major then component order
+  init_soc[n_storage]   the SOCs the reference drew (np.random.seed(0))
+  obs0[obs_dim]         reset observation
+  obs[T, obs_dim], rew[T, A], done[T], agent_p[T, A], volt[T+1, n_nodes]
+  node_names, act_dim, obs_dim
+
+Also stores the three EV-station episode totals printed in
+examples/envs/ev-charging.ipynb cells 5-7 next to what the reference computes
+here (they agree bit for bit).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+
+from tests import scenarios as S  # noqa: E402
+from tests.flatten import flat_obs, unflatten_action, action_layout  # noqa: E402
+from oracle.ref_harness import load_reference, quiet_stdout  # noqa: E402
+from oracle.powerflow import OracleOpenDSSSolver  # noqa: E402
+
+
+def reference_namespace(ref):
+    class ThisPVEnv(ref.PVEnv):                       # scenarios/heterogeneous.py:46-52
+        def step_reward(self, **kwargs):
+            v = kwargs["min_voltage"]
+            viol = min(0, v - 0.95) + min(0, 1.05 - v)
+            return -(1000 * viol) ** 2, {}
+
+    class Coordinated(ref.MultiAgentEnv):             # examples/marl/openai/train.py:37-88
+        VOLTAGE_LIMITS = [0.95, 1.05]
+        VV_UNIT_PENALTY = 1e4
+
+        def reward_transform(self, rew_dict):
+            pen = self.get_voltage_violation() * self.VV_UNIT_PENALTY
+            n = len(rew_dict)
+            for k in rew_dict.keys():
+                rew_dict[k] -= (pen / n)
+            return rew_dict
+
+        def get_voltage_violation(self):
+            bus_id = list(set(self.agent_name_bus_map.values()))[0]
+            v = self.pf_solver.get_bus_voltage_by_name(bus_id)
+            return max([0.0, self.VOLTAGE_LIMITS[0] - v, v - self.VOLTAGE_LIMITS[1]])
+
+    return types.SimpleNamespace(
+        MultiComponentEnv=ref.MultiComponentEnv,
+        FiveZoneROMThermalEnergyEnv=ref.FiveZoneROMThermalEnergyEnv,
+        PVEnv=ref.PVEnv, GridAwarePVEnv=ThisPVEnv, EnergyStorageEnv=ref.EnergyStorageEnv,
+        EVChargingEnv=ref.EVChargingEnv, MultiAgentEnv=ref.MultiAgentEnv,
+        CoordinatedMultiBuildingControlEnv=Coordinated)
+
+
+def storage_socs(ref, env):
+    out = []
+    for a in env.agents:
+        for e in getattr(a, "envs", [a]):
+            if isinstance(e, ref.EnergyStorageEnv):
+                out.append(e.current_storage)
+    return np.array(out, dtype=np.float64)
+
+
+def draw_actions(layout, rng):
+    """U(-1.2, 1.2) on rescaled dims (exercises the clip), U(low, high) on raw ones."""
+    parts = []
+    for _, _, low, high, rescaled in layout:
+        if rescaled:
+            parts.append(rng.uniform(-1.2, 1.2, size=low.shape))
+        else:
+            parts.append(rng.uniform(low, high))
+    return np.concatenate(parts)
+
+
+def record(name, env_cls, cfg, ref, seed=1234):
+    with quiet_stdout():
+        np.random.seed(0)
+        env = env_cls(**cfg)
+        obs0 = env.reset()
+    socs = storage_socs(ref, env)
+    layout = action_layout(env)
+    rng = np.random.default_rng(seed)
+    names = list(env.pf_solver.get_bus_voltages().keys())
+    A, O, R, D, P, V = [], [], [], [], [], [np.array([env.voltages[k] for k in names])]
+    done = False
+    while not done:
+        a = draw_actions(layout, rng)
+        with quiet_stdout():
+            ob, rew, dn, _ = env.step(unflatten_action(env, a))
+        A.append(a)
+        O.append(flat_obs(env, ob))
+        R.append(np.array([rew[ag.name] for ag in env.agents], dtype=np.float64))
+        D.append(dn["__all__"])
+        P.append(np.array(env.history["agent_power_p"][-1], dtype=np.float64))
+        V.append(np.array([env.voltages[k] for k in names]))
+        done = dn["__all__"]
+    out = dict(actions=np.array(A), init_soc=socs, obs0=flat_obs(env, obs0), obs=np.array(O),
+               rew=np.array(R), done=np.array(D), agent_p=np.array(P), volt=np.array(V),
+               node_names=np.array(names))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: T={len(A)} act_dim={out['actions'].shape[1]} obs_dim={out['obs'].shape[1]} "
+          f"vmin={out['volt'].min():.4f} vmax={out['volt'].max():.4f}")
+
+
+def ev_totals(ref):
+    cfg = {"num_vehicles": 100, "minutes_per_step": 5, "max_charge_rate_kw": 7.,
+           "peak_threshold": 250., "vehicle_multiplier": 5., "rescale_spaces": False}
+    notebook = {"high": -934170.2851237846, "low": -2659771.95782906,
+                "const0.8": -1161670.9270816303}
+    got = {}
+    for k, pol in [("high", lambda e: e.action_space.high), ("low", lambda e: e.action_space.low),
+                   ("const0.8", lambda e: np.array([.8]))]:
+        env = ref.EVChargingEnv(**cfg)
+        env.reset()
+        done, tot = False, 0.
+        while not done:
+            _, r, done, _ = env.step(pol(env))
+            tot += r
+        got[k] = tot * env.reward_scale
+        assert got[k] == notebook[k], (k, got[k], notebook[k])
+    np.savez(os.path.join(HERE, "ev_totals.npz"),
+             keys=np.array(list(notebook)), notebook=np.array([notebook[k] for k in notebook]),
+             reference_here=np.array([got[k] for k in notebook]))
+    print("EV totals reproduced bit-exactly:", got)
+
+
+def main():
+    ref = load_reference()
+    ns = reference_namespace(ref)
+    pf = OracleOpenDSSSolver
+    record("c0_buildings", ns.CoordinatedMultiBuildingControlEnv,
+           S.buildings_scenario(ns, pf, system_load_rescale_factor=1.2), ref)
+    record("heterogeneous", ns.MultiAgentEnv, S.heterogeneous_scenario(ns, pf, 0.65), ref)
+    record("heterogeneous_max250", ns.MultiAgentEnv,
+           S.heterogeneous_scenario(ns, pf, 0.6, max_episode_steps=250), ref)
+    record("test_heterogeneous", ns.MultiAgentEnv, S.test_heterogeneous_scenario(ns, pf), ref)
+    ev_totals(ref)
+
+
+if __name__ == "__main__":
+    main()

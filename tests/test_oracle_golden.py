@@ -1,0 +1,81 @@
+"""The CPU oracle against golden traces recorded from the unmodified reference
+(tests/golden/make_golden.py) and against the reference's own known answers."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import scenarios as S
+from tests.flatten import flat_obs, unflatten_action
+from tests.oracle_ns import ORACLE_NS as NS, storage_socs_to_dict
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+CASES = {
+    "c0_buildings": lambda: (NS.CoordinatedMultiBuildingControlEnv,
+                             S.buildings_scenario(NS, NS.OpenDSSSolver, 1.2)),
+    "heterogeneous": lambda: (NS.MultiAgentEnv,
+                              S.heterogeneous_scenario(NS, NS.OpenDSSSolver, 0.65)),
+    "heterogeneous_max250": lambda: (NS.MultiAgentEnv, S.heterogeneous_scenario(
+        NS, NS.OpenDSSSolver, 0.6, max_episode_steps=250)),
+    "test_heterogeneous": lambda: (NS.MultiAgentEnv,
+                                   S.test_heterogeneous_scenario(NS, NS.OpenDSSSolver)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_replays_reference_trace(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    cls, cfg = CASES[name]()
+    env = cls(**cfg)
+    obs0 = env.reset(init_storage=storage_socs_to_dict(env, g["init_soc"]))
+    # same float64 arithmetic in the same order: the oracle is expected to be exact
+    np.testing.assert_array_equal(flat_obs(env, obs0), g["obs0"])
+    names = [str(n) for n in g["node_names"]]
+    np.testing.assert_array_equal(np.array([env.voltages[k] for k in names]), g["volt"][0])
+    T = g["actions"].shape[0]
+    for t in range(T):
+        ob, rew, dn, _ = env.step(unflatten_action(env, g["actions"][t]))
+        np.testing.assert_array_equal(flat_obs(env, ob), g["obs"][t], err_msg=f"obs t={t}")
+        np.testing.assert_array_equal(
+            np.array([rew[a.name] for a in env.agents]), g["rew"][t], err_msg=f"rew t={t}")
+        np.testing.assert_array_equal(
+            np.array([env.voltages[k] for k in names]), g["volt"][t + 1], err_msg=f"volt t={t}")
+        assert dn["__all__"] == bool(g["done"][t])
+    assert dn["__all__"]
+
+
+def test_episode_lengths_match_reference_facts():
+    # PV profile (287 rows) ends first -> 286; max_episode_steps=250 -> 249
+    assert np.load(os.path.join(GOLD, "c0_buildings.npz"))["actions"].shape[0] == 286
+    assert np.load(os.path.join(GOLD, "heterogeneous_max250.npz"))["actions"].shape[0] == 249
+
+
+def test_ev_notebook_totals_bit_exact():
+    """examples/envs/ev-charging.ipynb cells 5-7 (always-max, always-min, constant 0.8)."""
+    g = np.load(os.path.join(GOLD, "ev_totals.npz"))
+    np.testing.assert_array_equal(g["notebook"], g["reference_here"])
+    cfg = {"num_vehicles": 100, "minutes_per_step": 5, "max_charge_rate_kw": 7.,
+           "peak_threshold": 250., "vehicle_multiplier": 5., "rescale_spaces": False}
+    pol = {"high": lambda e: e.action_space.high, "low": lambda e: e.action_space.low,
+           "const0.8": lambda e: np.array([.8])}
+    for key, want in zip(g["keys"], g["notebook"]):
+        env = NS.EVChargingEnv(**cfg)
+        env.reset()
+        done, tot, n = False, 0.0, 0
+        while not done:
+            _, r, done, _ = env.step(pol[str(key)](env))
+            tot += r
+            n += 1
+        assert n == 286
+        assert tot * env.reward_scale == want
+
+
+def test_storage_episode_is_287_steps():
+    env = NS.EnergyStorageEnv(name="s")
+    env.reset(init_storage=30.0)
+    n, done = 0, False
+    while not done:
+        _, _, done, _ = env.step(np.array([0.3]))
+        n += 1
+    assert n == 287

@@ -575,7 +575,19 @@ def solve_snapshot(ckt: Circuit, load_kw, load_kvar, v_start=None, tol=1e-10, ma
                     if a >= 0 and b >= 0:
                         Ysys[a, b] += sa * sb * yeq
             branch.append((p, q, ld["model"], s_ph, ld["vbase"], ld["vminpu"], ld["vmaxpu"], yeq))
-    lu = np.linalg.inv(Ysys)
+    import scipy.linalg as sla
+    fac = sla.lu_factor(Ysys)
+    Ysys_x = Ysys.astype(np.clongdouble)
+
+    def solve(rhs):
+        # LU solve with two refinement sweeps on extended-precision residuals
+        # (cond(Y) ~ 2e8: a 1e-7 ohm switch and a very stiff source)
+        x = sla.lu_solve(fac, rhs)
+        for _ in range(2):
+            r = (rhs.astype(np.clongdouble) - Ysys_x @ x.astype(np.clongdouble)).astype(np.complex128)
+            x = x + sla.lu_solve(fac, r)
+        return x
+
     v = np.linalg.solve(ckt.Ynet, ckt.Isrc) if v_start is None else v_start.copy()
     it = 0
     for it in range(1, max_iter + 1):
@@ -587,7 +599,7 @@ def solve_snapshot(ckt: Circuit, load_kw, load_kvar, v_start=None, tol=1e-10, ma
                 inj[p] += comp
             if q >= 0:
                 inj[q] -= comp
-        v_new = lu @ inj
+        v_new = solve(inj)
         err = np.max(np.abs(v_new - v) / ckt.vbase)
         v = v_new
         if err < tol:

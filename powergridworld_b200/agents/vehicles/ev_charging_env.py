@@ -1,0 +1,118 @@
+"""EV charging station description (gridworld/agents/vehicles/ev_charging_env.py:17-275).
+Dynamics: csrc/component_math.cuh ev_advance / ev_step / ev_reset.
+
+The vehicle roster (arrival, departure, energy) is shared by every env, so the
+"who is parked at minute t" half of the reference's charging set is a static
+per-step list compiled here; only the "still needs energy" half is per-env state.
+"""
+from collections import OrderedDict
+
+import numpy as np
+
+from powergridworld_b200 import _native as N
+from powergridworld_b200 import assets, spaces
+from powergridworld_b200.base import ComponentEnv
+from powergridworld_b200.utils import maybe_rescale_box_space
+
+
+def _read_vehicle_csv(path):
+    import pandas as pd
+    df = pd.read_csv(path)
+    return {c: df[c].values.astype(np.float64)
+            for c in ("start_time_min", "end_time_park_min", "energy_required_kwh")}
+
+
+class EVChargingEnv(ComponentEnv):
+
+    def __init__(self, num_vehicles: int = 100, minutes_per_step: int = 5,
+                 max_charge_rate_kw: float = 7.0, max_episode_steps: int = None,
+                 unserved_penalty: float = 1., peak_penalty: float = 1.,
+                 peak_threshold: float = 10., reward_scale: float = 1e5, name: str = None,
+                 randomize: bool = False, vehicle_csv: str = None, vehicle_multiplier: int = 1,
+                 rescale_spaces: bool = True, **kwargs):
+        super().__init__(name=name)
+        if randomize:
+            raise NotImplementedError(
+                "randomize=True (a different roster sample per reset, :155-156) is not "
+                "supported: all envs of a batch share one roster")
+        self.num_vehicles = num_vehicles
+        self.max_charge_rate_kw = max_charge_rate_kw
+        self.minutes_per_step = minutes_per_step
+        self.randomize = randomize
+        self.vehicle_multiplier = vehicle_multiplier
+        self.rescale_spaces = rescale_spaces
+        self.unserved_penalty = unserved_penalty
+        self.peak_penalty = peak_penalty
+        self.peak_threshold = peak_threshold
+        self.reward_scale = reward_scale
+        mes = max_episode_steps if max_episode_steps is not None else np.inf
+        self.max_episode_steps = min(mes, 24 * 60 / minutes_per_step)
+        self.simulation_times = np.arange(
+            0, self.max_episode_steps * minutes_per_step, minutes_per_step)
+        cols = _read_vehicle_csv(vehicle_csv) if vehicle_csv else {
+            c: assets.array(f"vehicles/{c}")
+            for c in ("start_time_min", "end_time_park_min", "energy_required_kwh")}
+        energy = cols["energy_required_kwh"] * self.vehicle_multiplier            # :72
+        rnd = lambda x: x - x % self.minutes_per_step                             # :273-275
+        self._roster_start = rnd(cols["start_time_min"])
+        self._roster_end = rnd(cols["end_time_park_min"])
+        self._roster_energy = energy
+        emax = energy.max()
+        obs_bounds = OrderedDict({
+            "time": (0, self.simulation_times[-1]),
+            "num_active_vehicles": (0, self.num_vehicles),
+            "real_power_consumed": (0, self.num_vehicles * self.max_charge_rate_kw),
+            "real_power_demand": (0, self.num_vehicles * emax),
+            "mean_charge_rate_deficit": (0, emax / (self.minutes_per_step / 60.)),
+            "real_power_unserved": (0, emax)})
+        self._observation_space = spaces.Box(
+            low=np.array([x[0] for x in obs_bounds.values()], dtype=np.float64),
+            high=np.array([x[1] for x in obs_bounds.values()], dtype=np.float64),
+            shape=(len(obs_bounds),), dtype=np.float64)
+        self.observation_space = maybe_rescale_box_space(self._observation_space, rescale_spaces)
+        self._action_space = spaces.Box(low=0., high=1., shape=(1,), dtype=np.float64)
+        self.action_space = maybe_rescale_box_space(self._action_space, rescale_spaces)
+        self.state = OrderedDict({k: None for k in obs_bounds.keys()})
+        self._obs_labels = list(self.state.keys())
+
+    def _terminal_after(self):
+        # reset leaves time_index == 1 (hidden step, :163); terminal at max_episode_steps - 1
+        return self.max_episode_steps - 2
+
+    def _emit(self, b, agent_index, standalone):
+        n = self.num_vehicles
+        start = np.floor(self._roster_start[:n])
+        end = np.floor(self._roster_end[:n])
+        times = self.simulation_times
+        idx = np.arange(n)
+
+        def window(k):
+            t = times[k]
+            return idx[(t >= start) & (t <= end)]          # :186-190, ascending index
+
+        n_ev = len(times) - 1                               # events 0 .. len-2 have a "next" time
+        wins = [window(k) for k in range(n_ev)]
+        lefts = [np.array([], dtype=int)] + [np.setdiff1d(wins[k - 1], wins[k]) for k in range(1, n_ev)]
+        cap = max(1, max(len(w) for w in wins), max(len(l) for l in lefts))
+        words = (n + 31) // 32
+
+        def dtab_fn(r):
+            k = min(r, n_ev - 1)
+            return [times[k], times[k + 1]]
+
+        def itab_fn(r):
+            k = min(r, n_ev - 1)
+            row = np.zeros(2 + 2 * cap, dtype=np.int32)
+            row[0], row[1] = len(wins[k]), len(lefts[k])
+            row[2:2 + len(wins[k])] = wins[k]
+            row[2 + cap:2 + cap + len(lefts[k])] = lefts[k]
+            return row
+
+        hi = self._observation_space.high
+        dpar = [self.max_charge_rate_kw, self.minutes_per_step / 60., float(self.vehicle_multiplier),
+                self.unserved_penalty, self.peak_penalty, self.peak_threshold, self.reward_scale]
+        dpar += list(hi) + list(self._roster_end[:n]) + list(self._roster_energy[:n])
+        b.add_component(self, N.EV, agent_index,
+                        flags=N.F_RESCALE if self.rescale_spaces else 0,
+                        dpar=dpar, ipar=[n, words, cap], sd_rows=n, si_rows=words,
+                        dtab_width=2, dtab_fn=dtab_fn, itab_width=2 + 2 * cap, itab_fn=itab_fn)

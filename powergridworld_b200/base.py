@@ -1,0 +1,106 @@
+"""Agent plugin protocol (mirrors gridworld/base.py:12-182).
+
+The classes keep the reference's names, constructor keywords and attributes
+(``name``, ``observation_space``, ``action_space``, ``_observation_space``,
+``_action_space``, ``rescale_spaces``, ``obs_labels``, ``envs``, ``env_dict`` ...),
+but they do not compute anything themselves: a component is a *description* that
+``MultiAgentEnv`` compiles into the structure-of-arrays tables of the CUDA
+kernels (``_emit``).  There is deliberately no Python implementation of the
+dynamics in this package -- no CPU fallback.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Dict, List
+
+from powergridworld_b200 import spaces
+
+_GPU_ONLY = ("{cls} is stepped on the GPU by powergridworld_b200.MultiAgentEnv "
+             "(wrap it as an agent; pf_config=None gives a component-only env); "
+             "this package has no CPU implementation of the dynamics.")
+
+
+class ComponentEnv(ABC):
+    """gridworld/base.py:12-71."""
+
+    def __init__(self, name: str = None, **kwargs):
+        self.name = name
+        self._real_power = 0.
+        self._reactive_power = 0.
+        self._obs_labels: List[str] = []
+
+    # ---- the reference's abstract protocol: served by the batched env, not per object
+    def reset(self, **kwargs):
+        raise NotImplementedError(_GPU_ONLY.format(cls=type(self).__name__))
+
+    def step(self, action, **kwargs):
+        raise NotImplementedError(_GPU_ONLY.format(cls=type(self).__name__))
+
+    def step_reward(self, **kwargs):
+        raise NotImplementedError(_GPU_ONLY.format(cls=type(self).__name__))
+
+    def get_obs(self, **kwargs):
+        raise NotImplementedError(_GPU_ONLY.format(cls=type(self).__name__))
+
+    @property
+    def real_power(self) -> float:
+        """kW, + load / - generation; refreshed by MultiAgentEnv after each step (E == 1)."""
+        return self._real_power
+
+    @property
+    def reactive_power(self) -> float:
+        return self._reactive_power          # always 0 in the reference (base.py:24)
+
+    @property
+    def obs_labels(self) -> list:
+        return self._obs_labels
+
+    # ---- spec compiler hooks
+    @abstractmethod
+    def _emit(self, builder, agent_index: int, standalone: bool) -> None:
+        """Append this component's descriptor / parameters / event blocks to ``builder``."""
+
+    @abstractmethod
+    def _terminal_after(self) -> float:
+        """Number of env steps after which the component's is_terminal() turns true."""
+
+    @property
+    def _act_dim(self) -> int:
+        return int(self.action_space.shape[0])
+
+    @property
+    def _obs_dim(self) -> int:
+        return int(self.observation_space.shape[0])
+
+
+class MultiComponentEnv(ComponentEnv):
+    """gridworld/base.py:74-182: one agent made of an ordered list of components."""
+
+    def __init__(self, name: str = None, components: List[dict] = None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.envs = [c["cls"](name=c["name"], **c["config"]) for c in components]
+        for e in self.envs:
+            if isinstance(e, MultiComponentEnv):
+                raise TypeError("nested MultiComponentEnv is not supported")
+        self.observation_space = spaces.Dict({e.name: e.observation_space for e in self.envs})
+        self.action_space = spaces.Dict({e.name: e.action_space for e in self.envs})
+        self._obs_labels_dict = {e.name: e.obs_labels for e in self.envs}
+        labels = []
+        for e in self.envs:
+            labels += e.obs_labels
+        self._obs_labels = list(set(labels))
+
+    def _emit(self, builder, agent_index, standalone):
+        for e in self.envs:
+            e._emit(builder, agent_index, standalone=False)
+
+    def _terminal_after(self):
+        return min(e._terminal_after() for e in self.envs)
+
+    @property
+    def obs_labels_dict(self) -> Dict[str, list]:
+        return self._obs_labels_dict
+
+    @property
+    def env_dict(self) -> Dict[str, ComponentEnv]:
+        return {e.name: e for e in self.envs}

@@ -1,0 +1,480 @@
+// C ABI of the batched simulator (include/pgw.h): owns the device-side tables and
+// state of one env batch and sequences the kernels of reset / step.
+//
+//   reset:  [power flow, base load only]  ->  [component reset kernel]
+//   step:   [component step kernel]       ->  [power flow + reward hook]
+//
+// The episode clock lives on the device and is advanced by the last CTA of the last
+// kernel of a step, so a step has constant launch parameters (CUDA-graph friendly).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "internal.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PGW_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return fail(PGW_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+  } while (0)
+
+template <typename T>
+cudaError_t upload(T** dst, const T* src, size_t n) {
+  *dst = nullptr;
+  if (n == 0) return cudaSuccess;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+template <typename T>
+cudaError_t alloc_zero(T** dst, size_t n) {
+  *dst = nullptr;
+  if (n == 0) return cudaSuccess;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemset(*dst, 0, n * sizeof(T));
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct pgw_env {
+  int E = 0, A = 0, C = 0, act_dim = 0, obs_dim = 0, sd_rows = 0, si_rows = 0;
+  int num_storage = 0, num_events = 0, dstride = 0, istride = 0;
+  bool has_feeder = false;
+  int nb = 0, nn = 0, nl = 0, nbp = 0, nnp = 0, max_iter = 0;
+  double tol = 0;
+  int penalty_node = -1;
+  double pvlo = 0, pvhi = 0, punit = 0;
+  int pf_kernel = 0;
+  int clock = -1;             // host mirror
+  long long launches = 0;
+  // device tables
+  pgw_agent* agents = nullptr;
+  pgw_component* comps = nullptr;
+  double* dpar = nullptr;
+  int32_t* ipar = nullptr;
+  double* dtab = nullptr;
+  int32_t* itab = nullptr;
+  double2 *zbbT = nullptr, *u0 = nullptr, *znbT = nullptr, *w = nullptr;
+  int32_t *branch_load = nullptr, *branch_model = nullptr;
+  double *branch_share = nullptr, *vminpu = nullptr, *vmaxpu = nullptr;
+  // device state
+  double* sd = nullptr;
+  uint32_t* si = nullptr;
+  double *agent_p = nullptr, *ep_ret = nullptr, *rew_last = nullptr;
+  double *vmag = nullptr, *vmin = nullptr, *vmax = nullptr, *vbus = nullptr, *viol = nullptr;
+  int32_t* iters = nullptr;
+  int* d_clock = nullptr;
+  unsigned int* d_ticket = nullptr;
+  // staging for the *_host entry points
+  double *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_soc = nullptr;
+  uint8_t* h_done = nullptr;
+  std::vector<void*> owned;
+  // optional per-kernel timing (pgw_set_timing)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;     // triples: start, after components, after power flow
+  size_t ev_used = 0;
+  double t_comp_ms = 0, t_pf_ms = 0, t_steps = 0;
+
+  ~pgw_env() {
+    for (void* p : owned) cudaFree(p);
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+  }
+  cudaEvent_t next_event() {
+    if (ev_used == ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev_pool.push_back(e);
+    }
+    return ev_pool[ev_used++];
+  }
+  template <typename T>
+  void own(T* p) {
+    if (p) owned.push_back(const_cast<void*>(reinterpret_cast<const void*>(p)));
+  }
+};
+
+extern "C" {
+
+const char* pgw_last_error(void) { return g_err.c_str(); }
+int pgw_abi_version(void) { return PGW_ABI_VERSION; }
+
+int pgw_create(const pgw_spec* spec, pgw_env** out) {
+  if (!spec || !out) return fail(PGW_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (spec->abi_version != PGW_ABI_VERSION) return fail(PGW_ERR_INVALID, "ABI version mismatch");
+  if (spec->num_envs <= 0 || spec->num_agents <= 0 || spec->num_components <= 0 ||
+      spec->num_events <= 1)
+    return fail(PGW_ERR_INVALID, "empty spec");
+  if (spec->dtab_stride % 2 || spec->itab_stride % 4)
+    return fail(PGW_ERR_INVALID, "event rows must be multiples of 16 bytes");
+  if (spec->num_agents > 65535) return fail(PGW_ERR_INVALID, "too many agents");
+  for (int a = 0; a < spec->num_agents; ++a) {
+    const pgw_agent& ag = spec->agents[a];
+    if (ag.comp_begin < 0 || ag.comp_end > spec->num_components || ag.comp_begin >= ag.comp_end)
+      return fail(PGW_ERR_INVALID, "agent component range out of bounds");
+    if (ag.load_slot >= 0 && (!spec->feeder || ag.load_slot >= spec->feeder->nl))
+      return fail(PGW_ERR_INVALID, "agent load slot out of range");
+    if (ag.bus_node >= 0 && (!spec->feeder || ag.bus_node >= spec->feeder->nn))
+      return fail(PGW_ERR_INVALID, "agent bus node out of range");
+  }
+  for (int c = 0; c < spec->num_components; ++c) {
+    const pgw_component& k = spec->components[c];
+    if (k.type < PGW_STORAGE || k.type > PGW_BUILDING)
+      return fail(PGW_ERR_INVALID, "unknown component type (no CPU fallback exists)");
+    if (k.obs_off < 0 || k.obs_off + k.obs_dim > spec->obs_dim || k.act_off < 0 ||
+        k.act_off >= spec->act_dim || k.dpar_off < 0 || k.dpar_off > spec->dpar_len ||
+        k.ipar_off < 0 || k.ipar_off > spec->ipar_len)
+      return fail(PGW_ERR_INVALID, "component offsets out of range");
+    if (!spec->feeder && (k.flags & (PGW_F_GRID_AWARE | PGW_F_PV_VOLT_REWARD)))
+      return fail(PGW_ERR_INVALID, "grid-aware component without a feeder");
+  }
+  int dev = 0;
+  PGW_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  PGW_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(PGW_ERR_ARCH, "this library is built for sm_100a (B200) only");
+
+  pgw_env* env = new (std::nothrow) pgw_env();
+  if (!env) return fail(PGW_ERR_NOMEM, "host allocation failed");
+  env->E = spec->num_envs; env->A = spec->num_agents; env->C = spec->num_components;
+  env->act_dim = spec->act_dim; env->obs_dim = spec->obs_dim;
+  env->sd_rows = spec->sd_rows; env->si_rows = spec->si_rows;
+  env->num_storage = spec->num_storage; env->num_events = spec->num_events;
+  env->dstride = spec->dtab_stride; env->istride = spec->itab_stride;
+  const size_t E = (size_t)env->E, A = (size_t)env->A;
+
+#define PGW_TRY(expr)                                                                  \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      delete env;                                                                      \
+      return fail(_e == cudaErrorMemoryAllocation ? PGW_ERR_NOMEM : PGW_ERR_CUDA,      \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+    }                                                                                  \
+  } while (0)
+
+  PGW_TRY(upload(&env->agents, spec->agents, A)); env->own(env->agents);
+  PGW_TRY(upload(&env->comps, spec->components, (size_t)env->C)); env->own(env->comps);
+  PGW_TRY(upload(&env->dpar, spec->dpar, (size_t)spec->dpar_len)); env->own(env->dpar);
+  PGW_TRY(upload(&env->ipar, spec->ipar, (size_t)spec->ipar_len)); env->own(env->ipar);
+  PGW_TRY(upload(&env->dtab, spec->dtab, (size_t)spec->num_events * spec->dtab_stride));
+  env->own(env->dtab);
+  PGW_TRY(upload(&env->itab, spec->itab, (size_t)spec->num_events * spec->itab_stride));
+  env->own(env->itab);
+
+  PGW_TRY(alloc_zero(&env->sd, (size_t)env->sd_rows * E)); env->own(env->sd);
+  PGW_TRY(alloc_zero(&env->si, (size_t)env->si_rows * E)); env->own(env->si);
+  PGW_TRY(alloc_zero(&env->agent_p, A * E)); env->own(env->agent_p);
+  PGW_TRY(alloc_zero(&env->ep_ret, A * E)); env->own(env->ep_ret);
+  PGW_TRY(alloc_zero(&env->rew_last, A * E)); env->own(env->rew_last);
+  PGW_TRY(alloc_zero(&env->d_clock, 1)); env->own(env->d_clock);
+  PGW_TRY(alloc_zero(&env->d_ticket, 1)); env->own(env->d_ticket);
+
+  if (spec->feeder) {
+    const pgw_feeder& f = *spec->feeder;
+    if (f.nb <= 0 || f.nn <= 0 || f.nl <= 0 || f.nb > 128 || f.max_iter <= 0) {
+      delete env;
+      return fail(PGW_ERR_INVALID, "feeder dimensions out of range (1..128 load branches)");
+    }
+    if (spec->dtab_stride < 2 + 2 * f.nl) {
+      delete env;
+      return fail(PGW_ERR_INVALID, "event row too short for the feeder base loads");
+    }
+    env->has_feeder = true;
+    env->nb = f.nb; env->nn = f.nn; env->nl = f.nl; env->max_iter = f.max_iter; env->tol = f.tol;
+    env->nbp = f.nb <= 16 ? 16 : round_up(f.nb, 32);
+    env->nnp = round_up(f.nn, 2);
+    env->penalty_node = f.penalty_node; env->pvlo = f.penalty_vlo; env->pvhi = f.penalty_vhi;
+    env->punit = f.penalty_unit;
+    if (env->punit != 0.0 && (f.penalty_node < 0 || f.penalty_node >= f.nn)) {
+      delete env;
+      return fail(PGW_ERR_INVALID, "penalty node out of range");
+    }
+    const int nb = f.nb, nn = f.nn, nbp = env->nbp, nnp = env->nnp;
+    std::vector<double2> zt((size_t)nb * nbp, make_double2(0, 0)), u0(nbp, make_double2(1, 0)),
+        znt((size_t)nb * nnp, make_double2(0, 0)), w(nnp, make_double2(0, 0));
+    for (int k = 0; k < nb; ++k)
+      for (int j = 0; j < nb; ++j)
+        zt[(size_t)j * nbp + k] = make_double2(f.zbb[2 * ((size_t)k * nb + j)], f.zbb[2 * ((size_t)k * nb + j) + 1]);
+    for (int k = 0; k < nb; ++k) u0[k] = make_double2(f.u0[2 * k], f.u0[2 * k + 1]);
+    for (int n = 0; n < nn; ++n) {
+      w[n] = make_double2(f.w[2 * n], f.w[2 * n + 1]);
+      for (int k = 0; k < nb; ++k)
+        znt[(size_t)k * nnp + n] = make_double2(f.znb[2 * ((size_t)n * nb + k)], f.znb[2 * ((size_t)n * nb + k) + 1]);
+    }
+    std::vector<int32_t> bl(nbp, 0), bm(nbp, 1);
+    std::vector<double> bs(nbp, 0.0), vlo(nbp, 0.95), vhi(nbp, 1.05);
+    for (int k = 0; k < nb; ++k) {
+      if (f.branch_load[k] < 0 || f.branch_load[k] >= f.nl) {
+        delete env;
+        return fail(PGW_ERR_INVALID, "branch load index out of range");
+      }
+      bl[k] = f.branch_load[k]; bm[k] = f.branch_model[k]; bs[k] = f.branch_share[k];
+      vlo[k] = f.vminpu[k]; vhi[k] = f.vmaxpu[k];
+    }
+    PGW_TRY(upload(&env->zbbT, zt.data(), zt.size())); env->own(env->zbbT);
+    PGW_TRY(upload(&env->u0, u0.data(), u0.size())); env->own(env->u0);
+    PGW_TRY(upload(&env->znbT, znt.data(), znt.size())); env->own(env->znbT);
+    PGW_TRY(upload(&env->w, w.data(), w.size())); env->own(env->w);
+    PGW_TRY(upload(&env->branch_load, bl.data(), bl.size())); env->own(env->branch_load);
+    PGW_TRY(upload(&env->branch_model, bm.data(), bm.size())); env->own(env->branch_model);
+    PGW_TRY(upload(&env->branch_share, bs.data(), bs.size())); env->own(env->branch_share);
+    PGW_TRY(upload(&env->vminpu, vlo.data(), vlo.size())); env->own(env->vminpu);
+    PGW_TRY(upload(&env->vmaxpu, vhi.data(), vhi.size())); env->own(env->vmaxpu);
+    PGW_TRY(alloc_zero(&env->vmag, (size_t)nn * E)); env->own(env->vmag);
+    PGW_TRY(alloc_zero(&env->vmin, E)); env->own(env->vmin);
+    PGW_TRY(alloc_zero(&env->vmax, E)); env->own(env->vmax);
+    PGW_TRY(alloc_zero(&env->vbus, A * E)); env->own(env->vbus);
+    PGW_TRY(alloc_zero(&env->viol, E)); env->own(env->viol);
+    PGW_TRY(alloc_zero(&env->iters, E)); env->own(env->iters);
+  }
+#undef PGW_TRY
+  *out = env;
+  return PGW_OK;
+}
+
+int pgw_destroy(pgw_env* env) {
+  if (!env) return PGW_OK;
+  if (env->h_act) cudaFree(env->h_act);
+  if (env->h_obs) cudaFree(env->h_obs);
+  if (env->h_rew) cudaFree(env->h_rew);
+  if (env->h_soc) cudaFree(env->h_soc);
+  if (env->h_done) cudaFree(env->h_done);
+  delete env;
+  return PGW_OK;
+}
+
+static pgw::CompParams comp_params(pgw_env* env) {
+  pgw::CompParams p{};
+  p.E = env->E; p.A = env->A;
+  p.agents = env->agents; p.comps = env->comps; p.dpar = env->dpar; p.ipar = env->ipar;
+  p.dtab = env->dtab; p.itab = env->itab; p.dstride = env->dstride; p.istride = env->istride;
+  p.sd = env->sd; p.si = env->si;
+  p.vmin = env->vmin; p.vmax = env->vmax; p.vbus = env->vbus;
+  p.agent_p = env->agent_p; p.ep_ret = env->ep_ret;
+  p.clock = env->d_clock; p.ticket = env->d_ticket;
+  return p;
+}
+
+static pgw::PfParams pf_params(pgw_env* env) {
+  pgw::PfParams p{};
+  p.E = env->E; p.A = env->A; p.nb = env->nb; p.nn = env->nn; p.nl = env->nl;
+  p.nbp = env->nbp; p.nnp = env->nnp; p.max_iter = env->max_iter; p.tol = env->tol;
+  p.zbbT = env->zbbT; p.u0 = env->u0; p.znbT = env->znbT; p.w = env->w;
+  p.branch_load = env->branch_load; p.branch_share = env->branch_share;
+  p.branch_model = env->branch_model; p.vminpu = env->vminpu; p.vmaxpu = env->vmaxpu;
+  p.agents = env->agents; p.dtab = env->dtab; p.dstride = env->dstride;
+  p.vmag = env->vmag; p.vmin = env->vmin; p.vmax = env->vmax; p.vbus = env->vbus;
+  p.iters = env->iters; p.ep_ret = env->ep_ret; p.viol = env->viol;
+  p.penalty_node = env->penalty_node; p.pvlo = env->pvlo; p.pvhi = env->pvhi; p.punit = env->punit;
+  p.clock = env->d_clock; p.ticket = env->d_ticket;
+  return p;
+}
+
+static int smem_for_events(const pgw_env* env) {
+  return env->dstride * 8 + env->istride * 4;
+}
+
+int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stream) {
+  if (!env || !obs) return fail(PGW_ERR_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  PGW_CUDA(cudaMemsetAsync(env->d_clock, 0, sizeof(int), s));
+  PGW_CUDA(cudaMemsetAsync(env->d_ticket, 0, sizeof(unsigned int), s));
+  if (env->has_feeder) {
+    pgw::PfParams pf = pf_params(env);
+    pf.event_mode = 0; pf.advance_clock = 0; pf.agent_p = nullptr; pf.rew = nullptr;
+    pf.punit = 0.0;
+    PGW_CUDA(pgw::launch_powerflow(pf, s));
+    ++env->launches;
+  }
+  pgw::CompParams cp = comp_params(env);
+  cp.event_mode = 0; cp.advance_clock = 0; cp.init_soc = init_soc; cp.obs = obs;
+  PGW_CUDA(pgw::launch_components(cp, smem_for_events(env), s));
+  ++env->launches;
+  env->clock = 0;
+  return PGW_OK;
+}
+
+int pgw_step(pgw_env* env, const double* actions, double* obs, double* rew, uint8_t* done,
+             void* cuda_stream) {
+  if (!env || !actions || !obs || !rew || !done) return fail(PGW_ERR_INVALID, "null argument");
+  if (env->clock < 0) return fail(PGW_ERR_STATE, "pgw_step before pgw_reset");
+  if (env->clock + 1 >= env->num_events)
+    return fail(PGW_ERR_STATE, "episode is over: call pgw_reset");
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  pgw::CompParams cp = comp_params(env);
+  cp.event_mode = 1; cp.advance_clock = env->has_feeder ? 0 : 1;
+  cp.actions = actions; cp.obs = obs; cp.rew = rew; cp.done = done;
+  if (env->timing) PGW_CUDA(cudaEventRecord(env->next_event(), s));
+  PGW_CUDA(pgw::launch_components(cp, smem_for_events(env), s));
+  ++env->launches;
+  if (env->timing) PGW_CUDA(cudaEventRecord(env->next_event(), s));
+  if (env->has_feeder) {
+    pgw::PfParams pf = pf_params(env);
+    pf.event_mode = 1; pf.advance_clock = 1; pf.agent_p = env->agent_p; pf.rew = rew;
+    PGW_CUDA(pgw::launch_powerflow(pf, s));
+    ++env->launches;
+  }
+  if (env->timing) PGW_CUDA(cudaEventRecord(env->next_event(), s));
+  // keep a copy of the step's rewards for pgw_stats
+  PGW_CUDA(cudaMemcpyAsync(env->rew_last, rew, (size_t)env->A * env->E * sizeof(double),
+                           cudaMemcpyDeviceToDevice, s));
+  ++env->clock;
+  return PGW_OK;
+}
+
+static int ensure_staging(pgw_env* env) {
+  const size_t E = (size_t)env->E;
+  if (!env->h_act) PGW_CUDA(cudaMalloc(&env->h_act, (size_t)env->act_dim * E * 8));
+  if (!env->h_obs) PGW_CUDA(cudaMalloc(&env->h_obs, (size_t)env->obs_dim * E * 8));
+  if (!env->h_rew) PGW_CUDA(cudaMalloc(&env->h_rew, (size_t)env->A * E * 8));
+  if (!env->h_done) PGW_CUDA(cudaMalloc(&env->h_done, E));
+  if (!env->h_soc && env->num_storage)
+    PGW_CUDA(cudaMalloc(&env->h_soc, (size_t)env->num_storage * E * 8));
+  return PGW_OK;
+}
+
+int pgw_reset_host(pgw_env* env, const double* init_soc, double* obs, void* cuda_stream) {
+  if (!env || !obs) return fail(PGW_ERR_INVALID, "null argument");
+  int rc = ensure_staging(env);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t E = (size_t)env->E;
+  if (init_soc && env->num_storage)
+    PGW_CUDA(cudaMemcpyAsync(env->h_soc, init_soc, (size_t)env->num_storage * E * 8,
+                             cudaMemcpyHostToDevice, s));
+  rc = pgw_reset(env, (init_soc && env->num_storage) ? env->h_soc : nullptr, env->h_obs, s);
+  if (rc) return rc;
+  PGW_CUDA(cudaMemcpyAsync(obs, env->h_obs, (size_t)env->obs_dim * E * 8, cudaMemcpyDeviceToHost, s));
+  PGW_CUDA(cudaStreamSynchronize(s));
+  return PGW_OK;
+}
+
+int pgw_step_host(pgw_env* env, const double* actions, double* obs, double* rew, uint8_t* done,
+                  void* cuda_stream) {
+  if (!env || !actions || !obs || !rew || !done) return fail(PGW_ERR_INVALID, "null argument");
+  int rc = ensure_staging(env);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t E = (size_t)env->E;
+  PGW_CUDA(cudaMemcpyAsync(env->h_act, actions, (size_t)env->act_dim * E * 8,
+                           cudaMemcpyHostToDevice, s));
+  rc = pgw_step(env, env->h_act, env->h_obs, env->h_rew, env->h_done, s);
+  if (rc) return rc;
+  PGW_CUDA(cudaMemcpyAsync(obs, env->h_obs, (size_t)env->obs_dim * E * 8, cudaMemcpyDeviceToHost, s));
+  PGW_CUDA(cudaMemcpyAsync(rew, env->h_rew, (size_t)env->A * E * 8, cudaMemcpyDeviceToHost, s));
+  PGW_CUDA(cudaMemcpyAsync(done, env->h_done, E, cudaMemcpyDeviceToHost, s));
+  PGW_CUDA(cudaStreamSynchronize(s));
+  return PGW_OK;
+}
+
+int pgw_get(pgw_env* env, int field, void* dst, size_t bytes, void* cuda_stream) {
+  if (!env || !dst) return fail(PGW_ERR_INVALID, "null argument");
+  const size_t E = (size_t)env->E, A = (size_t)env->A;
+  const void* src = nullptr;
+  size_t want = 0;
+  switch (field) {
+    case PGW_FIELD_STATE_D: src = env->sd; want = (size_t)env->sd_rows * E * 8; break;
+    case PGW_FIELD_STATE_I: src = env->si; want = (size_t)env->si_rows * E * 4; break;
+    case PGW_FIELD_AGENT_P: src = env->agent_p; want = A * E * 8; break;
+    case PGW_FIELD_VOLTAGES: src = env->vmag; want = (size_t)env->nn * E * 8; break;
+    case PGW_FIELD_VMIN: src = env->vmin; want = E * 8; break;
+    case PGW_FIELD_VMAX: src = env->vmax; want = E * 8; break;
+    case PGW_FIELD_VBUS: src = env->vbus; want = A * E * 8; break;
+    case PGW_FIELD_PF_ITERS: src = env->iters; want = E * 4; break;
+    case PGW_FIELD_EP_RETURN: src = env->ep_ret; want = A * E * 8; break;
+    default: return fail(PGW_ERR_INVALID, "unknown field");
+  }
+  if (want == 0) return PGW_OK;
+  if (!src) return fail(PGW_ERR_INVALID, "field not available (no feeder)");
+  if (bytes != want) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "size mismatch: field needs %zu bytes, got %zu", want, bytes);
+    return fail(PGW_ERR_INVALID, buf);
+  }
+  PGW_CUDA(cudaMemcpyAsync(dst, src, want, cudaMemcpyDeviceToDevice,
+                           static_cast<cudaStream_t>(cuda_stream)));
+  return PGW_OK;
+}
+
+int pgw_pf_solve(pgw_env* env, const double* load_kw, const double* load_kvar,
+                 void* cuda_stream) {
+  if (!env || !load_kw || !load_kvar) return fail(PGW_ERR_INVALID, "null argument");
+  if (!env->has_feeder) return fail(PGW_ERR_INVALID, "this env has no feeder");
+  pgw::PfParams pf = pf_params(env);
+  pf.event_mode = 0; pf.advance_clock = 0; pf.agent_p = nullptr; pf.rew = nullptr;
+  pf.punit = 0.0; pf.load_kw = load_kw; pf.load_kvar = load_kvar;
+  PGW_CUDA(pgw::launch_powerflow(pf, static_cast<cudaStream_t>(cuda_stream)));
+  ++env->launches;
+  return PGW_OK;
+}
+
+int pgw_stats(pgw_env* env, double* out, void* cuda_stream) {
+  if (!env || !out) return fail(PGW_ERR_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  static const double init[PGW_NUM_STATS] = {0, 0, 0, 0, 0, 0, 1e300, 0};
+  PGW_CUDA(cudaMemcpyAsync(out, init, sizeof init, cudaMemcpyHostToDevice, s));
+  pgw::StatsParams p{};
+  p.E = env->E; p.A = env->A; p.nn = env->nn;
+  p.rew = env->rew_last; p.ep_ret = env->ep_ret;
+  p.viol = env->viol; p.iters = env->has_feeder ? env->iters : nullptr;
+  p.vmin = env->vmin; p.vmax = env->vmax; p.clock = env->d_clock; p.out = out;
+  PGW_CUDA(pgw::launch_stats(p, s));
+  ++env->launches;
+  return PGW_OK;
+}
+
+int pgw_set_timing(pgw_env* env, int enabled) {
+  if (!env) return fail(PGW_ERR_INVALID, "null argument");
+  env->timing = enabled != 0;
+  env->ev_used = 0;
+  env->t_comp_ms = env->t_pf_ms = env->t_steps = 0;
+  return PGW_OK;
+}
+
+int pgw_get_timing(pgw_env* env, double* out3, void* cuda_stream) {
+  if (!env || !out3) return fail(PGW_ERR_INVALID, "null argument");
+  PGW_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+  for (size_t i = 0; i + 2 < env->ev_used; i += 3) {
+    float a = 0, b = 0;
+    PGW_CUDA(cudaEventElapsedTime(&a, env->ev_pool[i], env->ev_pool[i + 1]));
+    PGW_CUDA(cudaEventElapsedTime(&b, env->ev_pool[i + 1], env->ev_pool[i + 2]));
+    env->t_comp_ms += a;
+    env->t_pf_ms += b;
+    env->t_steps += 1;
+  }
+  env->ev_used = 0;
+  out3[0] = env->t_comp_ms; out3[1] = env->t_pf_ms; out3[2] = env->t_steps;
+  env->t_comp_ms = env->t_pf_ms = env->t_steps = 0;
+  return PGW_OK;
+}
+
+int pgw_clock(const pgw_env* env) { return env ? env->clock : -1; }
+long long pgw_launch_count(const pgw_env* env) { return env ? env->launches : 0; }
+
+int pgw_set_pf_kernel(pgw_env* env, int which) {
+  if (!env) return fail(PGW_ERR_INVALID, "null argument");
+  if (which != 0) return fail(PGW_ERR_INVALID, "tensor-core power flow is not built into this library yet");
+  env->pf_kernel = which;
+  return PGW_OK;
+}
+
+}  // extern "C"

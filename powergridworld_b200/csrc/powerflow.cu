@@ -1,0 +1,324 @@
+// K6 (FP64 SIMT form) + the fresh-voltage half of K7.
+//
+// Batched three-phase Z-bus fixed point over the load branches of a compiled feeder:
+//     u <- u0 - Zbb * i(u),      i_k(u_k) = load characteristic of branch k
+// followed by the expansion to all node voltages  v = w - Znb * i,  per-unit
+// magnitudes, per-env min/max, the voltage at each agent's bus node, and the
+// grid-level reward hook (shared voltage-violation penalty).
+//
+// Replaces `Solve mode=snap` + `_prepare_bus_voltages`
+// (gridworld/distribution_system/opendss.py:134, :156-165), the per-load kW/kvar
+// bookkeeping (:107-131), `get_external_obs_vars` (gridworld/multiagent_env.py:90-115)
+// and `CoordinatedMultiBuildingControlEnv.reward_transform`
+// (examples/marl/openai/train.py:51-88).
+//
+// Mapping: TPE threads cooperate on one env (branch rows strided over the lanes, R rows
+// per lane), so a 13-bus env (14 branches) is half a warp and convergence masking is
+// a per-half-warp predicate.  Zbb / Znb are shared by every env and stay L1/L2
+// resident (3.1 kB + 8.5 kB for IEEE-13); branch currents are exchanged through
+// shared memory.  Bound by FP64 FMA issue + latency, not by HBM.
+#include "internal.cuh"
+
+namespace pgw {
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// Current drawn by one load branch at branch voltage u (per unit), nominal power s:
+// OpenDSS load model 1 = constant PQ inside [vmin, vmax], constant Z outside
+// (continuous at the band edges); 2 = constant Z; 5 = constant current magnitude.
+__device__ __forceinline__ double2 branch_current(int model, double2 s, double2 u, double vmin,
+                                                  double vmax) {
+  const double m2 = u.x * u.x + u.y * u.y;
+  const double2 sc = make_double2(s.x, -s.y);            // conj(s) = yeq on a 1 p.u. base
+  if (model == 2) return cmul(sc, u);
+  if (model == 5) {
+    const double inv = m2 > 0.0 ? rsqrt(m2) : 0.0;
+    return cmul(sc, make_double2(u.x * inv, u.y * inv));
+  }
+  if (m2 <= vmin * vmin) {
+    const double k = 1.0 / (vmin * vmin);
+    return cmul(make_double2(sc.x * k, sc.y * k), u);
+  }
+  if (m2 > vmax * vmax) {
+    const double k = 1.0 / (vmax * vmax);
+    return cmul(make_double2(sc.x * k, sc.y * k), u);
+  }
+  // conj(s / u) = conj(s) * u / |u|^2
+  const double inv = 1.0 / m2;
+  const double2 t = cmul(sc, u);
+  return make_double2(t.x * inv, t.y * inv);
+}
+
+template <int TPE>
+__device__ __forceinline__ double group_max(double v, unsigned mask) {
+#pragma unroll
+  for (int o = TPE / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o, TPE));
+  return v;
+}
+template <int TPE>
+__device__ __forceinline__ double group_min(double v, unsigned mask) {
+#pragma unroll
+  for (int o = TPE / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(mask, v, o, TPE));
+  return v;
+}
+
+template <int TPE, int R>
+__global__ void __launch_bounds__(256) pf_fixed_point_kernel(const PfParams p) {
+  extern __shared__ __align__(16) unsigned char pf_smem[];
+  const int EPB = blockDim.x / TPE;                      // envs per block pass
+  const int lane = threadIdx.x % TPE;
+  const int le = threadIdx.x / TPE;
+  const int nbp = p.nbp;
+  double2* icur_all = reinterpret_cast<double2*>(pf_smem);
+  double* stage_all = reinterpret_cast<double*>(pf_smem + (size_t)EPB * nbp * sizeof(double2));
+  double2* icur = icur_all + (size_t)le * nbp;
+  double* stage = stage_all + (size_t)le * p.nn;
+  const unsigned gmask =
+      TPE == 32 ? 0xffffffffu : (((1u << TPE) - 1u) << (TPE * ((threadIdx.x & 31) / TPE)));
+
+  const int event = p.event_mode == 0 ? 0 : (*p.clock + 1);
+  const double* drow = p.dtab + (size_t)event * p.dstride;
+  const double* base_kw = drow + 2;
+  const double* base_kvar = drow + 2 + p.nl;
+  const int groups = (p.E + EPB - 1) / EPB;
+
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int e_raw = g * EPB + le;
+    const bool valid = e_raw < p.E;
+    const int e = valid ? e_raw : p.E - 1;
+
+    // ---- per-branch nominal power: base load of the event + the agents on that load
+    double2 s[R], u[R], u0[R];
+    double vlo[R], vhi[R];
+    int model[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const int k = lane + TPE * m;
+      s[m] = make_double2(0.0, 0.0);
+      u0[m] = p.u0[k];
+      model[m] = 1; vlo[m] = 0.95; vhi[m] = 1.05;
+      if (k < p.nb) {
+        const int l = p.branch_load[k];
+        double kw, kvar;
+        if (p.load_kw != nullptr) {
+          kw = p.load_kw[(size_t)l * p.E + e];
+          kvar = p.load_kvar[(size_t)l * p.E + e];
+        } else {
+          kw = base_kw[l];
+          kvar = base_kvar[l];
+        }
+        if (p.load_kw == nullptr && p.agent_p != nullptr) {
+          // multiagent_env.py:171-181: P summed per load name in agent order, then added
+          // to the scaled base load (opendss.py:128)
+          double ctrl = 0.0;
+          bool any = false;
+          for (int a = 0; a < p.A; ++a)
+            if (p.agents[a].load_slot == l) {
+              const double pa = p.agent_p[(size_t)a * p.E + e];
+              ctrl = any ? ctrl + pa : pa;
+              any = true;
+            }
+          if (any) kw += ctrl;
+        }
+        const double sh = p.branch_share[k] * 1e-3;      // kVA -> p.u. on 1 MVA
+        s[m] = make_double2(kw * sh, kvar * sh);
+        model[m] = p.branch_model[k];
+        vlo[m] = p.vminpu[k];
+        vhi[m] = p.vmaxpu[k];
+      }
+      u[m] = u0[m];
+    }
+
+    // ---- fixed point with per-env convergence masking
+    int it = 0;
+    bool conv = false;
+    while (true) {
+#pragma unroll
+      for (int m = 0; m < R; ++m)
+        icur[lane + TPE * m] = branch_current(model[m], s[m], u[m], vlo[m], vhi[m]);
+      __syncwarp(gmask);
+      double2 acc[R];
+#pragma unroll
+      for (int m = 0; m < R; ++m) acc[m] = u0[m];
+      for (int j = 0; j < p.nb; ++j) {
+        const double2 ij = icur[j];
+        const double2* zrow = p.zbbT + (size_t)j * nbp + lane;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          const double2 z = __ldg(zrow + TPE * m);
+          acc[m].x -= z.x * ij.x - z.y * ij.y;
+          acc[m].y -= z.x * ij.y + z.y * ij.x;
+        }
+      }
+      double d = 0.0;
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        d = fmax(d, fmax(fabs(acc[m].x - u[m].x), fabs(acc[m].y - u[m].y)));
+        u[m] = acc[m];
+      }
+      d = group_max<TPE>(d, gmask);
+      ++it;
+      conv = d < p.tol;
+      if (conv || it >= p.max_iter) break;
+      __syncwarp(gmask);
+    }
+
+    // ---- all node voltages from the currents of the last iteration
+    double lmin = 1e300, lmax = -1e300;
+    for (int n = lane; n < p.nn; n += TPE) {
+      double2 v = p.w[n];
+      for (int k = 0; k < p.nb; ++k) {
+        const double2 z = __ldg(p.znbT + (size_t)k * p.nnp + n);
+        const double2 ik = icur[k];
+        v.x -= z.x * ik.x - z.y * ik.y;
+        v.y -= z.x * ik.y + z.y * ik.x;
+      }
+      const double mag = sqrt(v.x * v.x + v.y * v.y);
+      stage[n] = mag;
+      lmin = fmin(lmin, mag);
+      lmax = fmax(lmax, mag);
+    }
+    lmin = group_min<TPE>(lmin, gmask);
+    lmax = group_max<TPE>(lmax, gmask);
+    __syncwarp(gmask);
+
+    if (valid) {
+      if (lane == 0) {
+        p.vmin[e] = lmin;
+        p.vmax[e] = lmax;
+        p.iters[e] = conv ? it : -it;
+      }
+      double pen_share = 0.0;
+      if (p.punit != 0.0) {
+        const double v = stage[p.penalty_node];
+        const double viol = fmax(0.0, fmax(p.pvlo - v, v - p.pvhi));   // train.py:71-88
+        if (lane == 0) p.viol[e] = viol;
+        pen_share = (viol * p.punit) / (double)p.A;                    // train.py:56-61
+      } else if (lane == 0) {
+        p.viol[e] = 0.0;
+      }
+      for (int a = lane; a < p.A; a += TPE) {
+        const int node = p.agents[a].bus_node;
+        const size_t ae = (size_t)a * p.E + e;
+        p.vbus[ae] = node >= 0 ? stage[node] : 1.0;
+        if (p.event_mode != 0) {
+          const double r = p.rew[ae] - pen_share;
+          p.rew[ae] = r;
+          p.ep_ret[ae] += r;
+        }
+      }
+    }
+    // ---- coalesced store of the magnitudes: [nn][E], EPB consecutive envs per row
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < p.nn * EPB; idx += blockDim.x) {
+      const int n = idx / EPB, j = idx % EPB;
+      const int ee = g * EPB + j;
+      if (ee < p.E) p.vmag[(size_t)n * p.E + ee] = stage_all[(size_t)j * p.nn + n];
+    }
+    __syncthreads();
+  }
+
+  if (p.advance_clock) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int t = atomicAdd(p.ticket, 1u);
+      if (t == gridDim.x - 1) {
+        *p.ticket = 0u;
+        *p.clock = event;
+        __threadfence();
+      }
+    }
+  }
+}
+
+template <int TPE, int R>
+static cudaError_t launch_pf_t(const PfParams& p, cudaStream_t s) {
+  const int threads = 256;
+  const int epb = threads / TPE;
+  const int groups = (p.E + epb - 1) / epb;
+  int grid = groups < 148 * 8 ? groups : 148 * 8;
+  if (grid < 1) grid = 1;
+  const size_t smem = (size_t)epb * p.nbp * sizeof(double2) + (size_t)epb * p.nn * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(pf_fixed_point_kernel<TPE, R>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+  }
+  pf_fixed_point_kernel<TPE, R><<<grid, threads, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_powerflow(const PfParams& p, cudaStream_t s) {
+  if (p.nbp == 16) return launch_pf_t<16, 1>(p, s);
+  if (p.nbp == 32) return launch_pf_t<32, 1>(p, s);
+  if (p.nbp == 64) return launch_pf_t<32, 2>(p, s);
+  if (p.nbp == 96) return launch_pf_t<32, 3>(p, s);
+  if (p.nbp == 128) return launch_pf_t<32, 4>(p, s);
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------ K8: episode statistics
+__global__ void __launch_bounds__(256) stats_kernel(const StatsParams p) {
+  __shared__ double red[5][8];
+  double rsum = 0.0, esum = 0.0, vsum = 0.0, nconv = 0.0, itsum = 0.0;
+  double vmn = 1e300, vmx = -1e300;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < p.E; e += gridDim.x * blockDim.x) {
+    for (int a = 0; a < p.A; ++a) {
+      rsum += p.rew[(size_t)a * p.E + e];
+      esum += p.ep_ret[(size_t)a * p.E + e];
+    }
+    if (p.iters != nullptr) {
+      vsum += p.viol[e];
+      const int it = p.iters[e];
+      nconv += it < 0 ? 1.0 : 0.0;
+      itsum += (double)(it < 0 ? -it : it);
+      vmn = fmin(vmn, p.vmin[e]);
+      vmx = fmax(vmx, p.vmax[e]);
+    }
+  }
+  double vals[5] = {rsum, esum, vsum, nconv, itsum};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) vals[q] += __shfl_xor_sync(0xffffffffu, vals[q], o);
+    vmn = fmin(vmn, __shfl_xor_sync(0xffffffffu, vmn, o));
+    vmx = fmax(vmx, __shfl_xor_sync(0xffffffffu, vmx, o));
+  }
+  const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  if (ln == 0) {
+    for (int q = 0; q < 5; ++q) red[q][warp] = vals[q];
+  }
+  __shared__ double mn[8], mx[8];
+  if (ln == 0) { mn[warp] = vmn; mx[warp] = vmx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[5] = {0, 0, 0, 0, 0}, a = 1e300, b = -1e300;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      for (int q = 0; q < 5; ++q) t[q] += red[q][w];
+      a = fmin(a, mn[w]);
+      b = fmax(b, mx[w]);
+    }
+    atomicAdd(p.out + 1, t[0]);
+    atomicAdd(p.out + 2, t[1]);
+    atomicAdd(p.out + 3, t[2]);
+    atomicAdd(p.out + 4, t[3]);
+    atomicAdd(p.out + 5, t[4]);
+    // min / max through the ordered-integer trick on positive doubles
+    atomicMin(reinterpret_cast<unsigned long long*>(p.out + 6), (unsigned long long)__double_as_longlong(a));
+    atomicMax(reinterpret_cast<unsigned long long*>(p.out + 7), (unsigned long long)__double_as_longlong(b > 0 ? b : 0.0));
+    if (blockIdx.x == 0) p.out[0] = (double)p.E * (double)(*p.clock);
+  }
+}
+
+cudaError_t launch_stats(const StatsParams& p, cudaStream_t s) {
+  // out[1..5] = 0, out[6] = +big, out[7] = 0 are set by the caller (memset + init kernel-free)
+  int grid = (p.E + 255) / 256;
+  if (grid > 148 * 4) grid = 148 * 4;
+  stats_kernel<<<grid, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace pgw

@@ -1,0 +1,609 @@
+"""Batched multi-agent env (mirrors gridworld/multiagent_env.py:20-230).
+
+``MultiAgentEnv(**env_config)`` takes the reference's config dict unchanged
+(``common_config`` / ``pf_config`` / ``agents`` with ``cls`` objects from this
+package) plus ``num_envs``.  The constructor is the *spec compiler*: it walks the
+agent tree, packs parameters, per-event exogenous tables and the compiled feeder
+into the structure-of-arrays tables of ``include/pgw.h`` and creates the device
+handle.  ``reset``/``step`` then run entirely on the GPU:
+
+  * ``num_envs == 1``: the reference's dict API (obs / reward / done / meta dicts
+    keyed by agent and component names);
+  * any ``num_envs``: ``reset_batch`` / ``step_batch`` on device tensors laid out
+    ``[rows, num_envs]`` (env index fastest), and ``step_host`` / ``reset_host`` on
+    pinned host arrays (the end-to-end path).
+
+Deviations from the reference, all deliberate: ``history`` is only recorded when
+``record_history=True``; ``meta`` dicts carry the grid-level entries only;
+overriding ``get_external_obs_vars`` is rejected (the grid variables are assembled
+on the device with the reference's one-step lag).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+
+from powergridworld_b200 import _native as N
+from powergridworld_b200.base import ComponentEnv, MultiComponentEnv
+from powergridworld_b200.distribution_system.opendss import ZBusSolver
+from powergridworld_b200.distribution_system.powerflow import PowerFlowSolver
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class SpecBuilder:
+    """Collects component descriptors, parameter blocks and per-event table writers."""
+
+    def __init__(self, nl: int):
+        self.header = 2 + 2 * nl          # done, reserved, base kW[nl], base kvar[nl]
+        self.comps: List[N.Component] = []
+        self.objs: List[ComponentEnv] = []
+        self.dpar: List[float] = []
+        self.ipar: List[int] = []
+        self.sd_rows = self.si_rows = self.act_dim = self.obs_dim = 0
+        self.dwidth = self.header
+        self.iwidth = 0
+        self.dwriters, self.iwriters = [], []
+        self.storages: List[ComponentEnv] = []
+        self.needs_grid = False
+        self.max_events = np.inf
+
+    def next_storage_ordinal(self, obj) -> int:
+        self.storages.append(obj)
+        return len(self.storages) - 1
+
+    def add_component(self, obj, ctype, agent_index, flags=0, dpar=(), ipar=(), sd_rows=0,
+                      si_rows=0, dtab_width=0, dtab_fn=None, itab_width=0, itab_fn=None,
+                      needs_grid=False, max_events=None):
+        c = N.Component()
+        c.type, c.agent, c.flags = ctype, agent_index, flags
+        c.act_off, c.obs_off, c.obs_dim = self.act_dim, self.obs_dim, obj._obs_dim
+        c.sd_off, c.si_off = self.sd_rows, self.si_rows
+        c.dtab_off, c.itab_off = self.dwidth, self.iwidth
+        c.dpar_off, c.ipar_off = len(self.dpar), len(self.ipar)
+        self.dpar += [float(x) for x in dpar]
+        self.ipar += [int(x) for x in ipar]
+        self.act_dim += obj._act_dim
+        self.obs_dim += obj._obs_dim
+        self.sd_rows += sd_rows
+        self.si_rows += si_rows
+        if dtab_width:
+            self.dwriters.append((self.dwidth, dtab_width, dtab_fn))
+            self.dwidth += dtab_width
+        if itab_width:
+            self.iwriters.append((self.iwidth, itab_width, itab_fn))
+            self.iwidth += itab_width
+        self.needs_grid |= bool(needs_grid)
+        if max_events is not None:
+            self.max_events = min(self.max_events, max_events)
+        obj._slot = {"act": (c.act_off, obj._act_dim), "obs": (c.obs_off, obj._obs_dim),
+                     "sd": (c.sd_off, sd_rows), "si": (c.si_off, si_rows)}
+        self.comps.append(c)
+        self.objs.append(obj)
+
+
+class MultiAgentEnv:
+    """gridworld/multiagent_env.py:20-230 over ``num_envs`` instances on one GPU."""
+
+    # grid-level reward hook; subclasses set these (see CoordinatedMultiBuildingControlEnv)
+    _penalty = None     # (vlo, vhi, unit_penalty) or None
+
+    def __init__(self, common_config: dict = {}, pf_config: dict = None, agents: list = None,
+                 max_episode_steps: int = None, rescale_spaces: bool = True,
+                 num_envs: int = 1, device=None, record_history: bool = False,
+                 pf_tol: float = None, pf_max_iter: int = None, _dry_run: bool = False,
+                 **kwargs):
+        if type(self).get_external_obs_vars is not MultiAgentEnv.get_external_obs_vars:
+            raise NotImplementedError(
+                "overriding get_external_obs_vars is not supported: grid variables are "
+                "assembled on the device (no CPU fallback)")
+        self.common_config = common_config
+        self.rescale_spaces = rescale_spaces
+        assert agents is not None and len(agents) > 0, "need at least one agent!"
+        self.start_time = pd.Timestamp(common_config["start_time"])
+        self.end_time = pd.Timestamp(common_config["end_time"])
+        self.control_timedelta = common_config["control_timedelta"]
+        self.pf_config = pf_config
+        self.max_episode_steps = max_episode_steps if max_episode_steps is not None else np.inf
+        self.num_envs = int(num_envs)
+        self.record_history = record_history
+        self.episode_step = None
+        self.time = None
+        self.history = None
+
+        # ---- agents (same constructor call as multiagent_env.py:57-70)
+        self.agents: List[ComponentEnv] = []
+        for a in agents:
+            cfg = {k: v for k, v in a["config"].items() if k != "name"}
+            self.agents.append(a["cls"](name=a["name"], **cfg, **self.common_config))
+        self.agent_name_bus_map = {a["name"]: a["bus"] for a in agents}
+        self.agent_names = [a.name for a in self.agents]
+        assert len(set(self.agent_names)) == len(agents), "all agents need unique names"
+        for ag in self.agents:
+            if not isinstance(ag, ComponentEnv):
+                raise TypeError(f"agent class {type(ag).__name__} is not a powergridworld_b200 "
+                                "component: arbitrary Python agents cannot run on the device")
+
+        # ---- power-flow plugin
+        self.pf_solver: Optional[ZBusSolver] = None
+        if pf_config and (pf_config.get("cls") is not None or "instance" in pf_config):
+            solver = pf_config["instance"] if "instance" in pf_config \
+                else pf_config["cls"](**pf_config.get("config", {}))
+            if not isinstance(solver, ZBusSolver):
+                raise TypeError("pf_config['cls'] must be powergridworld_b200's OpenDSSSolver/"
+                                "ZBusSolver: a Python PowerFlowSolver cannot run on the device")
+            if pf_tol is not None:
+                solver.tol = pf_tol
+            if pf_max_iter is not None:
+                solver.max_iter = pf_max_iter
+            solver._env = self
+            self.pf_solver = solver
+
+        self.observation_space = {a.name: a.observation_space for a in self.agents}
+        self.action_space = {a.name: a.action_space for a in self.agents}
+
+        self._compile()
+        self._h = None
+        if not _dry_run:        # tests inspect the compiled tables without a GPU
+            self._open(device)
+
+    # ------------------------------------------------------------------ spec compiler
+    def _compile(self):
+        feeder = self.pf_solver.feeder if self.pf_solver else None
+        nl = feeder.nl if feeder else 0
+        b = SpecBuilder(nl)
+        agent_recs = (N.Agent * len(self.agents))()
+        for ai, ag in enumerate(self.agents):
+            begin = len(b.comps)
+            ag._emit(b, ai, standalone=not isinstance(ag, MultiComponentEnv))
+            rec = agent_recs[ai]
+            rec.comp_begin, rec.comp_end = begin, len(b.comps)
+            rec.load_slot, rec.bus_node = -1, -1
+            if feeder is not None:
+                bus = self.agent_name_bus_map[ag.name]
+                rec.load_slot = feeder.load_index(bus)
+                node = self.pf_solver.node_for_bus_name(str(bus))
+                if "bus_voltage" in ag.obs_labels and node is None:
+                    raise ValueError(f"agent {ag.name!r} observes bus_voltage but {bus!r} is a "
+                                     "three-phase bus name (the reference yields a list there)")
+                rec.bus_node = node if node is not None else -1
+        if b.needs_grid and feeder is None:
+            raise ValueError("a component observes grid voltages but pf_config is empty")
+
+        # episode length: first step count at which anything reports done (:199-207)
+        span = (self.end_time - self.start_time) / self.control_timedelta
+        limits = [a._terminal_after() for a in self.agents] + \
+                 [self.max_episode_steps - 1, int(np.ceil(span)), b.max_events]
+        limits = [x for x in limits if x is not None and x >= 1]
+        L = int(min(limits))
+        self.episode_length = L
+        n_events = L + 1
+
+        dstride = b.dwidth + (b.dwidth % 2)
+        istride = (b.iwidth + 3) // 4 * 4
+        dtab = np.zeros((n_events, dstride), dtype=np.float64)
+        itab = np.zeros((n_events, max(istride, 0)), dtype=np.int32)
+        for r in range(n_events):
+            dtab[r, 0] = 1.0 if r == L else 0.0
+            if feeder is not None:
+                kw, kvar = self.pf_solver.base_load_at(self.start_time + r * self.control_timedelta)
+                dtab[r, 2:2 + nl] = kw
+                dtab[r, 2 + nl:2 + 2 * nl] = kvar
+            for off, width, fn in b.dwriters:
+                dtab[r, off:off + width] = fn(r)
+            for off, width, fn in b.iwriters:
+                itab[r, off:off + width] = fn(r)
+
+        self._b = b
+        self._agent_recs = agent_recs
+        self._dtab, self._itab = dtab, itab
+        self._dstride, self._istride = dstride, istride
+        self.act_dim, self.obs_dim = b.act_dim, b.obs_dim
+        self.num_storage = len(b.storages)
+        # name-keyed layout of the flat action / observation rows
+        self.act_slices, self.obs_slices = {}, {}
+        for ag in self.agents:
+            if isinstance(ag, MultiComponentEnv):
+                self.act_slices[ag.name] = {e.name: e._slot["act"] for e in ag.envs}
+                self.obs_slices[ag.name] = {e.name: e._slot["obs"] for e in ag.envs}
+            else:
+                self.act_slices[ag.name] = ag._slot["act"]
+                self.obs_slices[ag.name] = ag._slot["obs"]
+
+    def _open(self, device):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise N.NativeError("powergridworld_b200 needs a CUDA device (B200, sm_100a); "
+                                "there is no CPU fallback")
+        self.device = torch.device(device if device is not None else
+                                   f"cuda:{torch.cuda.current_device()}")
+        lib = N.lib()
+        b = self._b
+        spec = N.Spec()
+        spec.abi_version = N.ABI_VERSION
+        spec.num_envs, spec.num_agents, spec.num_components = self.num_envs, len(self.agents), len(b.comps)
+        spec.act_dim, spec.obs_dim = b.act_dim, b.obs_dim
+        spec.sd_rows, spec.si_rows = b.sd_rows, b.si_rows
+        spec.num_storage = self.num_storage
+        spec.num_events = self._dtab.shape[0]
+        spec.dtab_stride, spec.itab_stride = self._dstride, self._istride
+        comps = (N.Component * len(b.comps))(*b.comps)
+        dpar = np.asarray(b.dpar if b.dpar else [0.0], dtype=np.float64)
+        ipar = np.asarray(b.ipar if b.ipar else [0], dtype=np.int32)
+        spec.dpar_len, spec.ipar_len = len(b.dpar), len(b.ipar)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        spec.agents, spec.components = self._agent_recs, comps
+        spec.dpar, spec.ipar = dp(dpar), ip(ipar)
+        dtab = np.ascontiguousarray(self._dtab)
+        itab = np.ascontiguousarray(self._itab if self._istride else np.zeros((1, 4), np.int32))
+        spec.dtab, spec.itab = dp(dtab), ip(itab)
+        keep = [comps, dpar, ipar, dtab, itab]
+        if self.pf_solver is not None:
+            f = self.pf_solver.feeder
+            fd = N.Feeder()
+            fd.nb, fd.nn, fd.nl = f.nb, f.nn, f.nl
+            fd.max_iter, fd.tol = self.pf_solver.max_iter, self.pf_solver.tol
+            cplx = lambda a: np.ascontiguousarray(a, dtype=np.complex128).view(np.float64)
+            arrs = dict(zbb=cplx(f.zbb), u0=cplx(f.u0), znb=cplx(f.znb), w=cplx(f.w),
+                        share=np.ascontiguousarray(f.branch_share, dtype=np.float64),
+                        vmin=np.ascontiguousarray(f.branch_vmin, dtype=np.float64),
+                        vmax=np.ascontiguousarray(f.branch_vmax, dtype=np.float64),
+                        bl=np.ascontiguousarray(f.branch_load, dtype=np.int32),
+                        bm=np.ascontiguousarray(f.branch_model, dtype=np.int32))
+            fd.zbb, fd.u0, fd.znb, fd.w = dp(arrs["zbb"]), dp(arrs["u0"]), dp(arrs["znb"]), dp(arrs["w"])
+            fd.branch_share, fd.vminpu, fd.vmaxpu = dp(arrs["share"]), dp(arrs["vmin"]), dp(arrs["vmax"])
+            fd.branch_load, fd.branch_model = ip(arrs["bl"]), ip(arrs["bm"])
+            fd.penalty_node, fd.penalty_unit = -1, 0.0
+            if self._penalty is not None:
+                buses = set(self.agent_name_bus_map.values())
+                assert len(buses) == 1, "In this example, all buildings should be on the same bus."
+                node = self.pf_solver.node_for_bus_name(str(list(buses)[0]))
+                if node is None:
+                    raise ValueError("the shared-penalty bus must be a single-phase load name")
+                fd.penalty_node = node
+                fd.penalty_vlo, fd.penalty_vhi, fd.penalty_unit = self._penalty
+            spec.feeder = C.pointer(fd)
+            keep += [fd, arrs]
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(lib.pgw_create(C.byref(spec), C.byref(handle)))
+        self._h = handle
+        self._lib = lib
+        E, A = self.num_envs, len(self.agents)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.obs = torch.zeros((self.obs_dim, E), **f64)
+        self.rew = torch.zeros((A, E), **f64)
+        self.done = torch.zeros((E,), dtype=torch.uint8, device=self.device)
+        self._act = torch.zeros((self.act_dim, E), **f64)
+        self._pin = None
+        self._needs_reset = True
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pgw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ hooks (reference API)
+    def get_external_obs_vars(self, agent) -> dict:
+        """multiagent_env.py:90-115, evaluated from the device state (E == 1)."""
+        kw = {}
+        if "bus_voltage" in agent.obs_labels:
+            kw["bus_voltage"] = self.pf_solver.get_bus_voltage_by_name(
+                self.agent_name_bus_map[agent.name])
+        if "max_voltage" in agent.obs_labels:
+            kw["max_voltage"] = max(list(self.voltages.values()))
+        if "min_voltage" in agent.obs_labels:
+            kw["min_voltage"] = min(list(self.voltages.values()))
+        return kw
+
+    def reward_transform(self, rew_dict) -> dict:
+        return rew_dict
+
+    def meta_transform(self, meta) -> dict:
+        return meta
+
+    @property
+    def agent_dict(self) -> Dict[str, ComponentEnv]:
+        return {a.name: a for a in self.agents}
+
+    # ------------------------------------------------------------------ batched API
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def draw_initial_storage(self) -> np.ndarray:
+        """[num_storage, E] initial SOC drawn like the reference does on reset
+        (energy_storage_env.py:82-84): one scalar truncnorm draw per storage in agent /
+        component order for E == 1, a vectorised draw otherwise."""
+        if self.num_storage == 0:
+            return np.zeros((0, self.num_envs))
+        if self.num_envs == 1:
+            return np.array([[float(s.draw_initial_storage())] for s in self._b.storages])
+        return np.stack([s.draw_initial_storage(size=self.num_envs) for s in self._b.storages])
+
+    def reset_batch(self, init_storage=None):
+        """Reset all envs; returns the observation tensor ``[obs_dim, E]`` (reused buffer)."""
+        torch = _torch()
+        soc_ptr = None
+        if self.num_storage:
+            if init_storage is None:
+                init_storage = self.draw_initial_storage()
+            if not isinstance(init_storage, torch.Tensor):
+                init_storage = torch.as_tensor(np.ascontiguousarray(init_storage, dtype=np.float64))
+            soc = init_storage.to(self.device, dtype=torch.float64).contiguous()
+            if tuple(soc.shape) != (self.num_storage, self.num_envs):
+                raise ValueError(f"init_storage must be [{self.num_storage}, {self.num_envs}]")
+            self._soc = soc
+            soc_ptr = C.c_void_p(soc.data_ptr())
+        with torch.cuda.device(self.device):
+            N.check(self._lib.pgw_reset(self._h, soc_ptr, C.c_void_p(self.obs.data_ptr()),
+                                        self._stream()))
+        self.episode_step = 0
+        self.time = self.start_time
+        self._needs_reset = False
+        if self.record_history:
+            self.history = {"timestamp": [], "voltage": [], "agent_power_p": []}
+        return self.obs
+
+    def step_batch(self, actions):
+        """actions ``[act_dim, E]`` float64 device tensor -> (obs, rew, done, all_done).
+        The returned tensors are the env's own buffers, overwritten by the next call."""
+        torch = _torch()
+        if self._needs_reset:
+            raise RuntimeError("call reset before step")
+        if actions.dtype != torch.float64 or tuple(actions.shape) != (self.act_dim, self.num_envs) \
+                or not actions.is_contiguous() or actions.device != self.device:
+            raise ValueError(f"actions must be a contiguous float64 [{self.act_dim}, "
+                             f"{self.num_envs}] tensor on {self.device}")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.pgw_step(self._h, C.c_void_p(actions.data_ptr()),
+                                       C.c_void_p(self.obs.data_ptr()),
+                                       C.c_void_p(self.rew.data_ptr()),
+                                       C.c_void_p(self.done.data_ptr()), self._stream()))
+        self.episode_step += 1
+        self.time += self.control_timedelta
+        all_done = self.episode_step >= self.episode_length
+        if all_done:
+            self._needs_reset = True
+        return self.obs, self.rew, self.done, all_done
+
+    # ---- host-buffer (end-to-end) path
+    def _pinned(self):
+        if self._pin is None:
+            torch = _torch()
+            E, A = self.num_envs, len(self.agents)
+            mk = lambda *s, dt=torch.float64: torch.zeros(s, dtype=dt).pin_memory()
+            self._pin = dict(act=mk(self.act_dim, E), obs=mk(self.obs_dim, E), rew=mk(A, E),
+                             done=mk(E, dt=torch.uint8), soc=mk(max(self.num_storage, 1), E))
+        return self._pin
+
+    def reset_host(self, init_storage=None) -> np.ndarray:
+        torch = _torch()
+        pin = self._pinned()
+        soc_ptr = None
+        if self.num_storage:
+            if init_storage is None:
+                init_storage = self.draw_initial_storage()
+            pin["soc"][:self.num_storage].copy_(torch.as_tensor(np.asarray(init_storage, dtype=np.float64)))
+            soc_ptr = C.c_void_p(pin["soc"].data_ptr())
+        with torch.cuda.device(self.device):
+            N.check(self._lib.pgw_reset_host(self._h, soc_ptr, C.c_void_p(pin["obs"].data_ptr()),
+                                             self._stream()))
+        self.episode_step = 0
+        self.time = self.start_time
+        self._needs_reset = False
+        return pin["obs"].numpy()
+
+    def step_host(self, actions: np.ndarray):
+        """``actions`` host array [act_dim, E] -> (obs, rew, done) host arrays (pinned buffers
+        owned by the env).  Copies to and from the device are part of the call."""
+        torch = _torch()
+        if self._needs_reset:
+            raise RuntimeError("call reset before step")
+        pin = self._pinned()
+        src = actions if isinstance(actions, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(actions, dtype=np.float64))
+        if src.data_ptr() != pin["act"].data_ptr():
+            pin["act"].copy_(src.reshape(self.act_dim, self.num_envs))
+        with torch.cuda.device(self.device):
+            N.check(self._lib.pgw_step_host(
+                self._h, C.c_void_p(pin["act"].data_ptr()), C.c_void_p(pin["obs"].data_ptr()),
+                C.c_void_p(pin["rew"].data_ptr()), C.c_void_p(pin["done"].data_ptr()),
+                self._stream()))
+        self.episode_step += 1
+        self.time += self.control_timedelta
+        if self.episode_step >= self.episode_length:
+            self._needs_reset = True
+        return pin["obs"].numpy(), pin["rew"].numpy(), pin["done"].numpy()
+
+    # ---- device state access
+    def get_field(self, field: int):
+        torch = _torch()
+        E, A = self.num_envs, len(self.agents)
+        nn = self.pf_solver.feeder.nn if self.pf_solver else 0
+        shapes = {N.FIELD_STATE_D: ((self._b.sd_rows, E), torch.float64),
+                  N.FIELD_STATE_I: ((self._b.si_rows, E), torch.int32),
+                  N.FIELD_AGENT_P: ((A, E), torch.float64),
+                  N.FIELD_VOLTAGES: ((nn, E), torch.float64),
+                  N.FIELD_VMIN: ((E,), torch.float64), N.FIELD_VMAX: ((E,), torch.float64),
+                  N.FIELD_VBUS: ((A, E), torch.float64),
+                  N.FIELD_PF_ITERS: ((E,), torch.int32),
+                  N.FIELD_EP_RETURN: ((A, E), torch.float64)}
+        shape, dt = shapes[field]
+        out = torch.empty(shape, dtype=dt, device=self.device)
+        if out.numel():
+            with torch.cuda.device(self.device):
+                N.check(self._lib.pgw_get(self._h, field, C.c_void_p(out.data_ptr()),
+                                          out.numel() * out.element_size(), self._stream()))
+        return out
+
+    def stats(self):
+        """Episode statistics reduced on the device: tensor[8], see include/pgw.h."""
+        torch = _torch()
+        out = torch.empty((N.NUM_STATS,), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.pgw_stats(self._h, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def all_reduce_stats(self, group=None):
+        """The single collective of the multi-GPU path: sum (entries 0-5), min (6), max (7)
+        of ``stats()`` over the ranks of ``torch.distributed``."""
+        import torch.distributed as dist
+        s = self.stats()
+        if dist.is_available() and dist.is_initialized():
+            add, lo, hi = s[:6].clone(), s[6:7].clone(), s[7:8].clone()
+            dist.all_reduce(add, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+            s = _torch().cat([add, lo, hi])
+        return s
+
+    def set_kernel_timing(self, enabled: bool):
+        N.check(self._lib.pgw_set_timing(self._h, int(bool(enabled))))
+
+    def kernel_timing(self):
+        """(component-kernel ms, power-flow-kernel ms, steps) since the last call."""
+        out = (C.c_double * 3)()
+        N.check(self._lib.pgw_get_timing(self._h, C.cast(out, C.c_void_p), self._stream()))
+        return float(out[0]), float(out[1]), int(out[2])
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.pgw_launch_count(self._h))
+
+    # ---- stand-alone power flow (used by ZBusSolver.calculate_power_flow)
+    def _solve_loads(self, kw: np.ndarray, kvar: np.ndarray):
+        torch = _torch()
+        f = self.pf_solver.feeder
+        mk = lambda a: torch.as_tensor(np.ascontiguousarray(
+            np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(f.nl, -1),
+                            (f.nl, self.num_envs)))).to(self.device)
+        tkw, tkvar = mk(kw), mk(kvar)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.pgw_pf_solve(self._h, C.c_void_p(tkw.data_ptr()),
+                                           C.c_void_p(tkvar.data_ptr()), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def _voltage_dict(self, env_index: int = 0) -> Dict[str, float]:
+        v = self.get_field(N.FIELD_VOLTAGES)[:, env_index].cpu().numpy()
+        return {n: float(x) for n, x in zip(self.pf_solver.feeder.node_names, v)}
+
+    @property
+    def voltages(self):
+        """{node: p.u. magnitude} of env 0 (the reference's ``self.voltages``)."""
+        if self.pf_solver is None:
+            return None
+        return self._voltage_dict(0)
+
+    # ------------------------------------------------------------------ dict API (E == 1)
+    def _require_single(self):
+        if self.num_envs != 1:
+            raise RuntimeError("the dict API serves num_envs == 1; use reset_batch/step_batch")
+
+    def _obs_dict(self, flat: np.ndarray) -> dict:
+        out = {}
+        for ag in self.agents:
+            sl = self.obs_slices[ag.name]
+            if isinstance(sl, dict):
+                out[ag.name] = {k: flat[o:o + n].copy() for k, (o, n) in sl.items()}
+            else:
+                out[ag.name] = flat[sl[0]:sl[0] + sl[1]].copy()
+        return out
+
+    def flatten_action(self, action: dict) -> np.ndarray:
+        flat = np.zeros(self.act_dim, dtype=np.float64)
+        for ag in self.agents:
+            sl = self.act_slices[ag.name]
+            if isinstance(sl, dict):
+                for k, (o, n) in sl.items():
+                    flat[o:o + n] = np.asarray(action[ag.name][k], dtype=np.float64).reshape(-1)
+            else:
+                flat[sl[0]:sl[0] + sl[1]] = np.asarray(action[ag.name], dtype=np.float64).reshape(-1)
+        return flat
+
+    def reset(self, init_storage=None) -> Dict[str, any]:
+        """multiagent_env.py:125-140.  ``init_storage`` ([num_storage] or [num_storage, 1])
+        overrides the host RNG draw of the storages' initial SOC."""
+        self._require_single()
+        if init_storage is not None:
+            init_storage = np.asarray(init_storage, dtype=np.float64).reshape(self.num_storage, 1)
+        obs = self.reset_batch(init_storage)
+        return self._obs_dict(obs[:, 0].cpu().numpy())
+
+    def get_obs(self) -> Dict[str, any]:
+        self._require_single()
+        return self._obs_dict(self.obs[:, 0].cpu().numpy())
+
+    def step(self, action: Dict[str, any]):
+        """multiagent_env.py:151-212 for the single-env case."""
+        self._require_single()
+        torch = _torch()
+        self._act.copy_(torch.from_numpy(self.flatten_action(action)).reshape(self.act_dim, 1))
+        obs, rew, _, all_done = self.step_batch(self._act)
+        host = torch.cat([obs[:, 0], rew[:, 0]]).cpu().numpy()
+        obs_d = self._obs_dict(host[:self.obs_dim])
+        rew_d = {a.name: float(host[self.obs_dim + i]) for i, a in enumerate(self.agents)}
+        dones = {a.name: bool(all_done) for a in self.agents}
+        dones["__all__"] = bool(all_done)
+        meta = {a.name: ({e.name: {} for e in a.envs} if isinstance(a, MultiComponentEnv) else {})
+                for a in self.agents}
+        p = self.get_field(N.FIELD_AGENT_P)[:, 0].cpu().numpy()
+        for i, a in enumerate(self.agents):
+            a._real_power = float(p[i])             # agent.real_power (base.py:51-55)
+        if self.record_history:
+            self.history["timestamp"].append(self.time)
+            self.history["voltage"].append(self.voltages)
+            self.history["agent_power_p"].append([float(x) for x in p])
+        return obs_d, self.reward_transform(rew_d), dones, self.meta_transform(meta)
+
+
+class CoordinatedMultiBuildingControlEnv(MultiAgentEnv):
+    """examples/marl/openai/train.py:37-88: the voltage-violation penalty at the common
+    bus, computed from the fresh solve and split evenly over the agents -- applied on the
+    device in the power-flow kernel's epilogue."""
+
+    VOLTAGE_LIMITS = [0.95, 1.05]
+    VV_UNIT_PENALTY = 1e4
+
+    def __init__(self, *args, **kwargs):
+        self._penalty = (self.VOLTAGE_LIMITS[0], self.VOLTAGE_LIMITS[1], self.VV_UNIT_PENALTY)
+        super().__init__(*args, **kwargs)
+
+    def get_voltage_violation(self):
+        self._require_single()
+        bus_id = list(set(self.agent_name_bus_map.values()))[0]
+        v = self.pf_solver.get_bus_voltage_by_name(bus_id)
+        return max([0.0, self.VOLTAGE_LIMITS[0] - v, v - self.VOLTAGE_LIMITS[1]])
+
+    def meta_transform(self, meta) -> dict:
+        meta.update({'voltage_violation': self.get_voltage_violation()})
+        return meta
+
+
+class _SolverHostEnv(MultiAgentEnv):
+    """One-env handle that only hosts a feeder for stand-alone ``calculate_power_flow``."""
+    _is_solver_host = True
+
+
+def _standalone_solver_env(solver: ZBusSolver) -> MultiAgentEnv:
+    from powergridworld_b200.agents.energy_storage import EnergyStorageEnv
+
+    bus = solver.feeder.load_names[0]
+    env = _SolverHostEnv(
+        common_config={"start_time": "01-01-2021 00:00:00", "end_time": "01-02-2021 00:00:00",
+                       "control_timedelta": pd.Timedelta(3600, "s")},
+        pf_config={"instance": solver},
+        agents=[{"name": "_", "bus": bus, "cls": EnergyStorageEnv, "config": {}}])
+    return env

@@ -1,0 +1,296 @@
+"""GPU tier: the CUDA path, called through the C ABI, against (a) golden traces recorded
+from the unmodified reference, (b) the CPU oracle on seeded random batches, and (c) at
+BASELINE.json's full sizes through size-independent properties.
+
+Tolerances (BASELINE.json north_star): voltages 1e-4 p.u., component states 1e-6
+relative, rewards 1e-5 relative, integer EV state bit-exact.  What is asserted is
+tighter wherever float64 allows; see tests/test_host_tables_emu.py for why rewards that
+multiply a voltage by 1e4 carry an absolute floor."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import scenarios as S
+from tests.flatten import flat_obs, unflatten_action
+from tests.oracle_ns import ORACLE_NS as ONS, storage_socs_to_dict
+from tests.product_ns import PRODUCT_NS as PNS
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+OBS_ATOL, REW_RTOL, REW_ATOL, V_ATOL = 1e-7, 1e-5, 2e-5, 1e-7
+
+CASES = {
+    "c0_buildings": lambda ns, **k: ns.CoordinatedMultiBuildingControlEnv(
+        **S.buildings_scenario(ns, ns.OpenDSSSolver, 1.2), **k),
+    "heterogeneous": lambda ns, **k: ns.MultiAgentEnv(
+        **S.heterogeneous_scenario(ns, ns.OpenDSSSolver, 0.65), **k),
+    "heterogeneous_max250": lambda ns, **k: ns.MultiAgentEnv(
+        **S.heterogeneous_scenario(ns, ns.OpenDSSSolver, 0.6, max_episode_steps=250), **k),
+    "test_heterogeneous": lambda ns, **k: ns.MultiAgentEnv(
+        **S.test_heterogeneous_scenario(ns, ns.OpenDSSSolver), **k),
+}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_dict_api_replays_reference_trace(name):
+    """num_envs == 1 through the reference's dict API."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    env = CASES[name](PNS)
+    names = [str(n) for n in g["node_names"]]
+    obs0 = env.reset(init_storage=g["init_soc"])
+    np.testing.assert_allclose(flat_obs(env, obs0), g["obs0"], rtol=0, atol=OBS_ATOL)
+    v = env.voltages
+    np.testing.assert_allclose([v[k] for k in names], g["volt"][0], rtol=0, atol=V_ATOL)
+    T = g["actions"].shape[0]
+    for t in range(T):
+        ob, rew, dn, _ = env.step(unflatten_action(env, g["actions"][t]))
+        np.testing.assert_allclose(flat_obs(env, ob), g["obs"][t], rtol=0, atol=OBS_ATOL,
+                                   err_msg=f"obs t={t}")
+        np.testing.assert_allclose([rew[a.name] for a in env.agents], g["rew"][t],
+                                   rtol=REW_RTOL, atol=REW_ATOL, err_msg=f"rew t={t}")
+        np.testing.assert_allclose([a.real_power for a in env.agents], g["agent_p"][t],
+                                   rtol=1e-12, atol=1e-12)
+        assert dn["__all__"] == bool(g["done"][t])
+        if t % 40 == 0 or t == T - 1:
+            v = env.voltages
+            np.testing.assert_allclose([v[k] for k in names], g["volt"][t + 1], rtol=0, atol=V_ATOL)
+    with pytest.raises(RuntimeError):
+        env.step(unflatten_action(env, g["actions"][0]))     # episode over: reset required
+
+
+@pytest.mark.parametrize("name,E", [("c0_buildings", 33), ("heterogeneous", 130)])
+def test_batch_replicas_replay_reference_trace(name, E):
+    """Ragged batch sizes (not multiples of 16 / 32 / 128): every env gets the golden
+    actions, so every column must reproduce the golden trace."""
+    torch = _torch()
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    env = CASES[name](PNS, num_envs=E)
+    soc = np.repeat(g["init_soc"].reshape(-1, 1), E, axis=1)
+    obs0 = env.reset_batch(soc).cpu().numpy()
+    np.testing.assert_allclose(obs0, np.repeat(g["obs0"][:, None], E, 1), rtol=0, atol=OBS_ATOL)
+    T = g["actions"].shape[0]
+    for t in range(T):
+        a = torch.as_tensor(np.repeat(g["actions"][t][:, None], E, 1)).cuda()
+        obs, rew, done, all_done = env.step_batch(a)
+        if t % 15 == 0 or t == T - 1:
+            np.testing.assert_allclose(obs.cpu().numpy(), np.repeat(g["obs"][t][:, None], E, 1),
+                                       rtol=0, atol=OBS_ATOL, err_msg=f"t={t}")
+            np.testing.assert_allclose(rew.cpu().numpy(), np.repeat(g["rew"][t][:, None], E, 1),
+                                       rtol=REW_RTOL, atol=REW_ATOL)
+            assert bool(done.cpu().numpy().all()) == bool(g["done"][t])
+            assert bool(done.cpu().numpy().any()) == bool(g["done"][t])
+    assert all_done
+
+
+@pytest.mark.parametrize("name", ["c0_buildings", "heterogeneous", "test_heterogeneous"])
+def test_random_batch_matches_oracle(name):
+    """Different actions and initial SOC per env, checked env by env against the oracle."""
+    torch = _torch()
+    E, T = 6, 60
+    env = CASES[name](PNS, num_envs=E)
+    rng = np.random.default_rng(42)
+    soc = rng.uniform(5, 45, size=(env.num_storage, E))
+    acts = rng.uniform(-1.1, 1.1, size=(T, env.act_dim, E))
+    if name == "test_heterogeneous":          # raw (unscaled) action spaces there
+        acts = np.abs(acts)
+    obs0 = env.reset_batch(soc).cpu().numpy().copy()
+    O, R, V, SI = [], [], [], []
+    for t in range(T):
+        o, r, _, _ = env.step_batch(torch.as_tensor(acts[t]).cuda())
+        O.append(o.cpu().numpy().copy())
+        R.append(r.cpu().numpy().copy())
+        V.append(env.get_field(3).cpu().numpy())
+        SI.append(env.get_field(1).cpu().numpy())
+    node_names = env.pf_solver.feeder.node_names
+    for e in range(E):
+        ref = CASES[name](ONS)
+        o0 = ref.reset(init_storage=storage_socs_to_dict(ref, soc[:, e]))
+        np.testing.assert_allclose(obs0[:, e], flat_obs(ref, o0), rtol=0, atol=OBS_ATOL)
+        for t in range(T):
+            o, r, _, _ = ref.step(unflatten_action(ref, acts[t][:, e]))
+            np.testing.assert_allclose(O[t][:, e], flat_obs(ref, o), rtol=0, atol=OBS_ATOL,
+                                       err_msg=f"env {e} t={t}")
+            np.testing.assert_allclose(R[t][:, e], [r[a.name] for a in ref.agents],
+                                       rtol=REW_RTOL, atol=REW_ATOL, err_msg=f"env {e} t={t}")
+            np.testing.assert_allclose(V[t][:, e], [ref.voltages[n] for n in node_names],
+                                       rtol=0, atol=V_ATOL)
+            # integer EV state: the charging set, bit for bit
+            for ag_o, ag_p in zip(ref.agents, env.agents):
+                if hasattr(ag_o, "charging_vehicles"):
+                    off, words = ag_p._slot["si"]
+                    bits = 0
+                    for w in range(words):
+                        bits |= int(np.uint32(SI[t][off + w, e])) << (32 * w)
+                    want = 0
+                    for i in ag_o.charging_vehicles:
+                        want |= 1 << int(i)
+                    assert bits == want, f"EV charging set env {e} t={t}"
+
+
+def test_component_only_env_matches_oracle():
+    """BASELINE C2 composition (EV 100 vehicles + PV + storage, no feeder)."""
+    torch = _torch()
+    E, T = 5, 286
+    env = PNS.MultiAgentEnv(**S.ev_pv_storage_scenario(PNS), num_envs=E)
+    assert env.episode_length == 286
+    rng = np.random.default_rng(3)
+    soc = rng.uniform(5, 45, size=(env.num_storage, E))
+    acts = rng.uniform(-1.0, 1.0, size=(T, env.act_dim, E))
+    obs0 = env.reset_batch(soc).cpu().numpy().copy()
+    O, R, SD = [], [], []
+    for t in range(T):
+        o, r, d, all_done = env.step_batch(torch.as_tensor(acts[t]).cuda())
+        O.append(o.cpu().numpy().copy())
+        R.append(r.cpu().numpy().copy())
+    energy = env.get_field(0).cpu().numpy()
+    assert all_done
+
+    from oracle.multiagent import PowerFlowSolver
+
+    class NoPF(PowerFlowSolver):
+        def __init__(self, **kw):
+            pass
+
+        def calculate_power_flow(self, *a, **k):
+            pass
+
+        def get_bus_voltages(self):
+            return {}
+
+        def get_bus_voltage_by_name(self, n):
+            return 1.0
+
+    for e in range(E):
+        ref = ONS.MultiAgentEnv(**S.ev_pv_storage_scenario(ONS, NoPF))
+        o0 = ref.reset(init_storage=storage_socs_to_dict(ref, soc[:, e]))
+        np.testing.assert_allclose(obs0[:, e], flat_obs(ref, o0), rtol=1e-12, atol=1e-12)
+        for t in range(T):
+            o, r, dn, _ = ref.step(unflatten_action(ref, acts[t][:, e]))
+            np.testing.assert_allclose(O[t][:, e], flat_obs(ref, o), rtol=1e-10, atol=1e-10)
+            np.testing.assert_allclose(R[t][:, e], [r[a.name] for a in ref.agents],
+                                       rtol=1e-9, atol=1e-12)
+        assert dn["__all__"]
+        ev = ref.agents[0]
+        off, n = env.agents[0]._slot["sd"]
+        np.testing.assert_allclose(energy[off:off + n, e], ev.energy, rtol=1e-12, atol=1e-12)
+
+
+def test_full_size_c1_properties():
+    """4096 IEEE-13 envs (BASELINE C1): replicas given identical inputs stay bit-identical,
+    SOC stays inside its range, voltages stay physical, every solve converges, and the
+    on-device statistics agree with torch reductions."""
+    torch = _torch()
+    E, T = 4096, 25
+    env = CASES["c0_buildings"](PNS, num_envs=E)
+    rng = np.random.default_rng(0)
+    half = E // 2
+    soc_h = rng.uniform(5, 45, size=(env.num_storage, half))
+    soc = np.concatenate([soc_h, soc_h], axis=1)
+    env.reset_batch(soc)
+    for t in range(T):
+        a_h = rng.uniform(-1, 1, size=(env.act_dim, half))
+        a = torch.as_tensor(np.concatenate([a_h, a_h], axis=1)).cuda()
+        obs, rew, done, _ = env.step_batch(a)
+    assert torch.equal(obs[:, :half], obs[:, half:])
+    assert torch.equal(rew[:, :half], rew[:, half:])
+    sd = env.get_field(0)
+    for ag in env.agents:
+        st = ag.env_dict["storage"]
+        row = sd[st._slot["sd"][0]]
+        assert float(row.min()) >= st.storage_range[0] and float(row.max()) <= st.storage_range[1]
+    vmag = env.get_field(3)
+    assert 0.85 < float(vmag.min()) and float(vmag.max()) < 1.06
+    iters = env.get_field(7)
+    assert int(iters.min()) > 0, "a power flow did not converge"
+    s = env.stats().cpu().numpy()
+    assert s[0] == E * T
+    np.testing.assert_allclose(s[1], float(rew.sum()), rtol=1e-9)
+    np.testing.assert_allclose(s[2], float(env.get_field(8).sum()), rtol=1e-9)
+    assert s[4] == 0
+    np.testing.assert_allclose(s[5], float(iters.sum()))
+    np.testing.assert_allclose(s[6], float(env.get_field(4).min()))
+    np.testing.assert_allclose(s[7], float(env.get_field(5).max()))
+
+
+def test_host_buffer_path_equals_device_path():
+    torch = _torch()
+    E, T = 257, 10
+    a_env = CASES["c0_buildings"](PNS, num_envs=E)
+    b_env = CASES["c0_buildings"](PNS, num_envs=E)
+    rng = np.random.default_rng(5)
+    soc = rng.uniform(5, 45, size=(a_env.num_storage, E))
+    o_a = a_env.reset_batch(soc).cpu().numpy()
+    o_b = b_env.reset_host(soc)
+    np.testing.assert_array_equal(o_a, o_b)
+    for t in range(T):
+        act = rng.uniform(-1, 1, size=(a_env.act_dim, E))
+        oa, ra, da, _ = a_env.step_batch(torch.as_tensor(act).cuda())
+        ob, rb, db = b_env.step_host(act)
+        np.testing.assert_array_equal(oa.cpu().numpy(), ob)
+        np.testing.assert_array_equal(ra.cpu().numpy(), rb)
+        np.testing.assert_array_equal(da.cpu().numpy(), db)
+
+
+def test_standalone_solver_like_reference_test_opendss():
+    """tests/distribution_system/test_opendss.py:7-16 of the reference + a value check."""
+    cfg = dict(S.IEEE13, system_load_rescale_factor=0.7)
+    s = PNS.OpenDSSSolver(**cfg)
+    s.calculate_power_flow(current_time="01-01-2021 05:00:00")
+    v = s.get_bus_voltages()
+    o = ONS.OpenDSSSolver(**cfg)
+    o.calculate_power_flow(current_time="01-01-2021 05:00:00")
+    vo = o.get_bus_voltages()
+    assert set(v) == set(vo) and len(v) == 38
+    np.testing.assert_allclose([v[k] for k in vo], list(vo.values()), rtol=0, atol=V_ATOL)
+    s.calculate_power_flow(current_time="01-01-2021 05:00:00",
+                           p_controllable_consumed={"675c": 800.0, "634a": -50.0},
+                           q_controllable_consumed={"675c": 0.0, "634a": 10.0})
+    o.calculate_power_flow(current_time="01-01-2021 05:00:00",
+                           p_controllable_consumed={"675c": 800.0, "634a": -50.0},
+                           q_controllable_consumed={"675c": 0.0, "634a": 10.0})
+    vo = o.get_bus_voltages()
+    v = s.get_bus_voltages()
+    np.testing.assert_allclose([v[k] for k in vo], list(vo.values()), rtol=0, atol=V_ATOL)
+    assert s.get_bus_voltage_by_name("675c") == v["675.3"]
+    assert s.get_bus_voltage_by_name("671") == [v["671.1"], v["671.2"], v["671.3"]]
+
+
+def test_original_ieee13_feeder_on_gpu_matches_published_profile():
+    """All three load models, delta and wye, capacitors and regulator taps through the CUDA
+    solver: published IEEE 13-node voltages within 2e-3 p.u. (see test_oracle_powerflow)."""
+    import json
+    s = PNS.OpenDSSSolver(os.path.join(GOLD, "ieee13_original.dss"),
+                          "ieee_13_dss/annual_hourly_load_profile.csv", 1.0)
+    s.annual_hourly_load_profile = np.ones(8760)          # nominal loads
+    s.calculate_power_flow(current_time="01-01-2021 00:00:00")
+    v = s.get_bus_voltages()
+    pub = json.load(open(os.path.join(GOLD, "ieee13_published_voltages.json")))
+    for bus, vals in pub.items():
+        if bus.startswith("_"):
+            continue
+        for ph, want in enumerate(vals, 1):
+            if want is not None:
+                assert abs(v[f"{bus}.{ph}"] - want) < 2e-3, (bus, ph)
+
+
+def test_abi_error_paths():
+    env = CASES["c0_buildings"](PNS, num_envs=4)
+    torch = _torch()
+    with pytest.raises(RuntimeError):
+        env.step_batch(torch.zeros((env.act_dim, 4), dtype=torch.float64, device="cuda"))
+    env.reset_batch()
+    with pytest.raises(ValueError):
+        env.step_batch(torch.zeros((env.act_dim, 5), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        env.step_batch(torch.zeros((env.act_dim, 4), dtype=torch.float32, device="cuda"))
+    from powergridworld_b200 import _native as N
+    out = torch.empty(3, dtype=torch.float64, device="cuda")
+    import ctypes as C
+    rc = env._lib.pgw_get(env._h, N.FIELD_VMIN, C.c_void_p(out.data_ptr()), 24, None)
+    assert rc == -1 and b"size mismatch" in env._lib.pgw_last_error()

@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the MultiAgentEnv.step hot path (BASELINE.json metric: batched env-steps/s
+incl. power flow).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload = "C1"): the reference's IEEE-13 coordinated-buildings scenario
+(3 x building+PV+storage on load 675c, load factor 1.2, shared voltage penalty;
+examples/marl/openai/train.py:165-188) batched to 4096 envs per GPU.  One "step" = one
+pgw_step over the batch: fused component kernel + batched power flow.  Actions are
+synthetic U(-1, 1) float64, pre-generated and resident in HBM for `value`; `e2e` goes
+through the host-buffer call (pinned host actions in, obs/reward/done out, every step).
+
+Timing: W >= 3 untimed steps, then K steps each bracketed by CUDA events on the launch
+stream with a write of a 256 MiB buffer (> 126 MB L2) between steps, i.e. every timed step
+starts with a cold L2; value = envs x K / sum of step times, max over ranks.  N > 1 runs one
+process per GPU (torchrun), envs sharded with no data-path collective (weak scaling:
+4096 envs per GPU); the only collective is the all-reduce of the 8-entry statistics vector
+at the end of the timed region.
+
+--impl reference times the reference's CPU implementation of the same path: the oracle
+port (the reference's own Python classes are not on the GPU box, and its power flow,
+OpenDSS, is not installable) on all host cores via multiprocessing.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 4096
+METRIC, UNIT = "env_steps_per_s", "env-steps/s"
+SURVEY_BYTES_PER_ENV_STEP = 3 * (264 + 28 + 40) + 1      # SURVEY.md section 8(d), component kernels
+LOAD_FACTOR = 1.2
+
+
+def _config(n_gpus):
+    return {"workload": "C1: IEEE-13 coordinated buildings (3 x building+PV+storage @675c), "
+                        f"{ENVS_PER_GPU} envs per GPU",
+            "envs_per_gpu": ENVS_PER_GPU, "agents_per_env": 3, "global_envs": ENVS_PER_GPU * n_gpus,
+            "feeder": "IEEE-13 (38 nodes, 14 load branches)", "load_factor": LOAD_FACTOR,
+            "parallelism": f"env-sharded x{n_gpus}", "l2": "flushed between timed steps "
+            "(256 MiB write)", "pf_kernel": "fp64-simt"}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    """One independent oracle env stepped for `steps` steps (episodes restart as needed)."""
+    seed, steps = args
+    import numpy as np
+
+    from tests import scenarios as S
+    from tests.flatten import action_layout, unflatten_action
+    from tests.oracle_ns import ORACLE_NS as NS
+    env = NS.CoordinatedMultiBuildingControlEnv(
+        **S.buildings_scenario(NS, NS.OpenDSSSolver, LOAD_FACTOR))
+    rng = np.random.default_rng(seed)
+    np.random.seed(seed)
+    layout = action_layout(env)
+    dim = sum(len(lo) for _, _, lo, _, _ in layout)
+    env.reset()
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps:
+        _, _, dn, _ = env.step(unflatten_action(env, rng.uniform(-1, 1, size=dim)))
+        done += 1
+        if dn["__all__"]:
+            env.reset()
+    return time.perf_counter() - t0
+
+
+def cpu_throughput(total_seconds_target=15.0, steps_per_task=96):
+    """Oracle port on all host cores (multiprocessing, one independent env per task)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    # single-task probe (steady-state ms/step) to size the sample
+    t_probe = _cpu_worker((0, 30)) / 30.0
+    per_task = steps_per_task
+    rounds = max(1, int(round(total_seconds_target / (per_task * t_probe))))
+    tasks = [(i + 1, per_task) for i in range(cores * rounds)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_worker, tasks, chunksize=1)
+    wall = time.perf_counter() - t0
+    total = len(tasks) * per_task
+    return {"value": total / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(tasks)} independent oracle envs x {per_task} steps "
+                      f"(multiprocessing.Pool({cores})), {wall:.1f} s wall, "
+                      f"{1e3 * t_probe:.2f} ms/step single core"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    cb = cpu_throughput(total_seconds_target=max(10.0, min(60.0, 0.1 * args.steps)))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": _config(args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "note": "oracle port of the reference classes + complex128 power-flow restatement; "
+                    "the reference's OpenDSS engine is not installable (no network)",
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as exc:                      # NVML missing: report that, not a guess
+            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 3)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_throughput()                   # before CUDA is initialised (fork)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from tests import scenarios as S
+    from tests.product_ns import PRODUCT_NS as NS
+
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E = ENVS_PER_GPU
+    env = NS.CoordinatedMultiBuildingControlEnv(
+        **S.buildings_scenario(NS, NS.OpenDSSSolver, LOAD_FACTOR), num_envs=E, device=dev)
+    A = len(env.agents)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    pool_n = 64
+    act_pool = torch.rand((pool_n, env.act_dim, E), generator=gen, device=dev,
+                          dtype=torch.float64) * 2.0 - 1.0
+    rng = np.random.default_rng(rank)
+    soc = torch.as_tensor(30.0 + 5.0 * rng.uniform(-1, 1, size=(env.num_storage, E))).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step(i):
+        if env._needs_reset:
+            env.reset_batch(soc)
+        env.step_batch(act_pool[i % pool_n])
+
+    env.reset_batch(soc)
+    for i in range(W):
+        one_step(i)
+    barrier()
+
+    # ---- timed region: K steps, device-timed one by one, cold L2 before each
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = env.launch_count
+    env.set_kernel_timing(True)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()
+        starts[i].record()
+        one_step(W + i)
+        ends[i].record()
+    stats = env.all_reduce_stats()                    # the only collective of the path
+    barrier()
+    wall = time.perf_counter() - wall0
+    sampler.stop_flag = True
+    t_comp_ms, t_pf_ms, n_timed = env.kernel_timing()
+    env.set_kernel_timing(False)
+    launches = env.launch_count - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = float(sum(step_ms))
+    iters_mean = float(env.get_field(7).abs().double().mean())
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = E * world * K / (total_ms * 1e-3)
+
+    # ---- same loop with a warm L2 (reported next to the headline, not instead of it)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k2 = min(K, 200)
+    ev0.record()
+    for i in range(k2):
+        one_step(W + K + i)
+    ev1.record()
+    barrier()
+    warm_ms = ev0.elapsed_time(ev1) / k2
+
+    # ---- end to end: host buffers in, host buffers out, every step
+    host_act = [torch.rand((env.act_dim, E), dtype=torch.float64).mul_(2).sub_(1).pin_memory()
+                for _ in range(4)]
+    env.reset_host(soc.cpu().numpy())
+    for i in range(3):
+        env.step_host(host_act[i % 4])
+    barrier()
+    ke = min(K, 100)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t_host0 = time.perf_counter()
+    for i in range(ke):
+        if env._needs_reset:
+            env.reset_host(soc.cpu().numpy())
+        obs, rew, done = env.step_host(host_act[i % 4])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t_host0) * 1e3)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = E * world * ke / (e2e_ms * 1e-3)
+    h2d = env.act_dim * E * 8
+    d2h = env.obs_dim * E * 8 + A * E * 8 + E
+
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        comp_ms = t_comp_ms / max(n_timed, 1)
+        pf_ms = t_pf_ms / max(n_timed, 1)
+        alg_bytes = SURVEY_BYTES_PER_ENV_STEP * E
+        achieved = alg_bytes / (comp_ms * 1e-3) / 1e9 if comp_ms > 0 else 0.0
+        f = env.pf_solver.feeder
+        flops = (8.0 * f.nb * f.nb * iters_mean + 8.0 * f.nn * f.nb) * E
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": _config(world),
+            "agent_steps_per_s": value * A,
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / ke, "steps": ke},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "component_kernel", "bound": "hbm", "achieved": achieved,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "avg_launch_ms": comp_ms},
+            "roofline_pf": {"kernel": "pf_fixed_point_kernel<16,1>", "bound": "fp64-fma",
+                            "achieved": flops / (pf_ms * 1e-3) / 1e12 if pf_ms > 0 else 0.0,
+                            "peak": 37.0, "unit": "TFLOP/s", "peak_source": "nominal B200 FP64",
+                            "algorithmic_flops_per_launch": flops, "avg_launch_ms": pf_ms,
+                            "mean_iterations": iters_mean},
+            "kernel_share": {"components": comp_ms / max(comp_ms + pf_ms, 1e-12),
+                             "powerflow": pf_ms / max(comp_ms + pf_ms, 1e-12)},
+            "warm_l2": {"ms_per_step": warm_ms, "value": E * world / (warm_ms * 1e-3)},
+            "stats": [float(x) for x in stats.cpu()],
+            "wall_s_timed_region": wall,
+        }
+        line["roofline_pf"]["frac"] = line["roofline_pf"]["achieved"] / 37.0
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,20 +63,25 @@ typedef enum pgw_component_type {
  * One component instance of the scenario (identical for every env).
  * Parameter blocks live in pgw_spec.dpar / ipar at dpar_off / ipar_off:
  *
- *  STORAGE  dpar: lo, hi, eta_charge, eta_discharge, max_power, dt_hours, initial mean
+ *  (entries named 1/x hold the correctly rounded reciprocal, computed on the host, used
+ *   by the kernels' division-by-constant: multiply + one FMA correction = IEEE quotient)
+ *  STORAGE  dpar: lo, hi, eta_charge, eta_discharge, max_power, dt_hours, initial mean,
+ *                 1/(hi-lo), 1/eta_discharge, 1/dt_hours
  *           ipar: storage ordinal (row of init_soc)
  *           state: 1 double row (SOC)                      action 1, obs 1
- *  PV       dpar: obs_low0, obs_high0, obs_low1, obs_high1
+ *  PV       dpar: obs_low0, obs_high0, obs_low1, obs_high1, 1/(high0-low0), 1/(high1-low1)
  *           dtab: profile value of the event              action 1, obs 1 (+1 grid aware)
  *  EV       dpar: rate_kw, step_hours, multiplier, unserved_penalty, peak_penalty,
- *                 peak_threshold, reward_scale, obs_high[6], end_park_min[n], e0_kwh[n]
+ *                 peak_threshold, reward_scale, obs_high[6], 1/obs_high[6], 1/reward_scale,
+ *                 1/60, end_park_min[n], e0_kwh[n]
  *           ipar: n, words(=ceil(n/32)), list capacity m
  *           dtab: time_now, time_next
  *           itab: n_window, n_left, window[m], left[m]
  *           state: n double rows (remaining kWh), words uint32 rows (charging set)
  *                                                          action 1, obs 6
  *  BUILDING dpar: A[5], B[20] (float32-rounded), C[5], K[5], mean[5], T_init[5],
- *                 w_energy(=alpha*0.5), w_comfort(=1-alpha), low[obs_dim], high[obs_dim]
+ *                 w_energy(=alpha*0.5), w_comfort(=1-alpha), low[obs_dim], high[obs_dim],
+ *                 1/(high-low)[obs_dim]
  *           ipar: sel[20] (0-based input selector), nbr[20], obs_source_mask (24 bits)
  *           dtab: T_oa_dyn, Q_solar[5], Q_x[5], T_oa_obs, lb_obs, ub_obs, time_of_day,
  *                 lb_prev, ub_prev
@@ -228,9 +233,13 @@ int pgw_stats(pgw_env* env, double* out, void* cuda_stream);
 int pgw_clock(const pgw_env* env);
 /* Number of kernels this handle has launched since creation (bench accounting). */
 long long pgw_launch_count(const pgw_env* env);
-/* Choose the power-flow kernel: 0 = FP64 SIMT fixed point (default),
- * 1 = tcgen05 tensor-core fixed point (split-TF32 operands, FP32 accumulate in TMEM). */
-int pgw_set_pf_kernel(pgw_env* env, int which);
+/* Runtime options (pgw_set_option): */
+#define PGW_OPT_PF_KERNEL 0   /* 0 = FP64 SIMT fixed point (default); 1 = tcgen05 tensor-core
+                                 fixed point (split-TF32 operands, FP32 accumulate in TMEM)  */
+#define PGW_OPT_WARM_START 1  /* 1 (default): each solve starts from the env's previous solution */
+#define PGW_OPT_GRAPHS 2      /* 1 (default): pgw_step replays a captured CUDA graph per distinct
+                                 (actions, obs, rew, done) pointer set; needs a non-default stream */
+int pgw_set_option(pgw_env* env, int option, int value);
 
 /* Per-kernel device timing for benchmarks: when enabled, every launch of pgw_step is
  * bracketed by CUDA events on the launch stream.  pgw_get_timing synchronises the stream

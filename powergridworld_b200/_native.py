@@ -18,6 +18,8 @@ NUM_STATS = 8
 STORAGE, PV, EV, BUILDING = 1, 2, 3, 4
 F_RESCALE, F_GRID_AWARE, F_PV_VOLT_REWARD, F_STALE_REWARD = 1, 2, 4, 8
 
+OPT_PF_KERNEL, OPT_WARM_START, OPT_GRAPHS = 0, 1, 2
+
 (FIELD_STATE_D, FIELD_STATE_I, FIELD_AGENT_P, FIELD_VOLTAGES, FIELD_VMIN, FIELD_VMAX,
  FIELD_VBUS, FIELD_PF_ITERS, FIELD_EP_RETURN) = range(9)
 
@@ -72,7 +74,7 @@ SYMBOLS = {
     "pgw_stats": (C.c_int, [_vp, _vp, _vp]),
     "pgw_clock": (C.c_int, [_vp]),
     "pgw_launch_count": (C.c_longlong, [_vp]),
-    "pgw_set_pf_kernel": (C.c_int, [_vp, C.c_int]),
+    "pgw_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "pgw_pf_solve": (C.c_int, [_vp, _vp, _vp, _vp]),
     "pgw_set_timing": (C.c_int, [_vp, C.c_int]),
     "pgw_get_timing": (C.c_int, [_vp, _vp, _vp]),

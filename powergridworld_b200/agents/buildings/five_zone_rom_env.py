@@ -76,7 +76,8 @@ class FiveZoneROMEnv(ComponentEnv):
             if key in self._obs_labels:
                 mask |= 1 << src
         dpar = list(A) + list(B32.reshape(-1)) + list(Cm) + list(K) + list(mean) + \
-            list(self.zone_temp_init) + [alpha * 0.5, 1. - alpha] + list(low) + list(high)
+            list(self.zone_temp_init) + [alpha * 0.5, 1. - alpha] + list(low) + list(high) + \
+            list(1.0 / (high - low))
         ipar = list(sel.reshape(-1)) + list(nbr.reshape(-1)) + [mask]
         exo, comfort, mes = self.exo, self._comfort, self.max_episode_steps
 

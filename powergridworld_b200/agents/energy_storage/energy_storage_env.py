@@ -47,7 +47,9 @@ class EnergyStorageEnv(ComponentEnv):
     def _emit(self, b, agent_index, standalone):
         dpar = [self.storage_range[0], self.storage_range[1], self.charge_efficiency,
                 self.discharge_efficiency, self.max_power, self.control_interval_in_hr,
-                self.initial_storage_mean]
+                self.initial_storage_mean,
+                1.0 / (self.storage_range[1] - self.storage_range[0]),
+                1.0 / self.discharge_efficiency, 1.0 / self.control_interval_in_hr]
         b.add_component(self, N.STORAGE, agent_index,
                         flags=N.F_RESCALE if self.rescale_spaces else 0,
                         dpar=dpar, ipar=[b.next_storage_ordinal(self)], sd_rows=1)

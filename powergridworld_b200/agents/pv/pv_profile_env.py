@@ -69,7 +69,8 @@ class PVEnv(ComponentEnv):
                                  "the grid variables (gridworld/base.py:151)")
             flags |= N.F_PV_VOLT_REWARD
         lo, hi = self._observation_space.low, self._observation_space.high
-        dpar = [lo[0], hi[0], 0.9, 1.1]
+        with np.errstate(divide="ignore"):
+            dpar = [lo[0], hi[0], 0.9, 1.1, 1.0 / (hi[0] - lo[0]), 1.0 / (1.1 - 0.9)]
         data = self.data
         # event 0 (reset) shows row 0; step t acts on row t *before* advancing (:143-145)
         b.add_component(self, N.PV, agent_index, flags=flags, dpar=dpar,

@@ -111,7 +111,8 @@ class EVChargingEnv(ComponentEnv):
         hi = self._observation_space.high
         dpar = [self.max_charge_rate_kw, self.minutes_per_step / 60., float(self.vehicle_multiplier),
                 self.unserved_penalty, self.peak_penalty, self.peak_threshold, self.reward_scale]
-        dpar += list(hi) + list(self._roster_end[:n]) + list(self._roster_energy[:n])
+        dpar += list(hi) + list(1.0 / hi) + [1.0 / self.reward_scale, 1.0 / 60.0]
+        dpar += list(self._roster_end[:n]) + list(self._roster_energy[:n])
         b.add_component(self, N.EV, agent_index,
                         flags=N.F_RESCALE if self.rescale_spaces else 0,
                         dpar=dpar, ipar=[n, words, cap], sd_rows=n, si_rows=words,

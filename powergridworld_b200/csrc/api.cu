@@ -66,15 +66,23 @@ struct pgw_env {
   int clock = -1;             // host mirror
   long long launches = 0;
   // device tables
-  pgw_agent* agents = nullptr;
-  pgw_component* comps = nullptr;
-  double* dpar = nullptr;
-  int32_t* ipar = nullptr;
+  unsigned char* comp_blob = nullptr;   // [agents | comps | dpar | ipar]
+  int comp_blob_bytes = 0, off_comps = 0, off_dpar = 0, off_ipar = 0;
   double* dtab = nullptr;
   int32_t* itab = nullptr;
-  double2 *zbbT = nullptr, *u0 = nullptr, *znbT = nullptr, *w = nullptr;
-  int32_t *branch_load = nullptr, *branch_model = nullptr;
-  double *branch_share = nullptr, *vminpu = nullptr, *vmaxpu = nullptr;
+  unsigned char* pf_blob = nullptr;     // feeder tables, layout in internal.cuh
+  int pf_blob_bytes = 0, pf_stage = 0;
+  int off_u0 = 0, off_znbT = 0, off_w = 0, off_share = 0, off_vmin = 0, off_vmax = 0,
+      off_bload = 0, off_bmodel = 0, off_slot = 0, off_node = 0;
+  double2* u_state = nullptr;
+  bool warm_start = true;
+  // CUDA graphs of a step, keyed by the caller's buffer pointers
+  struct StepGraph {
+    const void *actions, *obs, *rew, *done;
+    cudaGraphExec_t exec;
+  };
+  std::vector<StepGraph> graphs;
+  bool use_graphs = true;
   // device state
   double* sd = nullptr;
   uint32_t* si = nullptr;
@@ -96,6 +104,7 @@ struct pgw_env {
   ~pgw_env() {
     for (void* p : owned) cudaFree(p);
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
   }
   cudaEvent_t next_event() {
     if (ev_used == ev_pool.size()) {
@@ -171,10 +180,27 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
     }                                                                                  \
   } while (0)
 
-  PGW_TRY(upload(&env->agents, spec->agents, A)); env->own(env->agents);
-  PGW_TRY(upload(&env->comps, spec->components, (size_t)env->C)); env->own(env->comps);
-  PGW_TRY(upload(&env->dpar, spec->dpar, (size_t)spec->dpar_len)); env->own(env->dpar);
-  PGW_TRY(upload(&env->ipar, spec->ipar, (size_t)spec->ipar_len)); env->own(env->ipar);
+  {
+    // static component tables as one blob, staged to shared memory by every CTA
+    const size_t b_ag = A * sizeof(pgw_agent);
+    const size_t b_co = (size_t)env->C * sizeof(pgw_component);
+    const size_t b_dp = (size_t)spec->dpar_len * sizeof(double);
+    const size_t b_ip = (size_t)spec->ipar_len * sizeof(int32_t);
+    env->off_comps = round_up((int)b_ag, 16);
+    env->off_dpar = round_up(env->off_comps + (int)b_co, 16);
+    env->off_ipar = round_up(env->off_dpar + (int)b_dp, 16);
+    env->comp_blob_bytes = round_up(env->off_ipar + (int)b_ip, 16);
+    std::vector<unsigned char> blob(env->comp_blob_bytes, 0);
+    memcpy(blob.data(), spec->agents, b_ag);
+    memcpy(blob.data() + env->off_comps, spec->components, b_co);
+    if (b_dp) memcpy(blob.data() + env->off_dpar, spec->dpar, b_dp);
+    if (b_ip) memcpy(blob.data() + env->off_ipar, spec->ipar, b_ip);
+    PGW_TRY(upload(&env->comp_blob, blob.data(), blob.size())); env->own(env->comp_blob);
+    if (env->comp_blob_bytes + spec->dtab_stride * 8 + spec->itab_stride * 4 > 200 * 1024) {
+      delete env;
+      return fail(PGW_ERR_INVALID, "scenario tables exceed the shared-memory staging budget");
+    }
+  }
   PGW_TRY(upload(&env->dtab, spec->dtab, (size_t)spec->num_events * spec->dtab_stride));
   env->own(env->dtab);
   PGW_TRY(upload(&env->itab, spec->itab, (size_t)spec->num_events * spec->itab_stride));
@@ -230,15 +256,36 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       bl[k] = f.branch_load[k]; bm[k] = f.branch_model[k]; bs[k] = f.branch_share[k];
       vlo[k] = f.vminpu[k]; vhi[k] = f.vmaxpu[k];
     }
-    PGW_TRY(upload(&env->zbbT, zt.data(), zt.size())); env->own(env->zbbT);
-    PGW_TRY(upload(&env->u0, u0.data(), u0.size())); env->own(env->u0);
-    PGW_TRY(upload(&env->znbT, znt.data(), znt.size())); env->own(env->znbT);
-    PGW_TRY(upload(&env->w, w.data(), w.size())); env->own(env->w);
-    PGW_TRY(upload(&env->branch_load, bl.data(), bl.size())); env->own(env->branch_load);
-    PGW_TRY(upload(&env->branch_model, bm.data(), bm.size())); env->own(env->branch_model);
-    PGW_TRY(upload(&env->branch_share, bs.data(), bs.size())); env->own(env->branch_share);
-    PGW_TRY(upload(&env->vminpu, vlo.data(), vlo.size())); env->own(env->vminpu);
-    PGW_TRY(upload(&env->vmaxpu, vhi.data(), vhi.size())); env->own(env->vmaxpu);
+    {
+      std::vector<int32_t> slot(env->A), node(env->A);
+      for (int a = 0; a < env->A; ++a) {
+        slot[a] = spec->agents[a].load_slot;
+        node[a] = spec->agents[a].bus_node;
+      }
+      std::vector<unsigned char> blob;
+      auto put = [&blob](const void* src, size_t bytes) {
+        const size_t off = (blob.size() + 15) / 16 * 16;
+        blob.resize(off + bytes, 0);
+        memcpy(blob.data() + off, src, bytes);
+        return (int)off;
+      };
+      put(zt.data(), zt.size() * sizeof(double2));
+      env->off_u0 = put(u0.data(), u0.size() * sizeof(double2));
+      env->off_znbT = put(znt.data(), znt.size() * sizeof(double2));
+      env->off_w = put(w.data(), w.size() * sizeof(double2));
+      env->off_share = put(bs.data(), bs.size() * 8);
+      env->off_vmin = put(vlo.data(), vlo.size() * 8);
+      env->off_vmax = put(vhi.data(), vhi.size() * 8);
+      env->off_bload = put(bl.data(), bl.size() * 4);
+      env->off_bmodel = put(bm.data(), bm.size() * 4);
+      env->off_slot = put(slot.data(), slot.size() * 4);
+      env->off_node = put(node.data(), node.size() * 4);
+      blob.resize((blob.size() + 15) / 16 * 16, 0);
+      env->pf_blob_bytes = (int)blob.size();
+      env->pf_stage = env->pf_blob_bytes <= 96 * 1024 ? 1 : 0;   // else read through L1/L2
+      PGW_TRY(upload(&env->pf_blob, blob.data(), blob.size())); env->own(env->pf_blob);
+    }
+    PGW_TRY(alloc_zero(&env->u_state, (size_t)nbp * E)); env->own(env->u_state);
     PGW_TRY(alloc_zero(&env->vmag, (size_t)nn * E)); env->own(env->vmag);
     PGW_TRY(alloc_zero(&env->vmin, E)); env->own(env->vmin);
     PGW_TRY(alloc_zero(&env->vmax, E)); env->own(env->vmax);
@@ -265,9 +312,10 @@ int pgw_destroy(pgw_env* env) {
 static pgw::CompParams comp_params(pgw_env* env) {
   pgw::CompParams p{};
   p.E = env->E; p.A = env->A;
-  p.agents = env->agents; p.comps = env->comps; p.dpar = env->dpar; p.ipar = env->ipar;
+  p.blob = env->comp_blob; p.blob_bytes = env->comp_blob_bytes;
+  p.off_comps = env->off_comps; p.off_dpar = env->off_dpar; p.off_ipar = env->off_ipar;
   p.dtab = env->dtab; p.itab = env->itab; p.dstride = env->dstride; p.istride = env->istride;
-  p.sd = env->sd; p.si = env->si;
+  p.sd = env->sd; p.si = env->si; p.rew_copy = env->rew_last;
   p.vmin = env->vmin; p.vmax = env->vmax; p.vbus = env->vbus;
   p.agent_p = env->agent_p; p.ep_ret = env->ep_ret;
   p.clock = env->d_clock; p.ticket = env->d_ticket;
@@ -278,10 +326,12 @@ static pgw::PfParams pf_params(pgw_env* env) {
   pgw::PfParams p{};
   p.E = env->E; p.A = env->A; p.nb = env->nb; p.nn = env->nn; p.nl = env->nl;
   p.nbp = env->nbp; p.nnp = env->nnp; p.max_iter = env->max_iter; p.tol = env->tol;
-  p.zbbT = env->zbbT; p.u0 = env->u0; p.znbT = env->znbT; p.w = env->w;
-  p.branch_load = env->branch_load; p.branch_share = env->branch_share;
-  p.branch_model = env->branch_model; p.vminpu = env->vminpu; p.vmaxpu = env->vmaxpu;
-  p.agents = env->agents; p.dtab = env->dtab; p.dstride = env->dstride;
+  p.blob = env->pf_blob; p.blob_bytes = env->pf_blob_bytes; p.stage_blob = env->pf_stage;
+  p.off_u0 = env->off_u0; p.off_znbT = env->off_znbT; p.off_w = env->off_w;
+  p.off_share = env->off_share; p.off_vmin = env->off_vmin; p.off_vmax = env->off_vmax;
+  p.off_bload = env->off_bload; p.off_bmodel = env->off_bmodel; p.off_slot = env->off_slot;
+  p.off_node = env->off_node; p.u_state = env->u_state; p.rew_copy = env->rew_last;
+  p.dtab = env->dtab; p.dstride = env->dstride;
   p.vmag = env->vmag; p.vmin = env->vmin; p.vmax = env->vmax; p.vbus = env->vbus;
   p.iters = env->iters; p.ep_ret = env->ep_ret; p.viol = env->viol;
   p.penalty_node = env->penalty_node; p.pvlo = env->pvlo; p.pvhi = env->pvhi; p.punit = env->punit;
@@ -290,7 +340,7 @@ static pgw::PfParams pf_params(pgw_env* env) {
 }
 
 static int smem_for_events(const pgw_env* env) {
-  return env->dstride * 8 + env->istride * 4;
+  return env->comp_blob_bytes + env->dstride * 8 + env->istride * 4;
 }
 
 int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stream) {
@@ -301,7 +351,7 @@ int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stre
   if (env->has_feeder) {
     pgw::PfParams pf = pf_params(env);
     pf.event_mode = 0; pf.advance_clock = 0; pf.agent_p = nullptr; pf.rew = nullptr;
-    pf.punit = 0.0;
+    pf.punit = 0.0; pf.warm_start = 0;
     PGW_CUDA(pgw::launch_powerflow(pf, s));
     ++env->launches;
   }
@@ -313,6 +363,25 @@ int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stre
   return PGW_OK;
 }
 
+// The kernels of one step, enqueued on `s` (directly, or while `s` is being captured).
+static int enqueue_step(pgw_env* env, const double* actions, double* obs, double* rew,
+                        uint8_t* done, cudaStream_t s, bool timed) {
+  pgw::CompParams cp = comp_params(env);
+  cp.event_mode = 1; cp.advance_clock = env->has_feeder ? 0 : 1;
+  cp.actions = actions; cp.obs = obs; cp.rew = rew; cp.done = done;
+  if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
+  PGW_CUDA(pgw::launch_components(cp, smem_for_events(env), s));
+  if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
+  if (env->has_feeder) {
+    pgw::PfParams pf = pf_params(env);
+    pf.event_mode = 1; pf.advance_clock = 1; pf.agent_p = env->agent_p; pf.rew = rew;
+    pf.warm_start = env->warm_start ? 1 : 0;
+    PGW_CUDA(pgw::launch_powerflow(pf, s));
+  }
+  if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
+  return PGW_OK;
+}
+
 int pgw_step(pgw_env* env, const double* actions, double* obs, double* rew, uint8_t* done,
              void* cuda_stream) {
   if (!env || !actions || !obs || !rew || !done) return fail(PGW_ERR_INVALID, "null argument");
@@ -320,23 +389,39 @@ int pgw_step(pgw_env* env, const double* actions, double* obs, double* rew, uint
   if (env->clock + 1 >= env->num_events)
     return fail(PGW_ERR_STATE, "episode is over: call pgw_reset");
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-  pgw::CompParams cp = comp_params(env);
-  cp.event_mode = 1; cp.advance_clock = env->has_feeder ? 0 : 1;
-  cp.actions = actions; cp.obs = obs; cp.rew = rew; cp.done = done;
-  if (env->timing) PGW_CUDA(cudaEventRecord(env->next_event(), s));
-  PGW_CUDA(pgw::launch_components(cp, smem_for_events(env), s));
-  ++env->launches;
-  if (env->timing) PGW_CUDA(cudaEventRecord(env->next_event(), s));
-  if (env->has_feeder) {
-    pgw::PfParams pf = pf_params(env);
-    pf.event_mode = 1; pf.advance_clock = 1; pf.agent_p = env->agent_p; pf.rew = rew;
-    PGW_CUDA(pgw::launch_powerflow(pf, s));
-    ++env->launches;
+  const int kernels = env->has_feeder ? 2 : 1;
+
+  // Replay a captured graph of the step when one exists for these buffers (the episode
+  // clock lives on the device, so the launch parameters of a step never change).
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  PGW_CUDA(cudaStreamIsCapturing(s, &cap));
+  const bool graphable = env->use_graphs && !env->timing && cap == cudaStreamCaptureStatusNone &&
+                         s != nullptr;
+  if (graphable) {
+    cudaGraphExec_t exec = nullptr;
+    for (auto& g : env->graphs)
+      if (g.actions == actions && g.obs == obs && g.rew == rew && g.done == done) exec = g.exec;
+    if (!exec) {
+      cudaGraph_t graph = nullptr;
+      PGW_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue_step(env, actions, obs, rew, done, s, false);
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc != PGW_OK) return rc;
+      if (ce != cudaSuccess) return fail(PGW_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+      PGW_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      if (env->graphs.size() >= 256) {               // bounded cache
+        cudaGraphExecDestroy(env->graphs.front().exec);
+        env->graphs.erase(env->graphs.begin());
+      }
+      env->graphs.push_back({actions, obs, rew, done, exec});
+    }
+    PGW_CUDA(cudaGraphLaunch(exec, s));
+  } else {
+    int rc = enqueue_step(env, actions, obs, rew, done, s, env->timing);
+    if (rc != PGW_OK) return rc;
   }
-  if (env->timing) PGW_CUDA(cudaEventRecord(env->next_event(), s));
-  // keep a copy of the step's rewards for pgw_stats
-  PGW_CUDA(cudaMemcpyAsync(env->rew_last, rew, (size_t)env->A * env->E * sizeof(double),
-                           cudaMemcpyDeviceToDevice, s));
+  env->launches += kernels;
   ++env->clock;
   return PGW_OK;
 }
@@ -421,7 +506,7 @@ int pgw_pf_solve(pgw_env* env, const double* load_kw, const double* load_kvar,
   if (!env->has_feeder) return fail(PGW_ERR_INVALID, "this env has no feeder");
   pgw::PfParams pf = pf_params(env);
   pf.event_mode = 0; pf.advance_clock = 0; pf.agent_p = nullptr; pf.rew = nullptr;
-  pf.punit = 0.0; pf.load_kw = load_kw; pf.load_kvar = load_kvar;
+  pf.punit = 0.0; pf.load_kw = load_kw; pf.load_kvar = load_kvar; pf.warm_start = 0;
   PGW_CUDA(pgw::launch_powerflow(pf, static_cast<cudaStream_t>(cuda_stream)));
   ++env->launches;
   return PGW_OK;
@@ -470,10 +555,21 @@ int pgw_get_timing(pgw_env* env, double* out3, void* cuda_stream) {
 int pgw_clock(const pgw_env* env) { return env ? env->clock : -1; }
 long long pgw_launch_count(const pgw_env* env) { return env ? env->launches : 0; }
 
-int pgw_set_pf_kernel(pgw_env* env, int which) {
+int pgw_set_option(pgw_env* env, int option, int value) {
   if (!env) return fail(PGW_ERR_INVALID, "null argument");
-  if (which != 0) return fail(PGW_ERR_INVALID, "tensor-core power flow is not built into this library yet");
-  env->pf_kernel = which;
+  switch (option) {
+    case PGW_OPT_PF_KERNEL:
+      if (value != 0)
+        return fail(PGW_ERR_INVALID, "tensor-core power flow is not built into this library yet");
+      env->pf_kernel = value;
+      return PGW_OK;
+    case PGW_OPT_WARM_START: env->warm_start = value != 0; break;
+    case PGW_OPT_GRAPHS: env->use_graphs = value != 0; break;
+    default: return fail(PGW_ERR_INVALID, "unknown option");
+  }
+  // the captured graphs bake the options in
+  for (auto& g : env->graphs) cudaGraphExecDestroy(g.exec);
+  env->graphs.clear();
   return PGW_OK;
 }
 

@@ -23,42 +23,55 @@
 #else
 #define PGW_HD inline
 #endif
+#define PGW_RESTRICT __restrict__
 
 namespace pgw {
 
 // Everything one (env, agent) worker needs; all per-env arrays are rows x E.
 struct AgentIO {
   int E;
-  const double* actions;   // [act_dim][E]   (unused at reset)
-  double* obs;             // [obs_dim][E]
-  double* sd;              // [sd_rows][E]
-  uint32_t* si;            // [si_rows][E]
-  const double* init_soc;  // [num_storage][E] or nullptr (reset only)
-  const double* vmin;      // [E]    lagged grid variables (previous solve) or nullptr
-  const double* vmax;      // [E]
-  const double* vbus;      // [A][E]
-  const double* dpar;
-  const int32_t* ipar;
-  const double* drow;      // event row (doubles)
-  const int32_t* irow;     // event row (int32)
+  // The arrays never alias each other; telling the compiler lets it overlap the many
+  // independent load -> divide -> store chains of one agent (the kernel is latency bound).
+  const double* PGW_RESTRICT actions;   // [act_dim][E]   (unused at reset)
+  double* PGW_RESTRICT obs;             // [obs_dim][E]
+  double* PGW_RESTRICT sd;              // [sd_rows][E]
+  uint32_t* PGW_RESTRICT si;            // [si_rows][E]
+  const double* PGW_RESTRICT init_soc;  // [num_storage][E] or nullptr (reset only)
+  const double* PGW_RESTRICT vmin;      // [E]    lagged grid variables (previous solve) or nullptr
+  const double* PGW_RESTRICT vmax;      // [E]
+  const double* PGW_RESTRICT vbus;      // [A][E]
+  const double* PGW_RESTRICT dpar;
+  const int32_t* PGW_RESTRICT ipar;
+  const double* PGW_RESTRICT drow;      // event row (doubles)
+  const int32_t* PGW_RESTRICT irow;     // event row (int32)
 };
 
 PGW_HD double clip(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+
+// x / d when r = RN(1/d) was computed on the host: one multiply plus one FMA-based
+// correction (Markstein) returns the correctly rounded IEEE quotient, i.e. the same bits
+// as the reference's division, at a third of the dependent latency of a full FP64
+// divide.  fma() is explicit here; everything else in this file is compiled -fmad=false.
+PGW_HD double div_by(double x, double d, double r) {
+  const double q = x * r;
+  const double rem = fma(-q, d, x);
+  return fma(rem, r, q);
+}
 
 // utils.py:27-43
 PGW_HD double to_raw(double y, double lo, double hi) {
   y = clip(y, -1.0, 1.0);
   return (y * (hi - lo) + (hi + lo)) / 2.0;
 }
-// utils.py:9-24
-PGW_HD double to_scaled(double x, double lo, double hi) {
+// utils.py:9-24; inv = RN(1 / (hi - lo))
+PGW_HD double to_scaled(double x, double lo, double hi, double inv) {
   x = clip(x, lo, hi);
-  return (2.0 * x - (lo + hi)) / (hi - lo);
+  return div_by(2.0 * x - (lo + hi), hi - lo, inv);
 }
 
 // ------------------------------------------------------------------ storage
 PGW_HD double storage_obs(const pgw_component& c, const double* dp, double soc) {
-  return (c.flags & PGW_F_RESCALE) ? to_scaled(soc, dp[0], dp[1]) : soc;
+  return (c.flags & PGW_F_RESCALE) ? to_scaled(soc, dp[0], dp[1], dp[7]) : soc;
 }
 
 PGW_HD void storage_reset(const pgw_component& c, const AgentIO& io, int e) {
@@ -73,6 +86,7 @@ PGW_HD void storage_reset(const pgw_component& c, const AgentIO& io, int e) {
 PGW_HD void storage_step(const pgw_component& c, const AgentIO& io, int e, double& p_out) {
   const double* dp = io.dpar + c.dpar_off;
   const double lo = dp[0], hi = dp[1], eta_c = dp[2], eta_d = dp[3], pmax = dp[4], dt = dp[5];
+  const double inv_eta_d = dp[8], inv_dt = dp[9];
   double a = io.actions[(size_t)c.act_off * io.E + e];
   if (c.flags & PGW_F_RESCALE) a = to_raw(a, -1.0, 1.0);
   double* soc_p = io.sd + (size_t)c.sd_off * io.E + e;
@@ -80,15 +94,15 @@ PGW_HD void storage_step(const pgw_component& c, const AgentIO& io, int e, doubl
   double p = a * pmax;
   // validate_power :100-128 (the clamps omit the efficiencies, as in the reference)
   if (p > 0.0) {
-    if (soc - p * dt / eta_d < lo) p = fmax(soc - lo, 0.0) / dt;
+    if (soc - div_by(p * dt, eta_d, inv_eta_d) < lo) p = div_by(fmax(soc - lo, 0.0), dt, inv_dt);
   } else if (p < 0.0) {
-    if (soc - eta_c * p * dt > hi) p = -fmax(hi - soc, 0.0) / dt;
+    if (soc - eta_c * p * dt > hi) p = div_by(-fmax(hi - soc, 0.0), dt, inv_dt);
   }
   if (p < 0.0) {
     soc -= eta_c * p * dt;
     soc = fmin(soc, hi);
   } else if (p > 0.0) {
-    soc -= p * dt / eta_d;
+    soc -= div_by(p * dt, eta_d, inv_eta_d);
     soc = fmax(soc, lo);
   }
   *soc_p = soc;
@@ -100,10 +114,10 @@ PGW_HD void storage_step(const pgw_component& c, const AgentIO& io, int e, doubl
 PGW_HD void pv_obs(const pgw_component& c, const AgentIO& io, int e, double raw_power) {
   const double* dp = io.dpar + c.dpar_off;
   const bool rs = (c.flags & PGW_F_RESCALE) != 0;
-  io.obs[(size_t)c.obs_off * io.E + e] = rs ? to_scaled(raw_power, dp[0], dp[1]) : raw_power;
+  io.obs[(size_t)c.obs_off * io.E + e] = rs ? to_scaled(raw_power, dp[0], dp[1], dp[4]) : raw_power;
   if (c.flags & PGW_F_GRID_AWARE) {
     const double v = io.vmin[e];
-    io.obs[(size_t)(c.obs_off + 1) * io.E + e] = rs ? to_scaled(v, dp[2], dp[3]) : v;
+    io.obs[(size_t)(c.obs_off + 1) * io.E + e] = rs ? to_scaled(v, dp[2], dp[3], dp[5]) : v;
   }
 }
 
@@ -134,7 +148,8 @@ PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double 
   const int n = ip[0], words = ip[1], cap = ip[2];
   const double rate = dp[0], mult = dp[2];
   const double* obs_high = dp + 7;
-  const double* end_park = dp + 13;
+  const double* inv_high = dp + 13;
+  const double* end_park = dp + 21;
   const double t_now = io.drow[c.dtab_off], t_next = io.drow[c.dtab_off + 1];
   const int32_t* ir = io.irow + c.itab_off;
   const int n_win = ir[0], n_left = ir[1];
@@ -160,7 +175,7 @@ PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double 
     word |= 1u << (i & 31);
     ++active;
     demand += need;                                   // :210
-    const double left_h = (end_park[i] - t_now) / 60.0;
+    const double left_h = div_by(end_park[i] - t_now, 60.0, dp[20]);
     if (left_h <= 0.0) continue;                      // :218-220
     deficit_sum += fmax(0.0, rate - need / left_h);   // :221-223
     ++n_deficit;
@@ -179,10 +194,11 @@ PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double 
   const bool rs = (c.flags & PGW_F_RESCALE) != 0;
 #pragma unroll
   for (int j = 0; j < 6; ++j)
-    io.obs[(size_t)(c.obs_off + j) * io.E + e] = rs ? to_scaled(raw[j], 0.0, obs_high[j]) : raw[j];
+    io.obs[(size_t)(c.obs_off + j) * io.E + e] =
+        rs ? to_scaled(raw[j], 0.0, obs_high[j], inv_high[j]) : raw[j];
   p_out = s_consumed;                                 // kWh per step reported as kW (:255)
   const double over = fmax(0.0, s_consumed - dp[5]);  // :135-142
-  rew = (-dp[3] * (unserved * unserved) + -dp[4] * (over * over)) / dp[6];
+  rew = div_by(-dp[3] * (unserved * unserved) + -dp[4] * (over * over), dp[6], dp[19]);
 }
 
 PGW_HD void ev_step(const pgw_component& c, const AgentIO& io, int e, double& p_out,
@@ -196,7 +212,7 @@ PGW_HD void ev_step(const pgw_component& c, const AgentIO& io, int e, double& p_
 PGW_HD void ev_reset(const pgw_component& c, const AgentIO& io, int e) {
   const double* dp = io.dpar + c.dpar_off;
   const int n = io.ipar[c.ipar_off];
-  const double* e0 = dp + 13 + n;
+  const double* e0 = dp + 21 + n;
   double* energy = io.sd + (size_t)c.sd_off * io.E + e;
   for (int i = 0; i < n; ++i) energy[(size_t)i * io.E] = e0[i];
   // Hidden step with action=None -> _action_space.low = 0 (:163, :178).  With
@@ -208,7 +224,7 @@ PGW_HD void ev_reset(const pgw_component& c, const AgentIO& io, int e) {
 
 // ------------------------------------------------------------------ five-zone building
 struct BuildingPar {
-  const double *A, *B, *C, *K, *mean, *Tinit, *low, *high;
+  const double *A, *B, *C, *K, *mean, *Tinit, *low, *high, *inv;
   double w_energy, w_comfort;
   const int32_t *sel, *nbr;
   uint32_t obs_mask;
@@ -220,7 +236,7 @@ PGW_HD BuildingPar building_par(const pgw_component& c, const AgentIO& io) {
   BuildingPar b;
   b.A = dp; b.B = dp + 5; b.C = dp + 25; b.K = dp + 30; b.mean = dp + 35; b.Tinit = dp + 40;
   b.w_energy = dp[45]; b.w_comfort = dp[46];
-  b.low = dp + 47; b.high = dp + 47 + c.obs_dim;
+  b.low = dp + 47; b.high = dp + 47 + c.obs_dim; b.inv = dp + 47 + 2 * c.obs_dim;
   b.sel = ip; b.nbr = ip + 20; b.obs_mask = (uint32_t)ip[40];
   return b;
 }
@@ -264,7 +280,7 @@ PGW_HD double building_x_next(const BuildingPar& b, int z, double x, const doubl
 // FiveZoneROMThermalEnergyEnv.step_reward (five_zone_rom_env.py:315-335)
 PGW_HD double building_reward(const BuildingPar& b, const double T[5], double lb, double ub,
                               double p_consumed) {
-  const double energy = -p_consumed / 12.0;
+  const double energy = div_by(-p_consumed, 12.0, 1.0 / 12.0);
   double comfort = 0.0;
 #pragma unroll
   for (int z = 0; z < 5; ++z) {
@@ -285,7 +301,7 @@ PGW_HD void building_obs(const pgw_component& c, const BuildingPar& b, const Age
   auto put = [&](int src, double v) {
     if (b.obs_mask & (1u << src)) {
       double o = clip(v, b.low[slot], b.high[slot]);
-      if (rs) o = to_scaled(o, b.low[slot], b.high[slot]);
+      if (rs) o = to_scaled(o, b.low[slot], b.high[slot], b.inv[slot]);
       io.obs[(size_t)(c.obs_off + slot) * io.E + e] = o;
       ++slot;
     }
@@ -360,7 +376,8 @@ PGW_HD void building_step(const pgw_component& c, const AgentIO& io, int e, doub
     sd[(size_t)z * io.E] = x[z];
   }
   const double flow = (((act[0] + act[1]) + act[2]) + act[3]) + act[4];
-  const double p = (0.0076 * pow(flow, 3.0) + 4.8865) + fmax(0.0, flow * (t_oa - act[5]));
+  // flow**3: the reference calls libm pow; x*x*x differs from it by at most 1 ulp
+  const double p = (0.0076 * ((flow * flow) * flow) + 4.8865) + fmax(0.0, flow * (t_oa - act[5]));
   sd[(size_t)5 * io.E] = p;
   building_obs(c, b, io, e, T, row[12], row[13], row[11], p, row[14]);
   if (!(c.flags & PGW_F_STALE_REWARD)) rew = building_reward(b, T, row[12], row[13], p);

@@ -11,16 +11,17 @@ struct CompParams {
   int E, A;
   int event_mode;          // 0 = reset (event row 0), 1 = step (event row clock+1)
   int advance_clock;       // 1 when this kernel is the last one of the step (no feeder)
-  const pgw_agent* agents;
-  const pgw_component* comps;
-  const double* dpar;
-  const int32_t* ipar;
+  // static tables, one contiguous 16-byte aligned blob: [agents | comps | dpar | ipar]
+  const unsigned char* blob;
+  int blob_bytes, off_comps, off_dpar, off_ipar;
   const double* dtab;
   const int32_t* itab;
   int dstride, istride;
   const double* actions;
   double* obs;
   double* rew;
+  double* rew_copy;        // internal copy of the step's rewards (pgw_stats), written when this
+                           // kernel owns the final reward (no feeder)
   uint8_t* done;
   double* sd;
   uint32_t* si;
@@ -39,16 +40,17 @@ struct PfParams {
   double tol;
   int event_mode;          // 0 = reset (base load only, event row 0), 1 = step
   int advance_clock;
-  const double2* zbbT;     // [nb][nbp]   zbbT[j*nbp+k] = Zbb[k][j]
-  const double2* u0;       // [nbp]
-  const double2* znbT;     // [nb][nnp]   znbT[k*nnp+n] = Znb[n][k]
-  const double2* w;        // [nnp]
-  const int32_t* branch_load;   // [nbp]
-  const double* branch_share;   // [nbp]
-  const int32_t* branch_model;  // [nbp]
-  const double* vminpu;         // [nbp]
-  const double* vmaxpu;         // [nbp]
-  const pgw_agent* agents;
+  int warm_start;          // start from the previous solution kept in u_state
+  // static tables, one contiguous 16-byte aligned blob (staged to shared memory by TMA
+  // when it fits):  zbbT [nb][nbp] double2 (zbbT[j*nbp+k] = Zbb[k][j]) | u0 [nbp] double2 |
+  // znbT [nb][nnp] double2 (znbT[k*nnp+n] = Znb[n][k]) | w [nnp] double2 |
+  // share, vminpu, vmaxpu [nbp] double each | branch_load, branch_model [nbp] int32 each |
+  // agent load_slot [A], agent bus_node [A] int32
+  const unsigned char* blob;
+  int blob_bytes, stage_blob;
+  int off_u0, off_znbT, off_w, off_share, off_vmin, off_vmax, off_bload, off_bmodel, off_slot,
+      off_node;
+  double2* u_state;        // [nbp][E] last converged branch voltages (warm start)
   const double* agent_p;   // [A][E]
   const double* load_kw;   // [nl][E] stand-alone solve: total kW per load (else nullptr)
   const double* load_kvar; // [nl][E]
@@ -60,6 +62,7 @@ struct PfParams {
   double* vbus;            // [A][E]
   int32_t* iters;          // [E]
   double* rew;             // [A][E] (step only)
+  double* rew_copy;        // [A][E] internal copy for pgw_stats
   double* ep_ret;          // [A][E]
   double* viol;            // [E] voltage violation at the penalty node
   int penalty_node;

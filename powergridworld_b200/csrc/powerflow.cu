@@ -13,11 +13,14 @@
 // (examples/marl/openai/train.py:51-88).
 //
 // Mapping: TPE threads cooperate on one env (branch rows strided over the lanes, R rows
-// per lane), so a 13-bus env (14 branches) is half a warp and convergence masking is
-// a per-half-warp predicate.  Zbb / Znb are shared by every env and stay L1/L2
-// resident (3.1 kB + 8.5 kB for IEEE-13); branch currents are exchanged through
-// shared memory.  Bound by FP64 FMA issue + latency, not by HBM.
+// per lane), so a 13-bus env (14 branches) is half a warp and convergence masking is a
+// per-half-warp predicate.  The feeder tables (Zbb, Znb, u0, w, branch table; 13.6 kB for
+// IEEE-13) and the event row are staged into shared memory by TMA bulk copies once per
+// CTA; for the half-warp mapping each lane additionally keeps its row of Zbb in
+// registers.  Branch currents are exchanged through shared memory.  The solve warm-starts
+// from the env's previous solution.  Bound by FP64 FMA latency, not by HBM.
 #include "internal.cuh"
+#include "tma.cuh"
 
 namespace pgw {
 
@@ -32,23 +35,20 @@ __device__ __forceinline__ double2 branch_current(int model, double2 s, double2 
                                                   double vmax) {
   const double m2 = u.x * u.x + u.y * u.y;
   const double2 sc = make_double2(s.x, -s.y);            // conj(s) = yeq on a 1 p.u. base
-  if (model == 2) return cmul(sc, u);
-  if (model == 5) {
-    const double inv = m2 > 0.0 ? rsqrt(m2) : 0.0;
-    return cmul(sc, make_double2(u.x * inv, u.y * inv));
+  double k;
+  if (model == 2) {
+    k = 1.0;
+  } else if (model == 5) {
+    k = m2 > 0.0 ? rsqrt(m2) : 0.0;
+  } else if (m2 <= vmin * vmin) {
+    k = __drcp_rn(vmin * vmin);
+  } else if (m2 > vmax * vmax) {
+    k = __drcp_rn(vmax * vmax);
+  } else {
+    k = __drcp_rn(m2);                                   // conj(s / u) = conj(s) u / |u|^2
   }
-  if (m2 <= vmin * vmin) {
-    const double k = 1.0 / (vmin * vmin);
-    return cmul(make_double2(sc.x * k, sc.y * k), u);
-  }
-  if (m2 > vmax * vmax) {
-    const double k = 1.0 / (vmax * vmax);
-    return cmul(make_double2(sc.x * k, sc.y * k), u);
-  }
-  // conj(s / u) = conj(s) * u / |u|^2
-  const double inv = 1.0 / m2;
   const double2 t = cmul(sc, u);
-  return make_double2(t.x * inv, t.y * inv);
+  return make_double2(t.x * k, t.y * k);
 }
 
 template <int TPE>
@@ -64,26 +64,68 @@ __device__ __forceinline__ double group_min(double v, unsigned mask) {
   return v;
 }
 
-template <int TPE, int R>
-__global__ void __launch_bounds__(256) pf_fixed_point_kernel(const PfParams p) {
+// acc -= z * i  (complex), as four FMAs
+__device__ __forceinline__ void cmac_sub(double2& acc, double2 z, double2 i) {
+  acc.x = fma(-z.x, i.x, acc.x);
+  acc.x = fma(z.y, i.y, acc.x);
+  acc.y = fma(-z.x, i.y, acc.y);
+  acc.y = fma(-z.y, i.x, acc.y);
+}
+
+// 2 CTAs of 256 threads per SM (<= 128 registers): 4096 envs = 256 CTAs fit in one wave.
+template <int TPE, int R, bool ZREG>
+__global__ void __launch_bounds__(256, 2) pf_fixed_point_kernel(const PfParams p) {
   extern __shared__ __align__(16) unsigned char pf_smem[];
+  __shared__ __align__(8) uint64_t mbar;
   const int EPB = blockDim.x / TPE;                      // envs per block pass
   const int lane = threadIdx.x % TPE;
   const int le = threadIdx.x / TPE;
   const int nbp = p.nbp;
-  double2* icur_all = reinterpret_cast<double2*>(pf_smem);
-  double* stage_all = reinterpret_cast<double*>(pf_smem + (size_t)EPB * nbp * sizeof(double2));
+  const int hdr = 2 + 2 * p.nl;                          // done, reserved, kW[nl], kvar[nl]
+
+  // shared memory: [feeder blob (if staged)] [event row header] [currents] [|v| staging]
+  const int blob_smem = p.stage_blob ? p.blob_bytes : 0;
+  double* drow = reinterpret_cast<double*>(pf_smem + blob_smem);
+  double2* icur_all = reinterpret_cast<double2*>(pf_smem + blob_smem + (size_t)hdr * 8);
+  double* stage_all = reinterpret_cast<double*>(icur_all + (size_t)EPB * nbp);
   double2* icur = icur_all + (size_t)le * nbp;
   double* stage = stage_all + (size_t)le * p.nn;
   const unsigned gmask =
       TPE == 32 ? 0xffffffffu : (((1u << TPE) - 1u) << (TPE * ((threadIdx.x & 31) / TPE)));
 
   const int event = p.event_mode == 0 ? 0 : (*p.clock + 1);
-  const double* drow = p.dtab + (size_t)event * p.dstride;
+  if (threadIdx.x == 0) {
+    mbar_init(&mbar, 1);
+    mbar_expect_tx(&mbar, (uint32_t)blob_smem + (uint32_t)hdr * 8u);
+    if (p.stage_blob) tma_bulk_g2s(pf_smem, p.blob, (uint32_t)p.blob_bytes, &mbar);
+    tma_bulk_g2s(drow, p.dtab + (size_t)event * p.dstride, (uint32_t)hdr * 8u, &mbar);
+  }
+  __syncthreads();
+  mbar_wait(&mbar, 0);
+
+  const unsigned char* tab = p.stage_blob ? pf_smem : p.blob;
+  const double2* zbbT = reinterpret_cast<const double2*>(tab);
+  const double2* u0t = reinterpret_cast<const double2*>(tab + p.off_u0);
+  const double2* znbT = reinterpret_cast<const double2*>(tab + p.off_znbT);
+  const double2* wt = reinterpret_cast<const double2*>(tab + p.off_w);
+  const double* share = reinterpret_cast<const double*>(tab + p.off_share);
+  const double* vminpu = reinterpret_cast<const double*>(tab + p.off_vmin);
+  const double* vmaxpu = reinterpret_cast<const double*>(tab + p.off_vmax);
+  const int32_t* bload = reinterpret_cast<const int32_t*>(tab + p.off_bload);
+  const int32_t* bmodel = reinterpret_cast<const int32_t*>(tab + p.off_bmodel);
+  const int32_t* aslot = reinterpret_cast<const int32_t*>(tab + p.off_slot);
+  const int32_t* anode = reinterpret_cast<const int32_t*>(tab + p.off_node);
   const double* base_kw = drow + 2;
   const double* base_kvar = drow + 2 + p.nl;
-  const int groups = (p.E + EPB - 1) / EPB;
 
+  // this lane's row of Zbb in registers (half-warp / one-row-per-lane mapping only)
+  double2 zr[ZREG ? TPE : 1];
+  if (ZREG) {
+#pragma unroll
+    for (int j = 0; j < TPE; ++j) zr[j] = zbbT[(size_t)j * nbp + lane];
+  }
+
+  const int groups = (p.E + EPB - 1) / EPB;
   for (int g = blockIdx.x; g < groups; g += gridDim.x) {
     const int e_raw = g * EPB + le;
     const bool valid = e_raw < p.E;
@@ -97,10 +139,11 @@ __global__ void __launch_bounds__(256) pf_fixed_point_kernel(const PfParams p) {
     for (int m = 0; m < R; ++m) {
       const int k = lane + TPE * m;
       s[m] = make_double2(0.0, 0.0);
-      u0[m] = p.u0[k];
+      u0[m] = u0t[k];
+      u[m] = u0[m];
       model[m] = 1; vlo[m] = 0.95; vhi[m] = 1.05;
       if (k < p.nb) {
-        const int l = p.branch_load[k];
+        const int l = bload[k];
         double kw, kvar;
         if (p.load_kw != nullptr) {
           kw = p.load_kw[(size_t)l * p.E + e];
@@ -115,20 +158,20 @@ __global__ void __launch_bounds__(256) pf_fixed_point_kernel(const PfParams p) {
           double ctrl = 0.0;
           bool any = false;
           for (int a = 0; a < p.A; ++a)
-            if (p.agents[a].load_slot == l) {
+            if (aslot[a] == l) {
               const double pa = p.agent_p[(size_t)a * p.E + e];
               ctrl = any ? ctrl + pa : pa;
               any = true;
             }
           if (any) kw += ctrl;
         }
-        const double sh = p.branch_share[k] * 1e-3;      // kVA -> p.u. on 1 MVA
+        const double sh = share[k] * 1e-3;               // kVA -> p.u. on 1 MVA
         s[m] = make_double2(kw * sh, kvar * sh);
-        model[m] = p.branch_model[k];
-        vlo[m] = p.vminpu[k];
-        vhi[m] = p.vmaxpu[k];
+        model[m] = bmodel[k];
+        vlo[m] = vminpu[k];
+        vhi[m] = vmaxpu[k];
+        if (p.warm_start) u[m] = p.u_state[(size_t)k * p.E + e];
       }
-      u[m] = u0[m];
     }
 
     // ---- fixed point with per-env convergence masking
@@ -139,22 +182,39 @@ __global__ void __launch_bounds__(256) pf_fixed_point_kernel(const PfParams p) {
       for (int m = 0; m < R; ++m)
         icur[lane + TPE * m] = branch_current(model[m], s[m], u[m], vlo[m], vhi[m]);
       __syncwarp(gmask);
-      double2 acc[R];
+      double2 acc[R], acc2[R];
 #pragma unroll
-      for (int m = 0; m < R; ++m) acc[m] = u0[m];
-      for (int j = 0; j < p.nb; ++j) {
-        const double2 ij = icur[j];
-        const double2* zrow = p.zbbT + (size_t)j * nbp + lane;
+      for (int m = 0; m < R; ++m) { acc[m] = u0[m]; acc2[m] = make_double2(0.0, 0.0); }
+      if (ZREG) {
 #pragma unroll
-        for (int m = 0; m < R; ++m) {
-          const double2 z = __ldg(zrow + TPE * m);
-          acc[m].x -= z.x * ij.x - z.y * ij.y;
-          acc[m].y -= z.x * ij.y + z.y * ij.x;
+        for (int j = 0; j < TPE; j += 2) {               // padded columns of Zbb are zero
+          cmac_sub(acc[0], zr[j], icur[j]);
+          cmac_sub(acc2[0], zr[j + 1], icur[j + 1]);
+        }
+      } else {
+        int j = 0;
+        for (; j + 1 < p.nb; j += 2) {
+          const double2 i0 = icur[j], i1 = icur[j + 1];
+          const double2* z0 = zbbT + (size_t)j * nbp + lane;
+          const double2* z1 = z0 + nbp;
+#pragma unroll
+          for (int m = 0; m < R; ++m) {
+            cmac_sub(acc[m], z0[TPE * m], i0);
+            cmac_sub(acc2[m], z1[TPE * m], i1);
+          }
+        }
+        if (j < p.nb) {
+          const double2 i0 = icur[j];
+          const double2* z0 = zbbT + (size_t)j * nbp + lane;
+#pragma unroll
+          for (int m = 0; m < R; ++m) cmac_sub(acc[m], z0[TPE * m], i0);
         }
       }
       double d = 0.0;
 #pragma unroll
       for (int m = 0; m < R; ++m) {
+        acc[m].x += acc2[m].x;
+        acc[m].y += acc2[m].y;
         d = fmax(d, fmax(fabs(acc[m].x - u[m].x), fabs(acc[m].y - u[m].y)));
         u[m] = acc[m];
       }
@@ -164,17 +224,26 @@ __global__ void __launch_bounds__(256) pf_fixed_point_kernel(const PfParams p) {
       if (conv || it >= p.max_iter) break;
       __syncwarp(gmask);
     }
+    if (valid) {
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const int k = lane + TPE * m;
+        if (k < p.nb) p.u_state[(size_t)k * p.E + e] = u[m];
+      }
+    }
 
     // ---- all node voltages from the currents of the last iteration
     double lmin = 1e300, lmax = -1e300;
     for (int n = lane; n < p.nn; n += TPE) {
-      double2 v = p.w[n];
-      for (int k = 0; k < p.nb; ++k) {
-        const double2 z = __ldg(p.znbT + (size_t)k * p.nnp + n);
-        const double2 ik = icur[k];
-        v.x -= z.x * ik.x - z.y * ik.y;
-        v.y -= z.x * ik.y + z.y * ik.x;
+      double2 v = wt[n], v2 = make_double2(0.0, 0.0);
+      int k = 0;
+      for (; k + 1 < p.nb; k += 2) {
+        cmac_sub(v, znbT[(size_t)k * p.nnp + n], icur[k]);
+        cmac_sub(v2, znbT[(size_t)(k + 1) * p.nnp + n], icur[k + 1]);
       }
+      if (k < p.nb) cmac_sub(v, znbT[(size_t)k * p.nnp + n], icur[k]);
+      v.x += v2.x;
+      v.y += v2.y;
       const double mag = sqrt(v.x * v.x + v.y * v.y);
       stage[n] = mag;
       lmin = fmin(lmin, mag);
@@ -200,12 +269,13 @@ __global__ void __launch_bounds__(256) pf_fixed_point_kernel(const PfParams p) {
         p.viol[e] = 0.0;
       }
       for (int a = lane; a < p.A; a += TPE) {
-        const int node = p.agents[a].bus_node;
+        const int node = anode[a];
         const size_t ae = (size_t)a * p.E + e;
         p.vbus[ae] = node >= 0 ? stage[node] : 1.0;
         if (p.event_mode != 0) {
           const double r = p.rew[ae] - pen_share;
           p.rew[ae] = r;
+          p.rew_copy[ae] = r;
           p.ep_ret[ae] += r;
         }
       }
@@ -220,49 +290,40 @@ __global__ void __launch_bounds__(256) pf_fixed_point_kernel(const PfParams p) {
     __syncthreads();
   }
 
-  if (p.advance_clock) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned int t = atomicAdd(p.ticket, 1u);
-      if (t == gridDim.x - 1) {
-        *p.ticket = 0u;
-        *p.clock = event;
-        __threadfence();
-      }
-    }
-  }
+  if (p.advance_clock) publish_clock_last_cta(p.ticket, p.clock, event, gridDim.x);
 }
 
-template <int TPE, int R>
+template <int TPE, int R, bool ZREG>
 static cudaError_t launch_pf_t(const PfParams& p, cudaStream_t s) {
   const int threads = 256;
   const int epb = threads / TPE;
   const int groups = (p.E + epb - 1) / epb;
-  int grid = groups < 148 * 8 ? groups : 148 * 8;
+  int grid = groups < 148 * 4 ? groups : 148 * 4;
   if (grid < 1) grid = 1;
-  const size_t smem = (size_t)epb * p.nbp * sizeof(double2) + (size_t)epb * p.nn * sizeof(double);
+  const size_t smem = (size_t)(p.stage_blob ? p.blob_bytes : 0) + (size_t)(2 + 2 * p.nl) * 8 +
+                      (size_t)epb * p.nbp * sizeof(double2) + (size_t)epb * p.nn * sizeof(double);
   if (smem > 48 * 1024) {
-    cudaError_t err = cudaFuncSetAttribute(pf_fixed_point_kernel<TPE, R>,
+    cudaError_t err = cudaFuncSetAttribute(pf_fixed_point_kernel<TPE, R, ZREG>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
   }
-  pf_fixed_point_kernel<TPE, R><<<grid, threads, smem, s>>>(p);
+  pf_fixed_point_kernel<TPE, R, ZREG><<<grid, threads, smem, s>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_powerflow(const PfParams& p, cudaStream_t s) {
-  if (p.nbp == 16) return launch_pf_t<16, 1>(p, s);
-  if (p.nbp == 32) return launch_pf_t<32, 1>(p, s);
-  if (p.nbp == 64) return launch_pf_t<32, 2>(p, s);
-  if (p.nbp == 96) return launch_pf_t<32, 3>(p, s);
-  if (p.nbp == 128) return launch_pf_t<32, 4>(p, s);
+  if (p.nbp == 16) return launch_pf_t<16, 1, true>(p, s);
+  if (p.nbp == 32) return launch_pf_t<32, 1, false>(p, s);
+  if (p.nbp == 64) return launch_pf_t<32, 2, false>(p, s);
+  if (p.nbp == 96) return launch_pf_t<32, 3, false>(p, s);
+  if (p.nbp == 128) return launch_pf_t<32, 4, false>(p, s);
   return cudaErrorInvalidValue;
 }
 
 // ------------------------------------------------------------------ K8: episode statistics
 __global__ void __launch_bounds__(256) stats_kernel(const StatsParams p) {
   __shared__ double red[5][8];
+  __shared__ double mn[8], mx[8];
   double rsum = 0.0, esum = 0.0, vsum = 0.0, nconv = 0.0, itsum = 0.0;
   double vmn = 1e300, vmx = -1e300;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < p.E; e += gridDim.x * blockDim.x) {
@@ -290,9 +351,9 @@ __global__ void __launch_bounds__(256) stats_kernel(const StatsParams p) {
   const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
   if (ln == 0) {
     for (int q = 0; q < 5; ++q) red[q][warp] = vals[q];
+    mn[warp] = vmn;
+    mx[warp] = vmx;
   }
-  __shared__ double mn[8], mx[8];
-  if (ln == 0) { mn[warp] = vmn; mx[warp] = vmx; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t[5] = {0, 0, 0, 0, 0}, a = 1e300, b = -1e300;
@@ -306,15 +367,16 @@ __global__ void __launch_bounds__(256) stats_kernel(const StatsParams p) {
     atomicAdd(p.out + 3, t[2]);
     atomicAdd(p.out + 4, t[3]);
     atomicAdd(p.out + 5, t[4]);
-    // min / max through the ordered-integer trick on positive doubles
-    atomicMin(reinterpret_cast<unsigned long long*>(p.out + 6), (unsigned long long)__double_as_longlong(a));
-    atomicMax(reinterpret_cast<unsigned long long*>(p.out + 7), (unsigned long long)__double_as_longlong(b > 0 ? b : 0.0));
+    // min / max through the ordered-integer view of positive doubles
+    atomicMin(reinterpret_cast<unsigned long long*>(p.out + 6),
+              (unsigned long long)__double_as_longlong(a));
+    atomicMax(reinterpret_cast<unsigned long long*>(p.out + 7),
+              (unsigned long long)__double_as_longlong(b > 0 ? b : 0.0));
     if (blockIdx.x == 0) p.out[0] = (double)p.E * (double)(*p.clock);
   }
 }
 
 cudaError_t launch_stats(const StatsParams& p, cudaStream_t s) {
-  // out[1..5] = 0, out[6] = +big, out[7] = 0 are set by the caller (memset + init kernel-free)
   int grid = (p.E + 255) / 256;
   if (grid > 148 * 4) grid = 148 * 4;
   stats_kernel<<<grid, 256, 0, s>>>(p);

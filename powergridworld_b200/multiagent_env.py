@@ -282,6 +282,9 @@ class MultiAgentEnv:
         self.rew = torch.zeros((A, E), **f64)
         self.done = torch.zeros((E,), dtype=torch.uint8, device=self.device)
         self._act = torch.zeros((self.act_dim, E), **f64)
+        self._act_shape = self._act.shape
+        self._obs_ptr, self._rew_ptr = self.obs.data_ptr(), self.rew.data_ptr()
+        self._done_ptr = self.done.data_ptr()
         self._pin = None
         self._needs_reset = True
 
@@ -363,15 +366,14 @@ class MultiAgentEnv:
         torch = _torch()
         if self._needs_reset:
             raise RuntimeError("call reset before step")
-        if actions.dtype != torch.float64 or tuple(actions.shape) != (self.act_dim, self.num_envs) \
+        if actions.dtype != torch.float64 or actions.shape != self._act_shape \
                 or not actions.is_contiguous() or actions.device != self.device:
             raise ValueError(f"actions must be a contiguous float64 [{self.act_dim}, "
                              f"{self.num_envs}] tensor on {self.device}")
-        with torch.cuda.device(self.device):
-            N.check(self._lib.pgw_step(self._h, C.c_void_p(actions.data_ptr()),
-                                       C.c_void_p(self.obs.data_ptr()),
-                                       C.c_void_p(self.rew.data_ptr()),
-                                       C.c_void_p(self.done.data_ptr()), self._stream()))
+        rc = self._lib.pgw_step(self._h, actions.data_ptr(), self._obs_ptr, self._rew_ptr,
+                                self._done_ptr, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            N.check(rc)
         self.episode_step += 1
         self.time += self.control_timedelta
         all_done = self.episode_step >= self.episode_length
@@ -469,6 +471,10 @@ class MultiAgentEnv:
             dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
             s = _torch().cat([add, lo, hi])
         return s
+
+    def set_option(self, option: int, value: int):
+        """Runtime options of the device handle (N.OPT_PF_KERNEL / OPT_WARM_START / OPT_GRAPHS)."""
+        N.check(self._lib.pgw_set_option(self._h, int(option), int(value)))
 
     def set_kernel_timing(self, enabled: bool):
         N.check(self._lib.pgw_set_timing(self._h, int(bool(enabled))))

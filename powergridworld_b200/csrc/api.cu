@@ -76,6 +76,11 @@ struct pgw_env {
       off_bload = 0, off_bmodel = 0, off_slot = 0, off_node = 0;
   double2* u_state = nullptr;
   bool warm_start = true;
+  // tensor-core power flow (powerflow_tc.cu): operand images + fp32 tables
+  unsigned char* tc_blob = nullptr;
+  int tc_blob_bytes = 0, tc_n2 = 0, tc_nnp8 = 0;
+  int tc_off_b2 = 0, tc_off_u0 = 0, tc_off_w = 0, tc_off_share = 0, tc_off_vlo = 0, tc_off_vhi = 0,
+      tc_off_bload = 0, tc_off_bmodel = 0, tc_off_slot = 0, tc_off_node = 0;
   // CUDA graphs of a step, keyed by the caller's buffer pointers
   struct StepGraph {
     const void *actions, *obs, *rew, *done;
@@ -286,6 +291,89 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       PGW_TRY(upload(&env->pf_blob, blob.data(), blob.size())); env->own(env->pf_blob);
     }
     PGW_TRY(alloc_zero(&env->u_state, (size_t)nbp * E)); env->own(env->u_state);
+    if (nb <= pgw::kTcNb && 32 + 2 * round_up(nn, 8) <= 128) {
+      // Operand images of the tcgen05 kernel, byte-exact as they sit in shared memory:
+      // canonical K-major no-swizzle UMMA layout, element (row, k) at
+      //   (row/8)*3072 + (k/4)*128 + (row%8)*16 + (k%4)*4,   K = 96 = [hi | hi | lo] of B.
+      const int NB = pgw::kTcNb, K3 = pgw::kTcK3, nnp8 = round_up(nn, 8), n2 = 2 * nnp8;
+      auto hi_of = [](double v) {
+        float f = (float)v;
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        u &= 0xFFFFE000u;
+        memcpy(&f, &u, 4);
+        return f;
+      };
+      auto image = [&](int rows, const std::vector<double>& b /* [rows][32] */) {
+        std::vector<unsigned char> img((size_t)rows * K3 * 4, 0);
+        for (int r = 0; r < rows; ++r)
+          for (int k = 0; k < 32; ++k) {
+            const double v = b[(size_t)r * 32 + k];
+            const float hi = hi_of(v), lo = (float)(v - (double)hi);
+            const float part[3] = {hi, hi, lo};
+            for (int q = 0; q < 3; ++q) {
+              const int kc = q * 32 + k;
+              const size_t off = (size_t)(r / 8) * 3072 + (size_t)(kc / 4) * 128 + (r % 8) * 16 + (kc % 4) * 4;
+              memcpy(img.data() + off, &part[q], 4);
+            }
+          }
+        return img;
+      };
+      auto Z = [&](int k, int j) { return make_double2(f.zbb[2 * ((size_t)k * nb + j)], f.zbb[2 * ((size_t)k * nb + j) + 1]); };
+      auto ZN = [&](int n, int k) { return make_double2(f.znb[2 * ((size_t)n * nb + k)], f.znb[2 * ((size_t)n * nb + k) + 1]); };
+      // D[e][n] = sum_k X[e][k] B[n][k],  X = [Re i (16) | Im i (16)],  D = [Re du (16) | Im du (16)]
+      std::vector<double> b1((size_t)32 * 32, 0.0), b2((size_t)n2 * 32, 0.0);
+      for (int k = 0; k < nb; ++k)
+        for (int j = 0; j < nb; ++j) {
+          const double2 z = Z(k, j);
+          b1[(size_t)k * 32 + j] = -z.x;            // Re du_k -= Zr Re i_j
+          b1[(size_t)k * 32 + NB + j] = z.y;        //           + Zi Im i_j
+          b1[(size_t)(NB + k) * 32 + j] = -z.y;     // Im du_k -= Zi Re i_j
+          b1[(size_t)(NB + k) * 32 + NB + j] = -z.x;  //         - Zr Im i_j
+        }
+      for (int n = 0; n < nn; ++n)                  // rows interleaved: 2n = Re dv_n, 2n+1 = Im dv_n
+        for (int k = 0; k < nb; ++k) {
+          const double2 z = ZN(n, k);
+          b2[(size_t)(2 * n) * 32 + k] = -z.x;
+          b2[(size_t)(2 * n) * 32 + NB + k] = z.y;
+          b2[(size_t)(2 * n + 1) * 32 + k] = -z.y;
+          b2[(size_t)(2 * n + 1) * 32 + NB + k] = -z.x;
+        }
+      std::vector<unsigned char> blob;
+      auto put = [&blob](const void* src, size_t bytes) {
+        const size_t off = (blob.size() + 127) / 128 * 128;
+        blob.resize(off + bytes, 0);
+        memcpy(blob.data() + off, src, bytes);
+        return (int)off;
+      };
+      std::vector<unsigned char> i1 = image(32, b1), i2 = image(n2, b2);
+      put(i1.data(), i1.size());
+      env->tc_off_b2 = put(i2.data(), i2.size());
+      std::vector<float> u0f(2 * NB, 0.f), wf(2 * nnp8, 0.f), vlf(NB, 0.95f), vhf(NB, 1.05f);
+      std::vector<double> shd(NB, 0.0);
+      std::vector<int32_t> bl16(NB, 0), bm16(NB, 1), slot(env->A), node(env->A);
+      for (int k = 0; k < NB; ++k) { u0f[2 * k] = 1.f; }
+      for (int k = 0; k < nb; ++k) {
+        u0f[2 * k] = (float)f.u0[2 * k]; u0f[2 * k + 1] = (float)f.u0[2 * k + 1];
+        vlf[k] = (float)f.vminpu[k]; vhf[k] = (float)f.vmaxpu[k]; shd[k] = f.branch_share[k];
+        bl16[k] = f.branch_load[k]; bm16[k] = f.branch_model[k];
+      }
+      for (int n = 0; n < nn; ++n) { wf[2 * n] = (float)f.w[2 * n]; wf[2 * n + 1] = (float)f.w[2 * n + 1]; }
+      for (int a = 0; a < env->A; ++a) { slot[a] = spec->agents[a].load_slot; node[a] = spec->agents[a].bus_node; }
+      env->tc_off_u0 = put(u0f.data(), u0f.size() * 4);
+      env->tc_off_w = put(wf.data(), wf.size() * 4);
+      env->tc_off_share = put(shd.data(), shd.size() * 8);
+      env->tc_off_vlo = put(vlf.data(), vlf.size() * 4);
+      env->tc_off_vhi = put(vhf.data(), vhf.size() * 4);
+      env->tc_off_bload = put(bl16.data(), bl16.size() * 4);
+      env->tc_off_bmodel = put(bm16.data(), bm16.size() * 4);
+      env->tc_off_slot = put(slot.data(), slot.size() * 4);
+      env->tc_off_node = put(node.data(), node.size() * 4);
+      blob.resize((blob.size() + 127) / 128 * 128, 0);
+      env->tc_blob_bytes = (int)blob.size();
+      env->tc_n2 = n2; env->tc_nnp8 = nnp8;
+      PGW_TRY(upload(&env->tc_blob, blob.data(), blob.size())); env->own(env->tc_blob);
+    }
     PGW_TRY(alloc_zero(&env->vmag, (size_t)nn * E)); env->own(env->vmag);
     PGW_TRY(alloc_zero(&env->vmin, E)); env->own(env->vmin);
     PGW_TRY(alloc_zero(&env->vmax, E)); env->own(env->vmax);
@@ -331,12 +419,23 @@ static pgw::PfParams pf_params(pgw_env* env) {
   p.off_share = env->off_share; p.off_vmin = env->off_vmin; p.off_vmax = env->off_vmax;
   p.off_bload = env->off_bload; p.off_bmodel = env->off_bmodel; p.off_slot = env->off_slot;
   p.off_node = env->off_node; p.u_state = env->u_state; p.rew_copy = env->rew_last;
+  p.tc_blob = env->tc_blob; p.tc_blob_bytes = env->tc_blob_bytes; p.tc_n2 = env->tc_n2;
+  p.tc_nnp8 = env->tc_nnp8; p.tc_off_b2 = env->tc_off_b2; p.tc_off_u0 = env->tc_off_u0;
+  p.tc_off_w = env->tc_off_w; p.tc_off_share = env->tc_off_share; p.tc_off_vlo = env->tc_off_vlo;
+  p.tc_off_vhi = env->tc_off_vhi; p.tc_off_bload = env->tc_off_bload;
+  p.tc_off_bmodel = env->tc_off_bmodel; p.tc_off_slot = env->tc_off_slot;
+  p.tc_off_node = env->tc_off_node;
+  p.tc_tol = (float)(env->tol > 1e-7 ? env->tol : 1e-7);
   p.dtab = env->dtab; p.dstride = env->dstride;
   p.vmag = env->vmag; p.vmin = env->vmin; p.vmax = env->vmax; p.vbus = env->vbus;
   p.iters = env->iters; p.ep_ret = env->ep_ret; p.viol = env->viol;
   p.penalty_node = env->penalty_node; p.pvlo = env->pvlo; p.pvhi = env->pvhi; p.punit = env->punit;
   p.clock = env->d_clock; p.ticket = env->d_ticket;
   return p;
+}
+
+static cudaError_t launch_pf(const pgw_env* env, const pgw::PfParams& pf, cudaStream_t s) {
+  return env->pf_kernel == 1 ? pgw::launch_powerflow_tc(pf, s) : pgw::launch_powerflow(pf, s);
 }
 
 static int smem_for_events(const pgw_env* env) {
@@ -352,7 +451,7 @@ int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stre
     pgw::PfParams pf = pf_params(env);
     pf.event_mode = 0; pf.advance_clock = 0; pf.agent_p = nullptr; pf.rew = nullptr;
     pf.punit = 0.0; pf.warm_start = 0;
-    PGW_CUDA(pgw::launch_powerflow(pf, s));
+    PGW_CUDA(launch_pf(env, pf, s));
     ++env->launches;
   }
   pgw::CompParams cp = comp_params(env);
@@ -376,7 +475,7 @@ static int enqueue_step(pgw_env* env, const double* actions, double* obs, double
     pgw::PfParams pf = pf_params(env);
     pf.event_mode = 1; pf.advance_clock = 1; pf.agent_p = env->agent_p; pf.rew = rew;
     pf.warm_start = env->warm_start ? 1 : 0;
-    PGW_CUDA(pgw::launch_powerflow(pf, s));
+    PGW_CUDA(launch_pf(env, pf, s));
   }
   if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
   return PGW_OK;
@@ -507,7 +606,7 @@ int pgw_pf_solve(pgw_env* env, const double* load_kw, const double* load_kvar,
   pgw::PfParams pf = pf_params(env);
   pf.event_mode = 0; pf.advance_clock = 0; pf.agent_p = nullptr; pf.rew = nullptr;
   pf.punit = 0.0; pf.load_kw = load_kw; pf.load_kvar = load_kvar; pf.warm_start = 0;
-  PGW_CUDA(pgw::launch_powerflow(pf, static_cast<cudaStream_t>(cuda_stream)));
+  PGW_CUDA(launch_pf(env, pf, static_cast<cudaStream_t>(cuda_stream)));
   ++env->launches;
   return PGW_OK;
 }
@@ -559,10 +658,12 @@ int pgw_set_option(pgw_env* env, int option, int value) {
   if (!env) return fail(PGW_ERR_INVALID, "null argument");
   switch (option) {
     case PGW_OPT_PF_KERNEL:
-      if (value != 0)
-        return fail(PGW_ERR_INVALID, "tensor-core power flow is not built into this library yet");
+      if (value != 0 && value != 1) return fail(PGW_ERR_INVALID, "unknown power-flow kernel");
+      if (value == 1 && !env->tc_blob)
+        return fail(PGW_ERR_INVALID, "tensor-core power flow needs a feeder with <= 16 load "
+                                     "branches and <= 48 nodes");
       env->pf_kernel = value;
-      return PGW_OK;
+      break;
     case PGW_OPT_WARM_START: env->warm_start = value != 0; break;
     case PGW_OPT_GRAPHS: env->use_graphs = value != 0; break;
     default: return fail(PGW_ERR_INVALID, "unknown option");

@@ -10,6 +10,7 @@ mkdir -p "$HERE/build"
 # component kernels: no FMA contraction, so float64 rounds exactly like the reference
 "$NVCC" $COMMON -fmad=false ${PTXAS_V:+-Xptxas -v} -c "$HERE/components.cu" -o "$HERE/build/components.o"
 "$NVCC" $COMMON ${PTXAS_V:+-Xptxas -v} -c "$HERE/powerflow.cu" -o "$HERE/build/powerflow.o"
+"$NVCC" $COMMON ${PTXAS_V:+-Xptxas -v} -c "$HERE/powerflow_tc.cu" -o "$HERE/build/powerflow_tc.o"
 "$NVCC" $COMMON -c "$HERE/api.cu" -o "$HERE/build/api.o"
-"$NVCC" -shared $ARCH -o "$OUT" "$HERE/build/components.o" "$HERE/build/powerflow.o" "$HERE/build/api.o" -lcudart
+"$NVCC" -shared $ARCH -o "$OUT" "$HERE/build/components.o" "$HERE/build/powerflow.o" "$HERE/build/powerflow_tc.o" "$HERE/build/api.o" -lcudart
 echo "built $OUT"

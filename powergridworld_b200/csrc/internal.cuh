@@ -51,6 +51,12 @@ struct PfParams {
   int off_u0, off_znbT, off_w, off_share, off_vmin, off_vmax, off_bload, off_bmodel, off_slot,
       off_node;
   double2* u_state;        // [nbp][E] last converged branch voltages (warm start)
+  // tensor-core form (powerflow_tc.cu): operand images + fp32 tables, see TcLayout in api.cu
+  const unsigned char* tc_blob;
+  int tc_blob_bytes, tc_n2, tc_nnp8;
+  int tc_off_b2, tc_off_u0, tc_off_w, tc_off_share, tc_off_vlo, tc_off_vhi, tc_off_bload,
+      tc_off_bmodel, tc_off_slot, tc_off_node;
+  float tc_tol;
   const double* agent_p;   // [A][E]
   const double* load_kw;   // [nl][E] stand-alone solve: total kW per load (else nullptr)
   const double* load_kvar; // [nl][E]
@@ -85,6 +91,9 @@ struct StatsParams {
 
 cudaError_t launch_components(const CompParams& p, int smem_bytes, cudaStream_t s);
 cudaError_t launch_powerflow(const PfParams& p, cudaStream_t s);
+cudaError_t launch_powerflow_tc(const PfParams& p, cudaStream_t s);
+constexpr int kTcNb = 16;      // branch slots of the tensor-core kernel (IEEE-13 class feeders)
+constexpr int kTcK3 = 96;      // 3 x 32: [x_hi | x_lo | x_hi] against [B_hi ; B_hi ; B_lo]
 cudaError_t launch_stats(const StatsParams& p, cudaStream_t s);
 
 }  // namespace pgw

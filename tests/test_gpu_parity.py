@@ -294,3 +294,57 @@ def test_abi_error_paths():
     import ctypes as C
     rc = env._lib.pgw_get(env._h, N.FIELD_VMIN, C.c_void_p(out.data_ptr()), 24, None)
     assert rc == -1 and b"size mismatch" in env._lib.pgw_last_error()
+
+
+@pytest.mark.parametrize("name,E", [("c0_buildings", 300), ("heterogeneous", 128)])
+def test_tensor_core_power_flow_matches_fp64_kernel(name, E):
+    """tcgen05 fixed point (split-TF32 operands, FP32 accumulate/epilogue) vs the FP64 SIMT
+    kernel on the same batch: node voltages within 1e-6 p.u. -- two orders inside the 1e-4 p.u.
+    tolerance of the reference's own solver -- and rewards within 1e-5 relative (+ the
+    1e4 x voltage floor of the violation penalty)."""
+    torch = _torch()
+    from powergridworld_b200 import _native as N
+    T = 40
+    a_env = CASES[name](PNS, num_envs=E)
+    b_env = CASES[name](PNS, num_envs=E)
+    b_env.set_option(N.OPT_PF_KERNEL, 1)
+    rng = np.random.default_rng(11)
+    soc = rng.uniform(5, 45, size=(a_env.num_storage, E))
+    oa = a_env.reset_batch(soc).cpu().numpy()
+    ob = b_env.reset_batch(soc).cpu().numpy()
+    np.testing.assert_allclose(ob, oa, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(b_env.get_field(3).cpu().numpy(), a_env.get_field(3).cpu().numpy(),
+                               rtol=0, atol=1e-6)
+    for t in range(T):
+        act = torch.as_tensor(rng.uniform(-1, 1, size=(a_env.act_dim, E))).cuda()
+        oa, ra, _, _ = a_env.step_batch(act)
+        ob, rb, _, _ = b_env.step_batch(act)
+        np.testing.assert_allclose(b_env.get_field(3).cpu().numpy(),
+                                   a_env.get_field(3).cpu().numpy(), rtol=0, atol=1e-6,
+                                   err_msg=f"voltages t={t}")
+        np.testing.assert_allclose(ob.cpu().numpy(), oa.cpu().numpy(), rtol=0, atol=2e-5)
+        np.testing.assert_allclose(rb.cpu().numpy(), ra.cpu().numpy(), rtol=1e-5, atol=1e-2)
+    it = b_env.get_field(7)
+    assert int(it.min()) > 0, "tensor-core solve did not converge"
+    assert float(it.double().mean()) < 25
+
+
+def test_tensor_core_golden_trace_within_north_star_tolerances():
+    """Reference golden trace through the tcgen05 solver: voltages 1e-4 p.u., observations
+    1e-6 (x10 for the scaled voltage entries), rewards 1e-5 relative."""
+    from powergridworld_b200 import _native as N
+    g = np.load(os.path.join(GOLD, "c0_buildings.npz"))
+    env = CASES["c0_buildings"](PNS)
+    env.set_option(N.OPT_PF_KERNEL, 1)
+    names = [str(n) for n in g["node_names"]]
+    obs0 = env.reset(init_storage=g["init_soc"])
+    np.testing.assert_allclose(flat_obs(env, obs0), g["obs0"], rtol=0, atol=1e-5)
+    for t in range(g["actions"].shape[0]):
+        ob, rew, dn, _ = env.step(unflatten_action(env, g["actions"][t]))
+        np.testing.assert_allclose(flat_obs(env, ob), g["obs"][t], rtol=0, atol=1e-5)
+        np.testing.assert_allclose([rew[a.name] for a in env.agents], g["rew"][t],
+                                   rtol=1e-5, atol=1e-2)
+        if t % 50 == 0:
+            v = env.voltages
+            np.testing.assert_allclose([v[k] for k in names], g["volt"][t + 1], rtol=0, atol=1e-4)
+            np.testing.assert_allclose([v[k] for k in names], g["volt"][t + 1], rtol=0, atol=2e-6)

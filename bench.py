@@ -33,7 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-ENVS_PER_GPU = 4096
+ENVS_PER_GPU = 4096          # BASELINE.json configs[1]; --envs overrides (size sweeps)
+PF_KERNEL = "fp64"           # --pf-kernel tc selects the tcgen05 solver
 METRIC, UNIT = "env_steps_per_s", "env-steps/s"
 SURVEY_BYTES_PER_ENV_STEP = 3 * (264 + 28 + 40) + 1      # SURVEY.md section 8(d), component kernels
 LOAD_FACTOR = 1.2
@@ -45,7 +46,8 @@ def _config(n_gpus):
             "envs_per_gpu": ENVS_PER_GPU, "agents_per_env": 3, "global_envs": ENVS_PER_GPU * n_gpus,
             "feeder": "IEEE-13 (38 nodes, 14 load branches)", "load_factor": LOAD_FACTOR,
             "parallelism": f"env-sharded x{n_gpus}", "l2": "flushed between timed steps "
-            "(256 MiB write)", "pf_kernel": "fp64-simt"}
+            "(256 MiB write)",
+            "pf_kernel": "tcgen05 split-tf32" if PF_KERNEL == "tc" else "fp64-simt"}
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -180,10 +182,13 @@ def run_ours(args):
     E = ENVS_PER_GPU
     env = NS.CoordinatedMultiBuildingControlEnv(
         **S.buildings_scenario(NS, NS.OpenDSSSolver, LOAD_FACTOR), num_envs=E, device=dev)
+    if PF_KERNEL == "tc":
+        from powergridworld_b200 import _native as N
+        env.set_option(N.OPT_PF_KERNEL, 1)
     A = len(env.agents)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    pool_n = 64
+    pool_n = 64 if E <= 65536 else 8
     act_pool = torch.rand((pool_n, env.act_dim, E), generator=gen, device=dev,
                           dtype=torch.float64) * 2.0 - 1.0
     rng = np.random.default_rng(rank)
@@ -290,6 +295,11 @@ def run_ours(args):
         achieved = alg_bytes / (comp_ms * 1e-3) / 1e9 if comp_ms > 0 else 0.0
         f = env.pf_solver.feeder
         flops = (8.0 * f.nb * f.nb * iters_mean + 8.0 * f.nn * f.nb) * E
+        if PF_KERNEL == "tc":      # dense TF32 = half the measured bf16 rate; flops counted once
+            pf_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
+            pf_peak_src = "0.5 x measured bf16 (tf32 dense), " + peak_src
+        else:
+            pf_peak, pf_peak_src = 37.0, "nominal B200 FP64 (no measured FP64 peak)"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
@@ -305,9 +315,11 @@ def run_ours(args):
                          "frac": achieved / peaks["hbm_gbs"], "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "avg_launch_ms": comp_ms},
-            "roofline_pf": {"kernel": "pf_fixed_point_kernel<16,1>", "bound": "fp64-fma",
+            "roofline_pf": {"kernel": "pf_tc_kernel" if PF_KERNEL == "tc"
+                            else "pf_fixed_point_kernel<16,1,true>",
+                            "bound": "tensor" if PF_KERNEL == "tc" else "fp64-fma",
                             "achieved": flops / (pf_ms * 1e-3) / 1e12 if pf_ms > 0 else 0.0,
-                            "peak": 37.0, "unit": "TFLOP/s", "peak_source": "nominal B200 FP64",
+                            "peak": pf_peak, "unit": "TFLOP/s", "peak_source": pf_peak_src,
                             "algorithmic_flops_per_launch": flops, "avg_launch_ms": pf_ms,
                             "mean_iterations": iters_mean},
             "kernel_share": {"components": comp_ms / max(comp_ms + pf_ms, 1e-12),
@@ -316,7 +328,7 @@ def run_ours(args):
             "stats": [float(x) for x in stats.cpu()],
             "wall_s_timed_region": wall,
         }
-        line["roofline_pf"]["frac"] = line["roofline_pf"]["achieved"] / 37.0
+        line["roofline_pf"]["frac"] = line["roofline_pf"]["achieved"] / pf_peak
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
@@ -325,13 +337,17 @@ def run_ours(args):
 
 
 def main():
+    global ENVS_PER_GPU, PF_KERNEL
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--pf-kernel", default="fp64", choices=["fp64", "tc"])
     args = ap.parse_args()
+    ENVS_PER_GPU, PF_KERNEL = args.envs, args.pf_kernel
     if args.impl == "reference":
         run_reference(args)
     else:

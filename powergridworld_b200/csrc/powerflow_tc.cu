@@ -4,9 +4,10 @@
 //   D[env, :] = X[env, :] * B^T        M = 128 envs (TMEM lanes), N = 2*16 (Re|Im of du),
 //                                       K = 96 = 3 x 32 (split-TF32, see below)
 //
-// * The env batch sits on the MMA M dimension, so after tcgen05.ld every thread owns the
-//   complete voltage-drop vector of ITS env: the nonlinear load characteristic, the
-//   convergence test and the convergence mask are thread-local (no shuffles, no reductions).
+// * The env batch sits on the MMA M dimension: TMEM lane r = env r of the tile.  The four
+//   warps sharing a lane quadrant split the D columns (4 branches each), so the nonlinear
+//   load characteristic is thread-local and the per-env convergence test is one shared-memory
+//   max over four partials; converged envs freeze their state (convergence mask).
 // * Real-ified complex product: x = [Re i | Im i] (32 reals), B = -[[Zr, -Zi], [Zi, Zr]].
 // * kind::tf32 keeps 10 mantissa bits, so operands are split  x = x_hi + x_lo,  B = B_hi + B_lo
 //   and the three significant products are one accumulation chain over a tripled K:
@@ -80,11 +81,32 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
 
-__global__ void __launch_bounds__(TC_M) pf_tc_kernel(const PfParams p) {
+// x4 variant for the 4-branch column slices of the iteration epilogue
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 512 threads = 4 warp groups x 128 envs.  Thread (g, r) owns branches 4g..4g+3 of env row r:
+// the four warps that share a TMEM lane quadrant (w, w+4, w+8, w+12) split the columns, which
+// quarters the serial epilogue chain and gives the SM 16-32 warps to hide latency with.
+constexpr int TC_THREADS = 512;
+constexpr int TC_BPT = kTcNb / 4;                      // branches per thread
+
+__global__ void __launch_bounds__(TC_THREADS, 2) pf_tc_kernel(const PfParams p) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   __shared__ __align__(8) uint64_t mbar_tma, mbar_mma;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_dpart[4][TC_M];                   // per-group partial max |d drop|
+  __shared__ float s_vmn[4][TC_M], s_vmx[4][TC_M];
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (TC_M - 1);                    // env row in the tile = TMEM lane
+  const int grp = tid >> 7;                            // branch group 0..3
   const int hdr = 2 + 2 * p.nl;
 
   unsigned char* sA = tc_smem;                                   // A' tile, 48 kB
@@ -128,49 +150,62 @@ __global__ void __launch_bounds__(TC_M) pf_tc_kernel(const PfParams p) {
   const uint32_t b1_addr = smem_u32(sT);
   const uint32_t b2_addr = smem_u32(sT + p.tc_off_b2);
   const uint32_t idesc1 = umma_idesc_tf32(32), idesc2 = umma_idesc_tf32(p.tc_n2);
-  unsigned char* a_row = sA + (size_t)(tid >> 3) * TC_SBO + (size_t)(tid & 7) * 16;
-  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+  // this thread's two 16-byte chunks of A' row `row`: Re(i) of its 4 branches, Im(i) of them
+  unsigned char* a_re = sA + (size_t)(row >> 3) * TC_SBO + (size_t)(row & 7) * 16 + grp * 128;
+  unsigned char* a_im = a_re + 4 * 128;
+  const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // lane quadrant of this warp
   uint32_t mma_phase = 0;
+
+  // per-branch constants of this thread's slice
+  float u0r[TC_BPT], u0i[TC_BPT], vlo2[TC_BPT], vhi2[TC_BPT];
+  int model[TC_BPT];
+  bool any_model5 = false;
+#pragma unroll
+  for (int j = 0; j < TC_BPT; ++j) {
+    const int k = grp * TC_BPT + j;
+    u0r[j] = u0f[k].x; u0i[j] = u0f[k].y;
+    model[j] = bmodel[k];
+    vlo2[j] = model[j] == 2 ? 1.f : vlo[k] * vlo[k];
+    vhi2[j] = model[j] == 2 ? 1.f : vhi[k] * vhi[k];
+    any_model5 |= model[j] == 5;
+  }
+  any_model5 = __syncthreads_or(any_model5 ? 1 : 0) != 0;     // CTA-uniform
+  // loop-invariant UMMA descriptors; K step kk advances the start-address field by 256 B >> 4
+  const uint64_t adesc0 = umma_smem_desc(a_addr), b1desc0 = umma_smem_desc(b1_addr),
+                 b2desc0 = umma_smem_desc(b2_addr);
 
   const int tiles = (p.E + TC_M - 1) / TC_M;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int e_raw = tile * TC_M + tid;
+    const int e_raw = tile * TC_M + row;
     const bool valid = e_raw < p.E;
     const int e = valid ? e_raw : p.E - 1;
 
-    // ---- per-branch nominal power (p.u. on 1 MVA) and warm start, in registers
-    float sr[kTcNb], si[kTcNb], dr[kTcNb], di[kTcNb];
+    // ---- nominal power (p.u. on 1 MVA) and warm start of this thread's branches
+    float sr[TC_BPT], si[TC_BPT], dr[TC_BPT], di[TC_BPT];
 #pragma unroll
-    for (int k = 0; k < kTcNb; ++k) {
-      sr[k] = si[k] = dr[k] = di[k] = 0.f;
+    for (int j = 0; j < TC_BPT; ++j) {
+      const int k = grp * TC_BPT + j;
+      sr[j] = si[j] = dr[j] = di[j] = 0.f;
       if (k < p.nb) {
         const int l = bload[k];
-        double kw, kvar;
+        float kw, kvar;                                // fp32: this solver's working precision
         if (p.load_kw != nullptr) {
-          kw = p.load_kw[(size_t)l * p.E + e];
-          kvar = p.load_kvar[(size_t)l * p.E + e];
+          kw = (float)p.load_kw[(size_t)l * p.E + e];
+          kvar = (float)p.load_kvar[(size_t)l * p.E + e];
         } else {
-          kw = base_kw[l];
-          kvar = base_kvar[l];
-          if (p.agent_p != nullptr) {                 // multiagent_env.py:171-181, opendss.py:128
-            double ctrl = 0.0;
-            bool any = false;
+          kw = (float)base_kw[l];
+          kvar = (float)base_kvar[l];
+          if (p.agent_p != nullptr)                    // multiagent_env.py:171-181, opendss.py:128
             for (int a = 0; a < p.A; ++a)
-              if (aslot[a] == l) {
-                const double pa = p.agent_p[(size_t)a * p.E + e];
-                ctrl = any ? ctrl + pa : pa;
-                any = true;
-              }
-            if (any) kw += ctrl;
-          }
+              if (aslot[a] == l) kw += (float)p.agent_p[(size_t)a * p.E + e];
         }
-        const double sh = share[k] * 1e-3;
-        sr[k] = (float)(kw * sh);
-        si[k] = (float)(kvar * sh);
+        const float sh = (float)(share[k] * 1e-3);
+        sr[j] = kw * sh;
+        si[j] = kvar * sh;
         if (p.warm_start) {
           const double2 up = p.u_state[(size_t)k * p.E + e];
-          dr[k] = (float)(up.x - (double)u0f[k].x);
-          di[k] = (float)(up.y - (double)u0f[k].y);
+          dr[j] = (float)(up.x - (double)u0r[j]);
+          di[j] = (float)(up.y - (double)u0i[j]);
         }
       }
     }
@@ -178,32 +213,32 @@ __global__ void __launch_bounds__(TC_M) pf_tc_kernel(const PfParams p) {
     int it = 0;
     bool conv = !valid, conv_ok = true;
     while (true) {
-      // ---- branch currents at u = u0 + drop, split hi/lo, written as this env's row of A'
-      float xr[kTcNb], xi[kTcNb];
+      // ---- currents of my branches at u = u0 + drop, split hi/lo, into my chunks of A'
+      float xr[TC_BPT], xi[TC_BPT];
 #pragma unroll
-      for (int k = 0; k < kTcNb; ++k) {
-        const float ur = u0f[k].x + dr[k], ui = u0f[k].y + di[k];
+      for (int j = 0; j < TC_BPT; ++j) {
+        const float ur = u0r[j] + dr[j], ui = u0i[j] + di[j];
         const float m2 = ur * ur + ui * ui;
-        const int model = bmodel[k];
-        float kf;
-        if (model == 2) kf = 1.f;
-        else if (model == 5) kf = m2 > 0.f ? rsqrtf(m2) : 0.f;
-        else if (m2 <= vlo[k] * vlo[k]) kf = __frcp_rn(vlo[k] * vlo[k]);
-        else if (m2 > vhi[k] * vhi[k]) kf = __frcp_rn(vhi[k] * vhi[k]);
-        else kf = __frcp_rn(m2);
-        xr[k] = (sr[k] * ur + si[k] * ui) * kf;       // conj(s) u k
-        xi[k] = (sr[k] * ui - si[k] * ur) * kf;
+        // constant PQ inside the band, constant Z outside = 1 / clamp(|u|^2, vlo^2, vhi^2);
+        // a constant-Z load is the degenerate band [1, 1]
+        float kf = __fdividef(1.f, fminf(fmaxf(m2, vlo2[j]), vhi2[j]));
+        if (any_model5 && model[j] == 5) kf = m2 > 0.f ? rsqrtf(m2) : 0.f;
+        xr[j] = (sr[j] * ur + si[j] * ui) * kf;       // conj(s) u k
+        xi[j] = (sr[j] * ui - si[j] * ur) * kf;
       }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 full, hi, lo;
-        const float* src = q < 4 ? &xr[4 * q] : &xi[4 * (q - 4)];
-        full = make_float4(src[0], src[1], src[2], src[3]);
-        hi = make_float4(tf32_hi(full.x), tf32_hi(full.y), tf32_hi(full.z), tf32_hi(full.w));
-        lo = make_float4(full.x - hi.x, full.y - hi.y, full.z - hi.z, full.w - hi.w);
-        *reinterpret_cast<float4*>(a_row + q * 128) = hi;            // K  0..31  x_hi
-        *reinterpret_cast<float4*>(a_row + 1024 + q * 128) = lo;     // K 32..63  x_lo
-        *reinterpret_cast<float4*>(a_row + 2048 + q * 128) = hi;     // K 64..95  x_hi
+      {
+        const float4 fr = make_float4(xr[0], xr[1], xr[2], xr[3]);
+        const float4 fi = make_float4(xi[0], xi[1], xi[2], xi[3]);
+        const float4 hr = make_float4(tf32_hi(fr.x), tf32_hi(fr.y), tf32_hi(fr.z), tf32_hi(fr.w));
+        const float4 hi = make_float4(tf32_hi(fi.x), tf32_hi(fi.y), tf32_hi(fi.z), tf32_hi(fi.w));
+        const float4 lr = make_float4(fr.x - hr.x, fr.y - hr.y, fr.z - hr.z, fr.w - hr.w);
+        const float4 li = make_float4(fi.x - hi.x, fi.y - hi.y, fi.z - hi.z, fi.w - hi.w);
+        *reinterpret_cast<float4*>(a_re) = hr;                       // K  0..31  x_hi
+        *reinterpret_cast<float4*>(a_im) = hi;
+        *reinterpret_cast<float4*>(a_re + 1024) = lr;                // K 32..63  x_lo
+        *reinterpret_cast<float4*>(a_im + 1024) = li;
+        *reinterpret_cast<float4*>(a_re + 2048) = hr;                // K 64..95  x_hi
+        *reinterpret_cast<float4*>(a_im + 2048) = hi;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.shared -> tensor core
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -214,25 +249,28 @@ __global__ void __launch_bounds__(TC_M) pf_tc_kernel(const PfParams p) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int kk = 0; kk < kTcK3 / 8; ++kk)
-          umma_tf32(tmem, umma_smem_desc(a_addr + kk * 256), umma_smem_desc(b1_addr + kk * 256),
-                    idesc1, kk > 0 ? 1u : 0u);
+          umma_tf32(tmem, adesc0 + 16u * kk, b1desc0 + 16u * kk, idesc1, kk > 0 ? 1u : 0u);
         umma_commit(&mbar_mma);
       }
       mbar_wait(&mbar_mma, mma_phase);
       mma_phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-      float nr[16], ni[16];
-      tmem_ld16(t_lane + 0, nr);                                     // Re(drop_k)
-      tmem_ld16(t_lane + 16, ni);                                    // Im(drop_k)
-      if (!conv) {
-        float d = 0.f;
+      float nr[TC_BPT], ni[TC_BPT];
+      tmem_ld4(t_lane + grp * TC_BPT, nr);                           // Re(drop) of my branches
+      tmem_ld4(t_lane + kTcNb + grp * TC_BPT, ni);                   // Im(drop)
+      float dpart = 0.f;
 #pragma unroll
-        for (int k = 0; k < kTcNb; ++k) {
-          d = fmaxf(d, fmaxf(fabsf(nr[k] - dr[k]), fabsf(ni[k] - di[k])));
-          dr[k] = nr[k];
-          di[k] = ni[k];
-        }
+      for (int j = 0; j < TC_BPT; ++j)
+        dpart = fmaxf(dpart, fmaxf(fabsf(nr[j] - dr[j]), fabsf(ni[j] - di[j])));
+      s_dpart[grp][row] = dpart;
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (!conv) {                                                   // per-env convergence mask
+        const float d = fmaxf(fmaxf(s_dpart[0][row], s_dpart[1][row]),
+                              fmaxf(s_dpart[2][row], s_dpart[3][row]));
+#pragma unroll
+        for (int j = 0; j < TC_BPT; ++j) { dr[j] = nr[j]; di[j] = ni[j]; }
         ++it;
         conv_ok = d < p.tc_tol;
         conv = conv_ok || it >= p.max_iter;
@@ -244,8 +282,7 @@ __global__ void __launch_bounds__(TC_M) pf_tc_kernel(const PfParams p) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int kk = 0; kk < kTcK3 / 8; ++kk)
-        umma_tf32(tmem + 32, umma_smem_desc(a_addr + kk * 256), umma_smem_desc(b2_addr + kk * 256),
-                  idesc2, kk > 0 ? 1u : 0u);
+        umma_tf32(tmem + 32, adesc0 + 16u * kk, b2desc0 + 16u * kk, idesc2, kk > 0 ? 1u : 0u);
       umma_commit(&mbar_mma);
     }
     mbar_wait(&mbar_mma, mma_phase);
@@ -253,7 +290,7 @@ __global__ void __launch_bounds__(TC_M) pf_tc_kernel(const PfParams p) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     float vmn = 3.0e38f, vmx = -3.0e38f;
-    for (int c = 0; c < p.tc_n2 / 16; ++c) {                         // 8 nodes per chunk: (Re, Im) pairs
+    for (int c = grp; c < p.tc_n2 / 16; c += 4) {                    // 8 nodes per chunk: (Re, Im) pairs
       float v[16];
       tmem_ld16(t_lane + 32 + 16 * c, v);
 #pragma unroll
@@ -268,24 +305,34 @@ __global__ void __launch_bounds__(TC_M) pf_tc_kernel(const PfParams p) {
         }
       }
     }
-
+    s_vmn[grp][row] = vmn;
+    s_vmx[grp][row] = vmx;
     if (valid) {
 #pragma unroll
-      for (int k = 0; k < kTcNb; ++k)
+      for (int j = 0; j < TC_BPT; ++j) {
+        const int k = grp * TC_BPT + j;
         if (k < p.nb)
           p.u_state[(size_t)k * p.E + e] =
-              make_double2((double)u0f[k].x + (double)dr[k], (double)u0f[k].y + (double)di[k]);
-      p.vmin[e] = (double)vmn;
-      p.vmax[e] = (double)vmx;
+              make_double2((double)u0r[j] + (double)dr[j], (double)u0i[j] + (double)di[j]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                        // vmag / partial min-max of the other groups visible
+
+    if (valid && grp == 0) {
+      p.vmin[e] = (double)fminf(fminf(s_vmn[0][row], s_vmn[1][row]), fminf(s_vmn[2][row], s_vmn[3][row]));
+      p.vmax[e] = (double)fmaxf(fmaxf(s_vmx[0][row], s_vmx[1][row]), fmaxf(s_vmx[2][row], s_vmx[3][row]));
       p.iters[e] = conv_ok ? it : -it;
+    }
+    if (valid) {
       double pen_share = 0.0, viol = 0.0;
       if (p.punit != 0.0) {
-        const double v = p.vmag[(size_t)p.penalty_node * p.E + e];   // this thread's own store
+        const double v = p.vmag[(size_t)p.penalty_node * p.E + e];
         viol = fmax(0.0, fmax(p.pvlo - v, v - p.pvhi));
         pen_share = (viol * p.punit) / (double)p.A;
       }
-      p.viol[e] = viol;
-      for (int a = 0; a < p.A; ++a) {
+      if (grp == 0) p.viol[e] = viol;
+      for (int a = grp; a < p.A; a += 4) {
         const int node = anode[a];
         const size_t ae = (size_t)a * p.E + e;
         p.vbus[ae] = node >= 0 ? p.vmag[(size_t)node * p.E + e] : 1.0;
@@ -297,9 +344,7 @@ __global__ void __launch_bounds__(TC_M) pf_tc_kernel(const PfParams p) {
         }
       }
     }
-    // all TMEM reads of this tile are complete (tcgen05.wait::ld) before the next tile's MMAs
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    __syncthreads();                        // s_* and A' are reused by the next tile
   }
 
   __syncthreads();
@@ -317,7 +362,7 @@ cudaError_t launch_powerflow_tc(const PfParams& p, cudaStream_t s) {
   cudaError_t err = cudaFuncSetAttribute(pf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
   if (err != cudaSuccess) return err;
-  pf_tc_kernel<<<grid, TC_M, smem, s>>>(p);
+  pf_tc_kernel<<<grid, TC_THREADS, smem, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -460,17 +460,9 @@ class MultiAgentEnv:
         return out
 
     def all_reduce_stats(self, group=None):
-        """The single collective of the multi-GPU path: sum (entries 0-5), min (6), max (7)
-        of ``stats()`` over the ranks of ``torch.distributed``."""
-        import torch.distributed as dist
-        s = self.stats()
-        if dist.is_available() and dist.is_initialized():
-            add, lo, hi = s[:6].clone(), s[6:7].clone(), s[7:8].clone()
-            dist.all_reduce(add, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
-            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
-            s = _torch().cat([add, lo, hi])
-        return s
+        """The single collective of the multi-GPU path (envs are sharded over ranks with no
+        data-path exchange): the 8-entry statistics vector reduced over ``torch.distributed``."""
+        return reduce_stats(self.stats(), group)
 
     def set_option(self, option: int, value: int):
         """Runtime options of the device handle (N.OPT_PF_KERNEL / OPT_WARM_START / OPT_GRAPHS)."""
@@ -573,6 +565,30 @@ class MultiAgentEnv:
             self.history["voltage"].append(self.voltages)
             self.history["agent_power_p"].append([float(x) for x in p])
         return obs_d, self.reward_transform(rew_d), dones, self.meta_transform(meta)
+
+
+def reduce_stats(s, group=None):
+    """All-reduce of a ``pgw_stats`` vector: SUM on the additive entries 0-5 (env-steps,
+    reward sum, episode returns, violation sum, non-converged count, iterations), MIN on
+    entry 6 (min voltage), MAX on entry 7.  One NCCL call for the sums, two scalar ones for
+    the extrema; identity when no process group is initialised."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return s
+    add, lo, hi = s[:6].clone(), s[6:7].clone(), s[7:8].clone()
+    dist.all_reduce(add, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    return _torch().cat([add, lo, hi])
+
+
+def shard_envs(total_envs: int, rank: int, world_size: int):
+    """Contiguous block of env instances owned by ``rank`` (envs never interact, so the
+    partition needs no halo and no collective): returns (first_env, num_envs)."""
+    base, rem = divmod(int(total_envs), int(world_size))
+    n = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, n
 
 
 class CoordinatedMultiBuildingControlEnv(MultiAgentEnv):

@@ -54,8 +54,11 @@ typedef enum pgw_component_type {
 
 /* pgw_component.flags */
 #define PGW_F_RESCALE 1u        /* rescale_spaces=True: actions/obs in [-1, 1] (gridworld/utils.py:9-43) */
-#define PGW_F_GRID_AWARE 2u     /* PVEnv(grid_aware=True): min_voltage appended to the obs              */
+#define PGW_F_GRID_AWARE 2u     /* PVEnv(grid_aware=True): min_voltage appended to the obs; building:
+                                   some bus/min/max_voltage entry is observed                          */
 #define PGW_F_PV_VOLT_REWARD 4u /* ThisPVEnv.step_reward, gridworld/scenarios/heterogeneous.py:46-52   */
+#define PGW_F_BUILDING_FAST 16u /* building with the shipped model's input pattern and the default
+                                   15-entry observation set: straight-line register code path   */
 #define PGW_F_STALE_REWARD 8u   /* stand-alone building agent: reward from the pre-step state
                                    (five_zone_rom_env.py:215 precedes :223)                            */
 
@@ -82,7 +85,9 @@ typedef enum pgw_component_type {
  *  BUILDING dpar: A[5], B[20] (float32-rounded), C[5], K[5], mean[5], T_init[5],
  *                 w_energy(=alpha*0.5), w_comfort(=1-alpha), low[obs_dim], high[obs_dim],
  *                 1/(high-low)[obs_dim]
- *           ipar: sel[20] (0-based input selector), nbr[20], obs_source_mask (24 bits)
+ *           ipar: u_kind[20], u_arg[20] (model input j of zone z: 0 outdoor, 1 solar,
+ *                 2 internal, 3 neighbour(arg), 4 cooling), obs_src[obs_dim] (state-dict
+ *                 index of each observation slot, 0..23)
  *           dtab: T_oa_dyn, Q_solar[5], Q_x[5], T_oa_obs, lb_obs, ub_obs, time_of_day,
  *                 lb_prev, ub_prev
  *           state: 6 double rows (x[5], p_consumed)        action 6, obs popcount(mask)

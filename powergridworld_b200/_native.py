@@ -16,7 +16,7 @@ ABI_VERSION = 1
 NUM_STATS = 8
 
 STORAGE, PV, EV, BUILDING = 1, 2, 3, 4
-F_RESCALE, F_GRID_AWARE, F_PV_VOLT_REWARD, F_STALE_REWARD = 1, 2, 4, 8
+F_RESCALE, F_GRID_AWARE, F_PV_VOLT_REWARD, F_STALE_REWARD, F_BUILDING_FAST = 1, 2, 4, 8, 16
 
 OPT_PF_KERNEL, OPT_WARM_START, OPT_GRAPHS = 0, 1, 2
 

@@ -71,14 +71,25 @@ class FiveZoneROMEnv(ComponentEnv):
         nbr = assets.array("building/neighbors")
         alpha = 0.2                                                          # :318
         low, high = self._observation_space.low, self._observation_space.high
-        mask = 0
-        for src, key in enumerate(STATE_ORDER):
-            if key in self._obs_labels:
-                mask |= 1 << src
+        # observation slots: selected sources in state-dict order (:256-276)
+        obs_src = [src for src, key in enumerate(STATE_ORDER) if key in self._obs_labels]
+        assert len(obs_src) == self._obs_dim
+        # model inputs: input_sel_list picks 4 of the 8 candidates of build_u_vector
+        # (0 outdoor, 1 solar, 2 internal, 3-6 neighbour i, 7 cooling), dynamics.py:12-41
+        u_kind, u_arg = [], []
+        for z in range(5):
+            for j in range(4):
+                cand = int(sel[z, j])
+                if cand <= 2:
+                    u_kind.append(cand); u_arg.append(0)
+                elif cand <= 6:
+                    u_kind.append(3); u_arg.append(int(nbr[z, cand - 3]))
+                else:
+                    u_kind.append(4); u_arg.append(0)
         dpar = list(A) + list(B32.reshape(-1)) + list(Cm) + list(K) + list(mean) + \
             list(self.zone_temp_init) + [alpha * 0.5, 1. - alpha] + list(low) + list(high) + \
             list(1.0 / (high - low))
-        ipar = list(sel.reshape(-1)) + list(nbr.reshape(-1)) + [mask]
+        ipar = u_kind + u_arg + obs_src
         exo, comfort, mes = self.exo, self._comfort, self.max_episode_steps
 
         def dtab_fn(r):
@@ -90,9 +101,13 @@ class FiveZoneROMEnv(ComponentEnv):
                     comfort[t + 1, 0], comfort[t + 1, 1], 1. * (t + 1) / mes,
                     comfort[t, 0], comfort[t, 1]]
 
-        flags = (N.F_RESCALE if self.rescale_spaces else 0) | \
-                (N.F_STALE_REWARD if standalone else 0)
         grid = any(k in self._obs_labels for k in ("bus_voltage", "min_voltage", "max_voltage"))
+        flags = (N.F_RESCALE if self.rescale_spaces else 0) | \
+                (N.F_STALE_REWARD if standalone else 0) | (N.F_GRID_AWARE if grid else 0)
+        # straight-line kernel path for the shipped model + default observation set
+        default_src = list(range(5, 15)) + [15, 16, 17, 18, 19]
+        if u_kind == [0, 4, 3, 1] * 5 and obs_src == default_src and not standalone:
+            flags |= N.F_BUILDING_FAST
         b.add_component(self, N.BUILDING, agent_index, flags=flags, dpar=dpar, ipar=ipar,
                         sd_rows=6, dtab_width=17, dtab_fn=dtab_fn, needs_grid=grid,
                         max_events=self.exo.shape[0] - 1)

@@ -58,6 +58,7 @@ struct pgw_env {
   int E = 0, A = 0, C = 0, act_dim = 0, obs_dim = 0, sd_rows = 0, si_rows = 0;
   int num_storage = 0, num_events = 0, dstride = 0, istride = 0;
   bool has_feeder = false;
+  bool need_scratch = false, need_scratch_reset = false;
   int nb = 0, nn = 0, nl = 0, nbp = 0, nnp = 0, max_iter = 0;
   double tol = 0;
   int penalty_node = -1;
@@ -159,6 +160,8 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       return fail(PGW_ERR_INVALID, "component offsets out of range");
     if (!spec->feeder && (k.flags & (PGW_F_GRID_AWARE | PGW_F_PV_VOLT_REWARD)))
       return fail(PGW_ERR_INVALID, "grid-aware component without a feeder");
+    if (k.type == PGW_BUILDING && (k.flags & PGW_F_BUILDING_FAST) && k.obs_dim != 15)
+      return fail(PGW_ERR_INVALID, "PGW_F_BUILDING_FAST requires the 15-entry observation set");
   }
   int dev = 0;
   PGW_CUDA(cudaGetDevice(&dev));
@@ -173,6 +176,11 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
   env->sd_rows = spec->sd_rows; env->si_rows = spec->si_rows;
   env->num_storage = spec->num_storage; env->num_events = spec->num_events;
   env->dstride = spec->dtab_stride; env->istride = spec->itab_stride;
+  for (int c = 0; c < spec->num_components; ++c)
+    if (spec->components[c].type == PGW_BUILDING) {
+      env->need_scratch_reset = true;                // reset always takes the table-driven path
+      if (!(spec->components[c].flags & PGW_F_BUILDING_FAST)) env->need_scratch = true;
+    }
   const size_t E = (size_t)env->E, A = (size_t)env->A;
 
 #define PGW_TRY(expr)                                                                  \
@@ -438,8 +446,11 @@ static cudaError_t launch_pf(const pgw_env* env, const pgw::PfParams& pf, cudaSt
   return env->pf_kernel == 1 ? pgw::launch_powerflow_tc(pf, s) : pgw::launch_powerflow(pf, s);
 }
 
-static int smem_for_events(const pgw_env* env) {
-  return env->comp_blob_bytes + env->dstride * 8 + env->istride * 4;
+static int smem_for_events(const pgw_env* env, bool reset = false) {
+  // static blob | event rows | per-thread scratch (component_math.cuh kScratchDoubles x 64
+  // threads; only the table-driven building path uses it)
+  return env->comp_blob_bytes + env->dstride * 8 + env->istride * 4 +
+         ((reset ? env->need_scratch_reset : env->need_scratch) ? 35 * 64 * 8 : 0);
 }
 
 int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stream) {
@@ -456,7 +467,7 @@ int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stre
   }
   pgw::CompParams cp = comp_params(env);
   cp.event_mode = 0; cp.advance_clock = 0; cp.init_soc = init_soc; cp.obs = obs;
-  PGW_CUDA(pgw::launch_components(cp, smem_for_events(env), s));
+  PGW_CUDA(pgw::launch_components(cp, smem_for_events(env, true), s));
   ++env->launches;
   env->clock = 0;
   return PGW_OK;

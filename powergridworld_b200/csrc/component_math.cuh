@@ -24,11 +24,25 @@
 #define PGW_HD inline
 #endif
 #define PGW_RESTRICT __restrict__
+#if defined(__CUDACC__)
+#define PGW_NO_UNROLL _Pragma("unroll 1")
+#else
+#define PGW_NO_UNROLL
+#endif
 
 namespace pgw {
 
+// Per-thread scratch array: element i lives at p[i * stride].
+struct Scratch {
+  double* p;
+  int stride;
+  PGW_HD double& operator[](int i) const { return p[(size_t)i * stride]; }
+};
+constexpr int kScratchDoubles = 35;
+
 // Everything one (env, agent) worker needs; all per-env arrays are rows x E.
 struct AgentIO {
+  Scratch scr;
   int E;
   // The arrays never alias each other; telling the compiler lets it overlap the many
   // independent load -> divide -> store chains of one agent (the kernel is latency bound).
@@ -223,11 +237,17 @@ PGW_HD void ev_reset(const pgw_component& c, const AgentIO& io, int e) {
 }
 
 // ------------------------------------------------------------------ five-zone building
+// Rolled loops over zones and observation slots: the per-thread arrays they index live in
+// a scratch area (shared memory on the GPU, strided by the CTA size so lanes hit distinct
+// banks; a plain local array in the host build).  Keeps the kernel's code small -- the
+// fully unrolled form was 140 kB of SASS and stalled on instruction-cache misses.
+enum { BSCR_T = 0, BSCR_ACT = 5, BSCR_SRC = 11, BSCR_SIZE = 35 };   // T[5], act[6], src[24]
+enum { U_OUTDOOR = 0, U_SOLAR = 1, U_INTERNAL = 2, U_NEIGHBOR = 3, U_COOLING = 4 };
+
 struct BuildingPar {
   const double *A, *B, *C, *K, *mean, *Tinit, *low, *high, *inv;
   double w_energy, w_comfort;
-  const int32_t *sel, *nbr;
-  uint32_t obs_mask;
+  const int32_t *u_kind, *u_arg, *obs_src;
 };
 
 PGW_HD BuildingPar building_par(const pgw_component& c, const AgentIO& io) {
@@ -237,150 +257,229 @@ PGW_HD BuildingPar building_par(const pgw_component& c, const AgentIO& io) {
   b.A = dp; b.B = dp + 5; b.C = dp + 25; b.K = dp + 30; b.mean = dp + 35; b.Tinit = dp + 40;
   b.w_energy = dp[45]; b.w_comfort = dp[46];
   b.low = dp + 47; b.high = dp + 47 + c.obs_dim; b.inv = dp + 47 + 2 * c.obs_dim;
-  b.sel = ip; b.nbr = ip + 20; b.obs_mask = (uint32_t)ip[40];
+  b.u_kind = ip; b.u_arg = ip + 20; b.obs_src = ip + 40;
   return b;
 }
 
-// build_u_vector (dynamics.py:12-41): candidate inputs, then the model's selection of 4
-PGW_HD void building_inputs(const BuildingPar& b, const double T[5], double t_oa,
-                            const double* q_solar, const double* q_x, bool use_q_cool,
-                            const double* flow, double t_dis, double u[5][4]) {
-#pragma unroll
-  for (int z = 0; z < 5; ++z) {
-    double cand[8];
-    cand[0] = t_oa - T[z];
-    cand[1] = q_solar[z];
-    cand[2] = use_q_cool ? 0.0 : q_x[z];              // q_int (never selected by the shipped model)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int y = b.nbr[z * 4 + i];
-      double ty = T[0];
-#pragma unroll
-      for (int q = 1; q < 5; ++q) ty = (y == q) ? T[q] : ty;
-      cand[3 + i] = ty - T[z];
-    }
-    cand[7] = use_q_cool ? q_x[z] : flow[z] * (t_dis - T[z]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int s = b.sel[z * 4 + j];
-      double v = cand[0];
-#pragma unroll
-      for (int q = 1; q < 8; ++q) v = (s == q) ? cand[q] : v;
-      u[z][j] = v;
-    }
+// One selected model input of zone z (build_u_vector, dynamics.py:12-41; the host resolved
+// the model's input_sel_list / neighbors into a kind + argument per input).
+PGW_HD double building_input(const BuildingPar& b, const Scratch& scr, int z, int j, double t_oa,
+                             const double* q_solar, const double* q_x, bool at_reset) {
+  const int kind = b.u_kind[z * 4 + j];
+  const double Tz = scr[BSCR_T + z];
+  switch (kind) {
+    case U_OUTDOOR: return t_oa - Tz;
+    case U_SOLAR: return q_solar[z];
+    case U_INTERNAL: return at_reset ? 0.0 : q_x[z];
+    case U_NEIGHBOR: return scr[BSCR_T + b.u_arg[z * 4 + j]] - Tz;
+    default:  // U_COOLING: q_cool at reset, m_dot (T_discharge - T_z) afterwards
+      return at_reset ? q_x[z] : scr[BSCR_ACT + z] * (scr[BSCR_ACT + 5] - Tz);
   }
 }
 
 // state_update (dynamics.py:44-55); B already rounded through float32 on the host
-PGW_HD double building_x_next(const BuildingPar& b, int z, double x, const double u[4]) {
+PGW_HD double building_x_next(const BuildingPar& b, int z, double x, double u0, double u1,
+                              double u2, double u3) {
   const double* B = b.B + z * 4;
-  return b.A[z] * x + (((B[0] * u[0] + B[1] * u[1]) + B[2] * u[2]) + B[3] * u[3]);
+  return b.A[z] * x + (((B[0] * u0 + B[1] * u1) + B[2] * u2) + B[3] * u3);
 }
 
-// FiveZoneROMThermalEnergyEnv.step_reward (five_zone_rom_env.py:315-335)
-PGW_HD double building_reward(const BuildingPar& b, const double T[5], double lb, double ub,
-                              double p_consumed) {
+// FiveZoneROMThermalEnergyEnv.step_reward (five_zone_rom_env.py:315-335) on temps T[0..5)
+PGW_HD double building_reward(const BuildingPar& b, const Scratch& scr, int t_off, double lb,
+                              double ub, double p_consumed) {
   const double energy = div_by(-p_consumed, 12.0, 1.0 / 12.0);
   double comfort = 0.0;
-#pragma unroll
+  PGW_NO_UNROLL
   for (int z = 0; z < 5; ++z) {
-    const double err = fmax(fmax(T[z] - ub, lb - T[z]), 0.0);
+    const double T = scr[t_off + z];
+    const double err = fmax(fmax(T - ub, lb - T), 0.0);
     comfort += err * err;
   }
   comfort = -comfort;
   return b.w_energy * energy + b.w_comfort * comfort;
 }
 
-// get_obs (five_zone_rom_env.py:228-283): values in state-dict order, bounds in label order
+// get_obs (five_zone_rom_env.py:228-283): the 24 possible sources in state-dict order, then
+// the selected ones (obs_src, in that same order) against the bounds in label order.
 PGW_HD void building_obs(const pgw_component& c, const BuildingPar& b, const AgentIO& io,
-                         int e, const double T[5], double lb, double ub, double t_oa,
-                         double p_consumed, double tod) {
-  const bool rs = (c.flags & PGW_F_RESCALE) != 0;
-  const int a = c.agent;
-  int slot = 0;
-  auto put = [&](int src, double v) {
-    if (b.obs_mask & (1u << src)) {
-      double o = clip(v, b.low[slot], b.high[slot]);
-      if (rs) o = to_scaled(o, b.low[slot], b.high[slot], b.inv[slot]);
-      io.obs[(size_t)(c.obs_off + slot) * io.E + e] = o;
-      ++slot;
-    }
-  };
-#pragma unroll
-  for (int z = 0; z < 5; ++z) put(z, T[z]);
-#pragma unroll
-  for (int z = 0; z < 5; ++z) put(5 + z, T[z] - ub);
-#pragma unroll
-  for (int z = 0; z < 5; ++z) put(10 + z, lb - T[z]);
-  put(15, lb);
-  put(16, ub);
-  put(17, t_oa);
-  put(18, p_consumed);
-  put(19, tod);
-  if (b.obs_mask & (7u << 20)) {
-    put(20, io.vbus[(size_t)a * io.E + e]);
-    put(21, io.vmin[e]);
-    put(22, io.vmax[e]);
+                         int e, const Scratch& scr, double lb, double ub, double t_oa,
+                         double p_consumed, double tod, bool grid) {
+  PGW_NO_UNROLL
+  for (int z = 0; z < 5; ++z) {
+    const double T = scr[BSCR_T + z];
+    scr[BSCR_SRC + z] = T;
+    scr[BSCR_SRC + 5 + z] = T - ub;
+    scr[BSCR_SRC + 10 + z] = lb - T;
   }
-  put(23, INFINITY);                                   // p_setpoint default (:268)
+  scr[BSCR_SRC + 15] = lb;
+  scr[BSCR_SRC + 16] = ub;
+  scr[BSCR_SRC + 17] = t_oa;
+  scr[BSCR_SRC + 18] = p_consumed;
+  scr[BSCR_SRC + 19] = tod;
+  if (grid) {
+    scr[BSCR_SRC + 20] = io.vbus[(size_t)c.agent * io.E + e];
+    scr[BSCR_SRC + 21] = io.vmin[e];
+    scr[BSCR_SRC + 22] = io.vmax[e];
+  }
+  scr[BSCR_SRC + 23] = INFINITY;                        // p_setpoint default (:268)
+  const bool rs = (c.flags & PGW_F_RESCALE) != 0;
+  PGW_NO_UNROLL
+  for (int slot = 0; slot < c.obs_dim; ++slot) {
+    const double lo = b.low[slot], hi = b.high[slot];
+    double o = clip(scr[BSCR_SRC + b.obs_src[slot]], lo, hi);   // np.clip; to_scaled's own clip
+    if (rs) o = div_by(2.0 * o - (lo + hi), hi - lo, b.inv[slot]);   // is then the identity
+    io.obs[(size_t)(c.obs_off + slot) * io.E + e] = o;
+  }
 }
 
 PGW_HD void building_reset(const pgw_component& c, const AgentIO& io, int e) {
   const BuildingPar b = building_par(c, io);
+  const Scratch& scr = io.scr;
   const double* row = io.drow + c.dtab_off;
   double* sd = io.sd + (size_t)c.sd_off * io.E + e;
-  double x[5], T[5], u[5][4];
-#pragma unroll
-  for (int z = 0; z < 5; ++z) { x[z] = sd[(size_t)z * io.E]; T[z] = b.Tinit[z]; }   // x persists (:94)
-  building_inputs(b, T, row[0], row + 1, row + 6, true, nullptr, 0.0, u);
-  for (int rep = 0; rep < 2; ++rep) {                  // filter_update x2 (dynamics.py:58-72)
-#pragma unroll
-    for (int z = 0; z < 5; ++z) {
-      x[z] = building_x_next(b, z, x[z], u[z]);
-      x[z] += b.K[z] * ((T[z] - b.mean[z]) - b.C[z] * x[z]);
-    }
-  }
-#pragma unroll
+  for (int z = 0; z < 5; ++z) scr[BSCR_T + z] = b.Tinit[z];
+  PGW_NO_UNROLL
   for (int z = 0; z < 5; ++z) {
-    T[z] = b.C[z] * x[z] + b.mean[z];
-    sd[(size_t)z * io.E] = x[z];
+    // the inputs are built once from T_init; two filter updates (dynamics.py:58-72)
+    const double u0 = building_input(b, scr, z, 0, row[0], row + 1, row + 6, true);
+    const double u1 = building_input(b, scr, z, 1, row[0], row + 1, row + 6, true);
+    const double u2 = building_input(b, scr, z, 2, row[0], row + 1, row + 6, true);
+    const double u3 = building_input(b, scr, z, 3, row[0], row + 1, row + 6, true);
+    double x = sd[(size_t)z * io.E];                    // x persists across resets (:94)
+    for (int rep = 0; rep < 2; ++rep) {
+      x = building_x_next(b, z, x, u0, u1, u2, u3);
+      x += b.K[z] * ((b.Tinit[z] - b.mean[z]) - b.C[z] * x);
+    }
+    sd[(size_t)z * io.E] = x;
+    scr[BSCR_ACT + z] = b.C[z] * x + b.mean[z];         // new temps, parked until all zones are done
   }
-  sd[(size_t)5 * io.E] = 0.0;                          // p_consumed
-  building_obs(c, b, io, e, T, row[12], row[13], row[11], 0.0, row[14]);
+  for (int z = 0; z < 5; ++z) scr[BSCR_T + z] = scr[BSCR_ACT + z];
+  sd[(size_t)5 * io.E] = 0.0;                           // p_consumed
+  building_obs(c, b, io, e, scr, row[12], row[13], row[11], 0.0, row[14],
+               (c.flags & PGW_F_GRID_AWARE) != 0);
 }
 
 PGW_HD void building_step(const pgw_component& c, const AgentIO& io, int e, double& p_out,
                           double& rew) {
-  const double kLow[6] = {0.22, 0.22, 0.22, 0.22, 0.32, 10.0};   // :22-26
-  const double kHigh[6] = {2.2, 2.2, 2.2, 2.2, 3.2, 16.0};
   const BuildingPar b = building_par(c, io);
+  const Scratch& scr = io.scr;
   const double* row = io.drow + c.dtab_off;
   double* sd = io.sd + (size_t)c.sd_off * io.E + e;
-  double act[6];
+  const bool rs = (c.flags & PGW_F_RESCALE) != 0;
+  double flow = 0.0;
+  PGW_NO_UNROLL
+  for (int i = 0; i < 6; ++i) {                         // action bounds :22-26
+    const double lo = i < 4 ? 0.22 : (i == 4 ? 0.32 : 10.0);
+    const double hi = i < 4 ? 2.2 : (i == 4 ? 3.2 : 16.0);
+    const double a = io.actions[(size_t)(c.act_off + i) * io.E + e];
+    const double raw = rs ? to_raw(a, lo, hi) : a;
+    scr[BSCR_ACT + i] = raw;
+    if (i < 5) flow = i == 0 ? raw : flow + raw;
+  }
+  for (int z = 0; z < 5; ++z) scr[BSCR_T + z] = b.C[z] * sd[(size_t)z * io.E] + b.mean[z];
+  if (c.flags & PGW_F_STALE_REWARD)                     // stand-alone agent: pre-step state (:215)
+    rew = building_reward(b, scr, BSCR_T, row[15], row[16], sd[(size_t)5 * io.E]);
+  const double t_oa = row[0], t_dis = scr[BSCR_ACT + 5];
+  PGW_NO_UNROLL
+  for (int z = 0; z < 5; ++z) {                         // all inputs use the OLD temperatures
+    const double u0 = building_input(b, scr, z, 0, t_oa, row + 1, row + 6, false);
+    const double u1 = building_input(b, scr, z, 1, t_oa, row + 1, row + 6, false);
+    const double u2 = building_input(b, scr, z, 2, t_oa, row + 1, row + 6, false);
+    const double u3 = building_input(b, scr, z, 3, t_oa, row + 1, row + 6, false);
+    const double x = building_x_next(b, z, sd[(size_t)z * io.E], u0, u1, u2, u3);
+    sd[(size_t)z * io.E] = x;
+    scr[BSCR_SRC + z] = b.C[z] * x + b.mean[z];         // new temps, parked in the source area
+  }
+  for (int z = 0; z < 5; ++z) scr[BSCR_T + z] = scr[BSCR_SRC + z];
+  // flow**3: the reference calls libm pow; x*x*x differs from it by at most 1 ulp
+  const double p = (0.0076 * ((flow * flow) * flow) + 4.8865) + fmax(0.0, flow * (t_oa - t_dis));
+  sd[(size_t)5 * io.E] = p;
+  building_obs(c, b, io, e, scr, row[12], row[13], row[11], p, row[14],
+               (c.flags & PGW_F_GRID_AWARE) != 0);
+  if (!(c.flags & PGW_F_STALE_REWARD)) rew = building_reward(b, scr, BSCR_T, row[12], row[13], p);
+  p_out = p;
+}
+
+// ---- fast path: the reference's shipped model + default observation set ----------------
+// PGW_F_BUILDING_FAST is set by the host when (a) every zone's model inputs are
+// [outdoor, cooling, neighbour, solar] (the input_sel_list of state_space_model.p) and
+// (b) the observation set is defaults.obs_config (upper/lower violation per zone, comfort
+// band, outdoor temperature, p_consumed, time of day).  Same arithmetic, same order of
+// operations as the generic path, but straight-line code on registers: the table-driven
+// form spends ~85 % of its instructions on indexing rather than on float64 math.
+PGW_HD double pick5(const double T[5], int i) {
+  double v = T[0];
+  v = i == 1 ? T[1] : v;
+  v = i == 2 ? T[2] : v;
+  v = i == 3 ? T[3] : v;
+  v = i == 4 ? T[4] : v;
+  return v;
+}
+
+PGW_HD void building_step_fast(const pgw_component& c, const AgentIO& io, int e, double& p_out,
+                               double& rew) {
+  const double* dp = io.dpar + c.dpar_off;
+  const int32_t* u_arg = io.ipar + c.ipar_off + 20;
+  const double *A = dp, *B = dp + 5, *C = dp + 25, *mean = dp + 35;
+  const double *low = dp + 47, *high = dp + 62, *inv = dp + 77;     // obs_dim == 15
+  const double* row = io.drow + c.dtab_off;
+  const size_t E = (size_t)io.E;
+  const bool rs = (c.flags & PGW_F_RESCALE) != 0;
+  const double kLow[6] = {0.22, 0.22, 0.22, 0.22, 0.32, 10.0};      // action bounds :22-26
+  const double kHigh[6] = {2.2, 2.2, 2.2, 2.2, 3.2, 16.0};
+
+  const double* ap = io.actions + (size_t)c.act_off * E + e;
+  double* sp = io.sd + (size_t)c.sd_off * E + e;
+  double act[6], x[5], T[5], Tn[5];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
-    const double a = io.actions[(size_t)(c.act_off + i) * io.E + e];
-    act[i] = (c.flags & PGW_F_RESCALE) ? to_raw(a, kLow[i], kHigh[i]) : a;
+    const double a = ap[i * E];
+    act[i] = rs ? to_raw(a, kLow[i], kHigh[i]) : a;
   }
-  double x[5], T[5], u[5][4];
-#pragma unroll
-  for (int z = 0; z < 5; ++z) { x[z] = sd[(size_t)z * io.E]; T[z] = b.C[z] * x[z] + b.mean[z]; }
-  if (c.flags & PGW_F_STALE_REWARD)                    // stand-alone agent: pre-step state (:215)
-    rew = building_reward(b, T, row[15], row[16], sd[(size_t)5 * io.E]);
-  const double t_oa = row[0];
-  building_inputs(b, T, t_oa, row + 1, row + 6, false, act, act[5], u);
 #pragma unroll
   for (int z = 0; z < 5; ++z) {
-    x[z] = building_x_next(b, z, x[z], u[z]);
-    T[z] = b.C[z] * x[z] + b.mean[z];
-    sd[(size_t)z * io.E] = x[z];
+    x[z] = sp[z * E];
+    T[z] = C[z] * x[z] + mean[z];
+  }
+  const double t_oa = row[0], t_dis = act[5];
+#pragma unroll
+  for (int z = 0; z < 5; ++z) {                  // inputs [outdoor, cooling, neighbour, solar]
+    const double u0 = t_oa - T[z];
+    const double u1 = act[z] * (t_dis - T[z]);
+    const double u2 = pick5(T, u_arg[z * 4 + 2]) - T[z];
+    const double u3 = row[1 + z];
+    const double* Bz = B + z * 4;
+    const double xn = A[z] * x[z] + (((Bz[0] * u0 + Bz[1] * u1) + Bz[2] * u2) + Bz[3] * u3);
+    sp[z * E] = xn;
+    Tn[z] = C[z] * xn + mean[z];
   }
   const double flow = (((act[0] + act[1]) + act[2]) + act[3]) + act[4];
-  // flow**3: the reference calls libm pow; x*x*x differs from it by at most 1 ulp
-  const double p = (0.0076 * ((flow * flow) * flow) + 4.8865) + fmax(0.0, flow * (t_oa - act[5]));
-  sd[(size_t)5 * io.E] = p;
-  building_obs(c, b, io, e, T, row[12], row[13], row[11], p, row[14]);
-  if (!(c.flags & PGW_F_STALE_REWARD)) rew = building_reward(b, T, row[12], row[13], p);
+  const double p = (0.0076 * ((flow * flow) * flow) + 4.8865) + fmax(0.0, flow * (t_oa - t_dis));
+  sp[5 * E] = p;
+
+  const double lb = row[12], ub = row[13];
+  double* op = io.obs + (size_t)c.obs_off * E + e;
+  double comfort = 0.0;
+#pragma unroll
+  for (int z = 0; z < 5; ++z) {
+    const double up = Tn[z] - ub, lo = lb - Tn[z];
+    double o = clip(up, low[z], high[z]);
+    op[z * E] = rs ? div_by(2.0 * o - (low[z] + high[z]), high[z] - low[z], inv[z]) : o;
+    o = clip(lo, low[5 + z], high[5 + z]);
+    op[(5 + z) * E] =
+        rs ? div_by(2.0 * o - (low[5 + z] + high[5 + z]), high[5 + z] - low[5 + z], inv[5 + z]) : o;
+    const double err = fmax(fmax(up, lo), 0.0);
+    comfort += err * err;
+  }
+  const double tail[5] = {lb, ub, row[11], p, row[14]};
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int s = 10 + j;
+    const double o = clip(tail[j], low[s], high[s]);
+    op[s * E] = rs ? div_by(2.0 * o - (low[s] + high[s]), high[s] - low[s], inv[s]) : o;
+  }
+  const double energy = div_by(-p, 12.0, 1.0 / 12.0);
+  rew = dp[45] * energy + dp[46] * (-comfort);
   p_out = p;
 }
 
@@ -399,7 +498,10 @@ PGW_HD void agent_step(const pgw_agent& ag, const pgw_component* comps, const Ag
       case PGW_STORAGE: storage_step(c, io, e, p); break;
       case PGW_PV: pv_step(c, io, e, p, r); break;
       case PGW_EV: ev_step(c, io, e, p, r); break;
-      case PGW_BUILDING: building_step(c, io, e, p, r); break;
+      case PGW_BUILDING:
+        if (c.flags & PGW_F_BUILDING_FAST) building_step_fast(c, io, e, p, r);
+        else building_step(c, io, e, p, r);
+        break;
       default: break;
     }
     p_agent += p;

@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(64) component_kernel(const CompParams p) {
   unsigned char* s_blob = smem_raw;
   double* drow = reinterpret_cast<double*>(smem_raw + p.blob_bytes);
   int32_t* irow = reinterpret_cast<int32_t*>(smem_raw + p.blob_bytes + (size_t)p.dstride * 8);
+  double* scratch = reinterpret_cast<double*>(
+      smem_raw + p.blob_bytes + (size_t)p.dstride * 8 + (size_t)p.istride * 4);
 
   // Two staging phases so that the latency of reading the device clock (which selects the
   // event row) overlaps the copy of the static tables and the threads' own prefetches.
@@ -43,54 +45,65 @@ __global__ void __launch_bounds__(64) component_kernel(const CompParams p) {
   __syncthreads();
   mbar_wait(&mbar[0], 0);
 
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int a = blockIdx.y;
   const int event = s_event;
   const pgw_agent ag = reinterpret_cast<const pgw_agent*>(s_blob)[a];
   const pgw_component* comps = reinterpret_cast<const pgw_component*>(s_blob + p.off_comps);
-  if (e < p.E && p.event_mode != 0) {
-    // pull this thread's action and (small) state rows towards the SM while the event row lands
-    for (int ci = ag.comp_begin; ci < ag.comp_end; ++ci) {
-      const pgw_component c = comps[ci];
-      const int na = c.type == PGW_BUILDING ? 6 : 1;
-      for (int r = 0; r < na; ++r)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.actions + (size_t)(c.act_off + r) * p.E + e));
-      const int ns = c.type == PGW_BUILDING ? 6 : (c.type == PGW_STORAGE ? 1 : 0);
-      for (int r = 0; r < ns; ++r)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.sd + (size_t)(c.sd_off + r) * p.E + e));
-    }
-  }
-  mbar_wait(&mbar[1], 0);
-  if (e < p.E) {
-    AgentIO io;
-    io.E = p.E;
-    io.actions = p.actions;
-    io.obs = p.obs;
-    io.sd = p.sd;
-    io.si = p.si;
-    io.init_soc = p.init_soc;
-    io.vmin = p.vmin;
-    io.vmax = p.vmax;
-    io.vbus = p.vbus;
-    io.dpar = reinterpret_cast<const double*>(s_blob + p.off_dpar);
-    io.ipar = reinterpret_cast<const int32_t*>(s_blob + p.off_ipar);
-    io.drow = drow;
-    io.irow = irow;
-    const size_t ae = (size_t)a * p.E + e;
-    if (p.event_mode == 0) {
-      agent_reset(ag, comps, io, e);
-      p.agent_p[ae] = 0.0;
-      p.ep_ret[ae] = 0.0;
-    } else {
-      double pw, rw;
-      agent_step(ag, comps, io, e, pw, rw);
-      p.agent_p[ae] = pw;
-      p.rew[ae] = rw;
-      if (p.advance_clock) {                        // no feeder: this kernel owns the reward
-        p.ep_ret[ae] += rw;
-        p.rew_copy[ae] = rw;
+
+  AgentIO io;
+  io.scr.p = scratch + threadIdx.x;          // [kScratchDoubles][blockDim.x]: conflict-free
+  io.scr.stride = blockDim.x;
+  io.E = p.E;
+  io.actions = p.actions;
+  io.obs = p.obs;
+  io.sd = p.sd;
+  io.si = p.si;
+  io.init_soc = p.init_soc;
+  io.vmin = p.vmin;
+  io.vmax = p.vmax;
+  io.vbus = p.vbus;
+  io.dpar = reinterpret_cast<const double*>(s_blob + p.off_dpar);
+  io.ipar = reinterpret_cast<const int32_t*>(s_blob + p.off_ipar);
+  io.drow = drow;
+  io.irow = irow;
+
+  // Persistent CTA: the tables are staged once, then the CTA walks env blocks of its agent.
+  bool first = true;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e - (int)threadIdx.x < p.E;
+       e += gridDim.x * blockDim.x) {
+    if (e < p.E && p.event_mode != 0) {
+      // pull this thread's action and (small) state rows towards the SM early
+      for (int ci = ag.comp_begin; ci < ag.comp_end; ++ci) {
+        const pgw_component c = comps[ci];
+        const int na = c.type == PGW_BUILDING ? 6 : 1;
+        for (int r = 0; r < na; ++r)
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(p.actions + (size_t)(c.act_off + r) * p.E + e));
+        const int ns = c.type == PGW_BUILDING ? 6 : (c.type == PGW_STORAGE ? 1 : 0);
+        for (int r = 0; r < ns; ++r)
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(p.sd + (size_t)(c.sd_off + r) * p.E + e));
       }
-      if (a == 0) p.done[e] = drow[0] != 0.0 ? 1 : 0;
+    }
+    if (first) {
+      mbar_wait(&mbar[1], 0);                  // event row has landed
+      first = false;
+    }
+    if (e < p.E) {
+      const size_t ae = (size_t)a * p.E + e;
+      if (p.event_mode == 0) {
+        agent_reset(ag, comps, io, e);
+        p.agent_p[ae] = 0.0;
+        p.ep_ret[ae] = 0.0;
+      } else {
+        double pw, rw;
+        agent_step(ag, comps, io, e, pw, rw);
+        p.agent_p[ae] = pw;
+        p.rew[ae] = rw;
+        if (p.advance_clock) {                  // no feeder: this kernel owns the reward
+          p.ep_ret[ae] += rw;
+          p.rew_copy[ae] = rw;
+        }
+        if (a == 0) p.done[e] = drow[0] != 0.0 ? 1 : 0;
+      }
     }
   }
   if (p.advance_clock) publish_clock_last_cta(p.ticket, p.clock, event, gridDim.x * gridDim.y);
@@ -98,7 +111,11 @@ __global__ void __launch_bounds__(64) component_kernel(const CompParams p) {
 
 cudaError_t launch_components(const CompParams& p, int smem_bytes, cudaStream_t s) {
   const int threads = 64;      // small CTAs: a 4096-env batch still reaches every SM
-  dim3 grid((p.E + threads - 1) / threads, p.A);
+  const int blocks = (p.E + threads - 1) / threads;
+  // persistent for big batches: ~16 CTAs per SM in total, each walking several env blocks
+  int per_agent = (148 * 16 + p.A - 1) / p.A;
+  if (per_agent < 1) per_agent = 1;
+  dim3 grid(blocks < per_agent ? blocks : per_agent, p.A);
   if (smem_bytes > 48 * 1024) {
     cudaError_t err = cudaFuncSetAttribute(component_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

@@ -35,12 +35,20 @@ if ROOT not in sys.path:
 
 ENVS_PER_GPU = 4096          # BASELINE.json configs[1]; --envs overrides (size sweeps)
 PF_KERNEL = "fp64"           # --pf-kernel tc selects the tcgen05 solver
+WORKLOAD = "c1"              # --workload c2 = component-only EV+PV+storage (BASELINE configs[2])
 METRIC, UNIT = "env_steps_per_s", "env-steps/s"
-SURVEY_BYTES_PER_ENV_STEP = 3 * (264 + 28 + 40) + 1      # SURVEY.md section 8(d), component kernels
 LOAD_FACTOR = 1.2
+# algorithmic bytes per env-step of the component kernel, SURVEY.md section 8(d)
+SURVEY_BYTES = {"c1": 3 * (264 + 28 + 40) + 1, "c2": (16 * 100 + 72 + 8 * 4) + 28 + 40 + 1}
 
 
 def _config(n_gpus):
+    if WORKLOAD == "c2":
+        return {"workload": "C2: component-only EV station (100 vehicles) + PV + storage, "
+                            f"{ENVS_PER_GPU} envs per GPU, no power flow",
+                "envs_per_gpu": ENVS_PER_GPU, "agents_per_env": 3,
+                "global_envs": ENVS_PER_GPU * n_gpus, "parallelism": f"env-sharded x{n_gpus}",
+                "l2": "flushed between timed steps (256 MiB write)"}
     return {"workload": "C1: IEEE-13 coordinated buildings (3 x building+PV+storage @675c), "
                         f"{ENVS_PER_GPU} envs per GPU",
             "envs_per_gpu": ENVS_PER_GPU, "agents_per_env": 3, "global_envs": ENVS_PER_GPU * n_gpus,
@@ -50,17 +58,41 @@ def _config(n_gpus):
             "pf_kernel": "tcgen05 split-tf32" if PF_KERNEL == "tc" else "fp64-simt"}
 
 
+def _make_env(ns, **kw):
+    """The benchmark scenario against a plugin namespace (product or oracle)."""
+    from tests import scenarios as S
+    if WORKLOAD == "c2":
+        if ns.__dict__.get("_is_oracle"):
+            from oracle.multiagent import PowerFlowSolver
+
+            class NoPF(PowerFlowSolver):
+                def __init__(self, **k):
+                    pass
+
+                def calculate_power_flow(self, *a, **k):
+                    pass
+
+                def get_bus_voltages(self):
+                    return {}
+
+                def get_bus_voltage_by_name(self, n):
+                    return 1.0
+            return ns.MultiAgentEnv(**S.ev_pv_storage_scenario(ns, NoPF), **kw)
+        return ns.MultiAgentEnv(**S.ev_pv_storage_scenario(ns), **kw)
+    return ns.CoordinatedMultiBuildingControlEnv(
+        **S.buildings_scenario(ns, ns.OpenDSSSolver, LOAD_FACTOR), **kw)
+
+
 # --------------------------------------------------------------------------- CPU arm
 def _cpu_worker(args):
     """One independent oracle env stepped for `steps` steps (episodes restart as needed)."""
     seed, steps = args
     import numpy as np
 
-    from tests import scenarios as S
     from tests.flatten import action_layout, unflatten_action
     from tests.oracle_ns import ORACLE_NS as NS
-    env = NS.CoordinatedMultiBuildingControlEnv(
-        **S.buildings_scenario(NS, NS.OpenDSSSolver, LOAD_FACTOR))
+    NS._is_oracle = True
+    env = _make_env(NS)
     rng = np.random.default_rng(seed)
     np.random.seed(seed)
     layout = action_layout(env)
@@ -140,7 +172,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if mask & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
+                time.sleep(0.002)
         except Exception as exc:                      # NVML missing: report that, not a guess
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
 
@@ -172,7 +204,6 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from tests import scenarios as S
     from tests.product_ns import PRODUCT_NS as NS
 
     torch.cuda.set_device(local)
@@ -180,9 +211,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E = ENVS_PER_GPU
-    env = NS.CoordinatedMultiBuildingControlEnv(
-        **S.buildings_scenario(NS, NS.OpenDSSSolver, LOAD_FACTOR), num_envs=E, device=dev)
-    if PF_KERNEL == "tc":
+    env = _make_env(NS, num_envs=E, device=dev)
+    has_pf = env.pf_solver is not None
+    if PF_KERNEL == "tc" and has_pf:
         from powergridworld_b200 import _native as N
         env.set_option(N.OPT_PF_KERNEL, 1)
     A = len(env.agents)
@@ -210,9 +241,18 @@ def run_ours(args):
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     env.reset_batch(soc)
-    for i in range(max(W, pool_n + 2)):               # warm-up also captures the step graphs
+    for i in range(pool_n + 2):                       # captures the step graphs (untimed)
         one_step(i)
-    barrier()
+
+    def begin_pass():
+        """Every pass starts from a fresh episode + W untimed steps, so that all passes see
+        the same events (the EV station's work depends on the time of day)."""
+        env.reset_batch(soc)
+        for i in range(W):
+            one_step(i)
+        barrier()
+
+    begin_pass()
 
     # ---- timed region: K steps, device-timed one by one, cold L2 before each
     sampler = ClockSampler(local)
@@ -232,7 +272,7 @@ def run_ours(args):
     launches = env.launch_count - launches0 - 1       # minus the stats kernel
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(sum(step_ms))
-    iters_mean = float(env.get_field(7).abs().double().mean())
+    iters_mean = float(env.get_field(7).abs().double().mean()) if has_pf else 0.0
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -241,22 +281,23 @@ def run_ours(args):
 
     # ---- per-kernel durations for the roofline: same loop (cold L2 before each step), plain
     #      launches with CUDA events between the kernels on the launch stream
+    begin_pass()
     env.set_kernel_timing(True)
-    k1 = min(K, 100)
+    k1 = K
     for i in range(k1):
         flush.zero_()
-        one_step(W + K + i)
+        one_step(W + i)
     t_comp_ms, t_pf_ms, n_timed = env.kernel_timing()
     env.set_kernel_timing(False)
     sampler.stop_flag = True
 
     # ---- same loop with a warm L2 (reported next to the headline, not instead of it)
-    barrier()
+    begin_pass()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k2 = min(K, 200)
+    k2 = K
     ev0.record()
     for i in range(k2):
-        one_step(W + K + i)
+        one_step(W + i)
     ev1.record()
     barrier()
     warm_ms = ev0.elapsed_time(ev1) / k2
@@ -291,10 +332,22 @@ def run_ours(args):
         peaks, peak_src = _peaks()
         comp_ms = t_comp_ms / max(n_timed, 1)
         pf_ms = t_pf_ms / max(n_timed, 1)
-        alg_bytes = SURVEY_BYTES_PER_ENV_STEP * E
+        alg_bytes = SURVEY_BYTES[WORKLOAD] * E
+        survey_bytes = alg_bytes
+        if WORKLOAD == "c2":
+            # The EV kernel only touches the vehicles parked at the event's minute (a static
+            # per-event list), not all n: count what it really moves.  Per parked vehicle one
+            # 8 B read and (at most) one 8 B write, 8 B per just-departed vehicle, the 4-word
+            # charging-set mask (cleared + written), plus the fixed action/obs/reward traffic.
+            ev = [c for c in env._b.comps if c.type == 3][0]
+            rows = env._itab[W + 1:W + 1 + K]
+            n_win = float(rows[:, ev.itab_off].mean())
+            n_left = float(rows[:, ev.itab_off + 1].mean())
+            per_env = 16.0 * n_win + 8.0 * n_left + 32.0 + 72.0 + 28.0 + 40.0 + 1.0
+            alg_bytes = per_env * E
         achieved = alg_bytes / (comp_ms * 1e-3) / 1e9 if comp_ms > 0 else 0.0
-        f = env.pf_solver.feeder
-        flops = (8.0 * f.nb * f.nb * iters_mean + 8.0 * f.nn * f.nb) * E
+        f = env.pf_solver.feeder if has_pf else None
+        flops = (8.0 * f.nb * f.nb * iters_mean + 8.0 * f.nn * f.nb) * E if has_pf else 0.0
         if PF_KERNEL == "tc":      # dense TF32 = half the measured bf16 rate; flops counted once
             pf_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
             pf_peak_src = "0.5 x measured bf16 (tf32 dense), " + peak_src
@@ -314,6 +367,9 @@ def run_ours(args):
                          "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "survey_bytes_per_launch": survey_bytes,
+                         "frac_survey_bytes": (survey_bytes / (comp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
+                         if comp_ms > 0 else 0.0,
                          "avg_launch_ms": comp_ms},
             "roofline_pf": {"kernel": "pf_tc_kernel" if PF_KERNEL == "tc"
                             else "pf_fixed_point_kernel<16,1,true>",
@@ -329,6 +385,8 @@ def run_ours(args):
             "wall_s_timed_region": wall,
         }
         line["roofline_pf"]["frac"] = line["roofline_pf"]["achieved"] / pf_peak
+        if not has_pf:
+            del line["roofline_pf"]
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
@@ -337,7 +395,7 @@ def run_ours(args):
 
 
 def main():
-    global ENVS_PER_GPU, PF_KERNEL
+    global ENVS_PER_GPU, PF_KERNEL, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -346,8 +404,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--pf-kernel", default="fp64", choices=["fp64", "tc"])
+    ap.add_argument("--workload", default="c1", choices=["c1", "c2"])
     args = ap.parse_args()
-    ENVS_PER_GPU, PF_KERNEL = args.envs, args.pf_kernel
+    ENVS_PER_GPU, PF_KERNEL, WORKLOAD = args.envs, args.pf_kernel, args.workload
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -177,25 +177,38 @@ PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double 
   uint32_t word = 0;
   int cur_word = 0;
   for (int w = 0; w < words; ++w) mask[(size_t)w * io.E] = 0u;
-  for (int k = 0; k < n_win; ++k) {                   // ascending vehicle index
-    const int i = win[k];
-    const double need = energy[(size_t)i * io.E];
-    if (!(need > 0.0)) continue;                      // :191
-    if ((i >> 5) != cur_word) {
-      if (word) mask[(size_t)cur_word * io.E] = word;
-      cur_word = i >> 5;
-      word = 0;
+  // Ascending vehicle index, four vehicles per trip: their energies are loaded up front so
+  // that four independent HBM/L2 requests are in flight per thread (a vehicle's store can
+  // never alias another vehicle's load, which the compiler cannot know).
+  for (int k0 = 0; k0 < n_win; k0 += 4) {
+    int idx[4];
+    double need4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      idx[j] = k0 + j < n_win ? win[k0 + j] : -1;
+      need4[j] = idx[j] >= 0 ? energy[(size_t)idx[j] * io.E] : 0.0;
     }
-    word |= 1u << (i & 31);
-    ++active;
-    demand += need;                                   // :210
-    const double left_h = div_by(end_park[i] - t_now, 60.0, dp[20]);
-    if (left_h <= 0.0) continue;                      // :218-220
-    deficit_sum += fmax(0.0, rate - need / left_h);   // :221-223
-    ++n_deficit;
-    const double delta = fmin(kwh, need);             // :226-228
-    energy[(size_t)i * io.E] = need - delta;
-    consumed += delta;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = idx[j];
+      const double need = need4[j];
+      if (i < 0 || !(need > 0.0)) continue;             // :191
+      if ((i >> 5) != cur_word) {
+        if (word) mask[(size_t)cur_word * io.E] = word;
+        cur_word = i >> 5;
+        word = 0;
+      }
+      word |= 1u << (i & 31);
+      ++active;
+      demand += need;                                   // :210
+      const double left_h = div_by(end_park[i] - t_now, 60.0, dp[20]);
+      if (left_h <= 0.0) continue;                      // :218-220
+      deficit_sum += fmax(0.0, rate - need / left_h);   // :221-223
+      ++n_deficit;
+      const double delta = fmin(kwh, need);             // :226-228
+      energy[(size_t)i * io.E] = need - delta;
+      consumed += delta;
+    }
   }
   if (word) mask[(size_t)cur_word * io.E] = word;
   double unserved = 0.0;                              // :240-243 over window(k-1) \ window(k)

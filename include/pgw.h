@@ -184,7 +184,9 @@ typedef enum pgw_field {
   PGW_FIELD_VMAX = 5,      /* [E]                                                   */
   PGW_FIELD_VBUS = 6,      /* [A][E] voltage at each agent's bus node               */
   PGW_FIELD_PF_ITERS = 7,  /* [E] int32, negative = not converged within max_iter   */
-  PGW_FIELD_EP_RETURN = 8  /* [A][E] reward summed since the last reset             */
+  PGW_FIELD_EP_RETURN = 8, /* [A][E] reward summed since the last reset             */
+  PGW_FIELD_PF_STATE = 9   /* [nbp][E] complex: last converged branch voltages (warm start;
+                              nbp = branch count padded to 16 / a multiple of 32)   */
 } pgw_field;
 
 #define PGW_NUM_STATS 8
@@ -229,6 +231,14 @@ int pgw_pf_solve(pgw_env* env, const double* load_kw, const double* load_kvar, v
 
 /* Copy an internal field to a device buffer of `bytes` bytes (must match exactly). */
 int pgw_get(pgw_env* env, int field, void* dst, size_t bytes, void* cuda_stream);
+
+/* Checkpoint / resume: overwrite an internal field from a device buffer (same sizes as
+ * pgw_get; the voltage fields, agent power, episode returns and both state arrays are
+ * writable) and set the episode clock (steps since reset, 0 <= steps < num_events).  The
+ * reference has no env-level checkpointing; restoring every field of
+ * pgw_get plus the clock reproduces the trajectory bit for bit. */
+int pgw_set(pgw_env* env, int field, const void* src, size_t bytes, void* cuda_stream);
+int pgw_set_clock(pgw_env* env, int steps, void* cuda_stream);
 
 /* Episode statistics (see PGW_NUM_STATS) reduced on the device into out[8] (device
  * pointer); the caller all-reduces it across ranks (one NCCL call per report). */

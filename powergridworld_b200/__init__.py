@@ -7,3 +7,4 @@ __version__ = "0.1.0"
 
 from .base import ComponentEnv, MultiComponentEnv
 from .multiagent_env import CoordinatedMultiBuildingControlEnv, MultiAgentEnv
+from .multiagent_list_interface_env import MultiAgentListInterfaceEnv

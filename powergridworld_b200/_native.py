@@ -21,7 +21,7 @@ F_RESCALE, F_GRID_AWARE, F_PV_VOLT_REWARD, F_STALE_REWARD, F_BUILDING_FAST = 1, 
 OPT_PF_KERNEL, OPT_WARM_START, OPT_GRAPHS = 0, 1, 2
 
 (FIELD_STATE_D, FIELD_STATE_I, FIELD_AGENT_P, FIELD_VOLTAGES, FIELD_VMIN, FIELD_VMAX,
- FIELD_VBUS, FIELD_PF_ITERS, FIELD_EP_RETURN) = range(9)
+ FIELD_VBUS, FIELD_PF_ITERS, FIELD_EP_RETURN, FIELD_PF_STATE) = range(10)
 
 
 class Component(C.Structure):
@@ -71,6 +71,8 @@ SYMBOLS = {
     "pgw_reset_host": (C.c_int, [_vp, _vp, _vp, _vp]),
     "pgw_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "pgw_get": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _vp]),
+    "pgw_set": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _vp]),
+    "pgw_set_clock": (C.c_int, [_vp, C.c_int, _vp]),
     "pgw_stats": (C.c_int, [_vp, _vp, _vp]),
     "pgw_clock": (C.c_int, [_vp]),
     "pgw_launch_count": (C.c_longlong, [_vp]),

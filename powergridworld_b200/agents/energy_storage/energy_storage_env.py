@@ -41,6 +41,9 @@ class EnergyStorageEnv(ComponentEnv):
         from scipy.stats import truncnorm
         return truncnorm(-1, 1).rvs(size=size) * self.initial_storage_std + self.initial_storage_mean
 
+    def _reset_result(self, obs):
+        return obs, {"state_of_charge": None}      # (obs, meta) like the reference (:97)
+
     def _terminal_after(self):
         return self.max_episode_steps - 1           # simulation_step + 1 == max (:155-157, :181)
 

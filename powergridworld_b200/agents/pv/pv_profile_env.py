@@ -56,6 +56,9 @@ class PVEnv(ComponentEnv):
         self.action_space = maybe_rescale_box_space(self._action_space, rescale_spaces)
         self.index = None
 
+    def _reset_result(self, obs):
+        return None                                 # PVEnv.reset returns nothing (:127-130)
+
     def _terminal_after(self):
         return self.episode_length - 1              # index == episode_length - 1 (:117-119)
 

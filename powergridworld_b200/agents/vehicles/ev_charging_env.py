@@ -75,6 +75,9 @@ class EVChargingEnv(ComponentEnv):
         self.state = OrderedDict({k: None for k in obs_bounds.keys()})
         self._obs_labels = list(self.state.keys())
 
+    def _reset_result(self, obs):
+        return obs, {}                              # (obs, {}) like the reference (:168)
+
     def _terminal_after(self):
         # reset leaves time_index == 1 (hidden step, :163); terminal at max_episode_steps - 1
         return self.max_episode_steps - 2

@@ -29,18 +29,57 @@ class ComponentEnv(ABC):
         self._reactive_power = 0.
         self._obs_labels: List[str] = []
 
-    # ---- the reference's abstract protocol: served by the batched env, not per object
+    # ---- the reference's per-object protocol (gridworld/base.py:29-49), as used by its
+    # tests/agents/*.py and notebooks: a component stepped on its own.  Served by a private
+    # one-env, one-agent device handle without a feeder -- still the CUDA path, there is no
+    # Python implementation of the dynamics.  Grid variables cannot be injected this way.
+    _standalone = None
+
+    def _runner(self):
+        if self._standalone is None:
+            import pandas as pd
+            from powergridworld_b200.multiagent_env import MultiAgentEnv
+            if any(k in self.obs_labels for k in ("bus_voltage", "min_voltage", "max_voltage")):
+                raise NotImplementedError(_GPU_ONLY.format(cls=type(self).__name__))
+            me = self
+            self.name = self.name if self.name is not None else type(self).__name__
+            self._standalone = MultiAgentEnv(
+                common_config={"start_time": "01-01-2021 00:00:00",
+                               "end_time": "01-01-2031 00:00:00",
+                               "control_timedelta": pd.Timedelta(300, "s")},
+                pf_config=None,
+                agents=[{"name": self.name, "bus": None, "cls": lambda name, **kw: me,
+                         "config": {}}])
+            self._last = None
+        return self._standalone
+
     def reset(self, **kwargs):
-        raise NotImplementedError(_GPU_ONLY.format(cls=type(self).__name__))
+        r = self._runner()
+        obs = r.reset(init_storage=[kwargs["init_storage"]]
+                      if kwargs.get("init_storage") is not None and r.num_storage == 1 else None)
+        self._last = (obs[self.name], 0.0, False, {})
+        return self._reset_result(obs[self.name])
+
+    def _reset_result(self, obs):
+        return obs
 
     def step(self, action, **kwargs):
-        raise NotImplementedError(_GPU_ONLY.format(cls=type(self).__name__))
+        r = self._runner()
+        if r._needs_reset:
+            raise RuntimeError("call reset before step")
+        obs, rew, dones, meta = r.step({self.name: action})
+        self._last = (obs[self.name], rew[self.name], dones["__all__"], meta[self.name])
+        return self._last
 
     def step_reward(self, **kwargs):
-        raise NotImplementedError(_GPU_ONLY.format(cls=type(self).__name__))
+        if self._last is None:
+            raise RuntimeError("no step has been taken")
+        return self._last[1], {}
 
     def get_obs(self, **kwargs):
-        raise NotImplementedError(_GPU_ONLY.format(cls=type(self).__name__))
+        if self._last is None:
+            raise RuntimeError("call reset first")
+        return self._last[0], {}
 
     @property
     def real_power(self) -> float:
@@ -89,6 +128,9 @@ class MultiComponentEnv(ComponentEnv):
         for e in self.envs:
             labels += e.obs_labels
         self._obs_labels = list(set(labels))
+
+    def _reset_result(self, obs):
+        return obs, {e.name: {} for e in self.envs}          # (obs, meta), base.py:108-111
 
     def _emit(self, builder, agent_index, standalone):
         for e in self.envs:

@@ -581,32 +581,66 @@ int pgw_step_host(pgw_env* env, const double* actions, double* obs, double* rew,
   return PGW_OK;
 }
 
-int pgw_get(pgw_env* env, int field, void* dst, size_t bytes, void* cuda_stream) {
-  if (!env || !dst) return fail(PGW_ERR_INVALID, "null argument");
+static int field_location(pgw_env* env, int field, void** ptr, size_t* want) {
   const size_t E = (size_t)env->E, A = (size_t)env->A;
-  const void* src = nullptr;
-  size_t want = 0;
   switch (field) {
-    case PGW_FIELD_STATE_D: src = env->sd; want = (size_t)env->sd_rows * E * 8; break;
-    case PGW_FIELD_STATE_I: src = env->si; want = (size_t)env->si_rows * E * 4; break;
-    case PGW_FIELD_AGENT_P: src = env->agent_p; want = A * E * 8; break;
-    case PGW_FIELD_VOLTAGES: src = env->vmag; want = (size_t)env->nn * E * 8; break;
-    case PGW_FIELD_VMIN: src = env->vmin; want = E * 8; break;
-    case PGW_FIELD_VMAX: src = env->vmax; want = E * 8; break;
-    case PGW_FIELD_VBUS: src = env->vbus; want = A * E * 8; break;
-    case PGW_FIELD_PF_ITERS: src = env->iters; want = E * 4; break;
-    case PGW_FIELD_EP_RETURN: src = env->ep_ret; want = A * E * 8; break;
+    case PGW_FIELD_STATE_D: *ptr = env->sd; *want = (size_t)env->sd_rows * E * 8; break;
+    case PGW_FIELD_STATE_I: *ptr = env->si; *want = (size_t)env->si_rows * E * 4; break;
+    case PGW_FIELD_AGENT_P: *ptr = env->agent_p; *want = A * E * 8; break;
+    case PGW_FIELD_VOLTAGES: *ptr = env->vmag; *want = (size_t)env->nn * E * 8; break;
+    case PGW_FIELD_VMIN: *ptr = env->vmin; *want = E * 8; break;
+    case PGW_FIELD_VMAX: *ptr = env->vmax; *want = E * 8; break;
+    case PGW_FIELD_VBUS: *ptr = env->vbus; *want = A * E * 8; break;
+    case PGW_FIELD_PF_ITERS: *ptr = env->iters; *want = E * 4; break;
+    case PGW_FIELD_EP_RETURN: *ptr = env->ep_ret; *want = A * E * 8; break;
+    case PGW_FIELD_PF_STATE: *ptr = env->u_state; *want = (size_t)env->nbp * E * 16; break;
     default: return fail(PGW_ERR_INVALID, "unknown field");
   }
+  return PGW_OK;
+}
+
+static int check_size(size_t want, size_t bytes) {
+  if (bytes == want) return PGW_OK;
+  char buf[128];
+  snprintf(buf, sizeof buf, "size mismatch: field needs %zu bytes, got %zu", want, bytes);
+  return fail(PGW_ERR_INVALID, buf);
+}
+
+int pgw_get(pgw_env* env, int field, void* dst, size_t bytes, void* cuda_stream) {
+  if (!env || !dst) return fail(PGW_ERR_INVALID, "null argument");
+  void* src = nullptr;
+  size_t want = 0;
+  int rc = field_location(env, field, &src, &want);
+  if (rc) return rc;
   if (want == 0) return PGW_OK;
   if (!src) return fail(PGW_ERR_INVALID, "field not available (no feeder)");
-  if (bytes != want) {
-    char buf[128];
-    snprintf(buf, sizeof buf, "size mismatch: field needs %zu bytes, got %zu", want, bytes);
-    return fail(PGW_ERR_INVALID, buf);
-  }
+  if ((rc = check_size(want, bytes))) return rc;
   PGW_CUDA(cudaMemcpyAsync(dst, src, want, cudaMemcpyDeviceToDevice,
                            static_cast<cudaStream_t>(cuda_stream)));
+  return PGW_OK;
+}
+
+int pgw_set(pgw_env* env, int field, const void* src, size_t bytes, void* cuda_stream) {
+  if (!env || !src) return fail(PGW_ERR_INVALID, "null argument");
+  void* dst = nullptr;
+  size_t want = 0;
+  int rc = field_location(env, field, &dst, &want);
+  if (rc) return rc;
+  if (want == 0) return PGW_OK;
+  if (!dst) return fail(PGW_ERR_INVALID, "field not available (no feeder)");
+  if ((rc = check_size(want, bytes))) return rc;
+  PGW_CUDA(cudaMemcpyAsync(dst, src, want, cudaMemcpyDeviceToDevice,
+                           static_cast<cudaStream_t>(cuda_stream)));
+  return PGW_OK;
+}
+
+int pgw_set_clock(pgw_env* env, int steps, void* cuda_stream) {
+  if (!env) return fail(PGW_ERR_INVALID, "null argument");
+  if (steps < 0 || steps >= env->num_events) return fail(PGW_ERR_INVALID, "clock out of range");
+  PGW_CUDA(cudaMemcpyAsync(env->d_clock, &steps, sizeof(int), cudaMemcpyHostToDevice,
+                           static_cast<cudaStream_t>(cuda_stream)));
+  PGW_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+  env->clock = steps;
   return PGW_OK;
 }
 

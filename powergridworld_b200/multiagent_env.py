@@ -442,7 +442,8 @@ class MultiAgentEnv:
                   N.FIELD_VMIN: ((E,), torch.float64), N.FIELD_VMAX: ((E,), torch.float64),
                   N.FIELD_VBUS: ((A, E), torch.float64),
                   N.FIELD_PF_ITERS: ((E,), torch.int32),
-                  N.FIELD_EP_RETURN: ((A, E), torch.float64)}
+                  N.FIELD_EP_RETURN: ((A, E), torch.float64),
+                  N.FIELD_PF_STATE: ((self._nbp(), E, 2), torch.float64)}
         shape, dt = shapes[field]
         out = torch.empty(shape, dtype=dt, device=self.device)
         if out.numel():
@@ -450,6 +451,41 @@ class MultiAgentEnv:
                 N.check(self._lib.pgw_get(self._h, field, C.c_void_p(out.data_ptr()),
                                           out.numel() * out.element_size(), self._stream()))
         return out
+
+    def _nbp(self):
+        if self.pf_solver is None:
+            return 0
+        nb = self.pf_solver.feeder.nb
+        return 16 if nb <= 16 else (nb + 31) // 32 * 32
+
+    # ---- checkpoint / resume (the reference has none at the env level)
+    _STATE_FIELDS = (N.FIELD_STATE_D, N.FIELD_STATE_I, N.FIELD_AGENT_P, N.FIELD_VOLTAGES,
+                     N.FIELD_VMIN, N.FIELD_VMAX, N.FIELD_VBUS, N.FIELD_PF_ITERS,
+                     N.FIELD_EP_RETURN, N.FIELD_PF_STATE)
+
+    def state_dict(self) -> dict:
+        """Everything needed to resume the batch bit for bit: device fields + episode clock."""
+        fields = {}
+        for f in self._STATE_FIELDS:
+            if self.pf_solver is None and f in (N.FIELD_VOLTAGES, N.FIELD_VMIN, N.FIELD_VMAX,
+                                                N.FIELD_VBUS, N.FIELD_PF_ITERS, N.FIELD_PF_STATE):
+                continue
+            fields[f] = self.get_field(f).clone()
+        return {"fields": fields, "episode_step": self.episode_step, "obs": self.obs.clone(),
+                "needs_reset": self._needs_reset}
+
+    def load_state_dict(self, state: dict):
+        torch = _torch()
+        for f, t in state["fields"].items():
+            t = t.to(self.device).contiguous()
+            if t.numel():
+                N.check(self._lib.pgw_set(self._h, int(f), C.c_void_p(t.data_ptr()),
+                                          t.numel() * t.element_size(), self._stream()))
+        N.check(self._lib.pgw_set_clock(self._h, int(state["episode_step"]), self._stream()))
+        self.episode_step = int(state["episode_step"])
+        self.time = self.start_time + self.episode_step * self.control_timedelta
+        self.obs.copy_(state["obs"])
+        self._needs_reset = bool(state["needs_reset"])
 
     def stats(self):
         """Episode statistics reduced on the device: tensor[8], see include/pgw.h."""

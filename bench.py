@@ -39,7 +39,9 @@ WORKLOAD = "c1"              # --workload c2 = component-only EV+PV+storage (BAS
 METRIC, UNIT = "env_steps_per_s", "env-steps/s"
 LOAD_FACTOR = 1.2
 # algorithmic bytes per env-step of the component kernel, SURVEY.md section 8(d)
-SURVEY_BYTES = {"c1": 3 * (264 + 28 + 40) + 1, "c2": (16 * 100 + 72 + 8 * 4) + 28 + 40 + 1}
+SURVEY_BYTES = {"c1": 3 * (264 + 28 + 40) + 1, "c2": (16 * 100 + 72 + 8 * 4) + 28 + 40 + 1,
+                # C3: 40 PV + 30 storage + 10 EV(25) + 20 x (building + PV + storage)
+                "c3": 40 * 28 + 30 * 40 + 10 * (16 * 25 + 72 + 8) + 20 * (264 + 28 + 40) + 1}
 
 
 def _config(n_gpus):
@@ -49,6 +51,12 @@ def _config(n_gpus):
                 "envs_per_gpu": ENVS_PER_GPU, "agents_per_env": 3,
                 "global_envs": ENVS_PER_GPU * n_gpus, "parallelism": f"env-sharded x{n_gpus}",
                 "l2": "flushed between timed steps (256 MiB write)"}
+    if WORKLOAD == "c3":
+        return {"workload": "C3: 123-bus-class synthetic feeder (251 nodes, 85 load branches), 100 "
+                            f"heterogeneous DER agents, {ENVS_PER_GPU} envs per GPU",
+                "envs_per_gpu": ENVS_PER_GPU, "agents_per_env": 100,
+                "global_envs": ENVS_PER_GPU * n_gpus, "parallelism": f"env-sharded x{n_gpus}",
+                "l2": "flushed between timed steps (256 MiB write)", "pf_kernel": "fp64-simt"}
     return {"workload": "C1: IEEE-13 coordinated buildings (3 x building+PV+storage @675c), "
                         f"{ENVS_PER_GPU} envs per GPU",
             "envs_per_gpu": ENVS_PER_GPU, "agents_per_env": 3, "global_envs": ENVS_PER_GPU * n_gpus,
@@ -79,6 +87,11 @@ def _make_env(ns, **kw):
                     return 1.0
             return ns.MultiAgentEnv(**S.ev_pv_storage_scenario(ns, NoPF), **kw)
         return ns.MultiAgentEnv(**S.ev_pv_storage_scenario(ns), **kw)
+    if WORKLOAD == "c3":
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return ns.MultiAgentEnv(**S.der123_scenario(ns, ns.OpenDSSSolver), **kw)
     return ns.CoordinatedMultiBuildingControlEnv(
         **S.buildings_scenario(ns, ns.OpenDSSSolver, LOAD_FACTOR), **kw)
 
@@ -219,7 +232,7 @@ def run_ours(args):
     A = len(env.agents)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    pool_n = 64 if E <= 65536 else 8
+    pool_n = 64 if E * env.act_dim <= 65536 * 24 else 8
     act_pool = torch.rand((pool_n, env.act_dim, E), generator=gen, device=dev,
                           dtype=torch.float64) * 2.0 - 1.0
     rng = np.random.default_rng(rank)
@@ -404,7 +417,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--pf-kernel", default="fp64", choices=["fp64", "tc"])
-    ap.add_argument("--workload", default="c1", choices=["c1", "c2"])
+    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3"])
     args = ap.parse_args()
     ENVS_PER_GPU, PF_KERNEL, WORKLOAD = args.envs, args.pf_kernel, args.workload
     if args.impl == "reference":

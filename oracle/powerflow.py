@@ -626,12 +626,22 @@ def _asset_text_opener(prefix):
 def compile_feeder(feeder_file: str = None, text: str = None) -> Circuit:
     if text is not None:
         return Circuit(Script().read(text, lambda f: "").finish())
+    packaged = os.path.join(os.path.dirname(_ASSET_PATH), "feeders", feeder_file)
+    if not os.path.isfile(feeder_file) and os.path.isfile(packaged):
+        feeder_file = packaged                     # e.g. the authored "synthetic123.dss"
     if os.path.isfile(feeder_file):
         base = os.path.dirname(feeder_file)
 
         def opener(name):
-            with open(os.path.join(base, name)) as fh:
-                return fh.read()
+            path = os.path.join(base, name)
+            if os.path.isfile(path):
+                with open(path) as fh:
+                    return fh.read()
+            with np.load(_ASSET_PATH) as z:         # redirected IEEE data from the asset bundle
+                for k in z.files:
+                    if k.startswith("dss/") and k.lower().endswith("/" + name.lower()):
+                        return z[k].tobytes().decode("utf-8", errors="replace")
+            raise FileNotFoundError(path)
         with open(feeder_file) as fh:
             body = fh.read()
     else:

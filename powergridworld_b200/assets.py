@@ -32,3 +32,10 @@ def dss_text(rel_path: str) -> str:
         if k.lower() == want:
             return v.tobytes().decode("utf-8", errors="replace")
     raise FileNotFoundError(f"no packaged DSS script {rel_path!r}")
+
+
+def dss_text_by_basename(name: str) -> str:
+    for k, v in _bundle().items():
+        if k.startswith("dss/") and k.lower().endswith("/" + name.lower()):
+            return v.tobytes().decode("utf-8", errors="replace")
+    raise FileNotFoundError(f"no packaged DSS script named {name!r}")

@@ -673,12 +673,19 @@ _CACHE: Dict[str, CompiledFeeder] = {}
 def compile_feeder(feeder_file: str) -> CompiledFeeder:
     """``feeder_file`` as the reference takes it: a path relative to the packaged DSS data
     (e.g. ``ieee_13_dss/IEEE13Nodeckt.dss``), or any readable file path."""
+    packaged = os.path.join(os.path.dirname(os.path.abspath(assets.__file__)), "data", "feeders",
+                            feeder_file)
+    if not os.path.isfile(feeder_file) and os.path.isfile(packaged):
+        feeder_file = packaged                      # e.g. "synthetic123.dss"
     key = os.path.abspath(feeder_file) if os.path.isfile(feeder_file) else feeder_file
     if key not in _CACHE:
         if os.path.isfile(feeder_file):
             def reader(p):
-                with open(p, "r", errors="replace") as fh:
-                    return fh.read()
+                if os.path.isfile(p):
+                    with open(p, "r", errors="replace") as fh:
+                        return fh.read()
+                # a redirected file that is not next to the script: the packaged IEEE data
+                return assets.dss_text_by_basename(os.path.basename(p))
         else:
             reader = assets.dss_text
         _CACHE[key] = FeederCompiler(reader).run(feeder_file).compile()

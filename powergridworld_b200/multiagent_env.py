@@ -168,6 +168,13 @@ class MultiAgentEnv:
             if feeder is not None:
                 bus = self.agent_name_bus_map[ag.name]
                 rec.load_slot = feeder.load_index(bus)
+                if feeder.load_model[rec.load_slot] != 1:
+                    # the reference only manipulates Model=1 (PQ) loads (opendss.py:54-77,
+                    # :115-129): power of an agent on any other load never reaches the feeder
+                    import warnings
+                    warnings.warn(f"agent {ag.name!r} sits on load {bus!r} whose model is not 1: "
+                                  "its power is ignored by the power flow, as in the reference")
+                    rec.load_slot = -1
                 node = self.pf_solver.node_for_bus_name(str(bus))
                 if "bus_voltage" in ag.obs_labels and node is None:
                     raise ValueError(f"agent {ag.name!r} observes bus_voltage but {bus!r} is a "

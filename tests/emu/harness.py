@@ -35,9 +35,12 @@ def zbus_solve(f, kw, kvar, tol=1e-12, max_iter=200):
     u = f.u0.copy()
     for _ in range(max_iter):
         m = np.abs(u)
+        us = np.where(u == 0, 1, u)
         i = np.where(m <= f.branch_vmin, np.conj(s) / f.branch_vmin ** 2 * u,
                      np.where(m > f.branch_vmax, np.conj(s) / f.branch_vmax ** 2 * u,
-                              np.conj(s / np.where(u == 0, 1, u))))
+                              np.conj(s / us)))                      # model 1: PQ with Z band
+        i = np.where(f.branch_model == 2, np.conj(s) * u, i)         # constant impedance
+        i = np.where(f.branch_model == 5, np.conj(s) * us / np.abs(us), i)   # constant |I|
         un = f.u0 - f.zbb @ i
         d = np.abs(un - u).max() if len(u) else 0.0
         u = un
@@ -95,6 +98,8 @@ class EmulatedEnv:
                 add = {}
                 for ai in range(self.A):
                     l = env._agent_recs[ai].load_slot
+                    if l < 0:
+                        continue
                     add[l] = add[l] + self.agent_p[ai, e] if l in add else self.agent_p[ai, e]
                 for l, v in add.items():
                     kw[l] += v

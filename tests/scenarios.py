@@ -134,3 +134,50 @@ def test_heterogeneous_scenario(ns, pf_cls):
 # keep pytest from collecting the builders above as tests
 test_multicomponent_components.__test__ = False
 test_heterogeneous_scenario.__test__ = False
+
+
+def synthetic123_load_names():
+    """Load names of the authored 123-bus-class feeder, in definition order."""
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "powergridworld_b200",
+                        "data", "feeders", "synthetic123.dss")
+    with open(path) as fh:
+        return [m.group(1).lower() for m in re.finditer(r"^New Load\.(\S+)", fh.read(), re.M)]
+
+
+def der123_scenario(ns, pf_cls, n_agents=100, system_load_rescale_factor=0.9):
+    """BASELINE C3: 123-bus-class feeder with ~100 heterogeneous DER agents, one per load
+    (PV 40 %, storage 30 %, EV station 10 %, building+PV+storage composite 20 %)."""
+    loads = synthetic123_load_names()
+    agents = []
+    for i in range(n_agents):
+        kind, bus = i % 10, loads[i % len(loads)]
+        if kind <= 3:
+            agents.append({"name": f"pv-{i}", "bus": bus, "cls": ns.PVEnv,
+                           "config": {"profile_csv": ["pv_profile.csv", "off-peak.csv"][i % 2],
+                                      "scaling_factor": 20. + i}})
+        elif kind <= 6:
+            agents.append({"name": f"storage-{i}", "bus": bus, "cls": ns.EnergyStorageEnv,
+                           "config": {"max_power": 10. + i % 7, "storage_range": (3., 60. + i)}})
+        elif kind == 7:
+            agents.append({"name": f"ev-{i}", "bus": bus, "cls": ns.EVChargingEnv,
+                           "config": {"num_vehicles": 25, "max_charge_rate_kw": 7.,
+                                      "peak_threshold": 60., "vehicle_multiplier": 2.}})
+        else:
+            comps = [
+                {"name": "building", "cls": ns.FiveZoneROMThermalEnergyEnv, "config": {}},
+                {"name": "pv", "cls": ns.PVEnv,
+                 "config": {"profile_csv": "pv_profile.csv", "scaling_factor": 30.}},
+                {"name": "storage", "cls": ns.EnergyStorageEnv,
+                 "config": {"max_power": 15., "storage_range": (3., 50.)}}]
+            agents.append({"name": f"house-{i}", "bus": bus, "cls": ns.MultiComponentEnv,
+                           "config": {"components": comps}})
+    return {
+        "common_config": {"start_time": "08-12-2021 00:00:00", "end_time": "08-13-2021 00:00:00",
+                          "control_timedelta": pd.Timedelta(300, "s")},
+        "pf_config": {"cls": pf_cls,
+                      "config": {"feeder_file": "synthetic123.dss",
+                                 "loadshape_file": "ieee_13_dss/annual_hourly_load_profile.csv",
+                                 "system_load_rescale_factor": system_load_rescale_factor}},
+        "agents": agents}

@@ -348,3 +348,36 @@ def test_tensor_core_golden_trace_within_north_star_tolerances():
             v = env.voltages
             np.testing.assert_allclose([v[k] for k in names], g["volt"][t + 1], rtol=0, atol=1e-4)
             np.testing.assert_allclose([v[k] for k in names], g["volt"][t + 1], rtol=0, atol=2e-6)
+
+
+def test_der123_scenario_matches_oracle():
+    """BASELINE C3 composition on the authored 123-bus-class feeder (251 nodes, 85 load
+    branches -> the 3-rows-per-lane FP64 kernel, feeder tables read through L1/L2; load models
+    1, 2 and 5; 100 heterogeneous agents)."""
+    import warnings
+    torch = _torch()
+    E, T = 3, 12
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = PNS.MultiAgentEnv(**S.der123_scenario(PNS, PNS.OpenDSSSolver), num_envs=E)
+    rng = np.random.default_rng(5)
+    soc = rng.uniform(10, 50, size=(env.num_storage, E))
+    acts = rng.uniform(-1, 1, size=(T, env.act_dim, E))
+    obs0 = env.reset_batch(soc).cpu().numpy().copy()
+    O, R, V = [], [], []
+    for t in range(T):
+        o, r, _, _ = env.step_batch(torch.as_tensor(acts[t]).cuda())
+        O.append(o.cpu().numpy().copy())
+        R.append(r.cpu().numpy().copy())
+        V.append(env.get_field(3).cpu().numpy())
+    assert int(env.get_field(7).min()) > 0
+    names = env.pf_solver.feeder.node_names
+    for e in range(E):
+        ref = ONS.MultiAgentEnv(**S.der123_scenario(ONS, ONS.OpenDSSSolver))
+        o0 = ref.reset(init_storage=storage_socs_to_dict(ref, soc[:, e]))
+        np.testing.assert_allclose(obs0[:, e], flat_obs(ref, o0), rtol=0, atol=1e-9)
+        for t in range(T):
+            o, r, _, _ = ref.step(unflatten_action(ref, acts[t][:, e]))
+            np.testing.assert_allclose(O[t][:, e], flat_obs(ref, o), rtol=0, atol=1e-9)
+            np.testing.assert_allclose(R[t][:, e], [r[a.name] for a in ref.agents], rtol=1e-9, atol=1e-10)
+            np.testing.assert_allclose(V[t][:, e], [ref.voltages[n] for n in names], rtol=0, atol=1e-8)

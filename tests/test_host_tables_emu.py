@@ -59,3 +59,32 @@ def test_exogenous_recipes_agree():
     from oracle.exogenous import synthetic_exogenous_table
     from powergridworld_b200.agents.buildings.exogenous import synthetic_table
     np.testing.assert_array_equal(synthetic_exogenous_table(), synthetic_table())
+
+
+def test_der123_scenario_tables_and_arithmetic_vs_oracle():
+    """BASELINE C3 composition (123-bus-class feeder, 100 heterogeneous agents incl. loads with
+    models 2 and 5): compiled tables + device arithmetic + NumPy Z-bus vs the oracle."""
+    import warnings
+    from tests.flatten import flat_obs, unflatten_action
+    from tests.oracle_ns import ORACLE_NS as ONS, storage_socs_to_dict
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = NS.MultiAgentEnv(**S.der123_scenario(NS, NS.OpenDSSSolver), _dry_run=True)
+    assert (env.act_dim, env.obs_dim, len(env.agents)) == (240, 470, 100)
+    f = env.pf_solver.feeder
+    assert (f.nn, f.nb, f.nl) == (251, 85, 85)
+    emu = EmulatedEnv(env)
+    ref = ONS.MultiAgentEnv(**S.der123_scenario(ONS, ONS.OpenDSSSolver))
+    rng = np.random.default_rng(0)
+    soc = rng.uniform(10, 50, size=(env.num_storage, 1))
+    o0 = emu.reset(soc)
+    r0 = ref.reset(init_storage=storage_socs_to_dict(ref, soc[:, 0]))
+    np.testing.assert_allclose(o0[:, 0], flat_obs(ref, r0), rtol=0, atol=1e-12)
+    names = f.node_names
+    for t in range(6):
+        a = rng.uniform(-1, 1, size=(env.act_dim, 1))
+        o, r, d = emu.step(a)
+        ro, rr, rd, _ = ref.step(unflatten_action(ref, a[:, 0]))
+        np.testing.assert_allclose(o[:, 0], flat_obs(ref, ro), rtol=0, atol=1e-12)
+        np.testing.assert_allclose(r[:, 0], [rr[x.name] for x in ref.agents], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(emu.vmag[:, 0], [ref.voltages[n] for n in names], rtol=0, atol=1e-10)

@@ -44,6 +44,9 @@ SURVEY_BYTES = {"c1": 3 * (264 + 28 + 40) + 1, "c2": (16 * 100 + 72 + 8 * 4) + 2
                 "c3": 40 * 28 + 30 * 40 + 10 * (16 * 25 + 72 + 8) + 20 * (264 + 28 + 40) + 1}
 
 
+_PF_NAMES = {"fp64": "fp64-simt", "tc": "tcgen05 split-tf32", "tc2": "tcgen05 split-fp16, Z-bus in smem"}
+
+
 def _config(n_gpus):
     if WORKLOAD == "c2":
         return {"workload": "C2: component-only EV station (100 vehicles) + PV + storage, "
@@ -56,14 +59,14 @@ def _config(n_gpus):
                             f"heterogeneous DER agents, {ENVS_PER_GPU} envs per GPU",
                 "envs_per_gpu": ENVS_PER_GPU, "agents_per_env": 100,
                 "global_envs": ENVS_PER_GPU * n_gpus, "parallelism": f"env-sharded x{n_gpus}",
-                "l2": "flushed between timed steps (256 MiB write)", "pf_kernel": "fp64-simt"}
+                "l2": "flushed between timed steps (256 MiB write)", "pf_kernel": _PF_NAMES[PF_KERNEL]}
     return {"workload": "C1: IEEE-13 coordinated buildings (3 x building+PV+storage @675c), "
                         f"{ENVS_PER_GPU} envs per GPU",
             "envs_per_gpu": ENVS_PER_GPU, "agents_per_env": 3, "global_envs": ENVS_PER_GPU * n_gpus,
             "feeder": "IEEE-13 (38 nodes, 14 load branches)", "load_factor": LOAD_FACTOR,
             "parallelism": f"env-sharded x{n_gpus}", "l2": "flushed between timed steps "
             "(256 MiB write)",
-            "pf_kernel": "tcgen05 split-tf32" if PF_KERNEL == "tc" else "fp64-simt"}
+            "pf_kernel": _PF_NAMES[PF_KERNEL]}
 
 
 def _make_env(ns, **kw):
@@ -226,9 +229,9 @@ def run_ours(args):
     E = ENVS_PER_GPU
     env = _make_env(NS, num_envs=E, device=dev)
     has_pf = env.pf_solver is not None
-    if PF_KERNEL == "tc" and has_pf:
+    if PF_KERNEL != "fp64" and has_pf:
         from powergridworld_b200 import _native as N
-        env.set_option(N.OPT_PF_KERNEL, 1)
+        env.set_option(N.OPT_PF_KERNEL, {"tc": 1, "tc2": 2}[PF_KERNEL])
     A = len(env.agents)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -364,6 +367,9 @@ def run_ours(args):
         if PF_KERNEL == "tc":      # dense TF32 = half the measured bf16 rate; flops counted once
             pf_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
             pf_peak_src = "0.5 x measured bf16 (tf32 dense), " + peak_src
+        elif PF_KERNEL == "tc2":   # dense FP16 = the measured bf16 rate; flops counted once
+            pf_peak = peaks.get("bf16_tflops", 1590.0)
+            pf_peak_src = "measured bf16 (= fp16 dense), " + peak_src
         else:
             pf_peak, pf_peak_src = 37.0, "nominal B200 FP64 (no measured FP64 peak)"
         line = {
@@ -384,9 +390,9 @@ def run_ours(args):
                          "frac_survey_bytes": (survey_bytes / (comp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
                          if comp_ms > 0 else 0.0,
                          "avg_launch_ms": comp_ms},
-            "roofline_pf": {"kernel": "pf_tc_kernel" if PF_KERNEL == "tc"
-                            else "pf_fixed_point_kernel<16,1,true>",
-                            "bound": "tensor" if PF_KERNEL == "tc" else "fp64-fma",
+            "roofline_pf": {"kernel": {"tc": "pf_tc_kernel", "tc2": "pf_tc2_kernel"}.get(
+                                PF_KERNEL, "pf_fixed_point_kernel"),
+                            "bound": "tensor" if PF_KERNEL != "fp64" else "fp64-fma",
                             "achieved": flops / (pf_ms * 1e-3) / 1e12 if pf_ms > 0 else 0.0,
                             "peak": pf_peak, "unit": "TFLOP/s", "peak_source": pf_peak_src,
                             "algorithmic_flops_per_launch": flops, "avg_launch_ms": pf_ms,
@@ -416,7 +422,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
-    ap.add_argument("--pf-kernel", default="fp64", choices=["fp64", "tc"])
+    ap.add_argument("--pf-kernel", default="fp64", choices=["fp64", "tc", "tc2"])
     ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3"])
     args = ap.parse_args()
     ENVS_PER_GPU, PF_KERNEL, WORKLOAD = args.envs, args.pf_kernel, args.workload

@@ -250,7 +250,10 @@ int pgw_clock(const pgw_env* env);
 long long pgw_launch_count(const pgw_env* env);
 /* Runtime options (pgw_set_option): */
 #define PGW_OPT_PF_KERNEL 0   /* 0 = FP64 SIMT fixed point (default); 1 = tcgen05 tensor-core
-                                 fixed point (split-TF32 operands, FP32 accumulate in TMEM)  */
+                                 fixed point (split-TF32 operands, FP32 accumulate in TMEM),
+                                 feeders with <= 16 load branches; 2 = tcgen05 split-FP16 fixed
+                                 point with the Z-bus resident in shared memory, feeders with
+                                 <= 88 load branches (123-bus class)                          */
 #define PGW_OPT_WARM_START 1  /* 1 (default): each solve starts from the env's previous solution */
 #define PGW_OPT_GRAPHS 2      /* 1 (default): pgw_step replays a captured CUDA graph per distinct
                                  (actions, obs, rew, done) pointer set; needs a non-default stream */

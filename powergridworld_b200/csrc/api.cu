@@ -6,8 +6,10 @@
 //
 // The episode clock lives on the device and is advanced by the last CTA of the last
 // kernel of a step, so a step has constant launch parameters (CUDA-graph friendly).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -82,6 +84,9 @@ struct pgw_env {
   int tc_blob_bytes = 0, tc_n2 = 0, tc_nnp8 = 0;
   int tc_off_b2 = 0, tc_off_u0 = 0, tc_off_w = 0, tc_off_share = 0, tc_off_vlo = 0, tc_off_vhi = 0,
       tc_off_bload = 0, tc_off_bmodel = 0, tc_off_slot = 0, tc_off_node = 0;
+  // FP16 tensor-core power flow for up to 88 load branches (powerflow_tc2.cu)
+  unsigned char* tc2_blob = nullptr;
+  pgw::Tc2Params tc2{};
   // CUDA graphs of a step, keyed by the caller's buffer pointers
   struct StepGraph {
     const void *actions, *obs, *rew, *done;
@@ -382,6 +387,111 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       env->tc_n2 = n2; env->tc_nnp8 = nnp8;
       PGW_TRY(upload(&env->tc_blob, blob.data(), blob.size())); env->own(env->tc_blob);
     }
+    if (nb <= 8 * pgw::kTc2MaxChunks) {
+      // Operand images of the FP16 tcgen05 kernel (powerflow_tc2.cu), byte-exact as they sit in
+      // shared memory: canonical K-major no-swizzle UMMA tiles, element (row, k) of an image
+      // with K columns at  (row/8)*SBO + (k/8)*128 + (row%8)*16 + (k%8)*2,  SBO = (K/8)*128.
+      // Row / column order: 16c + j = Re (j < 8) or Im (j >= 8) of item 8c + (j % 8).
+      pgw::Tc2Params& t = env->tc2;
+      const int nch = (nb + 7) / 8, N = 16 * nch, NBP = 8 * nch;
+      const int ncc = (nn + NBP - 1) / NBP;
+      const size_t sbo = (size_t)(N / 8) * 128, part = (size_t)(N / 8) * sbo;
+      auto pos = [](int item, bool im) { return 16 * (item / 8) + (item % 8) + (im ? 8 : 0); };
+      auto Z = [&](int k, int j) { return make_double2(f.zbb[2 * ((size_t)k * nb + j)], f.zbb[2 * ((size_t)k * nb + j) + 1]); };
+      auto ZN = [&](int n, int k) { return make_double2(f.znb[2 * ((size_t)n * nb + k)], f.znb[2 * ((size_t)n * nb + k) + 1]); };
+      // real-ified operator rows:  D[pos(out)] = sum_k X[pos(k)] * M[pos(out)][pos(k)]
+      auto realify = [&](int rows_items, int item0, int nitems, auto&& zget) {
+        std::vector<double> m((size_t)N * N, 0.0);
+        for (int r = 0; r < rows_items; ++r) {
+          const int item = item0 + r;
+          if (item >= nitems) break;
+          for (int k = 0; k < nb; ++k) {
+            const double2 z = zget(item, k);
+            m[(size_t)pos(r, false) * N + pos(k, false)] = -z.x;   // Re out -= Zr Re i
+            m[(size_t)pos(r, false) * N + pos(k, true)] = z.y;     //         + Zi Im i
+            m[(size_t)pos(r, true) * N + pos(k, false)] = -z.y;    // Im out -= Zi Re i
+            m[(size_t)pos(r, true) * N + pos(k, true)] = -z.x;     //         - Zr Im i
+          }
+        }
+        return m;
+      };
+      auto scale_for = [](double mx) {
+        return mx > 0.0 ? std::ldexp(1.0, (int)std::floor(std::log2(16384.0 / mx))) : 1.0;
+      };
+      auto images = [&](const std::vector<double>& m, double scale, unsigned char* dst) {
+        for (int r = 0; r < N; ++r)
+          for (int k = 0; k < N; ++k) {
+            const double v = m[(size_t)r * N + k] * scale;
+            const __half hi = __float2half_rn((float)v);
+            const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+            const size_t off = (size_t)(r / 8) * sbo + (size_t)(k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2;
+            memcpy(dst + off, &hi, 2);
+            memcpy(dst + part + off, &lo, 2);
+          }
+      };
+      double mx1 = 0.0, mx2 = 0.0;
+      for (size_t i = 0; i < 2 * (size_t)nb * nb; ++i) mx1 = std::fmax(mx1, std::fabs(f.zbb[i]));
+      for (size_t i = 0; i < 2 * (size_t)nn * nb; ++i) mx2 = std::fmax(mx2, std::fabs(f.znb[i]));
+      const double sb1 = scale_for(mx1), sb2 = scale_for(mx2), xs = 2048.0;
+      std::vector<unsigned char> blob((size_t)(1 + ncc) * 2 * part, 0);
+      images(realify(NBP, 0, nb, Z), sb1, blob.data());
+      for (int cc = 0; cc < ncc; ++cc)
+        images(realify(NBP, cc * NBP, nn, ZN), sb2, blob.data() + (size_t)(1 + cc) * 2 * part);
+      t.nch = nch; t.ncc = ncc; t.part_bytes = (int)part; t.off_zn = (int)(2 * part);
+      t.off_tab = (int)blob.size();
+      t.xscale = (float)xs; t.descale1 = (float)(1.0 / (sb1 * xs)); t.descale2 = (float)(1.0 / (sb2 * xs));
+      t.tol = (float)(f.tol > 1e-7 ? f.tol : 1e-7);
+      t.tmem_cols = 32;
+      while (t.tmem_cols < 2 * N) t.tmem_cols *= 2;
+      std::vector<float> u0f(2 * NBP, 0.f), vl2(NBP, 1.f), vh2(NBP, 1.f), shf(NBP, 0.f), wf(2 * (size_t)nn, 0.f);
+      std::vector<int32_t> m5(NBP, 0), blp(NBP, 0), lptr(f.nl + 1, 0), lidx(env->A, 0), node(env->A);
+      for (int k = 0; k < NBP; ++k) u0f[2 * k] = 1.f;
+      for (int k = 0; k < nb; ++k) {
+        u0f[2 * k] = (float)f.u0[2 * k]; u0f[2 * k + 1] = (float)f.u0[2 * k + 1];
+        if (f.branch_model[k] != 2) {
+          vl2[k] = (float)(f.vminpu[k] * f.vminpu[k]); vh2[k] = (float)(f.vmaxpu[k] * f.vmaxpu[k]);
+        }
+        shf[k] = (float)(f.branch_share[k] * 1e-3);
+        m5[k] = f.branch_model[k] == 5 ? 1 : 0;
+        if (m5[k]) t.any_m5 = 1;
+        blp[k] = f.branch_load[k];
+      }
+      for (int n = 0; n < nn; ++n) { wf[2 * n] = (float)f.w[2 * n]; wf[2 * n + 1] = (float)f.w[2 * n + 1]; }
+      for (int a = 0; a < env->A; ++a) {
+        node[a] = spec->agents[a].bus_node;
+        if (spec->agents[a].load_slot >= 0) ++lptr[spec->agents[a].load_slot + 1];
+      }
+      for (int l = 0; l < f.nl; ++l) lptr[l + 1] += lptr[l];
+      {
+        std::vector<int32_t> fill(lptr.begin(), lptr.end() - 1);
+        for (int a = 0; a < env->A; ++a)              // agent order inside a load slot
+          if (spec->agents[a].load_slot >= 0) lidx[fill[spec->agents[a].load_slot]++] = a;
+      }
+      auto put = [&blob, &t](const void* src, size_t bytes) {
+        const size_t off = (blob.size() + 15) / 16 * 16;
+        blob.resize(off + bytes, 0);
+        if (bytes) memcpy(blob.data() + off, src, bytes);
+        return (int)(off - (size_t)t.off_tab);
+      };
+      t.t_u0 = put(u0f.data(), u0f.size() * 4);
+      t.t_vlo2 = put(vl2.data(), vl2.size() * 4);
+      t.t_vhi2 = put(vh2.data(), vh2.size() * 4);
+      t.t_share = put(shf.data(), shf.size() * 4);
+      t.t_m5 = put(m5.data(), m5.size() * 4);
+      t.t_bload = put(blp.data(), blp.size() * 4);
+      t.t_w = put(wf.data(), wf.size() * 4);
+      t.t_lptr = put(lptr.data(), lptr.size() * 4);
+      t.t_lidx = put(lidx.data(), lidx.size() * 4);
+      t.t_anode = put(node.data(), node.size() * 4);
+      blob.resize((blob.size() + 15) / 16 * 16, 0);
+      t.tab_bytes = (int)(blob.size() - (size_t)t.off_tab);
+      pgw::PfParams probe{};
+      probe.nl = f.nl; probe.tc2 = t;
+      if (pgw::tc2_smem_bytes(probe) + 6 * 1024 <= 227 * 1024) {   // + the kernel's static arrays
+        PGW_TRY(upload(&env->tc2_blob, blob.data(), blob.size())); env->own(env->tc2_blob);
+        env->tc2.blob = env->tc2_blob;
+      }
+    }
     PGW_TRY(alloc_zero(&env->vmag, (size_t)nn * E)); env->own(env->vmag);
     PGW_TRY(alloc_zero(&env->vmin, E)); env->own(env->vmin);
     PGW_TRY(alloc_zero(&env->vmax, E)); env->own(env->vmax);
@@ -434,6 +544,7 @@ static pgw::PfParams pf_params(pgw_env* env) {
   p.tc_off_bmodel = env->tc_off_bmodel; p.tc_off_slot = env->tc_off_slot;
   p.tc_off_node = env->tc_off_node;
   p.tc_tol = (float)(env->tol > 1e-7 ? env->tol : 1e-7);
+  p.tc2 = env->tc2;
   p.dtab = env->dtab; p.dstride = env->dstride;
   p.vmag = env->vmag; p.vmin = env->vmin; p.vmax = env->vmax; p.vbus = env->vbus;
   p.iters = env->iters; p.ep_ret = env->ep_ret; p.viol = env->viol;
@@ -443,6 +554,7 @@ static pgw::PfParams pf_params(pgw_env* env) {
 }
 
 static cudaError_t launch_pf(const pgw_env* env, const pgw::PfParams& pf, cudaStream_t s) {
+  if (env->pf_kernel == 2) return pgw::launch_powerflow_tc2(pf, s);
   return env->pf_kernel == 1 ? pgw::launch_powerflow_tc(pf, s) : pgw::launch_powerflow(pf, s);
 }
 
@@ -703,7 +815,10 @@ int pgw_set_option(pgw_env* env, int option, int value) {
   if (!env) return fail(PGW_ERR_INVALID, "null argument");
   switch (option) {
     case PGW_OPT_PF_KERNEL:
-      if (value != 0 && value != 1) return fail(PGW_ERR_INVALID, "unknown power-flow kernel");
+      if (value < 0 || value > 2) return fail(PGW_ERR_INVALID, "unknown power-flow kernel");
+      if (value == 2 && !env->tc2_blob)
+        return fail(PGW_ERR_INVALID, "FP16 tensor-core power flow needs a feeder with <= 88 load "
+                                     "branches whose tables fit shared memory");
       if (value == 1 && !env->tc_blob)
         return fail(PGW_ERR_INVALID, "tensor-core power flow needs a feeder with <= 16 load "
                                      "branches and <= 48 nodes");

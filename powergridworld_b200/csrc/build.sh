@@ -11,6 +11,7 @@ mkdir -p "$HERE/build"
 "$NVCC" $COMMON -fmad=false ${PTXAS_V:+-Xptxas -v} -c "$HERE/components.cu" -o "$HERE/build/components.o"
 "$NVCC" $COMMON ${PTXAS_V:+-Xptxas -v} -c "$HERE/powerflow.cu" -o "$HERE/build/powerflow.o"
 "$NVCC" $COMMON ${PTXAS_V:+-Xptxas -v} -c "$HERE/powerflow_tc.cu" -o "$HERE/build/powerflow_tc.o"
+"$NVCC" $COMMON ${PTXAS_V:+-Xptxas -v} -c "$HERE/powerflow_tc2.cu" -o "$HERE/build/powerflow_tc2.o"
 "$NVCC" $COMMON -c "$HERE/api.cu" -o "$HERE/build/api.o"
-"$NVCC" -shared $ARCH -o "$OUT" "$HERE/build/components.o" "$HERE/build/powerflow.o" "$HERE/build/powerflow_tc.o" "$HERE/build/api.o" -lcudart
+"$NVCC" -shared $ARCH -o "$OUT" "$HERE/build/components.o" "$HERE/build/powerflow.o" "$HERE/build/powerflow_tc.o" "$HERE/build/powerflow_tc2.o" "$HERE/build/api.o" -lcudart
 echo "built $OUT"

@@ -35,6 +35,15 @@ struct CompParams {
   unsigned int* ticket;
 };
 
+// Operand images + fp32 tables of the FP16 tensor-core power flow (powerflow_tc2.cu).
+// blob: [B_hi | B_lo] (2 x part_bytes) | ncc x [Zn_hi | Zn_lo] at off_zn | tables at off_tab.
+struct Tc2Params {
+  const unsigned char* blob;
+  int nch, ncc, part_bytes, off_zn, off_tab, tab_bytes, tmem_cols, any_m5;
+  int t_u0, t_vlo2, t_vhi2, t_share, t_m5, t_bload, t_w, t_lptr, t_lidx, t_anode;
+  float xscale, descale1, descale2, tol;
+};
+
 struct PfParams {
   int E, A, nb, nn, nl, nbp, nnp, max_iter;
   double tol;
@@ -57,6 +66,7 @@ struct PfParams {
   int tc_off_b2, tc_off_u0, tc_off_w, tc_off_share, tc_off_vlo, tc_off_vhi, tc_off_bload,
       tc_off_bmodel, tc_off_slot, tc_off_node;
   float tc_tol;
+  Tc2Params tc2;
   const double* agent_p;   // [A][E]
   const double* load_kw;   // [nl][E] stand-alone solve: total kW per load (else nullptr)
   const double* load_kvar; // [nl][E]
@@ -92,6 +102,9 @@ struct StatsParams {
 cudaError_t launch_components(const CompParams& p, int smem_bytes, cudaStream_t s);
 cudaError_t launch_powerflow(const PfParams& p, cudaStream_t s);
 cudaError_t launch_powerflow_tc(const PfParams& p, cudaStream_t s);
+cudaError_t launch_powerflow_tc2(const PfParams& p, cudaStream_t s);
+size_t tc2_smem_bytes(const PfParams& p);
+constexpr int kTc2MaxChunks = 11;   // 88 load branches: B and A images fill shared memory
 constexpr int kTcNb = 16;      // branch slots of the tensor-core kernel (IEEE-13 class feeders)
 constexpr int kTcK3 = 96;      // 3 x 32: [x_hi | x_lo | x_hi] against [B_hi ; B_hi ; B_lo]
 cudaError_t launch_stats(const StatsParams& p, cudaStream_t s);

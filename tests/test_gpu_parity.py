@@ -296,8 +296,9 @@ def test_abi_error_paths():
     assert rc == -1 and b"size mismatch" in env._lib.pgw_last_error()
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("name,E", [("c0_buildings", 300), ("heterogeneous", 128)])
-def test_tensor_core_power_flow_matches_fp64_kernel(name, E):
+def test_tensor_core_power_flow_matches_fp64_kernel(name, E, kernel):
     """tcgen05 fixed point (split-TF32 operands, FP32 accumulate/epilogue) vs the FP64 SIMT
     kernel on the same batch: node voltages within 1e-6 p.u. -- two orders inside the 1e-4 p.u.
     tolerance of the reference's own solver -- and rewards within 1e-5 relative (+ the
@@ -307,7 +308,7 @@ def test_tensor_core_power_flow_matches_fp64_kernel(name, E):
     T = 40
     a_env = CASES[name](PNS, num_envs=E)
     b_env = CASES[name](PNS, num_envs=E)
-    b_env.set_option(N.OPT_PF_KERNEL, 1)
+    b_env.set_option(N.OPT_PF_KERNEL, kernel)
     rng = np.random.default_rng(11)
     soc = rng.uniform(5, 45, size=(a_env.num_storage, E))
     oa = a_env.reset_batch(soc).cpu().numpy()
@@ -329,13 +330,14 @@ def test_tensor_core_power_flow_matches_fp64_kernel(name, E):
     assert float(it.double().mean()) < 25
 
 
-def test_tensor_core_golden_trace_within_north_star_tolerances():
-    """Reference golden trace through the tcgen05 solver: voltages 1e-4 p.u., observations
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_tensor_core_golden_trace_within_north_star_tolerances(kernel):
+    """Reference golden trace through the tcgen05 solvers: voltages 1e-4 p.u., observations
     1e-6 (x10 for the scaled voltage entries), rewards 1e-5 relative."""
     from powergridworld_b200 import _native as N
     g = np.load(os.path.join(GOLD, "c0_buildings.npz"))
     env = CASES["c0_buildings"](PNS)
-    env.set_option(N.OPT_PF_KERNEL, 1)
+    env.set_option(N.OPT_PF_KERNEL, kernel)
     names = [str(n) for n in g["node_names"]]
     obs0 = env.reset(init_storage=g["init_soc"])
     np.testing.assert_allclose(flat_obs(env, obs0), g["obs0"], rtol=0, atol=1e-5)
@@ -381,3 +383,45 @@ def test_der123_scenario_matches_oracle():
             np.testing.assert_allclose(O[t][:, e], flat_obs(ref, o), rtol=0, atol=1e-9)
             np.testing.assert_allclose(R[t][:, e], [r[a.name] for a in ref.agents], rtol=1e-9, atol=1e-10)
             np.testing.assert_allclose(V[t][:, e], [ref.voltages[n] for n in names], rtol=0, atol=1e-8)
+
+
+def test_der123_fp16_tensor_core_power_flow_matches_fp64_kernel():
+    """C3 composition (85 load branches, 251 nodes, load models 1/2/5, 100 agents) through the
+    split-FP16 tcgen05 solver with the Z-bus resident in shared memory vs the FP64 SIMT kernel on
+    the same batch: 300 envs = two full tiles of 128 + a ragged one.  Voltages within 1e-6 p.u.
+    (two orders inside the reference solver's 1e-4), rewards 1e-5 relative."""
+    import warnings
+    torch = _torch()
+    from powergridworld_b200 import _native as N
+    E, T = 300, 16
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a_env = PNS.MultiAgentEnv(**S.der123_scenario(PNS, PNS.OpenDSSSolver), num_envs=E)
+        b_env = PNS.MultiAgentEnv(**S.der123_scenario(PNS, PNS.OpenDSSSolver), num_envs=E)
+    b_env.set_option(N.OPT_PF_KERNEL, 2)
+    rng = np.random.default_rng(23)
+    soc = rng.uniform(10, 50, size=(a_env.num_storage, E))
+    oa = a_env.reset_batch(soc).cpu().numpy()
+    ob = b_env.reset_batch(soc).cpu().numpy()
+    va, vb = a_env.get_field(3).cpu().numpy(), b_env.get_field(3).cpu().numpy()
+    np.testing.assert_allclose(vb, va, rtol=0, atol=1e-6, err_msg="reset voltages")
+    np.testing.assert_allclose(ob, oa, rtol=0, atol=2e-5)
+    for t in range(T):
+        act = torch.as_tensor(rng.uniform(-1, 1, size=(a_env.act_dim, E))).cuda()
+        oa, ra, _, _ = a_env.step_batch(act)
+        ob, rb, _, _ = b_env.step_batch(act)
+        va, vb = a_env.get_field(3).cpu().numpy(), b_env.get_field(3).cpu().numpy()
+        np.testing.assert_allclose(vb, va, rtol=0, atol=1e-6, err_msg=f"voltages t={t}")
+        np.testing.assert_allclose(b_env.get_field(4).cpu().numpy(), va.min(axis=0), rtol=0, atol=1e-6)
+        np.testing.assert_allclose(b_env.get_field(5).cpu().numpy(), va.max(axis=0), rtol=0, atol=1e-6)
+        np.testing.assert_allclose(b_env.get_field(6).cpu().numpy(), a_env.get_field(6).cpu().numpy(),
+                                   rtol=0, atol=1e-6)
+        np.testing.assert_allclose(ob.cpu().numpy(), oa.cpu().numpy(), rtol=0, atol=2e-5)
+        np.testing.assert_allclose(rb.cpu().numpy(), ra.cpu().numpy(), rtol=1e-5, atol=1e-4)
+    # warm-start state agrees as well (branch voltages, complex)
+    ua, ub = a_env.get_field(9).cpu().numpy(), b_env.get_field(9).cpu().numpy()
+    nb = a_env.pf_solver.feeder.nb
+    np.testing.assert_allclose(ub.reshape(-1, E, 2)[:nb], ua.reshape(-1, E, 2)[:nb], rtol=0, atol=2e-6)
+    it = b_env.get_field(7)
+    assert int(it.min()) > 0, "tensor-core solve did not converge"
+    assert float(it.double().mean()) < 25

@@ -387,13 +387,13 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       env->tc_n2 = n2; env->tc_nnp8 = nnp8;
       PGW_TRY(upload(&env->tc_blob, blob.data(), blob.size())); env->own(env->tc_blob);
     }
-    if (nb <= 8 * pgw::kTc2MaxChunks) {
+    if (pgw::tc2_padded_chunks((nb + 7) / 8) > 0) {
       // Operand images of the FP16 tcgen05 kernel (powerflow_tc2.cu), byte-exact as they sit in
       // shared memory: canonical K-major no-swizzle UMMA tiles, element (row, k) of an image
       // with K columns at  (row/8)*SBO + (k/8)*128 + (row%8)*16 + (k%8)*2,  SBO = (K/8)*128.
       // Row / column order: 16c + j = Re (j < 8) or Im (j >= 8) of item 8c + (j % 8).
       pgw::Tc2Params& t = env->tc2;
-      const int nch = (nb + 7) / 8, N = 16 * nch, NBP = 8 * nch;
+      const int nch = pgw::tc2_padded_chunks((nb + 7) / 8), N = 16 * nch, NBP = 8 * nch;
       const int ncc = (nn + NBP - 1) / NBP;
       const size_t sbo = (size_t)(N / 8) * 128, part = (size_t)(N / 8) * sbo;
       auto pos = [](int item, bool im) { return 16 * (item / 8) + (item % 8) + (im ? 8 : 0); };
@@ -443,17 +443,20 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       t.tol = (float)(f.tol > 1e-7 ? f.tol : 1e-7);
       t.tmem_cols = 32;
       while (t.tmem_cols < 2 * N) t.tmem_cols *= 2;
-      std::vector<float> u0f(2 * NBP, 0.f), vl2(NBP, 1.f), vh2(NBP, 1.f), shf(NBP, 0.f), wf(2 * (size_t)nn, 0.f);
-      std::vector<int32_t> m5(NBP, 0), blp(NBP, 0), lptr(f.nl + 1, 0), lidx(env->A, 0), node(env->A);
-      for (int k = 0; k < NBP; ++k) u0f[2 * k] = 1.f;
+      // cst = {Re u0, Im u0, vlo^2, vhi^2}, gh = (1, 0) -> 1/clamp(|u|^2), (0, 1) -> 1/|u| (model 5)
+      std::vector<float> cst(4 * (size_t)NBP, 1.f), gh(2 * (size_t)NBP, 0.f), shf(NBP, 0.f), wf(2 * (size_t)nn, 0.f);
+      std::vector<int32_t> blp(NBP, 0), bag(NBP, -1), lptr(f.nl + 1, 0), lidx(env->A, 0), node(env->A);
+      for (int k = 0; k < NBP; ++k) { cst[4 * k + 1] = 0.f; gh[2 * k] = 1.f; }
       for (int k = 0; k < nb; ++k) {
-        u0f[2 * k] = (float)f.u0[2 * k]; u0f[2 * k + 1] = (float)f.u0[2 * k + 1];
-        if (f.branch_model[k] != 2) {
-          vl2[k] = (float)(f.vminpu[k] * f.vminpu[k]); vh2[k] = (float)(f.vmaxpu[k] * f.vmaxpu[k]);
+        cst[4 * k] = (float)f.u0[2 * k]; cst[4 * k + 1] = (float)f.u0[2 * k + 1];
+        if (f.branch_model[k] == 5) {
+          cst[4 * k + 2] = 1e-30f; cst[4 * k + 3] = 3e38f; gh[2 * k] = 0.f; gh[2 * k + 1] = 1.f;
+          t.any_m5 = 1;
+        } else if (f.branch_model[k] != 2) {
+          cst[4 * k + 2] = (float)(f.vminpu[k] * f.vminpu[k]);
+          cst[4 * k + 3] = (float)(f.vmaxpu[k] * f.vmaxpu[k]);
         }
         shf[k] = (float)(f.branch_share[k] * 1e-3);
-        m5[k] = f.branch_model[k] == 5 ? 1 : 0;
-        if (m5[k]) t.any_m5 = 1;
         blp[k] = f.branch_load[k];
       }
       for (int n = 0; n < nn; ++n) { wf[2 * n] = (float)f.w[2 * n]; wf[2 * n + 1] = (float)f.w[2 * n + 1]; }
@@ -473,12 +476,15 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
         if (bytes) memcpy(blob.data() + off, src, bytes);
         return (int)(off - (size_t)t.off_tab);
       };
-      t.t_u0 = put(u0f.data(), u0f.size() * 4);
-      t.t_vlo2 = put(vl2.data(), vl2.size() * 4);
-      t.t_vhi2 = put(vh2.data(), vh2.size() * 4);
+      for (int k = 0; k < nb; ++k) {                  // the one agent on the branch's load, or -2
+        const int l = blp[k], cnt = lptr[l + 1] - lptr[l];
+        bag[k] = cnt == 0 ? -1 : (cnt == 1 ? lidx[lptr[l]] : -2);
+      }
+      t.t_cst = put(cst.data(), cst.size() * 4);
+      t.t_gh = put(gh.data(), gh.size() * 4);
       t.t_share = put(shf.data(), shf.size() * 4);
-      t.t_m5 = put(m5.data(), m5.size() * 4);
       t.t_bload = put(blp.data(), blp.size() * 4);
+      t.t_bagent = put(bag.data(), bag.size() * 4);
       t.t_w = put(wf.data(), wf.size() * 4);
       t.t_lptr = put(lptr.data(), lptr.size() * 4);
       t.t_lidx = put(lidx.data(), lidx.size() * 4);
@@ -589,7 +595,8 @@ int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stre
 static int enqueue_step(pgw_env* env, const double* actions, double* obs, double* rew,
                         uint8_t* done, cudaStream_t s, bool timed) {
   pgw::CompParams cp = comp_params(env);
-  cp.event_mode = 1; cp.advance_clock = env->has_feeder ? 0 : 1;
+  const bool hook = env->has_feeder && env->punit != 0.0;   // power flow finishes the rewards
+  cp.event_mode = 1; cp.advance_clock = env->has_feeder ? 0 : 1; cp.owns_reward = hook ? 0 : 1;
   cp.actions = actions; cp.obs = obs; cp.rew = rew; cp.done = done;
   if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
   PGW_CUDA(pgw::launch_components(cp, smem_for_events(env), s));
@@ -597,6 +604,7 @@ static int enqueue_step(pgw_env* env, const double* actions, double* obs, double
   if (env->has_feeder) {
     pgw::PfParams pf = pf_params(env);
     pf.event_mode = 1; pf.advance_clock = 1; pf.agent_p = env->agent_p; pf.rew = rew;
+    pf.reward_hook = hook ? 1 : 0;
     pf.warm_start = env->warm_start ? 1 : 0;
     PGW_CUDA(launch_pf(env, pf, s));
   }

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(64) component_kernel(const CompParams p) {
         agent_step(ag, comps, io, e, pw, rw);
         p.agent_p[ae] = pw;
         p.rew[ae] = rw;
-        if (p.advance_clock) {                  // no feeder: this kernel owns the reward
+        if (p.owns_reward) {                    // no feeder / no penalty hook: the reward is final
           p.ep_ret[ae] += rw;
           p.rew_copy[ae] = rw;
         }

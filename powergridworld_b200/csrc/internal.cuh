@@ -11,6 +11,7 @@ struct CompParams {
   int E, A;
   int event_mode;          // 0 = reset (event row 0), 1 = step (event row clock+1)
   int advance_clock;       // 1 when this kernel is the last one of the step (no feeder)
+  int owns_reward;         // 1 when no later kernel changes the reward (no feeder / no penalty)
   // static tables, one contiguous 16-byte aligned blob: [agents | comps | dpar | ipar]
   const unsigned char* blob;
   int blob_bytes, off_comps, off_dpar, off_ipar;
@@ -40,7 +41,7 @@ struct CompParams {
 struct Tc2Params {
   const unsigned char* blob;
   int nch, ncc, part_bytes, off_zn, off_tab, tab_bytes, tmem_cols, any_m5;
-  int t_u0, t_vlo2, t_vhi2, t_share, t_m5, t_bload, t_w, t_lptr, t_lidx, t_anode;
+  int t_cst, t_gh, t_share, t_bload, t_bagent, t_w, t_lptr, t_lidx, t_anode;
   float xscale, descale1, descale2, tol;
 };
 
@@ -49,6 +50,8 @@ struct PfParams {
   double tol;
   int event_mode;          // 0 = reset (base load only, event row 0), 1 = step
   int advance_clock;
+  int reward_hook;         // step with a shared voltage penalty: this kernel finishes the rewards
+                           // (rew -= share, rew_copy, ep_ret); otherwise the component kernel did
   int warm_start;          // start from the previous solution kept in u_state
   // static tables, one contiguous 16-byte aligned blob (staged to shared memory by TMA
   // when it fits):  zbbT [nb][nbp] double2 (zbbT[j*nbp+k] = Zbb[k][j]) | u0 [nbp] double2 |
@@ -104,6 +107,7 @@ cudaError_t launch_powerflow(const PfParams& p, cudaStream_t s);
 cudaError_t launch_powerflow_tc(const PfParams& p, cudaStream_t s);
 cudaError_t launch_powerflow_tc2(const PfParams& p, cudaStream_t s);
 size_t tc2_smem_bytes(const PfParams& p);
+int tc2_padded_chunks(int nch);      // instantiated tile width for nch chunks of 8 branches (0 = none)
 constexpr int kTc2MaxChunks = 11;   // 88 load branches: B and A images fill shared memory
 constexpr int kTcNb = 16;      // branch slots of the tensor-core kernel (IEEE-13 class feeders)
 constexpr int kTcK3 = 96;      // 3 x 32: [x_hi | x_lo | x_hi] against [B_hi ; B_hi ; B_lo]

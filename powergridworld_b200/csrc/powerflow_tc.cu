@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) pf_tc_kernel(const PfParams p) 
         const int node = anode[a];
         const size_t ae = (size_t)a * p.E + e;
         p.vbus[ae] = node >= 0 ? p.vmag[(size_t)node * p.E + e] : 1.0;
-        if (p.event_mode != 0) {
+        if (p.reward_hook) {
           const double r = p.rew[ae] - pen_share;
           p.rew[ae] = r;
           p.rew_copy[ae] = r;

@@ -35,7 +35,6 @@ namespace pgw {
 
 constexpr int T2_M = 128;
 constexpr int T2_THREADS = 512;
-constexpr int T2_SLOTS = 3;                 // chunks per thread: c = grp + 4 * slot
 
 __device__ __forceinline__ uint64_t t2_smem_desc(uint32_t saddr, uint32_t sbo) {
   // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
@@ -103,6 +102,24 @@ __device__ __forceinline__ uint32_t t2_pack(float a, float b) {
   return r;
 }
 
+__device__ __forceinline__ float t2_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ bool t2_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // hi / lo FP16 images of 8 scaled values as two 16-byte vectors
 __device__ __forceinline__ void t2_split8(const float (&x)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
@@ -116,21 +133,41 @@ __device__ __forceinline__ void t2_split8(const float (&x)[8], uint4& hi, uint4&
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Per-branch constants (shared memory, read as warp-uniform broadcasts):
+//   cst[k] = {Re u0, Im u0, vlo^2, vhi^2}: current = conj(s) u / clamp(|u|^2, vlo^2, vhi^2), i.e.
+//            constant PQ inside the band and constant Z outside (OpenDSS model 1); a constant-Z
+//            load (model 2) is the degenerate band [1, 1]; a constant-current load (model 5) has
+//            the open band [1e-30, 3e38] and
+//   gh[k]  = {g, h}: k = r (r g + h) with r = rsqrt(clamp): (1, 0) -> 1/clamp, (0, 1) -> 1/|u|.
+template <bool ANY_M5>
+__device__ __forceinline__ void t2_current(float4 c, float2 gh, float dr, float di, float ds,
+                                           float sr, float si, float& x, float& y) {
+  const float ur = fmaf(dr, ds, c.x), ui = fmaf(di, ds, c.y);
+  const float m2 = fmaf(ur, ur, ui * ui);
+  const float r = t2_rsqrt(fminf(fmaxf(m2, c.z), c.w));
+  const float kf = ANY_M5 ? r * fmaf(r, gh.x, gh.y) : r * r;
+  const float tr = ur * kf, ti = ui * kf;
+  x = fmaf(sr, tr, si * ti);                           // conj(s) u k
+  y = fmaf(sr, ti, -(si * tr));
+}
+
+template <int NCH, bool ANY_M5>
 __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p) {
+  constexpr int SLOTS = (NCH + 3) / 4;                 // chunks per thread: c = grp + 4 * slot
+  constexpr int N = 16 * NCH;
+  constexpr uint32_t SBO = 256u * NCH;                 // bytes between 8-row groups
+  constexpr uint32_t PB = (uint32_t)(N / 8) * SBO;     // one B image: N rows
+  constexpr uint32_t APB = 16u * SBO;                  // one A image: 128 rows
   extern __shared__ __align__(1024) unsigned char t2_smem[];
   __shared__ __align__(8) uint64_t mbar_tab, mbar_b, mbar_mma;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_dpart[2][4][T2_M];                // per-group partial max |d drop|, 2 phases
   float (*s_vmn)[T2_M] = s_dpart[0], (*s_vmx)[T2_M] = s_dpart[1];   // reused after the solve
   const Tc2Params& t = p.tc2;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // provably warp-uniform
   const int row = tid & (T2_M - 1);                    // env row in the tile = TMEM lane
-  const int grp = tid >> 7;                            // chunk group 0..3
-  const int nch = t.nch;
-  const int N = 16 * nch;
-  const uint32_t sbo = 256u * (uint32_t)nch;           // bytes between 8-row groups
-  const uint32_t PB = (uint32_t)t.part_bytes;          // one B image: N rows
-  const uint32_t APB = 16u * sbo;                      // one A image: 128 rows
+  const int grp = warp >> 2;                           // chunk group 0..3
   const int hdr = 2 + 2 * p.nl;
 
   unsigned char* sB = t2_smem;                         // B_hi | B_lo (iteration) or a Znb chunk
@@ -162,12 +199,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
   const uint32_t tmem = tmem_base_s;
   mbar_wait(&mbar_tab, 0);
 
-  const float2* u0f = reinterpret_cast<const float2*>(sT + t.t_u0);
-  const float* vlo2 = reinterpret_cast<const float*>(sT + t.t_vlo2);
-  const float* vhi2 = reinterpret_cast<const float*>(sT + t.t_vhi2);
+  const float4* cst = reinterpret_cast<const float4*>(sT + t.t_cst);
+  const float2* ghp = reinterpret_cast<const float2*>(sT + t.t_gh);
   const float* share = reinterpret_cast<const float*>(sT + t.t_share);
-  const int32_t* m5 = reinterpret_cast<const int32_t*>(sT + t.t_m5);
   const int32_t* bload = reinterpret_cast<const int32_t*>(sT + t.t_bload);
+  const int32_t* bagent = reinterpret_cast<const int32_t*>(sT + t.t_bagent);
   const float2* wf = reinterpret_cast<const float2*>(sT + t.t_w);
   const int32_t* lptr = reinterpret_cast<const int32_t*>(sT + t.t_lptr);
   const int32_t* lidx = reinterpret_cast<const int32_t*>(sT + t.t_lidx);
@@ -176,25 +212,41 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
   const double* base_kvar = drow + 2 + p.nl;
 
   const uint32_t idesc = t2_idesc_f16(N);
-  const uint64_t a_hi = t2_smem_desc(smem_u32(sA), sbo), a_lo = t2_smem_desc(smem_u32(sA + APB), sbo);
-  const uint64_t b_hi = t2_smem_desc(smem_u32(sB), sbo), b_lo = t2_smem_desc(smem_u32(sB + PB), sbo);
+  const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
   // this thread's 16-byte Re slot of chunk 0 in A_hi; chunk c is +256 c, Im +128, A_lo +APB
-  unsigned char* a_row = sA + (size_t)(row >> 3) * sbo + (size_t)(row & 7) * 16;
+  unsigned char* a_row = sA + (size_t)(row >> 3) * SBO + (size_t)(row & 7) * 16;
   const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // lane quadrant of this warp
   const float xs = t.xscale, ds1 = t.descale1, ds2 = t.descale2;
   const float tol_s = t.tol / ds1;                     // tolerance in accumulator units
-  uint32_t mma_phase = 0, b_phase = 0;                 // b_phase is tracked by thread 0 only
+  uint32_t mma_phase = 0, b_phase = 0;                 // b_phase is used by the MMA issuer only
 
-  // One accumulation chain D = A_lo B_hi + A_hi B_lo + A_hi B_hi (small terms first).
-  auto issue_chain = [&](uint32_t d_col) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int kk = 0; kk < nch; ++kk)
-      t2_umma_f16(tmem + d_col, a_lo + 16u * kk, b_hi + 16u * kk, idesc, kk > 0 ? 1u : 0u);
-    for (int kk = 0; kk < nch; ++kk)
-      t2_umma_f16(tmem + d_col, a_hi + 16u * kk, b_lo + 16u * kk, idesc, 1u);
-    for (int kk = 0; kk < nch; ++kk)
-      t2_umma_f16(tmem + d_col, a_hi + 16u * kk, b_hi + 16u * kk, idesc, 1u);
-    t2_commit(&mbar_mma);
+  // One accumulation chain D = A_lo B_hi + A_hi B_lo + A_hi B_hi (small terms first), issued by
+  // one elected lane of warp 0; all operands are warp-uniform (uniform registers in SASS).
+  auto issue_chain = [&](uint32_t d_col, bool wait_b) {
+    if (warp == 0) {
+      if (t2_elect_one()) {
+        if (wait_b) mbar_wait(&mbar_b, b_phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t a_hi = t2_smem_desc(sA_u, SBO), a_lo = t2_smem_desc(sA_u + APB, SBO);
+        const uint64_t b_hi = t2_smem_desc(sB_u, SBO), b_lo = t2_smem_desc(sB_u + PB, SBO);
+#pragma unroll
+        for (int kk = 0; kk < NCH; ++kk)
+          t2_umma_f16(tmem + d_col, a_lo + 16u * kk, b_hi + 16u * kk, idesc, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < NCH; ++kk)
+          t2_umma_f16(tmem + d_col, a_hi + 16u * kk, b_lo + 16u * kk, idesc, 1u);
+#pragma unroll
+        for (int kk = 0; kk < NCH; ++kk)
+          t2_umma_f16(tmem + d_col, a_hi + 16u * kk, b_hi + 16u * kk, idesc, 1u);
+        t2_commit(&mbar_mma);
+      }
+      if (wait_b) b_phase ^= 1u;
+      __syncwarp();
+    }
+  };
+  auto load_b = [&](const unsigned char* src) {        // stage two images over sB (thread 0)
+    mbar_expect_tx(&mbar_b, 2 * PB);
+    tma_bulk_g2s(sB, src, 2 * PB, &mbar_b);
   };
 
   const int tiles = (p.E + T2_M - 1) / T2_M;
@@ -204,49 +256,62 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
     const int e = valid ? e_raw : p.E - 1;
     const bool more_tiles = tile + (int)gridDim.x < tiles;
 
-    // ---- nominal power (p.u. on 1 MVA, scaled by xs) of my branches; initial drop into D[1]
-    float sr[T2_SLOTS][8], si[T2_SLOTS][8];
+    // ---- nominal power (p.u. on 1 MVA, scaled by xs) of my branches; initial drop into D[1].
+    //      All global loads of a chunk are issued before any of them is used.
+    float sr[SLOTS][8], si[SLOTS][8];
 #pragma unroll
-    for (int s = 0; s < T2_SLOTS; ++s) {
+    for (int s = 0; s < SLOTS; ++s) {
       const int c = grp + 4 * s;
-      if (c < nch) {
+      if (c < NCH) {
         float d0[16], x[8], y[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = 8 * c + j;
-          sr[s][j] = si[s][j] = 0.f;
-          d0[j] = d0[8 + j] = 0.f;
-          if (k < p.nb) {
-            const int l = bload[k];
-            float kw, kvar;                            // fp32: this solver's working precision
-            if (p.load_kw != nullptr) {
-              kw = (float)p.load_kw[(size_t)l * p.E + e];
-              kvar = (float)p.load_kvar[(size_t)l * p.E + e];
-            } else {
-              double kwd = base_kw[l];
-              kvar = (float)base_kvar[l];
-              if (p.agent_p != nullptr)                // multiagent_env.py:171-181, opendss.py:128
-                for (int q = lptr[l]; q < lptr[l + 1]; ++q)
-                  kwd += p.agent_p[(size_t)lidx[q] * p.E + e];
-              kw = (float)kwd;
-            }
-            const float sh = share[k] * xs;
-            sr[s][j] = kw * sh;
-            si[s][j] = kvar * sh;
-            if (p.warm_start) {
-              const double2 up = p.u_state[(size_t)k * p.E + e];
-              d0[j] = (float)(up.x - (double)u0f[k].x);
-              d0[8 + j] = (float)(up.y - (double)u0f[k].y);
-            }
+        for (int h = 0; h < 8; h += 4) {               // half chunks: 12 loads in flight per thread
+          double kwd[4], kvd[4];
+          double2 up[4];
+          int ld[4], ag[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ld[j] = bload[8 * c + h + j];
+            ag[j] = bagent[8 * c + h + j];
           }
-          const float ur = u0f[k].x + d0[j], ui = u0f[k].y + d0[8 + j];
-          const float m2 = ur * ur + ui * ui;
-          float kf = __fdividef(1.f, fminf(fmaxf(m2, vlo2[k]), vhi2[k]));
-          if (t.any_m5 && m5[k]) kf = m2 > 0.f ? rsqrtf(m2) : 0.f;
-          x[j] = (sr[s][j] * ur + si[s][j] * ui) * kf;
-          y[j] = (sr[s][j] * ui - si[s][j] * ur) * kf;
-          d0[j] *= 1.f / ds1;
-          d0[8 + j] *= 1.f / ds1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = 8 * c + h + j;
+            kwd[j] = 0.0;
+            kvd[j] = 0.0;
+            if (p.load_kw != nullptr) {
+              if (k < p.nb) {
+                kwd[j] = p.load_kw[(size_t)ld[j] * p.E + e];
+                kvd[j] = p.load_kvar[(size_t)ld[j] * p.E + e];
+              }
+            } else if (p.agent_p != nullptr && ag[j] >= 0) {
+              kwd[j] = p.agent_p[(size_t)ag[j] * p.E + e];
+            }
+            up[j] = make_double2((double)cst[k].x, (double)cst[k].y);
+            if (p.warm_start && k < p.nb) up[j] = p.u_state[(size_t)k * p.E + e];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = 8 * c + h + j, jj = h + j;
+            if (p.load_kw == nullptr) {
+              double kw = base_kw[ld[j]];
+              // multiagent_env.py:171-181: P summed per load name in agent order, then added to
+              // the scaled base load (opendss.py:128); ag == -2: several agents on this load
+              if (p.agent_p != nullptr && ag[j] == -2)
+                for (int q = lptr[ld[j]]; q < lptr[ld[j] + 1]; ++q)
+                  kw += p.agent_p[(size_t)lidx[q] * p.E + e];
+              kwd[j] += kw;
+              kvd[j] = base_kvar[ld[j]];
+            }
+            const float sh = share[k] * xs;            // 0 for the padded branches
+            sr[s][jj] = (float)kwd[j] * sh;
+            si[s][jj] = (float)kvd[j] * sh;
+            const float4 cc = cst[k];
+            d0[jj] = (float)(up[j].x - (double)cc.x) * (1.f / ds1);
+            d0[8 + jj] = (float)(up[j].y - (double)cc.y) * (1.f / ds1);
+            t2_current<ANY_M5>(cc, ANY_M5 ? ghp[k] : make_float2(1.f, 0.f), d0[jj], d0[8 + jj], ds1,
+                               sr[s][jj], si[s][jj], x[jj], y[jj]);
+          }
         }
         uint4 hi, lo;
         t2_split8(x, hi, lo);
@@ -267,6 +332,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       s_dpart[it & 1][grp][row] = dpart;
       const int all_done = __syncthreads_and((conv || dpart < tol_s || it >= p.max_iter) ? 1 : 0);
+      if (!all_done) issue_chain((uint32_t)(cur * N), it == 0);      // Zbb images land before it 0
       if (it > 0 && !conv) {                           // per-env convergence mask
         const float d = fmaxf(fmaxf(s_dpart[it & 1][0][row], s_dpart[it & 1][1][row]),
                               fmaxf(s_dpart[it & 1][2][row], s_dpart[it & 1][3][row]));
@@ -276,39 +342,30 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
       }
       if (all_done) break;                             // A = currents at the final u
 
-      if (tid == 0) {
-        if (it == 0) { mbar_wait(&mbar_b, b_phase); b_phase ^= 1u; }     // Zbb images landed
-        issue_chain((uint32_t)(cur * N));
-      }
       mbar_wait(&mbar_mma, mma_phase);
       mma_phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
       dpart = 0.f;
 #pragma unroll
-      for (int s = 0; s < T2_SLOTS; ++s) {
+      for (int s = 0; s < SLOTS; ++s) {
         const int c = grp + 4 * s;
-        if (c < nch) {
+        if (c < NCH) {                                 // warp-uniform: tcgen05.ld is collective
           float dn[16], x[8], y[8];
           {
             float dold[16];
             t2_ld16(t_lane + cur * N + 16 * c, dn);
             t2_ld16(t_lane + (cur ^ 1) * N + 16 * c, dold);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dpart = fmaxf(dpart, fabsf(dn[j] - dold[j]));
+            for (int j = 0; j < 16; j += 2)
+              dpart = fmaxf(dpart, fmaxf(fabsf(dn[j] - dold[j]), fabsf(dn[j + 1] - dold[j + 1])));
           }
           if (!conv) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int k = 8 * c + j;
-              const float ur = fmaf(dn[j], ds1, u0f[k].x), ui = fmaf(dn[8 + j], ds1, u0f[k].y);
-              const float m2 = ur * ur + ui * ui;
-              // constant PQ inside the band, constant Z outside = 1 / clamp(|u|^2, vlo^2, vhi^2);
-              // a constant-Z load is the degenerate band [1, 1]
-              float kf = __fdividef(1.f, fminf(fmaxf(m2, vlo2[k]), vhi2[k]));
-              if (t.any_m5 && m5[k]) kf = m2 > 0.f ? rsqrtf(m2) : 0.f;
-              x[j] = (sr[s][j] * ur + si[s][j] * ui) * kf;       // conj(s) u k
-              y[j] = (sr[s][j] * ui - si[s][j] * ur) * kf;
+              t2_current<ANY_M5>(cst[k], ANY_M5 ? ghp[k] : make_float2(1.f, 0.f), dn[j], dn[8 + j],
+                                 ds1, sr[s][j], si[s][j], x[j], y[j]);
             }
             uint4 hi, lo;
             t2_split8(x, hi, lo);
@@ -326,14 +383,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
     const int last = cur ^ 1;                          // D[last] = final drop
 
     // ---- expansion to all node voltages, Znb row chunks streamed over the B images
-    if (tid == 0) {
-      mbar_expect_tx(&mbar_b, 2 * PB);
-      tma_bulk_g2s(sB, t.blob + t.off_zn, 2 * PB, &mbar_b);
-    }
+    if (tid == 0) load_b(t.blob + t.off_zn);
 #pragma unroll
-    for (int s = 0; s < T2_SLOTS; ++s) {
+    for (int s = 0; s < SLOTS; ++s) {
       const int c = grp + 4 * s;
-      if (c < nch) {                                   // warp-uniform: tcgen05.ld is collective
+      if (c < NCH) {
         float dn[16];
         t2_ld16(t_lane + last * N + 16 * c, dn);
 #pragma unroll
@@ -341,8 +395,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
           const int k = 8 * c + j;
           if (valid && k < p.nb)
             p.u_state[(size_t)k * p.E + e] =
-                make_double2((double)u0f[k].x + (double)(dn[j] * ds1),
-                             (double)u0f[k].y + (double)(dn[8 + j] * ds1));
+                make_double2((double)cst[k].x + (double)(dn[j] * ds1),
+                             (double)cst[k].y + (double)(dn[8 + j] * ds1));
         }
       }
     }
@@ -352,24 +406,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
     float vmn = 3.0e38f, vmx = -3.0e38f;
     for (int cc = 0; cc < t.ncc; ++cc) {
       const int dsel = (cur + cc) & 1;
-      if (tid == 0) {
-        mbar_wait(&mbar_b, b_phase);
-        b_phase ^= 1u;
-        issue_chain((uint32_t)(dsel * N));
-      }
+      issue_chain((uint32_t)(dsel * N), true);
       mbar_wait(&mbar_mma, mma_phase);
       mma_phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (tid == 0 && (cc + 1 < t.ncc || more_tiles)) {               // the B images are free again
-        mbar_expect_tx(&mbar_b, 2 * PB);
-        tma_bulk_g2s(sB, cc + 1 < t.ncc ? t.blob + t.off_zn + (size_t)(cc + 1) * 2 * PB : t.blob,
-                     2 * PB, &mbar_b);
-      }
+      if (tid == 0 && (cc + 1 < t.ncc || more_tiles))  // the B images are free again
+        load_b(cc + 1 < t.ncc ? t.blob + t.off_zn + (size_t)(cc + 1) * 2 * PB : t.blob);
 #pragma unroll
-      for (int s = 0; s < T2_SLOTS; ++s) {
+      for (int s = 0; s < SLOTS; ++s) {
         const int c = grp + 4 * s;
-        if (c < nch) {
-          const int n0 = 8 * (cc * nch + c);
+        if (c < NCH) {
+          const int n0 = 8 * (cc * NCH + c);
           if (n0 < p.nn) {
             float v[16];
             t2_ld16(t_lane + dsel * N + 16 * c, v);
@@ -378,7 +425,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
               const int n = n0 + j;
               if (n < p.nn) {
                 const float vr = fmaf(v[j], ds2, wf[n].x), vi = fmaf(v[8 + j], ds2, wf[n].y);
-                const float mag = __fsqrt_rn(vr * vr + vi * vi);
+                const float m2 = fmaf(vr, vr, vi * vi);
+                const float mag = m2 * t2_rsqrt(fmaxf(m2, 1e-30f));
                 vmn = fminf(vmn, mag);
                 vmx = fmaxf(vmx, mag);
                 if (valid) p.vmag[(size_t)n * p.E + e] = (double)mag;
@@ -407,15 +455,34 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
         pen_share = (viol * p.punit) / (double)p.A;
       }
       if (grp == 0) p.viol[e] = viol;
-      for (int a = grp; a < p.A; a += 4) {
-        const int node = anode[a];
-        const size_t ae = (size_t)a * p.E + e;
-        p.vbus[ae] = node >= 0 ? p.vmag[(size_t)node * p.E + e] : 1.0;
-        if (p.event_mode != 0) {
-          const double r = p.rew[ae] - pen_share;
-          p.rew[ae] = r;
-          p.rew_copy[ae] = r;
-          p.ep_ret[ae] += r;
+      // agents a = grp, grp + 4, ...: batches of 4 so that the loads of a batch are in flight
+      // together (rew / ep_ret may alias as far as the compiler knows)
+      for (int a0 = grp; a0 < p.A; a0 += 16) {
+        double vb[4], rw[4], er[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int a = a0 + 4 * q;
+          vb[q] = 1.0; rw[q] = 0.0; er[q] = 0.0;
+          if (a < p.A) {
+            const int node = anode[a];
+            const size_t ae = (size_t)a * p.E + e;
+            if (node >= 0) vb[q] = p.vmag[(size_t)node * p.E + e];
+            if (p.reward_hook) { rw[q] = p.rew[ae]; er[q] = p.ep_ret[ae]; }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int a = a0 + 4 * q;
+          if (a < p.A) {
+            const size_t ae = (size_t)a * p.E + e;
+            p.vbus[ae] = vb[q];
+            if (p.reward_hook) {
+              const double r = rw[q] - pen_share;
+              p.rew[ae] = r;
+              p.rew_copy[ae] = r;
+              p.ep_ret[ae] = er[q] + r;
+            }
+          }
         }
       }
     }
@@ -435,16 +502,31 @@ size_t tc2_smem_bytes(const PfParams& p) {
          (size_t)(2 + 2 * p.nl) * 8 + 16;
 }
 
+int tc2_padded_chunks(int nch) {            // instantiated tile widths
+  return nch <= 2 ? 2 : nch <= 4 ? 4 : nch <= 8 ? 8 : nch <= 11 ? 11 : 0;
+}
+
+template <int NCH>
+static cudaError_t launch_tc2_t(const PfParams& p, int grid, size_t smem, cudaStream_t s) {
+  auto kern = p.tc2.any_m5 ? pf_tc2_kernel<NCH, true> : pf_tc2_kernel<NCH, false>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  kern<<<grid, T2_THREADS, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_powerflow_tc2(const PfParams& p, cudaStream_t s) {
   const int tiles = (p.E + T2_M - 1) / T2_M;
   int grid = tiles < 148 ? tiles : 148;
   if (grid < 1) grid = 1;
   const size_t smem = tc2_smem_bytes(p);
-  cudaError_t err = cudaFuncSetAttribute(pf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-  if (err != cudaSuccess) return err;
-  pf_tc2_kernel<<<grid, T2_THREADS, smem, s>>>(p);
-  return cudaGetLastError();
+  switch (p.tc2.nch) {
+    case 2: return launch_tc2_t<2>(p, grid, smem, s);
+    case 4: return launch_tc2_t<4>(p, grid, smem, s);
+    case 8: return launch_tc2_t<8>(p, grid, smem, s);
+    case 11: return launch_tc2_t<11>(p, grid, smem, s);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace pgw

@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -71,6 +72,8 @@ struct pgw_env {
   // device tables
   unsigned char* comp_blob = nullptr;   // [agents | comps | dpar | ipar]
   int comp_blob_bytes = 0, off_comps = 0, off_dpar = 0, off_ipar = 0;
+  pgw::AgentSlice* slices = nullptr;    // per-agent staging ranges
+  int max_cn = 0, max_dn = 0, max_in = 0;
   double* dtab = nullptr;
   int32_t* itab = nullptr;
   unsigned char* pf_blob = nullptr;     // feeder tables, layout in internal.cuh
@@ -214,7 +217,45 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
     if (b_dp) memcpy(blob.data() + env->off_dpar, spec->dpar, b_dp);
     if (b_ip) memcpy(blob.data() + env->off_ipar, spec->ipar, b_ip);
     PGW_TRY(upload(&env->comp_blob, blob.data(), blob.size())); env->own(env->comp_blob);
-    if (env->comp_blob_bytes + spec->dtab_stride * 8 + spec->itab_stride * 4 > 200 * 1024) {
+    // per-agent slices: components [begin, end), and the span of their parameter blocks (a
+    // block ends where the next larger offset of any component starts)
+    std::vector<int> dstart, istart;
+    for (int c = 0; c < env->C; ++c) {
+      dstart.push_back(spec->components[c].dpar_off);
+      istart.push_back(spec->components[c].ipar_off);
+    }
+    dstart.push_back(spec->dpar_len); istart.push_back(spec->ipar_len);
+    std::sort(dstart.begin(), dstart.end()); std::sort(istart.begin(), istart.end());
+    auto block_end = [](const std::vector<int>& starts, int off) {
+      return *std::upper_bound(starts.begin(), starts.end(), off);
+    };
+    std::vector<pgw::AgentSlice> sl(env->A);
+    for (int a = 0; a < env->A; ++a) {
+      const pgw_agent& ag = spec->agents[a];
+      int dlo = spec->dpar_len, dhi = 0, ilo = spec->ipar_len, ihi = 0;
+      for (int c = ag.comp_begin; c < ag.comp_end; ++c) {
+        const pgw_component& k = spec->components[c];
+        if (k.dpar_off < spec->dpar_len) {
+          dlo = std::min(dlo, k.dpar_off); dhi = std::max(dhi, block_end(dstart, k.dpar_off));
+        }
+        if (k.ipar_off < spec->ipar_len) {
+          ilo = std::min(ilo, k.ipar_off); ihi = std::max(ihi, block_end(istart, k.ipar_off));
+        }
+      }
+      if (dhi <= dlo) dlo = dhi = 0;
+      if (ihi <= ilo) ilo = ihi = 0;
+      pgw::AgentSlice& s = sl[a];
+      s.c_lo = ag.comp_begin; s.c_n = ag.comp_end - ag.comp_begin;
+      s.d_lo = dlo / 2 * 2; s.d_n = round_up(dhi - s.d_lo, 2);
+      s.i_lo = ilo / 4 * 4; s.i_n = round_up(ihi - s.i_lo, 4);
+      s.pad0 = s.pad1 = 0;
+      env->max_cn = std::max(env->max_cn, s.c_n);
+      env->max_dn = std::max(env->max_dn, s.d_n);
+      env->max_in = std::max(env->max_in, s.i_n);
+    }
+    PGW_TRY(upload(&env->slices, sl.data(), sl.size())); env->own(env->slices);
+    if (env->max_cn * (int)sizeof(pgw_component) + env->max_dn * 8 + env->max_in * 4 +
+            spec->dtab_stride * 8 + spec->itab_stride * 4 > 160 * 1024) {
       delete env;
       return fail(PGW_ERR_INVALID, "scenario tables exceed the shared-memory staging budget");
     }
@@ -394,11 +435,41 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       // Row / column order: 16c + j = Re (j < 8) or Im (j >= 8) of item 8c + (j % 8).
       pgw::Tc2Params& t = env->tc2;
       const int nch = pgw::tc2_padded_chunks((nb + 7) / 8), N = 16 * nch, NBP = 8 * nch;
-      const int ncc = (nn + NBP - 1) / NBP;
       const size_t sbo = (size_t)(N / 8) * 128, part = (size_t)(N / 8) * sbo;
       auto pos = [](int item, bool im) { return 16 * (item / 8) + (item % 8) + (im ? 8 : 0); };
       auto Z = [&](int k, int j) { return make_double2(f.zbb[2 * ((size_t)k * nb + j)], f.zbb[2 * ((size_t)k * nb + j) + 1]); };
       auto ZN = [&](int n, int k) { return make_double2(f.znb[2 * ((size_t)n * nb + k)], f.znb[2 * ((size_t)n * nb + k) + 1]); };
+      // Nodes whose voltage IS a load-branch voltage up to a real factor c (a wye load between
+      // the node and ground: row n of Znb = c x row k of Zbb and w[n] = c u0[k], c = the ratio
+      // of the two voltage bases) need no expansion: |v_n| = c |u_k|.
+      std::vector<int32_t> dnode(NBP, -1), xnode;
+      std::vector<float> dscale(NBP, 0.f);
+      {
+        std::vector<char> taken(nb, 0);
+        for (int n = 0; n < nn; ++n) {
+          int hit = -1;
+          double cr = 0.0;
+          for (int k = 0; k < nb && hit < 0; ++k) {
+            if (taken[k]) continue;
+            const double ur = f.u0[2 * k], ui = f.u0[2 * k + 1], wr = f.w[2 * n], wi = f.w[2 * n + 1];
+            const double den = ur * ur + ui * ui;
+            if (den <= 0.0) continue;
+            const double c = (wr * ur + wi * ui) / den;
+            if (!(c > 0.0)) continue;
+            double err = std::hypot(wr - c * ur, wi - c * ui), ref = std::hypot(wr, wi);
+            for (int j = 0; j < nb; ++j) {
+              const double2 a = ZN(n, j), b = Z(k, j);
+              err = std::fmax(err, std::hypot(a.x - c * b.x, a.y - c * b.y));
+              ref = std::fmax(ref, std::hypot(a.x, a.y));
+            }
+            if (err <= 1e-10 * ref) { hit = k; cr = c; }
+          }
+          if (hit >= 0) { taken[hit] = 1; dnode[hit] = n; dscale[hit] = (float)cr; }
+          else xnode.push_back(n);
+        }
+      }
+      const int nx = (int)xnode.size(), ncc = (nx + NBP - 1) / NBP;
+      xnode.resize((size_t)std::max(ncc, 1) * NBP, -1);
       // real-ified operator rows:  D[pos(out)] = sum_k X[pos(k)] * M[pos(out)][pos(k)]
       auto realify = [&](int rows_items, int item0, int nitems, auto&& zget) {
         std::vector<double> m((size_t)N * N, 0.0);
@@ -436,15 +507,16 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       std::vector<unsigned char> blob((size_t)(1 + ncc) * 2 * part, 0);
       images(realify(NBP, 0, nb, Z), sb1, blob.data());
       for (int cc = 0; cc < ncc; ++cc)
-        images(realify(NBP, cc * NBP, nn, ZN), sb2, blob.data() + (size_t)(1 + cc) * 2 * part);
-      t.nch = nch; t.ncc = ncc; t.part_bytes = (int)part; t.off_zn = (int)(2 * part);
+        images(realify(NBP, cc * NBP, nx, [&](int slot, int k) { return ZN(xnode[slot], k); }), sb2,
+               blob.data() + (size_t)(1 + cc) * 2 * part);
+      t.nch = nch; t.ncc = ncc; t.nx = nx; t.part_bytes = (int)part; t.off_zn = (int)(2 * part);
       t.off_tab = (int)blob.size();
       t.xscale = (float)xs; t.descale1 = (float)(1.0 / (sb1 * xs)); t.descale2 = (float)(1.0 / (sb2 * xs));
       t.tol = (float)(f.tol > 1e-7 ? f.tol : 1e-7);
       t.tmem_cols = 32;
       while (t.tmem_cols < 2 * N) t.tmem_cols *= 2;
       // cst = {Re u0, Im u0, vlo^2, vhi^2}, gh = (1, 0) -> 1/clamp(|u|^2), (0, 1) -> 1/|u| (model 5)
-      std::vector<float> cst(4 * (size_t)NBP, 1.f), gh(2 * (size_t)NBP, 0.f), shf(NBP, 0.f), wf(2 * (size_t)nn, 0.f);
+      std::vector<float> cst(4 * (size_t)NBP, 1.f), gh(2 * (size_t)NBP, 0.f), shf(NBP, 0.f), wf(2 * xnode.size(), 0.f);
       std::vector<int32_t> blp(NBP, 0), bag(NBP, -1), lptr(f.nl + 1, 0), lidx(env->A, 0), node(env->A);
       for (int k = 0; k < NBP; ++k) { cst[4 * k + 1] = 0.f; gh[2 * k] = 1.f; }
       for (int k = 0; k < nb; ++k) {
@@ -459,7 +531,9 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
         shf[k] = (float)(f.branch_share[k] * 1e-3);
         blp[k] = f.branch_load[k];
       }
-      for (int n = 0; n < nn; ++n) { wf[2 * n] = (float)f.w[2 * n]; wf[2 * n + 1] = (float)f.w[2 * n + 1]; }
+      for (int sidx = 0; sidx < nx; ++sidx) {
+        wf[2 * sidx] = (float)f.w[2 * xnode[sidx]]; wf[2 * sidx + 1] = (float)f.w[2 * xnode[sidx] + 1];
+      }
       for (int a = 0; a < env->A; ++a) {
         node[a] = spec->agents[a].bus_node;
         if (spec->agents[a].load_slot >= 0) ++lptr[spec->agents[a].load_slot + 1];
@@ -486,6 +560,9 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       t.t_bload = put(blp.data(), blp.size() * 4);
       t.t_bagent = put(bag.data(), bag.size() * 4);
       t.t_w = put(wf.data(), wf.size() * 4);
+      t.t_xnode = put(xnode.data(), xnode.size() * 4);
+      t.t_dnode = put(dnode.data(), dnode.size() * 4);
+      t.t_dscale = put(dscale.data(), dscale.size() * 4);
       t.t_lptr = put(lptr.data(), lptr.size() * 4);
       t.t_lidx = put(lidx.data(), lidx.size() * 4);
       t.t_anode = put(node.data(), node.size() * 4);
@@ -526,6 +603,7 @@ static pgw::CompParams comp_params(pgw_env* env) {
   p.E = env->E; p.A = env->A;
   p.blob = env->comp_blob; p.blob_bytes = env->comp_blob_bytes;
   p.off_comps = env->off_comps; p.off_dpar = env->off_dpar; p.off_ipar = env->off_ipar;
+  p.slices = env->slices; p.max_cn = env->max_cn; p.max_dn = env->max_dn; p.max_in = env->max_in;
   p.dtab = env->dtab; p.itab = env->itab; p.dstride = env->dstride; p.istride = env->istride;
   p.sd = env->sd; p.si = env->si; p.rew_copy = env->rew_last;
   p.vmin = env->vmin; p.vmax = env->vmax; p.vbus = env->vbus;
@@ -567,7 +645,8 @@ static cudaError_t launch_pf(const pgw_env* env, const pgw::PfParams& pf, cudaSt
 static int smem_for_events(const pgw_env* env, bool reset = false) {
   // static blob | event rows | per-thread scratch (component_math.cuh kScratchDoubles x 64
   // threads; only the table-driven building path uses it)
-  return env->comp_blob_bytes + env->dstride * 8 + env->istride * 4 +
+  return env->max_cn * (int)sizeof(pgw_component) + env->max_dn * 8 + env->max_in * 4 +
+         env->dstride * 8 + env->istride * 4 +
          ((reset ? env->need_scratch_reset : env->need_scratch) ? 35 * 64 * 8 : 0);
 }
 

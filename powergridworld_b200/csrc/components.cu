@@ -18,37 +18,48 @@
 
 namespace pgw {
 
-__global__ void __launch_bounds__(64) component_kernel(const CompParams p) {
+__global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t mbar[2];
-  __shared__ int s_event;
-  unsigned char* s_blob = smem_raw;
-  double* drow = reinterpret_cast<double*>(smem_raw + p.blob_bytes);
-  int32_t* irow = reinterpret_cast<int32_t*>(smem_raw + p.blob_bytes + (size_t)p.dstride * 8);
+  // [comps slice | dpar slice | ipar slice | double event row | int event row | scratch]
+  const size_t b_comps = (size_t)p.max_cn * sizeof(pgw_component);
+  const size_t b_dpar = (size_t)p.max_dn * 8, b_ipar = (size_t)p.max_in * 4;
+  pgw_component* s_comps = reinterpret_cast<pgw_component*>(smem_raw);
+  double* s_dpar = reinterpret_cast<double*>(smem_raw + b_comps);
+  int32_t* s_ipar = reinterpret_cast<int32_t*>(smem_raw + b_comps + b_dpar);
+  const size_t static_bytes = b_comps + b_dpar + b_ipar;
+  double* drow = reinterpret_cast<double*>(smem_raw + static_bytes);
+  int32_t* irow = reinterpret_cast<int32_t*>(smem_raw + static_bytes + (size_t)p.dstride * 8);
   double* scratch = reinterpret_cast<double*>(
-      smem_raw + p.blob_bytes + (size_t)p.dstride * 8 + (size_t)p.istride * 4);
+      smem_raw + static_bytes + (size_t)p.dstride * 8 + (size_t)p.istride * 4);
 
+  // the three independent global reads of the prologue, issued back to back
+  const int a = blockIdx.y;
+  const AgentSlice sl = p.slices[a];
+  const pgw_agent ag = reinterpret_cast<const pgw_agent*>(p.blob)[a];
+  const int ev = p.event_mode == 0 ? 0 : (*p.clock + 1);
   // Two staging phases so that the latency of reading the device clock (which selects the
   // event row) overlaps the copy of the static tables and the threads' own prefetches.
+  // A CTA serves one agent, so only that agent's slice of the tables is staged.
   if (threadIdx.x == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
-    mbar_expect_tx(&mbar[0], (uint32_t)p.blob_bytes);
-    tma_bulk_g2s(s_blob, p.blob, (uint32_t)p.blob_bytes, &mbar[0]);
-    const int ev = p.event_mode == 0 ? 0 : (*p.clock + 1);
+    const uint32_t cb = (uint32_t)sl.c_n * (uint32_t)sizeof(pgw_component);
+    const uint32_t db = (uint32_t)sl.d_n * 8u, ib = (uint32_t)sl.i_n * 4u;
+    mbar_expect_tx(&mbar[0], cb + db + ib);
+    tma_bulk_g2s(s_comps, p.blob + p.off_comps + (size_t)sl.c_lo * sizeof(pgw_component), cb, &mbar[0]);
+    if (db) tma_bulk_g2s(s_dpar, p.blob + p.off_dpar + (size_t)sl.d_lo * 8, db, &mbar[0]);
+    if (ib) tma_bulk_g2s(s_ipar, p.blob + p.off_ipar + (size_t)sl.i_lo * 4, ib, &mbar[0]);
     const uint32_t dbytes = (uint32_t)p.dstride * 8u, ibytes = (uint32_t)p.istride * 4u;
     mbar_expect_tx(&mbar[1], dbytes + ibytes);
     tma_bulk_g2s(drow, p.dtab + (size_t)ev * p.dstride, dbytes, &mbar[1]);
     if (ibytes) tma_bulk_g2s(irow, p.itab + (size_t)ev * p.istride, ibytes, &mbar[1]);
-    s_event = ev;
   }
   __syncthreads();
   mbar_wait(&mbar[0], 0);
 
-  const int a = blockIdx.y;
-  const int event = s_event;
-  const pgw_agent ag = reinterpret_cast<const pgw_agent*>(s_blob)[a];
-  const pgw_component* comps = reinterpret_cast<const pgw_component*>(s_blob + p.off_comps);
+  const int event = ev;
+  const pgw_component* comps = s_comps - sl.c_lo;      // indexed by absolute component number
 
   AgentIO io;
   io.scr.p = scratch + threadIdx.x;          // [kScratchDoubles][blockDim.x]: conflict-free
@@ -62,8 +73,8 @@ __global__ void __launch_bounds__(64) component_kernel(const CompParams p) {
   io.vmin = p.vmin;
   io.vmax = p.vmax;
   io.vbus = p.vbus;
-  io.dpar = reinterpret_cast<const double*>(s_blob + p.off_dpar);
-  io.ipar = reinterpret_cast<const int32_t*>(s_blob + p.off_ipar);
+  io.dpar = s_dpar - sl.d_lo;                          // absolute dpar / ipar offsets
+  io.ipar = s_ipar - sl.i_lo;
   io.drow = drow;
   io.irow = irow;
 
@@ -94,12 +105,14 @@ __global__ void __launch_bounds__(64) component_kernel(const CompParams p) {
         p.agent_p[ae] = 0.0;
         p.ep_ret[ae] = 0.0;
       } else {
-        double pw, rw;
+        double pw, rw, er = 0.0;
+        if (p.owns_reward)                      // issued early: its latency hides behind the step
+          asm volatile("ld.global.f64 %0, [%1];" : "=d"(er) : "l"(p.ep_ret + ae));
         agent_step(ag, comps, io, e, pw, rw);
         p.agent_p[ae] = pw;
         p.rew[ae] = rw;
         if (p.owns_reward) {                    // no feeder / no penalty hook: the reward is final
-          p.ep_ret[ae] += rw;
+          p.ep_ret[ae] = er + rw;
           p.rew_copy[ae] = rw;
         }
         if (a == 0) p.done[e] = drow[0] != 0.0 ? 1 : 0;

@@ -7,6 +7,15 @@
 
 namespace pgw {
 
+// The part of the static tables one agent's CTA needs (component descriptors and their
+// parameter blocks), as 16-byte aligned ranges of the blob's comps / dpar / ipar sections.
+struct AgentSlice {
+  int c_lo, c_n;           // components [c_lo, c_lo + c_n)
+  int d_lo, d_n;           // dpar doubles, d_lo and d_n even
+  int i_lo, i_n;           // ipar int32, multiples of 4
+  int pad0, pad1;
+};
+
 struct CompParams {
   int E, A;
   int event_mode;          // 0 = reset (event row 0), 1 = step (event row clock+1)
@@ -15,6 +24,8 @@ struct CompParams {
   // static tables, one contiguous 16-byte aligned blob: [agents | comps | dpar | ipar]
   const unsigned char* blob;
   int blob_bytes, off_comps, off_dpar, off_ipar;
+  const AgentSlice* slices;   // [A] (device)
+  int max_cn, max_dn, max_in; // largest slice of any agent = the CTA's staging area
   const double* dtab;
   const int32_t* itab;
   int dstride, istride;
@@ -40,8 +51,9 @@ struct CompParams {
 // blob: [B_hi | B_lo] (2 x part_bytes) | ncc x [Zn_hi | Zn_lo] at off_zn | tables at off_tab.
 struct Tc2Params {
   const unsigned char* blob;
-  int nch, ncc, part_bytes, off_zn, off_tab, tab_bytes, tmem_cols, any_m5;
-  int t_cst, t_gh, t_share, t_bload, t_bagent, t_w, t_lptr, t_lidx, t_anode;
+  int nch, ncc, nx, part_bytes, off_zn, off_tab, tab_bytes, tmem_cols, any_m5;
+  int t_cst, t_gh, t_share, t_bload, t_bagent, t_w, t_xnode, t_dnode, t_dscale, t_lptr, t_lidx,
+      t_anode;
   float xscale, descale1, descale2, tol;
 };
 

@@ -133,6 +133,15 @@ __device__ __forceinline__ void t2_split8(const float (&x)[8], uint4& hi, uint4&
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Controllable kW of a load that several agents share (multiagent_env.py:171-181: summed per
+// load name in agent order).  Rare, so kept out of line: the prologue is unrolled 24 times.
+__device__ __noinline__ double t2_shared_load_kw(const double* agent_p, const int32_t* lidx, int q0,
+                                                 int q1, int E, int e) {
+  double s = 0.0;
+  for (int q = q0; q < q1; ++q) s += agent_p[(size_t)lidx[q] * E + e];
+  return s;
+}
+
 // Per-branch constants (shared memory, read as warp-uniform broadcasts):
 //   cst[k] = {Re u0, Im u0, vlo^2, vhi^2}: current = conj(s) u / clamp(|u|^2, vlo^2, vhi^2), i.e.
 //            constant PQ inside the band and constant Z outside (OpenDSS model 1); a constant-Z
@@ -186,6 +195,25 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
     mbar_expect_tx(&mbar_b, 2 * PB);
     tma_bulk_g2s(sB, t.blob, 2 * PB, &mbar_b);
   }
+  // Pull the tile's per-env inputs (warm-start voltages, agent powers) towards L2 while the
+  // tables, the operand images and the TMEM allocation are in flight: 32-byte sectors of
+  // [rows][128 envs], spread over the CTA.
+  auto prefetch_tile = [&](int tile) {
+    const size_t e0 = (size_t)tile * T2_M;
+    if (p.warm_start)
+      for (int i = tid; i < p.nb * 64; i += T2_THREADS) {
+        const size_t ee = e0 + (size_t)(i & 63) * 2;
+        if (ee < (size_t)p.E)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.u_state + (size_t)(i >> 6) * p.E + ee));
+      }
+    if (p.agent_p != nullptr && p.load_kw == nullptr)
+      for (int i = tid; i < p.A * 32; i += T2_THREADS) {
+        const size_t ee = e0 + (size_t)(i & 31) * 4;
+        if (ee < (size_t)p.E)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.agent_p + (size_t)(i >> 5) * p.E + ee));
+      }
+  };
+  prefetch_tile(blockIdx.x);
   if (warp == 0) {                                     // one warp owns TMEM alloc / free
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_base_s)),
@@ -204,7 +232,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
   const float* share = reinterpret_cast<const float*>(sT + t.t_share);
   const int32_t* bload = reinterpret_cast<const int32_t*>(sT + t.t_bload);
   const int32_t* bagent = reinterpret_cast<const int32_t*>(sT + t.t_bagent);
-  const float2* wf = reinterpret_cast<const float2*>(sT + t.t_w);
+  const float2* wx = reinterpret_cast<const float2*>(sT + t.t_w);        // w of the expanded slots
+  const int32_t* xnode = reinterpret_cast<const int32_t*>(sT + t.t_xnode);  // slot -> node or -1
+  const int32_t* dnode = reinterpret_cast<const int32_t*>(sT + t.t_dnode);  // branch -> node or -1
+  const float* dscale = reinterpret_cast<const float*>(sT + t.t_dscale);
   const int32_t* lptr = reinterpret_cast<const int32_t*>(sT + t.t_lptr);
   const int32_t* lidx = reinterpret_cast<const int32_t*>(sT + t.t_lidx);
   const int32_t* anode = reinterpret_cast<const int32_t*>(sT + t.t_anode);
@@ -219,6 +250,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
   const float xs = t.xscale, ds1 = t.descale1, ds2 = t.descale2;
   const float tol_s = t.tol / ds1;                     // tolerance in accumulator units
   uint32_t mma_phase = 0, b_phase = 0;                 // b_phase is used by the MMA issuer only
+  bool b_fresh = true;                                 // a load of the Zbb images is in flight
 
   // One accumulation chain D = A_lo B_hi + A_hi B_lo + A_hi B_hi (small terms first), issued by
   // one elected lane of warp 0; all operands are warp-uniform (uniform registers in SASS).
@@ -298,8 +330,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
               // multiagent_env.py:171-181: P summed per load name in agent order, then added to
               // the scaled base load (opendss.py:128); ag == -2: several agents on this load
               if (p.agent_p != nullptr && ag[j] == -2)
-                for (int q = lptr[ld[j]]; q < lptr[ld[j] + 1]; ++q)
-                  kw += p.agent_p[(size_t)lidx[q] * p.E + e];
+                kw += t2_shared_load_kw(p.agent_p, lidx, lptr[ld[j]], lptr[ld[j] + 1], p.E, e);
               kwd[j] += kw;
               kvd[j] = base_kvar[ld[j]];
             }
@@ -332,7 +363,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       s_dpart[it & 1][grp][row] = dpart;
       const int all_done = __syncthreads_and((conv || dpart < tol_s || it >= p.max_iter) ? 1 : 0);
-      if (!all_done) issue_chain((uint32_t)(cur * N), it == 0);      // Zbb images land before it 0
+      if (!all_done) issue_chain((uint32_t)(cur * N), it == 0 && b_fresh);   // Zbb images landed
       if (it > 0 && !conv) {                           // per-env convergence mask
         const float d = fmaxf(fmaxf(s_dpart[it & 1][0][row], s_dpart[it & 1][1][row]),
                               fmaxf(s_dpart[it & 1][2][row], s_dpart[it & 1][3][row]));
@@ -383,27 +414,38 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
     const int last = cur ^ 1;                          // D[last] = final drop
 
     // ---- expansion to all node voltages, Znb row chunks streamed over the B images
-    if (tid == 0) load_b(t.blob + t.off_zn);
+    if (tid == 0 && t.ncc > 0) load_b(t.blob + t.off_zn);
+    b_fresh = t.ncc > 0;                               // the Zbb images are restaged after the chunks
+    if (more_tiles) prefetch_tile(tile + (int)gridDim.x);
+    // Final branch voltages: warm-start state, and the magnitudes of the nodes that ARE a
+    // load branch voltage up to a real factor (wye loads: v_node = dscale * u_branch).
+    float vmn = 3.0e38f, vmx = -3.0e38f;
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
       const int c = grp + 4 * s;
-      if (c < NCH) {
+      if (c < NCH) {                                   // warp-uniform: tcgen05.ld is collective
         float dn[16];
         t2_ld16(t_lane + last * N + 16 * c, dn);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int k = 8 * c + j;
+          const float ur = fmaf(dn[j], ds1, cst[k].x), ui = fmaf(dn[8 + j], ds1, cst[k].y);
           if (valid && k < p.nb)
-            p.u_state[(size_t)k * p.E + e] =
-                make_double2((double)cst[k].x + (double)(dn[j] * ds1),
-                             (double)cst[k].y + (double)(dn[8 + j] * ds1));
+            p.u_state[(size_t)k * p.E + e] = make_double2((double)ur, (double)ui);
+          const int n = dnode[k];
+          if (n >= 0) {
+            const float m2 = fmaf(ur, ur, ui * ui);
+            const float mag = m2 * t2_rsqrt(fmaxf(m2, 1e-30f)) * dscale[k];
+            vmn = fminf(vmn, mag);
+            vmx = fmaxf(vmx, mag);
+            if (valid) p.vmag[(size_t)n * p.E + e] = (double)mag;
+          }
         }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                                   // D[last] may be overwritten from chunk 1 on
 
-    float vmn = 3.0e38f, vmx = -3.0e38f;
     for (int cc = 0; cc < t.ncc; ++cc) {
       const int dsel = (cur + cc) & 1;
       issue_chain((uint32_t)(dsel * N), true);
@@ -416,15 +458,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
       for (int s = 0; s < SLOTS; ++s) {
         const int c = grp + 4 * s;
         if (c < NCH) {
-          const int n0 = 8 * (cc * NCH + c);
-          if (n0 < p.nn) {
+          const int s0 = 8 * (cc * NCH + c);           // expanded slots s0 .. s0 + 7
+          if (s0 < t.nx) {
             float v[16];
             t2_ld16(t_lane + dsel * N + 16 * c, v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int n = n0 + j;
-              if (n < p.nn) {
-                const float vr = fmaf(v[j], ds2, wf[n].x), vi = fmaf(v[8 + j], ds2, wf[n].y);
+              const int n = xnode[s0 + j];
+              if (n >= 0) {
+                const float2 w = wx[s0 + j];
+                const float vr = fmaf(v[j], ds2, w.x), vi = fmaf(v[8 + j], ds2, w.y);
                 const float m2 = fmaf(vr, vr, vi * vi);
                 const float mag = m2 * t2_rsqrt(fmaxf(m2, 1e-30f));
                 vmn = fminf(vmn, mag);

@@ -566,6 +566,23 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       t.t_lptr = put(lptr.data(), lptr.size() * 4);
       t.t_lidx = put(lidx.data(), lidx.size() * 4);
       t.t_anode = put(node.data(), node.size() * 4);
+      {
+        // up to two agents per branch whose bus node derives from it (vag); the others (more
+        // than two on a node, or a bus that is not a wye-load node) go to the tail list
+        std::vector<int32_t> vag(2 * (size_t)NBP, -1), vtail;
+        for (int a = 0; a < env->A; ++a) {
+          int k = -1;
+          for (int q = 0; q < NBP && k < 0; ++q)
+            if (dnode[q] >= 0 && node[a] == dnode[q]) k = q;
+          if (k >= 0 && vag[2 * k] < 0) vag[2 * k] = a;
+          else if (k >= 0 && vag[2 * k + 1] < 0) vag[2 * k + 1] = a;
+          else vtail.push_back(a);
+        }
+        t.ntail = (int)vtail.size();
+        vtail.push_back(0);
+        t.t_vag = put(vag.data(), vag.size() * 4);
+        t.t_vtail = put(vtail.data(), vtail.size() * 4);
+      }
       blob.resize((blob.size() + 15) / 16 * 16, 0);
       t.tab_bytes = (int)(blob.size() - (size_t)t.off_tab);
       pgw::PfParams probe{};

@@ -51,9 +51,9 @@ struct CompParams {
 // blob: [B_hi | B_lo] (2 x part_bytes) | ncc x [Zn_hi | Zn_lo] at off_zn | tables at off_tab.
 struct Tc2Params {
   const unsigned char* blob;
-  int nch, ncc, nx, part_bytes, off_zn, off_tab, tab_bytes, tmem_cols, any_m5;
+  int nch, ncc, nx, ntail, part_bytes, off_zn, off_tab, tab_bytes, tmem_cols, any_m5;
   int t_cst, t_gh, t_share, t_bload, t_bagent, t_w, t_xnode, t_dnode, t_dscale, t_lptr, t_lidx,
-      t_anode;
+      t_anode, t_vag, t_vtail;
   float xscale, descale1, descale2, tol;
 };
 

@@ -35,6 +35,7 @@ namespace pgw {
 
 constexpr int T2_M = 128;
 constexpr int T2_THREADS = 512;
+constexpr int T2_ISSUER = 15;               // warp that feeds the pipelined chains (fewest chunks)
 
 __device__ __forceinline__ uint64_t t2_smem_desc(uint32_t saddr, uint32_t sbo) {
   // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
@@ -102,6 +103,10 @@ __device__ __forceinline__ uint32_t t2_pack(float a, float b) {
   return r;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+
 __device__ __forceinline__ float t2_rsqrt(float x) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -138,7 +143,14 @@ __device__ __forceinline__ void t2_split8(const float (&x)[8], uint4& hi, uint4&
 __device__ __noinline__ double t2_shared_load_kw(const double* agent_p, const int32_t* lidx, int q0,
                                                  int q1, int E, int e) {
   double s = 0.0;
-  for (int q = q0; q < q1; ++q) s += agent_p[(size_t)lidx[q] * E + e];
+#pragma unroll 1
+  for (int q = q0; q < q1; q += 4) {                   // four loads in flight, summed in order
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = q + u < q1 ? agent_p[(size_t)lidx[q + u] * E + e] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s += v[u];
+  }
   return s;
 }
 
@@ -160,7 +172,9 @@ __device__ __forceinline__ void t2_current(float4 c, float2 gh, float dr, float 
   y = fmaf(sr, ti, -(si * tr));
 }
 
-template <int NCH, bool ANY_M5>
+// STANDALONE: the solve of pgw_pf_solve (total kW / kvar per load given per env) instead of the
+// step / reset solve (base load of the event + the agents' powers).
+template <int NCH, bool ANY_M5, bool STANDALONE>
 __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p) {
   constexpr int SLOTS = (NCH + 3) / 4;                 // chunks per thread: c = grp + 4 * slot
   constexpr int N = 16 * NCH;
@@ -168,7 +182,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
   constexpr uint32_t PB = (uint32_t)(N / 8) * SBO;     // one B image: N rows
   constexpr uint32_t APB = 16u * SBO;                  // one A image: 128 rows
   extern __shared__ __align__(1024) unsigned char t2_smem[];
-  __shared__ __align__(8) uint64_t mbar_tab, mbar_b, mbar_mma;
+  __shared__ __align__(8) uint64_t mbar_tab, mbar_b, mbar_mma, mbar_wave[SLOTS];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_dpart[2][4][T2_M];                // per-group partial max |d drop|, 2 phases
   float (*s_vmn)[T2_M] = s_dpart[0], (*s_vmx)[T2_M] = s_dpart[1];   // reused after the solve
@@ -189,6 +203,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
     mbar_init(&mbar_tab, 1);
     mbar_init(&mbar_b, 1);
     mbar_init(&mbar_mma, 1);
+    for (int w = 0; w < SLOTS; ++w)                    // one arrival per warp that owns a chunk of wave w
+      mbar_init(&mbar_wave[w], 4u * (uint32_t)(NCH - 4 * w < 4 ? NCH - 4 * w : 4));
     mbar_expect_tx(&mbar_tab, (uint32_t)t.tab_bytes + (uint32_t)hdr * 8u);
     tma_bulk_g2s(sT, t.blob + t.off_tab, (uint32_t)t.tab_bytes, &mbar_tab);
     tma_bulk_g2s(drow, p.dtab + (size_t)event * p.dstride, (uint32_t)hdr * 8u, &mbar_tab);
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
         if (ee < (size_t)p.E)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(p.u_state + (size_t)(i >> 6) * p.E + ee));
       }
-    if (p.agent_p != nullptr && p.load_kw == nullptr)
+    if (!STANDALONE && p.agent_p != nullptr)
       for (int i = tid; i < p.A * 32; i += T2_THREADS) {
         const size_t ee = e0 + (size_t)(i & 31) * 4;
         if (ee < (size_t)p.E)
@@ -236,6 +252,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
   const int32_t* xnode = reinterpret_cast<const int32_t*>(sT + t.t_xnode);  // slot -> node or -1
   const int32_t* dnode = reinterpret_cast<const int32_t*>(sT + t.t_dnode);  // branch -> node or -1
   const float* dscale = reinterpret_cast<const float*>(sT + t.t_dscale);
+  const int2* vag = reinterpret_cast<const int2*>(sT + t.t_vag);   // branch -> up to two agents whose
+  const int32_t* vtail = reinterpret_cast<const int32_t*>(sT + t.t_vtail);  // bus node it derives; rest
   const int32_t* lptr = reinterpret_cast<const int32_t*>(sT + t.t_lptr);
   const int32_t* lidx = reinterpret_cast<const int32_t*>(sT + t.t_lidx);
   const int32_t* anode = reinterpret_cast<const int32_t*>(sT + t.t_anode);
@@ -249,7 +267,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
   const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // lane quadrant of this warp
   const float xs = t.xscale, ds1 = t.descale1, ds2 = t.descale2;
   const float tol_s = t.tol / ds1;                     // tolerance in accumulator units
-  uint32_t mma_phase = 0, b_phase = 0;                 // b_phase is used by the MMA issuer only
+  uint32_t mma_phase = 0, wave_phase = 0, b_phase = 0; // b_phase is used by warp 0 only
   bool b_fresh = true;                                 // a load of the Zbb images is in flight
 
   // One accumulation chain D = A_lo B_hi + A_hi B_lo + A_hi B_hi (small terms first), issued by
@@ -311,7 +329,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
             const int k = 8 * c + h + j;
             kwd[j] = 0.0;
             kvd[j] = 0.0;
-            if (p.load_kw != nullptr) {
+            if (STANDALONE) {
               if (k < p.nb) {
                 kwd[j] = p.load_kw[(size_t)ld[j] * p.E + e];
                 kvd[j] = p.load_kvar[(size_t)ld[j] * p.E + e];
@@ -325,7 +343,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int k = 8 * c + h + j, jj = h + j;
-            if (p.load_kw == nullptr) {
+            if (!STANDALONE) {
               double kw = base_kw[ld[j]];
               // multiagent_env.py:171-181: P summed per load name in agent order, then added to
               // the scaled base load (opendss.py:128); ag == -2: several agents on this load
@@ -338,8 +356,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
             sr[s][jj] = (float)kwd[j] * sh;
             si[s][jj] = (float)kvd[j] * sh;
             const float4 cc = cst[k];
-            d0[jj] = (float)(up[j].x - (double)cc.x) * (1.f / ds1);
-            d0[8 + jj] = (float)(up[j].y - (double)cc.y) * (1.f / ds1);
+            d0[jj] = ((float)up[j].x - cc.x) * (1.f / ds1);        // initial guess: fp32 is plenty
+            d0[8 + jj] = ((float)up[j].y - cc.y) * (1.f / ds1);
             t2_current<ANY_M5>(cc, ANY_M5 ? ghp[k] : make_float2(1.f, 0.f), d0[jj], d0[8 + jj], ds1,
                                sr[s][jj], si[s][jj], x[jj], y[jj]);
           }
@@ -355,43 +373,58 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
       }
     }
 
-    int it = 0, my_it = 0, cur = 0;                    // D[cur] receives the next drop
+    // ---- fixed point.  Per iteration:
+    //   wait for the chain of this iteration (drop n in D[cur], drop n-1 still in D[cur^1])
+    //   pass 1: max |d drop| over my chunks -> CTA barrier -> per-env convergence mask
+    //   pass 2: chunk by chunk, currents at the new voltages into A; as soon as the four chunks
+    //           of a wave are written by all warps, the issuer warp feeds the K steps of those
+    //           chunks of the NEXT chain into D[cur^1] (free since the barrier), so the tensor
+    //           core works while the remaining chunks are still being evaluated.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // st.shared -> tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    issue_chain(0u, b_fresh);                          // first chain; the Zbb images have landed
+    int it = 0, my_it = 0, cur = 0;                    // D[cur] = newest drop once its chain is done
     bool conv = !valid, conv_ok = true;
-    float dpart = 3.0e38f;
     while (true) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.shared -> tensor core
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_wait(&mbar_mma, mma_phase);
+      mma_phase ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      ++it;
+
+      float dpart = 0.f;
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) {
+        const int c = grp + 4 * s;
+        if (c < NCH) {                                 // warp-uniform: tcgen05.ld is collective
+          float dn[16], dold[16];
+          t2_ld16(t_lane + cur * N + 16 * c, dn);
+          t2_ld16(t_lane + (cur ^ 1) * N + 16 * c, dold);
+#pragma unroll
+          for (int j = 0; j < 16; j += 2)
+            dpart = fmaxf(dpart, fmaxf(fabsf(dn[j] - dold[j]), fabsf(dn[j + 1] - dold[j + 1])));
+        }
+      }
       s_dpart[it & 1][grp][row] = dpart;
-      const int all_done = __syncthreads_and((conv || dpart < tol_s || it >= p.max_iter) ? 1 : 0);
-      if (!all_done) issue_chain((uint32_t)(cur * N), it == 0 && b_fresh);   // Zbb images landed
-      if (it > 0 && !conv) {                           // per-env convergence mask
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      const bool all_done =
+          __syncthreads_and((conv || dpart < tol_s || it >= p.max_iter) ? 1 : 0) != 0;
+      const bool frozen = conv;                        // converged before this iteration
+      if (!conv) {                                     // per-env convergence mask
         const float d = fmaxf(fmaxf(s_dpart[it & 1][0][row], s_dpart[it & 1][1][row]),
                               fmaxf(s_dpart[it & 1][2][row], s_dpart[it & 1][3][row]));
         conv_ok = d < tol_s;
         conv = conv_ok || it >= p.max_iter;
         my_it = it;
       }
-      if (all_done) break;                             // A = currents at the final u
 
-      mbar_wait(&mbar_mma, mma_phase);
-      mma_phase ^= 1u;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-      dpart = 0.f;
 #pragma unroll
       for (int s = 0; s < SLOTS; ++s) {
         const int c = grp + 4 * s;
-        if (c < NCH) {                                 // warp-uniform: tcgen05.ld is collective
+        if (c < NCH) {
           float dn[16], x[8], y[8];
-          {
-            float dold[16];
-            t2_ld16(t_lane + cur * N + 16 * c, dn);
-            t2_ld16(t_lane + (cur ^ 1) * N + 16 * c, dold);
-#pragma unroll
-            for (int j = 0; j < 16; j += 2)
-              dpart = fmaxf(dpart, fmaxf(fabsf(dn[j] - dold[j]), fabsf(dn[j + 1] - dold[j + 1])));
-          }
-          if (!conv) {
+          t2_ld16(t_lane + cur * N + 16 * c, dn);
+          if (!frozen) {                               // the env's last write holds x(u_final)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int k = 8 * c + j;
@@ -406,12 +439,36 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
             *reinterpret_cast<uint4*>(a_row + 256 * c + 128) = hi;
             *reinterpret_cast<uint4*>(a_row + 256 * c + 128 + APB) = lo;
           }
+          if (!all_done) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&mbar_wave[s]);
+          }
+        }
+        if (!all_done && warp == T2_ISSUER) {          // K steps of wave s of the next chain
+          if (t2_elect_one()) {
+            mbar_wait(&mbar_wave[s], wave_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_col = (uint32_t)((cur ^ 1) * N);
+            const uint64_t a_hi = t2_smem_desc(sA_u, SBO), a_lo = t2_smem_desc(sA_u + APB, SBO);
+            const uint64_t b_hi = t2_smem_desc(sB_u, SBO), b_lo = t2_smem_desc(sB_u + PB, SBO);
+#pragma unroll
+            for (int kk = 4 * s; kk < 4 * s + 4 && kk < NCH; ++kk) {
+              t2_umma_f16(tmem + d_col, a_lo + 16u * kk, b_hi + 16u * kk, idesc, kk > 0 ? 1u : 0u);
+              t2_umma_f16(tmem + d_col, a_hi + 16u * kk, b_lo + 16u * kk, idesc, 1u);
+              t2_umma_f16(tmem + d_col, a_hi + 16u * kk, b_hi + 16u * kk, idesc, 1u);
+            }
+            if (s == SLOTS - 1) t2_commit(&mbar_mma);
+          }
+          __syncwarp();
         }
       }
-      ++it;
+      if (all_done) break;                             // A = currents at the final voltages
+      wave_phase ^= 1u;
       cur ^= 1;
     }
-    const int last = cur ^ 1;                          // D[last] = final drop
+    const int last = cur;                              // D[last] = final drop
+    cur ^= 1;                                          // the expansion starts in the older buffer
 
     // ---- expansion to all node voltages, Znb row chunks streamed over the B images
     if (tid == 0 && t.ncc > 0) load_b(t.blob + t.off_zn);
@@ -438,7 +495,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
             const float mag = m2 * t2_rsqrt(fmaxf(m2, 1e-30f)) * dscale[k];
             vmn = fminf(vmn, mag);
             vmx = fmaxf(vmx, mag);
-            if (valid) p.vmag[(size_t)n * p.E + e] = (double)mag;
+            if (valid) {
+              p.vmag[(size_t)n * p.E + e] = (double)mag;
+              if (!p.reward_hook) {                    // bus voltage of the agents at this node
+                const int2 ag2 = vag[k];
+                if (ag2.x >= 0) p.vbus[(size_t)ag2.x * p.E + e] = (double)mag;
+                if (ag2.y >= 0) p.vbus[(size_t)ag2.y * p.E + e] = (double)mag;
+              }
+            }
           }
         }
       }
@@ -498,34 +562,41 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
         pen_share = (viol * p.punit) / (double)p.A;
       }
       if (grp == 0) p.viol[e] = viol;
-      // agents a = grp, grp + 4, ...: batches of 4 so that the loads of a batch are in flight
-      // together (rew / ep_ret may alias as far as the compiler knows)
-      for (int a0 = grp; a0 < p.A; a0 += 16) {
-        double vb[4], rw[4], er[4];
+      if (p.reward_hook) {
+        // every agent: bus voltage + the shared penalty.  Agents a = grp, grp + 4, ... in
+        // batches of 4 so that the loads of a batch are in flight together.
+        for (int a0 = grp; a0 < p.A; a0 += 16) {
+          double vb[4], rw[4], er[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int a = a0 + 4 * q;
-          vb[q] = 1.0; rw[q] = 0.0; er[q] = 0.0;
-          if (a < p.A) {
-            const int node = anode[a];
-            const size_t ae = (size_t)a * p.E + e;
-            if (node >= 0) vb[q] = p.vmag[(size_t)node * p.E + e];
-            if (p.reward_hook) { rw[q] = p.rew[ae]; er[q] = p.ep_ret[ae]; }
+          for (int q = 0; q < 4; ++q) {
+            const int a = a0 + 4 * q;
+            vb[q] = 1.0; rw[q] = 0.0; er[q] = 0.0;
+            if (a < p.A) {
+              const int node = anode[a];
+              const size_t ae = (size_t)a * p.E + e;
+              if (node >= 0) vb[q] = p.vmag[(size_t)node * p.E + e];
+              rw[q] = p.rew[ae];
+              er[q] = p.ep_ret[ae];
+            }
           }
-        }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int a = a0 + 4 * q;
-          if (a < p.A) {
-            const size_t ae = (size_t)a * p.E + e;
-            p.vbus[ae] = vb[q];
-            if (p.reward_hook) {
+          for (int q = 0; q < 4; ++q) {
+            const int a = a0 + 4 * q;
+            if (a < p.A) {
+              const size_t ae = (size_t)a * p.E + e;
               const double r = rw[q] - pen_share;
+              p.vbus[ae] = vb[q];
               p.rew[ae] = r;
               p.rew_copy[ae] = r;
               p.ep_ret[ae] = er[q] + r;
             }
           }
+        }
+      } else {
+        // the agents whose bus is not a wye-load node (none in the shipped scenarios)
+        for (int q = grp; q < t.ntail; q += 4) {
+          const int a = vtail[q], node = anode[a];
+          p.vbus[(size_t)a * p.E + e] = node >= 0 ? p.vmag[(size_t)node * p.E + e] : 1.0;
         }
       }
     }
@@ -551,7 +622,9 @@ int tc2_padded_chunks(int nch) {            // instantiated tile widths
 
 template <int NCH>
 static cudaError_t launch_tc2_t(const PfParams& p, int grid, size_t smem, cudaStream_t s) {
-  auto kern = p.tc2.any_m5 ? pf_tc2_kernel<NCH, true> : pf_tc2_kernel<NCH, false>;
+  auto kern = p.load_kw != nullptr
+                  ? (p.tc2.any_m5 ? pf_tc2_kernel<NCH, true, true> : pf_tc2_kernel<NCH, false, true>)
+                  : (p.tc2.any_m5 ? pf_tc2_kernel<NCH, true, false> : pf_tc2_kernel<NCH, false, false>);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   kern<<<grid, T2_THREADS, smem, s>>>(p);

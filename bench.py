@@ -34,7 +34,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 4096          # BASELINE.json configs[1]; --envs overrides (size sweeps)
-PF_KERNEL = "fp64"           # --pf-kernel tc selects the tcgen05 solver
+PF_KERNEL = "tc2"            # tcgen05 split-FP16 solver; --pf-kernel fp64 / tc select the others
 WORKLOAD = "c1"              # --workload c2 = component-only EV+PV+storage (BASELINE configs[2])
 METRIC, UNIT = "env_steps_per_s", "env-steps/s"
 LOAD_FACTOR = 1.2
@@ -232,6 +232,9 @@ def run_ours(args):
     if PF_KERNEL != "fp64" and has_pf:
         from powergridworld_b200 import _native as N
         env.set_option(N.OPT_PF_KERNEL, {"tc": 1, "tc2": 2}[PF_KERNEL])
+    if args.pdl:
+        from powergridworld_b200 import _native as N
+        env.set_option(N.OPT_PDL, 1)
     A = len(env.agents)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -421,10 +424,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
-    ap.add_argument("--pf-kernel", default="fp64", choices=["fp64", "tc", "tc2"])
+    ap.add_argument("--pdl", action="store_true",
+                    help="power flow as a programmatic dependent launch of the component kernel")
+    ap.add_argument("--envs", type=int, default=None,
+                    help="envs per GPU (default: 4096 for C1, 65536 for C2, 16384 for C3)")
+    ap.add_argument("--pf-kernel", default=PF_KERNEL, choices=["fp64", "tc", "tc2"])
     ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3"])
     args = ap.parse_args()
+    if args.envs is None:
+        args.envs = {"c1": 4096, "c2": 65536, "c3": 16384}[args.workload]
     ENVS_PER_GPU, PF_KERNEL, WORKLOAD = args.envs, args.pf_kernel, args.workload
     if args.impl == "reference":
         run_reference(args)

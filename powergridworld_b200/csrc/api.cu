@@ -97,6 +97,7 @@ struct pgw_env {
   };
   std::vector<StepGraph> graphs;
   bool use_graphs = true;
+  bool use_pdl = false;
   // device state
   double* sd = nullptr;
   uint32_t* si = nullptr;
@@ -701,6 +702,7 @@ static int enqueue_step(pgw_env* env, const double* actions, double* obs, double
     pgw::PfParams pf = pf_params(env);
     pf.event_mode = 1; pf.advance_clock = 1; pf.agent_p = env->agent_p; pf.rew = rew;
     pf.reward_hook = hook ? 1 : 0;
+    pf.pdl = (env->use_pdl && !timed) ? 1 : 0;
     pf.warm_start = env->warm_start ? 1 : 0;
     PGW_CUDA(launch_pf(env, pf, s));
   }
@@ -930,6 +932,7 @@ int pgw_set_option(pgw_env* env, int option, int value) {
       break;
     case PGW_OPT_WARM_START: env->warm_start = value != 0; break;
     case PGW_OPT_GRAPHS: env->use_graphs = value != 0; break;
+    case PGW_OPT_PDL: env->use_pdl = value != 0; break;
     default: return fail(PGW_ERR_INVALID, "unknown option");
   }
   // the captured graphs bake the options in

@@ -65,6 +65,7 @@ struct PfParams {
   int reward_hook;         // step with a shared voltage penalty: this kernel finishes the rewards
                            // (rew -= share, rew_copy, ep_ret); otherwise the component kernel did
   int warm_start;          // start from the previous solution kept in u_state
+  int pdl;                 // launch as a programmatic dependent of the component kernel
   // static tables, one contiguous 16-byte aligned blob (staged to shared memory by TMA
   // when it fits):  zbbT [nb][nbp] double2 (zbbT[j*nbp+k] = Zbb[k][j]) | u0 [nbp] double2 |
   // znbT [nb][nnp] double2 (znbT[k*nnp+n] = Znb[n][k]) | w [nnp] double2 |

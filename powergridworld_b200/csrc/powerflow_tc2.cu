@@ -242,6 +242,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
   mbar_wait(&mbar_tab, 0);
+  // Programmatic dependent launch: everything above overlapped the tail of the component kernel;
+  // its outputs (agent powers, rewards) are visible from here on.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const float4* cst = reinterpret_cast<const float4*>(sT + t.t_cst);
   const float2* ghp = reinterpret_cast<const float2*>(sT + t.t_gh);
@@ -627,8 +630,17 @@ static cudaError_t launch_tc2_t(const PfParams& p, int grid, size_t smem, cudaSt
                   : (p.tc2.any_m5 ? pf_tc2_kernel<NCH, true, false> : pf_tc2_kernel<NCH, false, false>);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  kern<<<grid, T2_THREADS, smem, s>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(T2_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = p.pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 cudaError_t launch_powerflow_tc2(const PfParams& p, cudaStream_t s) {

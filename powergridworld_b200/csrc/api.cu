@@ -90,6 +90,7 @@ struct pgw_env {
   // FP16 tensor-core power flow for up to 88 load branches (powerflow_tc2.cu)
   unsigned char* tc2_blob = nullptr;
   pgw::Tc2Params tc2{};
+  pgw::Tc2Consts tc2c{};
   // CUDA graphs of a step, keyed by the caller's buffer pointers
   struct StepGraph {
     const void *actions, *obs, *rew, *done;
@@ -555,8 +556,11 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
         const int l = blp[k], cnt = lptr[l + 1] - lptr[l];
         bag[k] = cnt == 0 ? -1 : (cnt == 1 ? lidx[lptr[l]] : -2);
       }
-      t.t_cst = put(cst.data(), cst.size() * 4);
-      t.t_gh = put(gh.data(), gh.size() * 4);
+      for (int k = 0; k < NBP; ++k) {
+        env->tc2c.cst[k] = make_float4(cst[4 * k], cst[4 * k + 1], cst[4 * k + 2], cst[4 * k + 3]);
+        env->tc2c.gh[k] = make_float2(gh[2 * k], gh[2 * k + 1]);
+      }
+      t.consts = &env->tc2c;
       t.t_share = put(shf.data(), shf.size() * 4);
       t.t_bload = put(blp.data(), blp.size() * 4);
       t.t_bagent = put(bag.data(), bag.size() * 4);

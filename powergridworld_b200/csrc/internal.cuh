@@ -49,10 +49,17 @@ struct CompParams {
 
 // Operand images + fp32 tables of the FP16 tensor-core power flow (powerflow_tc2.cu).
 // blob: [B_hi | B_lo] (2 x part_bytes) | ncc x [Zn_hi | Zn_lo] at off_zn | tables at off_tab.
+// Per-branch constants of the tc2 kernel, passed as a __grid_constant__ kernel parameter.
+struct Tc2Consts {
+  float4 cst[8 * 11];      // {Re u0, Im u0, vlo^2, vhi^2}
+  float2 gh[8 * 11];       // (1, 0): 1 / clamp(|u|^2);  (0, 1): 1 / |u| (constant-current load)
+};
+
 struct Tc2Params {
   const unsigned char* blob;
+  const Tc2Consts* consts; // host copy owned by the env handle
   int nch, ncc, nx, ntail, part_bytes, off_zn, off_tab, tab_bytes, tmem_cols, any_m5;
-  int t_cst, t_gh, t_share, t_bload, t_bagent, t_w, t_xnode, t_dnode, t_dscale, t_lptr, t_lidx,
+  int t_share, t_bload, t_bagent, t_w, t_xnode, t_dnode, t_dscale, t_lptr, t_lidx,
       t_anode, t_vag, t_vtail;
   float xscale, descale1, descale2, tol;
 };

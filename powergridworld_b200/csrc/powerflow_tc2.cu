@@ -175,7 +175,8 @@ __device__ __forceinline__ void t2_current(float4 c, float2 gh, float dr, float 
 // STANDALONE: the solve of pgw_pf_solve (total kW / kvar per load given per env) instead of the
 // step / reset solve (base load of the event + the agents' powers).
 template <int NCH, bool ANY_M5, bool STANDALONE>
-__global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p) {
+__global__ void __launch_bounds__(T2_THREADS, 1)
+    pf_tc2_kernel(const PfParams p, const __grid_constant__ Tc2Consts kc) {
   constexpr int SLOTS = (NCH + 3) / 4;                 // chunks per thread: c = grp + 4 * slot
   constexpr int N = 16 * NCH;
   constexpr uint32_t SBO = 256u * NCH;                 // bytes between 8-row groups
@@ -246,8 +247,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
   // its outputs (agent powers, rewards) are visible from here on.
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  const float4* cst = reinterpret_cast<const float4*>(sT + t.t_cst);
-  const float2* ghp = reinterpret_cast<const float2*>(sT + t.t_gh);
+  // per-branch constants come through the constant bank (kernel parameter), not shared memory:
+  // the tensor core's operand reads already take most of the shared-memory bandwidth
+  const float4* cst = kc.cst;
+  const float2* ghp = kc.gh;
   const float* share = reinterpret_cast<const float*>(sT + t.t_share);
   const int32_t* bload = reinterpret_cast<const int32_t*>(sT + t.t_bload);
   const int32_t* bagent = reinterpret_cast<const int32_t*>(sT + t.t_bagent);
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
     // Final branch voltages: warm-start state, and the magnitudes of the nodes that ARE a
     // load branch voltage up to a real factor (wye loads: v_node = dscale * u_branch).
     float vmn = 3.0e38f, vmx = -3.0e38f;
-#pragma unroll
+#pragma unroll 1                                       // executed once per tile: keep the code small
     for (int s = 0; s < SLOTS; ++s) {
       const int c = grp + 4 * s;
       if (c < NCH) {                                   // warp-uniform: tcgen05.ld is collective
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pf_tc2_kernel(const PfParams p)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tid == 0 && (cc + 1 < t.ncc || more_tiles))  // the B images are free again
         load_b(cc + 1 < t.ncc ? t.blob + t.off_zn + (size_t)(cc + 1) * 2 * PB : t.blob);
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < SLOTS; ++s) {
         const int c = grp + 4 * s;
         if (c < NCH) {
@@ -640,7 +643,7 @@ static cudaError_t launch_tc2_t(const PfParams& p, int grid, size_t smem, cudaSt
   attr[0].val.programmaticStreamSerializationAllowed = p.pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, p);
+  return cudaLaunchKernelEx(&cfg, kern, p, *p.tc2.consts);
 }
 
 cudaError_t launch_powerflow_tc2(const PfParams& p, cudaStream_t s) {

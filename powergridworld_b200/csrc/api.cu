@@ -515,8 +515,10 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       t.off_tab = (int)blob.size();
       t.xscale = (float)xs; t.descale1 = (float)(1.0 / (sb1 * xs)); t.descale2 = (float)(1.0 / (sb2 * xs));
       t.tol = (float)(f.tol > 1e-7 ? f.tol : 1e-7);
+      // small feeders keep every Znb chunk resident (64 kB of images, accumulators 2 + cc)
+      t.resident = ((2 + ncc) * N <= 512 && (size_t)ncc * 2 * part <= 64 * 1024) ? 1 : 0;
       t.tmem_cols = 32;
-      while (t.tmem_cols < 2 * N) t.tmem_cols *= 2;
+      while (t.tmem_cols < (t.resident ? 2 + ncc : 2) * N) t.tmem_cols *= 2;
       // cst = {Re u0, Im u0, vlo^2, vhi^2}, gh = (1, 0) -> 1/clamp(|u|^2), (0, 1) -> 1/|u| (model 5)
       std::vector<float> cst(4 * (size_t)NBP, 1.f), gh(2 * (size_t)NBP, 0.f), shf(NBP, 0.f), wf(2 * xnode.size(), 0.f);
       std::vector<int32_t> blp(NBP, 0), bag(NBP, -1), lptr(f.nl + 1, 0), lidx(env->A, 0), node(env->A);

@@ -58,7 +58,7 @@ struct Tc2Consts {
 struct Tc2Params {
   const unsigned char* blob;
   const Tc2Consts* consts; // host copy owned by the env handle
-  int nch, ncc, nx, ntail, part_bytes, off_zn, off_tab, tab_bytes, tmem_cols, any_m5;
+  int nch, ncc, nx, ntail, resident, part_bytes, off_zn, off_tab, tab_bytes, tmem_cols, any_m5;
   int t_share, t_bload, t_bagent, t_w, t_xnode, t_dnode, t_dscale, t_lptr, t_lidx,
       t_anode, t_vag, t_vtail;
   float xscale, descale1, descale2, tol;

@@ -195,7 +195,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
   const int hdr = 2 + 2 * p.nl;
 
   unsigned char* sB = t2_smem;                         // B_hi | B_lo (iteration) or a Znb chunk
-  unsigned char* sA = sB + 2 * PB;                     // A_hi | A_lo
+  // small feeders: every Znb chunk stays resident behind the Zbb images (no streaming, all
+  // expansion chains issued back to back into their own accumulators)
+  const int nres = t.resident ? t.ncc : 0;
+  unsigned char* sA = sB + (size_t)(1 + nres) * 2 * PB;   // A_hi | A_lo
   unsigned char* sT = sA + 2 * APB;                    // tables
   double* drow = reinterpret_cast<double*>(sT + t.tab_bytes);
 
@@ -208,9 +211,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
       mbar_init(&mbar_wave[w], 4u * (uint32_t)(NCH - 4 * w < 4 ? NCH - 4 * w : 4));
     mbar_expect_tx(&mbar_tab, (uint32_t)t.tab_bytes + (uint32_t)hdr * 8u);
     tma_bulk_g2s(sT, t.blob + t.off_tab, (uint32_t)t.tab_bytes, &mbar_tab);
+    mbar_expect_tx(&mbar_b, (uint32_t)(1 + nres) * 2 * PB);
+    tma_bulk_g2s(sB, t.blob, (uint32_t)(1 + nres) * 2 * PB, &mbar_b);   // chunks follow in the blob
+    // last: the event row's address waits for the device clock
     tma_bulk_g2s(drow, p.dtab + (size_t)event * p.dstride, (uint32_t)hdr * 8u, &mbar_tab);
-    mbar_expect_tx(&mbar_b, 2 * PB);
-    tma_bulk_g2s(sB, t.blob, 2 * PB, &mbar_b);
   }
   // Pull the tile's per-env inputs (warm-start voltages, agent powers) towards L2 while the
   // tables, the operand images and the TMEM allocation are in flight: 32-byte sectors of
@@ -226,8 +230,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
     if (!STANDALONE && p.agent_p != nullptr)
       for (int i = tid; i < p.A * 32; i += T2_THREADS) {
         const size_t ee = e0 + (size_t)(i & 31) * 4;
-        if (ee < (size_t)p.E)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.agent_p + (size_t)(i >> 5) * p.E + ee));
+        if (ee < (size_t)p.E) {
+          const size_t off = (size_t)(i >> 5) * p.E + ee;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.agent_p + off));
+          if (p.reward_hook) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.ep_ret + off));
+        }
       }
   };
   prefetch_tile(blockIdx.x);
@@ -278,13 +285,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
 
   // One accumulation chain D = A_lo B_hi + A_hi B_lo + A_hi B_hi (small terms first), issued by
   // one elected lane of warp 0; all operands are warp-uniform (uniform registers in SASS).
-  auto issue_chain = [&](uint32_t d_col, bool wait_b) {
+  auto issue_chain = [&](uint32_t d_col, bool wait_b, uint32_t b_off = 0u, bool commit = true) {
     if (warp == 0) {
       if (t2_elect_one()) {
         if (wait_b) mbar_wait(&mbar_b, b_phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t a_hi = t2_smem_desc(sA_u, SBO), a_lo = t2_smem_desc(sA_u + APB, SBO);
-        const uint64_t b_hi = t2_smem_desc(sB_u, SBO), b_lo = t2_smem_desc(sB_u + PB, SBO);
+        const uint64_t b_hi = t2_smem_desc(sB_u + b_off, SBO),
+                       b_lo = t2_smem_desc(sB_u + b_off + PB, SBO);
 #pragma unroll
         for (int kk = 0; kk < NCH; ++kk)
           t2_umma_f16(tmem + d_col, a_lo + 16u * kk, b_hi + 16u * kk, idesc, kk > 0 ? 1u : 0u);
@@ -294,7 +302,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
 #pragma unroll
         for (int kk = 0; kk < NCH; ++kk)
           t2_umma_f16(tmem + d_col, a_hi + 16u * kk, b_hi + 16u * kk, idesc, 1u);
-        t2_commit(&mbar_mma);
+        if (commit) t2_commit(&mbar_mma);
       }
       if (wait_b) b_phase ^= 1u;
       __syncwarp();
@@ -477,8 +485,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
     cur ^= 1;                                          // the expansion starts in the older buffer
 
     // ---- expansion to all node voltages, Znb row chunks streamed over the B images
-    if (tid == 0 && t.ncc > 0) load_b(t.blob + t.off_zn);
-    b_fresh = t.ncc > 0;                               // the Zbb images are restaged after the chunks
+    if (tid == 0 && t.ncc > 0 && !t.resident) load_b(t.blob + t.off_zn);
+    b_fresh = t.ncc > 0 && !t.resident;                // the Zbb images are restaged after the chunks
     if (more_tiles) prefetch_tile(tile + (int)gridDim.x);
     // Final branch voltages: warm-start state, and the magnitudes of the nodes that ARE a
     // load branch voltage up to a real factor (wye loads: v_node = dscale * u_branch).
@@ -516,14 +524,23 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                                   // D[last] may be overwritten from chunk 1 on
 
-    for (int cc = 0; cc < t.ncc; ++cc) {
-      const int dsel = (cur + cc) & 1;
-      issue_chain((uint32_t)(dsel * N), true);
+    if (t.resident && t.ncc > 0) {                     // accumulators 2 + cc, one commit for all
+      for (int cc = 0; cc < t.ncc; ++cc)
+        issue_chain((uint32_t)((2 + cc) * N), false, (uint32_t)(1 + cc) * 2 * PB, cc + 1 == t.ncc);
       mbar_wait(&mbar_mma, mma_phase);
       mma_phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (tid == 0 && (cc + 1 < t.ncc || more_tiles))  // the B images are free again
-        load_b(cc + 1 < t.ncc ? t.blob + t.off_zn + (size_t)(cc + 1) * 2 * PB : t.blob);
+    }
+    for (int cc = 0; cc < t.ncc; ++cc) {
+      const int dsel = t.resident ? 2 + cc : (cur + cc) & 1;
+      if (!t.resident) {
+        issue_chain((uint32_t)(dsel * N), true);
+        mbar_wait(&mbar_mma, mma_phase);
+        mma_phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0 && (cc + 1 < t.ncc || more_tiles))  // the B images are free again
+          load_b(cc + 1 < t.ncc ? t.blob + t.off_zn + (size_t)(cc + 1) * 2 * PB : t.blob);
+      }
 #pragma unroll 1
       for (int s = 0; s < SLOTS; ++s) {
         const int c = grp + 4 * s;
@@ -548,8 +565,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();                                 // this accumulator is rewritten two chunks on
+      if (!t.resident) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                               // this accumulator is rewritten two chunks on
+      }
     }
     s_vmn[grp][row] = vmn;
     s_vmx[grp][row] = vmx;
@@ -618,7 +637,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
 }
 
 size_t tc2_smem_bytes(const PfParams& p) {
-  return (size_t)2 * p.tc2.part_bytes + (size_t)2 * 16 * 256 * p.tc2.nch + (size_t)p.tc2.tab_bytes +
+  return (size_t)(1 + (p.tc2.resident ? p.tc2.ncc : 0)) * 2 * p.tc2.part_bytes +
+         (size_t)2 * 16 * 256 * p.tc2.nch + (size_t)p.tc2.tab_bytes +
          (size_t)(2 + 2 * p.nl) * 8 + 16;
 }
 

@@ -69,9 +69,10 @@ def _config(n_gpus):
             "pf_kernel": _PF_NAMES[PF_KERNEL]}
 
 
-def _make_env(ns, **kw):
+def _make_env(ns, workload=None, **kw):
     """The benchmark scenario against a plugin namespace (product or oracle)."""
     from tests import scenarios as S
+    WORKLOAD = workload or globals()["WORKLOAD"]
     if WORKLOAD == "c2":
         if ns.__dict__.get("_is_oracle"):
             from oracle.multiagent import PowerFlowSolver
@@ -416,6 +417,155 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- C4: scenario mix
+C4_MIX = (("c1", 65536), ("c3", 16384), ("c2", 49152))   # 131 072 envs per GPU, 1 048 576 on 8
+
+
+def run_mix(args):
+    """BASELINE configs[4]: heterogeneous scenario mix, ~1 M env instances over 8 GPUs.  Every GPU
+    holds three env batches (IEEE-13 buildings, 123-bus DER feeder, component-only EV station),
+    each with its own device handle and stream; one "step" advances all of them once, the
+    batches overlapping on the GPU.  The only collective is the statistics all-reduce."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from powergridworld_b200 import _native as N
+    from tests.product_ns import PRODUCT_NS as NS
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 3)
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    scale = args.envs / 131072.0 if args.envs else 1.0
+    parts = []
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    rng = np.random.default_rng(rank)
+    for wl, n in C4_MIX:
+        E = max(128, int(n * scale) // 128 * 128)
+        env = _make_env(NS, workload=wl, num_envs=E, device=dev)
+        if env.pf_solver is not None and PF_KERNEL != "fp64":
+            env.set_option(N.OPT_PF_KERNEL, {"tc": 1, "tc2": 2}[PF_KERNEL])
+        stream = torch.cuda.Stream(dev)
+        acts = torch.rand((4, env.act_dim, E), generator=gen, device=dev, dtype=torch.float64) * 2 - 1
+        soc = torch.as_tensor(30.0 + 5.0 * rng.uniform(-1, 1, size=(env.num_storage, E))).to(dev)
+        parts.append({"wl": wl, "E": E, "env": env, "stream": stream, "acts": acts, "soc": soc,
+                      "done": torch.cuda.Event()})
+    total_envs = sum(pt["E"] for pt in parts)
+    agent_steps = sum(pt["E"] * len(pt["env"].agents) for pt in parts)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+
+    def step_all(i, fence=None):
+        for pt in parts:
+            with torch.cuda.stream(pt["stream"]):
+                if fence is not None:
+                    pt["stream"].wait_event(fence)
+                if pt["env"]._needs_reset:
+                    pt["env"].reset_batch(pt["soc"])
+                pt["env"].step_batch(pt["acts"][i % 4])
+                pt["done"].record(pt["stream"])
+        for pt in parts:
+            main_stream.wait_event(pt["done"])
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for pt in parts:
+        with torch.cuda.stream(pt["stream"]):
+            pt["env"].reset_batch(pt["soc"])
+    for i in range(max(W, 6)):                        # captures the step graphs (untimed)
+        step_all(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = sum(pt["env"].launch_count for pt in parts)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for i in range(K):
+        flush.zero_()
+        starts[i].record(main_stream)
+        step_all(W + i, fence=starts[i])
+        ends[i].record(main_stream)
+    barrier()
+    launches = sum(pt["env"].launch_count for pt in parts) - launches0
+    sampler.stop_flag = True
+    total_ms = float(sum(s_.elapsed_time(e_) for s_, e_ in zip(starts, ends)))
+    stats = None
+    for pt in parts:                                   # the only collective of the path
+        with torch.cuda.stream(pt["stream"]):
+            st = pt["env"].all_reduce_stats()
+        torch.cuda.synchronize(dev)
+        stats = st.clone() if stats is None else torch.cat([stats[:6] + st[:6], torch.minimum(
+            stats[6:7], st[6:7]), torch.maximum(stats[7:8], st[7:8])])
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = total_envs * world * K / (total_ms * 1e-3)
+
+    # end to end: host buffers in and out for every batch, every step
+    host_act = [pt["acts"][0].cpu().pin_memory() for pt in parts]
+    for pt in parts:
+        with torch.cuda.stream(pt["stream"]):
+            pt["env"].reset_host(pt["soc"].cpu().numpy())
+    barrier()
+    ke = min(K, 20)
+    t0 = time.perf_counter()
+    for i in range(ke):
+        for pt, ha in zip(parts, host_act):
+            with torch.cuda.stream(pt["stream"]):
+                if pt["env"]._needs_reset:
+                    pt["env"].reset_host(pt["soc"].cpu().numpy())
+                pt["env"].step_host(ha)
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = sum(pt["env"].act_dim * pt["E"] * 8 for pt in parts)
+    d2h = sum((pt["env"].obs_dim + len(pt["env"].agents)) * pt["E"] * 8 + pt["E"] for pt in parts)
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        alg = float(sum(SURVEY_BYTES[pt["wl"]] * pt["E"] for pt in parts))
+        step_ms = total_ms / K
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4: scenario mix per GPU = " + " + ".join(
+                f"{pt['E']} x {pt['wl'].upper()}" for pt in parts) + ", one device handle and stream "
+                "per scenario", "envs_per_gpu": total_envs, "global_envs": total_envs * world,
+                "parallelism": f"env-sharded x{world}", "pf_kernel": _PF_NAMES[PF_KERNEL],
+                "l2": "flushed between timed steps (256 MiB write)"},
+            "agent_steps_per_s": agent_steps * world * K / (total_ms * 1e-3),
+            "clocks": sampler.summary(),
+            "e2e": {"value": total_envs * world * ke / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / ke, "steps": ke},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "component_kernel (all three batches; whole step as the "
+                         "denominator, power flow included)", "bound": "hbm",
+                         "achieved": alg / (step_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": alg / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg},
+            "stats": [float(x) for x in stats.cpu()],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     global ENVS_PER_GPU, PF_KERNEL, WORKLOAD
     ap = argparse.ArgumentParser()
@@ -429,13 +579,15 @@ def main():
     ap.add_argument("--envs", type=int, default=None,
                     help="envs per GPU (default: 4096 for C1, 65536 for C2, 16384 for C3)")
     ap.add_argument("--pf-kernel", default=PF_KERNEL, choices=["fp64", "tc", "tc2"])
-    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3"])
+    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3", "c4"])
     args = ap.parse_args()
-    if args.envs is None:
+    if args.envs is None and args.workload != "c4":
         args.envs = {"c1": 4096, "c2": 65536, "c3": 16384}[args.workload]
     ENVS_PER_GPU, PF_KERNEL, WORKLOAD = args.envs, args.pf_kernel, args.workload
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4":
+        run_mix(args)
     else:
         run_ours(args)
 

@@ -17,6 +17,12 @@ shipped scenarios without the reference tree:
                        (gridworld/distribution_system/data/ieee_13_dss/)
   building/<key>       five-zone state-space model, from state_space_model.p
                        (gridworld/agents/buildings/five_zone_rom_env.py:49-50)
+  hs/vehicles/<column> columns of gridworld/agents/vehicles/vehicles_hs.csv
+                       (ev_charging_env_hs.py:71-74)
+
+and copies the Home-Steward scenario data (numbers only: grid cost, timestamps, the PV /
+device / vehicle profiles and the component parameters of
+gridworld/scenarios/data/env_config.json) to ``powergridworld_b200/data/hs_env_config.json``.
 """
 import os
 import pickle
@@ -56,6 +62,14 @@ def main():
     out["building/input_sel_list"] = np.array([np.asarray(m["input_sel_list"]).reshape(-1) for m in models], dtype=np.int64)
     out["building/neighbors"] = np.array([m["neighbors"] for m in models], dtype=np.int64)
     out["building/x_k0"] = np.array([m["x_k"].squeeze() for m in models], dtype=np.float64)
+    veh_hs = pd.read_csv(os.path.join(REF, "gridworld/agents/vehicles/vehicles_hs.csv"))
+    for c in ["start_time_min", "end_time_park_min", "energy_required_kwh"]:
+        out[f"hs/vehicles/{c}"] = veh_hs[c].values.astype(np.float64)
+    import json
+    with open(os.path.join(REF, "gridworld/scenarios/data/env_config.json")) as fh:
+        hs_cfg = json.load(fh)
+    with open(os.path.join(os.path.dirname(OUT), "hs_env_config.json"), "w") as fh:
+        json.dump(hs_cfg, fh, separators=(",", ":"))
     np.savez_compressed(OUT, **out)
     for k, v in out.items():
         print(f"{k:60s} {v.dtype} {v.shape}")

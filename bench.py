@@ -41,7 +41,10 @@ LOAD_FACTOR = 1.2
 # algorithmic bytes per env-step of the component kernel, SURVEY.md section 8(d)
 SURVEY_BYTES = {"c1": 3 * (264 + 28 + 40) + 1, "c2": (16 * 100 + 72 + 8 * 4) + 28 + 40 + 1,
                 # C3: 40 PV + 30 storage + 10 EV(25) + 20 x (building + PV + storage)
-                "c3": 40 * 28 + 30 * 40 + 10 * (16 * 25 + 72 + 8) + 20 * (264 + 28 + 40) + 1}
+                "c3": 40 * 28 + 30 * 40 + 10 * (16 * 25 + 72 + 8) + 20 * (264 + 28 + 40) + 1,
+                # HS house: 4 actions in, 12 obs + P + reward (+ep_ret, rew_copy) out, meta state
+                # 5 rows r/w, storage 2 rows r/w, vehicle energy + cost + mask r/w
+                "hs": 4 * 8 + 12 * 8 + 5 * 8 + 5 * 16 + 2 * 16 + 2 * 16 + 8 + 1}
 
 
 _PF_NAMES = {"fp64": "fp64-simt", "tc": "tcgen05 split-tf32", "tc2": "tcgen05 split-fp16, Z-bus in smem"}
@@ -52,6 +55,12 @@ def _config(n_gpus):
         return {"workload": "C2: component-only EV station (100 vehicles) + PV + storage, "
                             f"{ENVS_PER_GPU} envs per GPU, no power flow",
                 "envs_per_gpu": ENVS_PER_GPU, "agents_per_env": 3,
+                "global_envs": ENVS_PER_GPU * n_gpus, "parallelism": f"env-sharded x{n_gpus}",
+                "l2": "flushed between timed steps (256 MiB write)"}
+    if WORKLOAD == "hs":
+        return {"workload": "HS: Home-Steward house (PV -> storage -> EV charger -> devices, blended "
+                            f"energy cost), {ENVS_PER_GPU} houses per GPU, no power flow",
+                "envs_per_gpu": ENVS_PER_GPU, "agents_per_env": 1,
                 "global_envs": ENVS_PER_GPU * n_gpus, "parallelism": f"env-sharded x{n_gpus}",
                 "l2": "flushed between timed steps (256 MiB write)"}
     if WORKLOAD == "c3":
@@ -91,6 +100,19 @@ def _make_env(ns, workload=None, **kw):
                     return 1.0
             return ns.MultiAgentEnv(**S.ev_pv_storage_scenario(ns, NoPF), **kw)
         return ns.MultiAgentEnv(**S.ev_pv_storage_scenario(ns), **kw)
+    if WORKLOAD == "hs":
+        from tests import scenarios_hs as SH
+        if ns.__dict__.get("_is_oracle"):
+            from tests.oracle_hs_ns import ORACLE_HS_NS as OHS
+            return _OracleHouse(OHS.HSMultiComponentEnv(**SH.shipped(OHS)))
+        from powergridworld_b200.base_hs import house_agent_config
+        from tests.product_hs_ns import PRODUCT_HS_NS as HNS
+        cfg = SH.shipped(HNS)
+        return ns.MultiAgentEnv(
+            common_config={"start_time": cfg["start_time"], "end_time": "01-01-2031 00:00:00",
+                           "control_timedelta": cfg["control_timedelta"]},
+            pf_config=None, agents=[{"name": "house", "bus": None, "cls": HNS.HSMultiComponentEnv,
+                                     "config": house_agent_config(cfg)}], **kw)
     if WORKLOAD == "c3":
         import warnings
         with warnings.catch_warnings():
@@ -98,6 +120,22 @@ def _make_env(ns, workload=None, **kw):
             return ns.MultiAgentEnv(**S.der123_scenario(ns, ns.OpenDSSSolver), **kw)
     return ns.CoordinatedMultiBuildingControlEnv(
         **S.buildings_scenario(ns, ns.OpenDSSSolver, LOAD_FACTOR), **kw)
+
+
+class _OracleHouse:
+    """The HS oracle house behind the MultiAgentEnv-shaped surface the CPU worker drives."""
+
+    def __init__(self, house):
+        self.house = house
+        self.agents = [house]
+        self.action_space = {"house": house.action_space}
+
+    def reset(self):
+        return {"house": self.house.reset(init_storage=8.1)}
+
+    def step(self, action):
+        ob, rew, done, _ = self.house.step(action["house"])
+        return {"house": ob}, {"house": rew}, {"__all__": done}, {}
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -579,10 +617,10 @@ def main():
     ap.add_argument("--envs", type=int, default=None,
                     help="envs per GPU (default: 4096 for C1, 65536 for C2, 16384 for C3)")
     ap.add_argument("--pf-kernel", default=PF_KERNEL, choices=["fp64", "tc", "tc2"])
-    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3", "c4", "hs"])
     args = ap.parse_args()
     if args.envs is None and args.workload != "c4":
-        args.envs = {"c1": 4096, "c2": 65536, "c3": 16384}[args.workload]
+        args.envs = {"c1": 4096, "c2": 65536, "c3": 16384, "hs": 262144}[args.workload]
     ENVS_PER_GPU, PF_KERNEL, WORKLOAD = args.envs, args.pf_kernel, args.workload
     if args.impl == "reference":
         run_reference(args)

@@ -49,7 +49,16 @@ typedef enum pgw_component_type {
   PGW_STORAGE = 1,   /* gridworld/agents/energy_storage/energy_storage_env.py:11-181 */
   PGW_PV = 2,        /* gridworld/agents/pv/pv_profile_env.py:15-148               */
   PGW_EV = 3,        /* gridworld/agents/vehicles/ev_charging_env.py:17-275        */
-  PGW_BUILDING = 4   /* gridworld/agents/buildings/five_zone_rom_env.py:60-335     */
+  PGW_BUILDING = 4,  /* gridworld/agents/buildings/five_zone_rom_env.py:60-335     */
+  /* Home-Steward house (gridworld/base_hs.py:12-199): an agent whose FIRST component is
+   * PGW_HS_BEGIN is stepped as an HSMultiComponentEnv -- its components share the step's
+   * available solar / battery / grid power and the composite reward is evaluated on the
+   * final meta state. */
+  PGW_HS_BEGIN = 5,    /* pseudo component: meta state + grid cost (no action, no observation) */
+  PGW_HS_PV = 6,       /* gridworld/agents/pv/pv_profile_env_hs.py:15-169                  */
+  PGW_HS_STORAGE = 7,  /* gridworld/agents/energy_storage/energy_storage_env_hs.py:10-273  */
+  PGW_HS_EV = 8,       /* gridworld/agents/vehicles/ev_charging_env_hs.py:15-336           */
+  PGW_HS_DEVICES = 9   /* gridworld/agents/devices/devices_env_hs.py:14-205                */
 } pgw_component_type;
 
 /* pgw_component.flags */
@@ -92,6 +101,22 @@ typedef enum pgw_component_type {
  *                 lb_prev, ub_prev
  *           state: 6 double rows (x[5], p_consumed)        action 6, obs popcount(mask)
  */
+/*  HS_BEGIN  dpar: max_grid_power      dtab: grid cost of the event
+ *            state: 5 double rows (pv_power, es_power, es_cost, pv_cost, grid_power = the
+ *            reference's meta state, kept from step to step and across resets)
+ *  HS_PV     dpar: obs_low, obs_high    dtab: scaled profile value       action 1, obs 1
+ *  HS_STORAGE dpar: lo, hi, eta_charge, eta_discharge, max_power, dt_hours, initial mean,
+ *                 initial cost, max_storage_cost     ipar: storage ordinal
+ *            state: 2 double rows (SOC, current cost)                    action 1, obs 2
+ *  HS_EV     dpar: the EV layout, then max_charge_cost, 60 / minutes_per_step
+ *            dtab: evaluation time, new time    itab: as EV
+ *            state: n + 1 double rows (remaining kWh, current cost), words uint32 rows
+ *                                                                        action 1, obs 7
+ *  HS_DEVICES dpar: minutes_per_step / 60, obs_high[k]    ipar: k
+ *            dtab: scaled row[k], unscaled row[k]                        action 1, obs k
+ */
+#define PGW_HS_MAX_COMPONENTS 8  /* components of one house, HS_BEGIN not counted */
+
 typedef struct pgw_component {
   int32_t type;      /* pgw_component_type */
   int32_t agent;     /* owning agent (index into pgw_spec.agents) */

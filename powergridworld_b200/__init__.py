@@ -6,5 +6,6 @@ hand-written sm_100a CUDA kernels behind the C ABI of ``include/pgw.h``."""
 __version__ = "0.1.0"
 
 from .base import ComponentEnv, MultiComponentEnv
+from .base_hs import HSMultiComponentEnv
 from .multiagent_env import CoordinatedMultiBuildingControlEnv, MultiAgentEnv
 from .multiagent_list_interface_env import MultiAgentListInterfaceEnv

@@ -1,1 +1,2 @@
 from .ev_charging_env import EVChargingEnv
+from .ev_charging_env_hs import HSEVChargingEnv

@@ -68,6 +68,8 @@ struct pgw_env {
   double pvlo = 0, pvhi = 0, punit = 0;
   int pf_kernel = 0;
   int clock = -1;             // host mirror
+  long long resets = 0;
+  bool has_house = false;
   long long launches = 0;
   // device tables
   unsigned char* comp_blob = nullptr;   // [agents | comps | dpar | ipar]
@@ -162,7 +164,7 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
   }
   for (int c = 0; c < spec->num_components; ++c) {
     const pgw_component& k = spec->components[c];
-    if (k.type < PGW_STORAGE || k.type > PGW_BUILDING)
+    if (k.type < PGW_STORAGE || k.type > PGW_HS_DEVICES)
       return fail(PGW_ERR_INVALID, "unknown component type (no CPU fallback exists)");
     if (k.obs_off < 0 || k.obs_off + k.obs_dim > spec->obs_dim || k.act_off < 0 ||
         k.act_off >= spec->act_dim || k.dpar_off < 0 || k.dpar_off > spec->dpar_len ||
@@ -186,6 +188,8 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
   env->sd_rows = spec->sd_rows; env->si_rows = spec->si_rows;
   env->num_storage = spec->num_storage; env->num_events = spec->num_events;
   env->dstride = spec->dtab_stride; env->istride = spec->itab_stride;
+  for (int c = 0; c < spec->num_components; ++c)
+    if (spec->components[c].type == PGW_HS_BEGIN) env->has_house = true;
   for (int c = 0; c < spec->num_components; ++c)
     if (spec->components[c].type == PGW_BUILDING) {
       env->need_scratch_reset = true;                // reset always takes the table-driven path
@@ -633,6 +637,7 @@ static pgw::CompParams comp_params(pgw_env* env) {
   p.vmin = env->vmin; p.vmax = env->vmax; p.vbus = env->vbus;
   p.agent_p = env->agent_p; p.ep_ret = env->ep_ret;
   p.clock = env->d_clock; p.ticket = env->d_ticket;
+  p.has_house = env->has_house ? 1 : 0;
   return p;
 }
 
@@ -688,6 +693,8 @@ int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stre
   }
   pgw::CompParams cp = comp_params(env);
   cp.event_mode = 0; cp.advance_clock = 0; cp.init_soc = init_soc; cp.obs = obs;
+  cp.first_reset = env->resets == 0 ? 1 : 0;
+  ++env->resets;
   PGW_CUDA(pgw::launch_components(cp, smem_for_events(env, true), s));
   ++env->launches;
   env->clock = 0;

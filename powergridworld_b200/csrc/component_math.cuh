@@ -155,16 +155,21 @@ PGW_HD void pv_step(const pgw_component& c, const AgentIO& io, int e, double& p_
 // One pass over the vehicles parked at the event's time (the roster is shared by
 // all envs, so the window is a per-event list; only the "energy > 0" part of the
 // reference's charging set is per-env).  kwh = energy one vehicle may take now.
-PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double kwh,
-                       double& p_out, double& rew) {
+struct EvTotals {
+  double consumed, demand, deficit_sum, unserved;
+  int active, n_deficit;
+};
+
+// The charging pass shared by the stock station and the Home-Steward charger: window of the
+// event's evaluation time t_now, per-vehicle energy update, charging-set mask, unserved energy
+// of the vehicles that left the window.
+PGW_HD EvTotals ev_charge_pass(const pgw_component& c, const AgentIO& io, int e, double kwh,
+                               double t_now) {
   const double* dp = io.dpar + c.dpar_off;
   const int32_t* ip = io.ipar + c.ipar_off;
-  const int n = ip[0], words = ip[1], cap = ip[2];
-  const double rate = dp[0], mult = dp[2];
-  const double* obs_high = dp + 7;
-  const double* inv_high = dp + 13;
+  const int words = ip[1], cap = ip[2];
+  const double rate = dp[0];
   const double* end_park = dp + 21;
-  const double t_now = io.drow[c.dtab_off], t_next = io.drow[c.dtab_off + 1];
   const int32_t* ir = io.irow + c.itab_off;
   const int n_win = ir[0], n_left = ir[1];
   const int32_t* win = ir + 2;
@@ -172,8 +177,9 @@ PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double 
   double* energy = io.sd + (size_t)c.sd_off * io.E + e;
   uint32_t* mask = io.si + (size_t)c.si_off * io.E + e;
 
-  double consumed = 0.0, demand = 0.0, deficit_sum = 0.0;
-  int active = 0, n_deficit = 0;
+  EvTotals t;
+  t.consumed = 0.0; t.demand = 0.0; t.deficit_sum = 0.0; t.unserved = 0.0;
+  t.active = 0; t.n_deficit = 0;
   uint32_t word = 0;
   int cur_word = 0;
   for (int w = 0; w < words; ++w) mask[(size_t)w * io.E] = 0u;
@@ -199,25 +205,36 @@ PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double 
         word = 0;
       }
       word |= 1u << (i & 31);
-      ++active;
-      demand += need;                                   // :210
+      ++t.active;
+      t.demand += need;                                 // :210
       const double left_h = div_by(end_park[i] - t_now, 60.0, dp[20]);
       if (left_h <= 0.0) continue;                      // :218-220
-      deficit_sum += fmax(0.0, rate - need / left_h);   // :221-223
-      ++n_deficit;
+      t.deficit_sum += fmax(0.0, rate - need / left_h); // :221-223
+      ++t.n_deficit;
       const double delta = fmin(kwh, need);             // :226-228
       energy[(size_t)i * io.E] = need - delta;
-      consumed += delta;
+      t.consumed += delta;
     }
   }
   if (word) mask[(size_t)cur_word * io.E] = word;
-  double unserved = 0.0;                              // :240-243 over window(k-1) \ window(k)
-  for (int k = 0; k < n_left; ++k) unserved += energy[(size_t)left[k] * io.E];
-  (void)n;
+  // :240-243 over window(k-1) \ window(k)
+  for (int k = 0; k < n_left; ++k) t.unserved += energy[(size_t)left[k] * io.E];
+  return t;
+}
 
-  const double s_consumed = mult * consumed;
-  const double raw[6] = {t_next, mult * (double)active, s_consumed, mult * demand,
-                         n_deficit == 0 ? 0.0 : deficit_sum / (double)n_deficit, unserved};
+PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double kwh,
+                       double& p_out, double& rew) {
+  const double* dp = io.dpar + c.dpar_off;
+  const double mult = dp[2];
+  const double* obs_high = dp + 7;
+  const double* inv_high = dp + 13;
+  const double t_now = io.drow[c.dtab_off], t_next = io.drow[c.dtab_off + 1];
+  const EvTotals t = ev_charge_pass(c, io, e, kwh, t_now);
+  const double unserved = t.unserved;
+
+  const double s_consumed = mult * t.consumed;
+  const double raw[6] = {t_next, mult * (double)t.active, s_consumed, mult * t.demand,
+                         t.n_deficit == 0 ? 0.0 : t.deficit_sum / (double)t.n_deficit, unserved};
   const bool rs = (c.flags & PGW_F_RESCALE) != 0;
 #pragma unroll
   for (int j = 0; j < 6; ++j)
@@ -496,10 +513,311 @@ PGW_HD void building_step_fast(const pgw_component& c, const AgentIO& io, int e,
   p_out = p;
 }
 
+// ------------------------------------------------------------------ Home-Steward house
+// gridworld/base_hs.py:12-199 + agents/*/*_hs.py: the components of a house are stepped in
+// order and share the step's available solar / battery / grid power through a "meta state"
+// that also survives from step to step.  On the device that state is a small per-thread record
+// loaded by the leading HS_BEGIN pseudo-component and stored by the trailing HS_END one.
+// Divisions are plain IEEE float64 divisions, as in the reference.
+struct HsMeta {
+  double pv_power, es_power, grid_power, pv_cost, es_cost, grid_cost;
+  double r[PGW_HS_MAX_COMPONENTS];        // per-component reward terms, summed in order at the end
+  double es_pen[PGW_HS_MAX_COMPONENTS];   // storage: pending penalty (needs the FINAL meta), or 0
+  int n;
+};
+
+// to_scaled / to_raw with a real division (the HS bounds come without host reciprocals)
+PGW_HD double hs_scaled(double x, double lo, double hi) {
+  x = clip(x, lo, hi);
+  return (2.0 * x - (lo + hi)) / (hi - lo);
+}
+
+// HS_BEGIN  dpar: max_grid_power   dtab: grid_cost of the event
+//           state: pv_power, es_power, es_cost, pv_cost, grid_power (5 rows, the meta state)
+PGW_HD void hs_begin(const pgw_component& c, const AgentIO& io, int e, HsMeta& m, bool first_reset) {
+  double* sd = io.sd + (size_t)c.sd_off * io.E + e;
+  if (first_reset) {                                   // base_hs.py:53-61
+    for (int r = 0; r < 5; ++r) sd[(size_t)r * io.E] = 0.0;
+  }
+  m.pv_power = sd[0];
+  m.es_power = sd[(size_t)1 * io.E];
+  m.es_cost = sd[(size_t)2 * io.E];
+  m.pv_cost = sd[(size_t)3 * io.E];
+  m.grid_power = io.dpar[c.dpar_off];                  // :125
+  m.grid_cost = io.drow[c.dtab_off];                   // :124
+  m.n = 0;
+}
+
+PGW_HD void hs_end(const pgw_component& c, const AgentIO& io, int e, const HsMeta& m, bool store,
+                   double& r_agent) {
+  if (store) {
+    double* sd = io.sd + (size_t)c.sd_off * io.E + e;  // c = the HS_BEGIN descriptor
+    sd[0] = m.pv_power;
+    sd[(size_t)1 * io.E] = m.es_power;
+    sd[(size_t)2 * io.E] = m.es_cost;
+    sd[(size_t)3 * io.E] = m.pv_cost;
+    sd[(size_t)4 * io.E] = m.grid_power;
+  }
+  // step_reward(**meta_state) after every component has stepped (base_hs.py:176, :184-199)
+  double r = 0.0;
+  const bool pen = m.pv_power > 0.0 && m.es_power > 0.0;     // energy_storage_env_hs.py:176-181
+  for (int i = 0; i < m.n; ++i) {
+    double ri = m.r[i];
+    if (pen && m.es_pen[i] != 0.0) ri -= m.es_pen[i];
+    r += ri;
+  }
+  r_agent = r;
+}
+
+// HS_PV  dpar: obs_low, obs_high   dtab: scaled profile value of the event
+PGW_HD void hs_pv_step(const pgw_component& c, const AgentIO& io, int e, HsMeta& m, bool reset,
+                       double& p_out) {
+  const double* dp = io.dpar + c.dpar_off;
+  const bool rs = (c.flags & PGW_F_RESCALE) != 0;
+  const double data = io.drow[c.dtab_off];
+  const double raw = -data;                            // pv_profile_env_hs.py:110
+  io.obs[(size_t)c.obs_off * io.E + e] = rs ? hs_scaled(raw, dp[0], dp[1]) : raw;
+  if (reset) {
+    m.pv_power = -raw;                                 // only the reset chain sees it (:121-124)
+    p_out = 0.0;
+    return;
+  }
+  double a = io.actions[(size_t)c.act_off * io.E + e];
+  if (rs) a = to_raw(a, 0.98, 1.0);                    // :100-101, :140-141
+  const double p = a * (-raw);                         // :149
+  m.pv_power = p;                                      // :153
+  m.r[m.n] = 0.0; m.es_pen[m.n] = 0.0; ++m.n;
+  p_out = p;
+}
+
+// HS_STORAGE  dpar: lo, hi, eta_c, eta_d, max_power, dt_hours, initial mean, initial cost,
+//                   max_storage_cost      ipar: storage ordinal
+//             state: SOC, current_cost
+PGW_HD void hs_storage_obs(const pgw_component& c, const AgentIO& io, int e, double soc, double cost) {
+  const double* dp = io.dpar + c.dpar_off;
+  const bool rs = (c.flags & PGW_F_RESCALE) != 0;
+  io.obs[(size_t)c.obs_off * io.E + e] = rs ? hs_scaled(soc, dp[0], dp[1]) : soc;
+  io.obs[(size_t)(c.obs_off + 1) * io.E + e] = rs ? hs_scaled(cost, 0.0, dp[8]) : cost;
+}
+
+PGW_HD void hs_storage_reset(const pgw_component& c, const AgentIO& io, int e, bool first_reset) {
+  const double* dp = io.dpar + c.dpar_off;
+  double* sd = io.sd + (size_t)c.sd_off * io.E + e;
+  const int ord = io.ipar[c.ipar_off];
+  const double init = io.init_soc != nullptr ? io.init_soc[(size_t)ord * io.E + e] : dp[6];
+  const double soc = clip(init, dp[0], dp[1]);         // energy_storage_env_hs.py:93-96
+  sd[0] = soc;
+  if (first_reset) sd[(size_t)1 * io.E] = dp[7];       // current_cost is never reset (:39)
+  hs_storage_obs(c, io, e, soc, sd[(size_t)1 * io.E]);
+}
+
+PGW_HD void hs_storage_step(const pgw_component& c, const AgentIO& io, int e, HsMeta& m,
+                            double& p_out) {
+  const double* dp = io.dpar + c.dpar_off;
+  const double lo = dp[0], hi = dp[1], eta_c = dp[2], eta_d = dp[3], pmax = dp[4], dt = dp[5];
+  double* sd = io.sd + (size_t)c.sd_off * io.E + e;
+  double soc = sd[0], cost = sd[(size_t)1 * io.E];
+  double a = io.actions[(size_t)c.act_off * io.E + e];
+  if (c.flags & PGW_F_RESCALE) a = to_raw(a, -1.0, 1.0);
+  double power = a * pmax;
+  // validate_power :111-143
+  if (power > 0.0) {
+    const double delta = power * dt / eta_d;
+    if (soc <= lo) power = 0.0;
+    else if (soc - delta < lo) power = (soc - lo) / dt * eta_d;
+  } else if (power < 0.0) {
+    const double delta = -(power * dt * eta_c);
+    if (soc >= hi) power = 0.0;
+    else if (soc + delta > hi) power = -((hi - soc) / dt / eta_c);
+  }
+  double delta_cost = 0.0;
+  if (power == 0.0) {                                  // :215-217
+    m.es_power = 0.0;
+  } else if (power < 0.0) {                            // charging :219-245
+    const double delta_storage = eta_c * power * dt;
+    const double solar_used = fmin(-power, m.pv_power);
+    const double grid_used = fmin(m.grid_power, -power - solar_used);
+    delta_cost = (m.pv_cost * solar_used + m.grid_cost * grid_used) / (solar_used + grid_used);
+    cost = (soc * cost - delta_storage * delta_cost) / (soc - delta_storage);
+    soc -= delta_storage;
+    soc = fmin(soc, hi);
+    m.pv_power = fmax(0.0, m.pv_power - solar_used);
+    m.grid_power = fmax(0.0, m.grid_power - grid_used);
+    m.es_power = 0.0;
+  } else {                                             // discharging :248-253
+    const double delta_storage = power * dt / eta_d;
+    soc = fmax(soc - delta_storage, lo);
+    m.es_power = power;
+  }
+  m.es_cost = 0.0;                                     // :256
+  sd[0] = soc;
+  sd[(size_t)1 * io.E] = cost;
+  hs_storage_obs(c, io, e, soc, cost);
+  const double real_power = -power;                    // :258
+  // step_reward :161-190; the solar-available penalty is decided on the final meta (hs_end)
+  double step_cost = 0.0;
+  if (!(real_power < 0.0)) step_cost = delta_cost * eta_c * real_power * dt;
+  const double smax = fmax(lo, hi);
+  m.r[m.n] = -step_cost;
+  m.es_pen[m.n] = soc < smax ? dp[8] * (smax - soc) : 0.0;
+  ++m.n;
+  p_out = real_power;
+}
+
+// HS_EV  dpar: as the stock station up to e0[n], then max_charge_cost, 60 / minutes_per_step
+//        dtab: evaluation time, new time      itab: as the stock station
+//        state: n energy rows + current_cost; words of the charging set
+PGW_HD void hs_ev_advance(const pgw_component& c, const AgentIO& io, int e, double a_raw, HsMeta& m,
+                          bool reset, double& p_out) {
+  const double* dp = io.dpar + c.dpar_off;
+  const int n = io.ipar[c.ipar_off];
+  const double mult = dp[2];
+  const double* obs_high = dp + 7;
+  const double max_cost = dp[21 + 2 * n], per_hour = dp[22 + 2 * n];
+  const double t_eval = io.drow[c.dtab_off], t_new = io.drow[c.dtab_off + 1];
+  double* cost_p = io.sd + (size_t)(c.sd_off + n) * io.E + e;
+  const double kwh = (a_raw * dp[0]) * dp[1];          // ev_charging_env_hs.py:203-204
+  const EvTotals t = ev_charge_pass(c, io, e, kwh, t_eval);
+  const double real_power = mult * t.consumed;         // :281
+  const double power = real_power * per_hour;          // :285
+  double cost = *cost_p;                               // kept across episodes, 0 at creation
+  HsMeta loc = m;                                      // the hidden step of reset discards these
+  if (power == 0.0 || a_raw == 0.0) {                  // :292-293
+    cost = 0.0;
+  } else {
+    const double solar_used = fmin(power, loc.pv_power);
+    double battery_used, grid_used;
+    if (loc.es_cost < loc.grid_cost) {                 // :304-309
+      battery_used = fmin(loc.es_power, power - solar_used);
+      grid_used = fmin(loc.grid_power, power - solar_used - battery_used);
+    } else {
+      grid_used = fmin(loc.grid_power, power - solar_used);
+      battery_used = fmin(loc.es_power, power - solar_used - grid_used);
+    }
+    if (solar_used + grid_used + battery_used > 0.0)
+      cost = (loc.pv_cost * solar_used + loc.grid_cost * grid_used + loc.es_cost * battery_used) /
+             (solar_used + grid_used + battery_used);
+    loc.pv_power = fmax(0.0, loc.pv_power - solar_used);
+    loc.es_power = fmax(0.0, loc.es_power - battery_used);
+    loc.grid_power = fmax(0.0, loc.grid_power - grid_used);
+  }
+  *cost_p = cost;
+  const double raw[7] = {t_new, mult * (double)t.active, real_power, mult * t.demand,
+                         t.n_deficit == 0 ? 0.0 : t.deficit_sum / (double)t.n_deficit, t.unserved,
+                         cost};
+  const bool rs = (c.flags & PGW_F_RESCALE) != 0;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const double hi = j < 6 ? obs_high[j] : max_cost;
+    io.obs[(size_t)(c.obs_off + j) * io.E + e] = rs ? hs_scaled(raw[j], 0.0, hi) : raw[j];
+  }
+  if (!reset) {
+    m.pv_power = loc.pv_power; m.es_power = loc.es_power; m.grid_power = loc.grid_power;
+    // :178-191
+    m.r[m.n] = -(cost * real_power + dp[3] * (t.unserved * t.unserved));
+    m.es_pen[m.n] = 0.0;
+    ++m.n;
+  }
+  p_out = real_power;
+}
+
+PGW_HD void hs_ev_reset(const pgw_component& c, const AgentIO& io, int e, HsMeta& m) {
+  const double* dp = io.dpar + c.dpar_off;
+  const int n = io.ipar[c.ipar_off];
+  const double* e0 = dp + 21 + n;
+  double* energy = io.sd + (size_t)c.sd_off * io.E + e;
+  for (int i = 0; i < n; ++i) energy[(size_t)i * io.E] = e0[i];
+  double a = 0.0, p;                                   // hidden step, action = space low (:151, :199)
+  if (c.flags & PGW_F_RESCALE) a = to_raw(a, 0.0, 1.0);
+  hs_ev_advance(c, io, e, a, m, true, p);
+}
+
+// HS_DEVICES  dpar: minutes_per_step / 60, obs_high[k]     ipar: k (columns)
+//             dtab: scaled row [k] (observation), unscaled row [k] (demand)
+PGW_HD void hs_devices_step(const pgw_component& c, const AgentIO& io, int e, HsMeta& m, bool reset,
+                            double& p_out) {
+  const double* dp = io.dpar + c.dpar_off;
+  const int k = io.ipar[c.ipar_off];
+  const bool rs = (c.flags & PGW_F_RESCALE) != 0;
+  const double* row = io.drow + c.dtab_off;
+  for (int j = 0; j < k; ++j)
+    io.obs[(size_t)(c.obs_off + j) * io.E + e] = rs ? hs_scaled(row[j], 0.0, dp[1 + j]) : row[j];
+  p_out = 0.0;
+  if (reset) return;
+  double a = io.actions[(size_t)c.act_off * io.E + e];
+  if (rs) a = to_raw(a, 0.99, 1.0);                    // devices_env_hs.py:98-99
+  double total = 0.0;
+  for (int j = 0; j < k; ++j) total += row[k + j];     // :165
+  const double p = a * total;
+  double cost = 0.0;
+  if (rint(p * 1000.0) != 0.0) {                       // round(p, 3) == 0.0 (:174)
+    const double solar_used = fmin(p, m.pv_power);
+    const double battery_used = fmin(m.es_power, p - solar_used);
+    const double grid_used = fmin(m.grid_power, p - solar_used - battery_used);
+    cost = (m.pv_cost * solar_used + m.grid_cost * grid_used + m.es_cost * battery_used) /
+           (solar_used + grid_used + battery_used);
+    // the reference hands back the meta it copied BEFORE this allocation (:163, :201):
+    // what the devices consume never reaches the meta state
+  }
+  m.r[m.n] = -(cost * p * dp[0]);                      // :128-131
+  m.es_pen[m.n] = 0.0;
+  ++m.n;
+  p_out = p;
+}
+
 // ------------------------------------------------------------------ one agent of one env
 // MultiComponentEnv.step (base.py:114-139): components in order, real power summed,
 // reward = sum of the components' post-step rewards.  A single-component agent is the
 // one-element case (its own step reward, multiagent_env.py:168).
+PGW_HD bool is_house(const pgw_agent& ag, const pgw_component* comps) {
+  return comps[ag.comp_begin].type == PGW_HS_BEGIN;
+}
+
+// Home-Steward house (base_hs.py:120-178).  Kept apart from agent_step so that kernels of
+// scenarios without a house do not carry its code and stack frame.
+PGW_HD void house_step(const pgw_agent& ag, const pgw_component* comps, const AgentIO& io, int e,
+                       double& p_agent, double& r_agent) {
+  p_agent = 0.0;
+  HsMeta m;
+  hs_begin(comps[ag.comp_begin], io, e, m, false);
+  for (int ci = ag.comp_begin + 1; ci < ag.comp_end; ++ci) {
+    const pgw_component c = comps[ci];
+    double p = 0.0;
+    switch (c.type) {
+      case PGW_HS_PV: hs_pv_step(c, io, e, m, false, p); break;
+      case PGW_HS_STORAGE: hs_storage_step(c, io, e, m, p); break;
+      case PGW_HS_EV: {
+        double a = io.actions[(size_t)c.act_off * io.E + e];
+        if (c.flags & PGW_F_RESCALE) a = to_raw(a, 0.0, 1.0);
+        hs_ev_advance(c, io, e, a, m, false, p);
+        break;
+      }
+      case PGW_HS_DEVICES: hs_devices_step(c, io, e, m, false, p); break;
+      default: break;
+    }
+    p_agent += p;
+  }
+  hs_end(comps[ag.comp_begin], io, e, m, true, r_agent);
+}
+
+// base_hs.py:67-92; the meta state itself is not reset
+PGW_HD void house_reset(const pgw_agent& ag, const pgw_component* comps, const AgentIO& io, int e,
+                        bool first_reset) {
+  HsMeta m;
+  hs_begin(comps[ag.comp_begin], io, e, m, first_reset);
+  for (int ci = ag.comp_begin + 1; ci < ag.comp_end; ++ci) {
+    const pgw_component c = comps[ci];
+    double p;
+    switch (c.type) {
+      case PGW_HS_PV: hs_pv_step(c, io, e, m, true, p); break;
+      case PGW_HS_STORAGE: hs_storage_reset(c, io, e, first_reset); break;
+      case PGW_HS_EV: hs_ev_reset(c, io, e, m); break;
+      case PGW_HS_DEVICES: hs_devices_step(c, io, e, m, true, p); break;
+      default: break;
+    }
+  }
+}
+
 PGW_HD void agent_step(const pgw_agent& ag, const pgw_component* comps, const AgentIO& io, int e,
                        double& p_agent, double& r_agent) {
   p_agent = 0.0;

@@ -18,6 +18,8 @@
 
 namespace pgw {
 
+// HOUSE: the scenario contains Home-Steward houses (their code stays out of the other kernel).
+template <bool HOUSE>
 __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t mbar[2];
@@ -101,14 +103,16 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
     if (e < p.E) {
       const size_t ae = (size_t)a * p.E + e;
       if (p.event_mode == 0) {
-        agent_reset(ag, comps, io, e);
+        if (HOUSE && is_house(ag, comps)) house_reset(ag, comps, io, e, p.first_reset != 0);
+        else agent_reset(ag, comps, io, e);
         p.agent_p[ae] = 0.0;
         p.ep_ret[ae] = 0.0;
       } else {
         double pw, rw, er = 0.0;
         if (p.owns_reward)                      // issued early: its latency hides behind the step
           asm volatile("ld.global.f64 %0, [%1];" : "=d"(er) : "l"(p.ep_ret + ae));
-        agent_step(ag, comps, io, e, pw, rw);
+        if (HOUSE && is_house(ag, comps)) house_step(ag, comps, io, e, pw, rw);
+        else agent_step(ag, comps, io, e, pw, rw);
         p.agent_p[ae] = pw;
         p.rew[ae] = rw;
         if (p.owns_reward) {                    // no feeder / no penalty hook: the reward is final
@@ -129,12 +133,12 @@ cudaError_t launch_components(const CompParams& p, int smem_bytes, cudaStream_t 
   int per_agent = (148 * 16 + p.A - 1) / p.A;
   if (per_agent < 1) per_agent = 1;
   dim3 grid(blocks < per_agent ? blocks : per_agent, p.A);
+  auto kern = p.has_house ? component_kernel<true> : component_kernel<false>;
   if (smem_bytes > 48 * 1024) {
-    cudaError_t err = cudaFuncSetAttribute(component_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (err != cudaSuccess) return err;
   }
-  component_kernel<<<grid, threads, smem_bytes, s>>>(p);
+  kern<<<grid, threads, smem_bytes, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -40,11 +40,17 @@ static pgw::AgentIO make_io(const EmuArgs* a) {
   return io;
 }
 
+static int g_first_reset = 1;
+void emu_set_first_reset(int v) { g_first_reset = v; }
+
 void emu_reset(const EmuArgs* a) {
   pgw::AgentIO io = make_io(a);
   for (int ag = 0; ag < a->A; ++ag)
     for (int e = 0; e < a->E; ++e) {
-      pgw::agent_reset(a->agents[ag], a->comps, io, e);
+      if (pgw::is_house(a->agents[ag], a->comps))
+        pgw::house_reset(a->agents[ag], a->comps, io, e, g_first_reset != 0);
+      else
+        pgw::agent_reset(a->agents[ag], a->comps, io, e);
       a->agent_p[(size_t)ag * a->E + e] = 0.0;
     }
 }
@@ -54,7 +60,10 @@ void emu_step(const EmuArgs* a) {
   for (int ag = 0; ag < a->A; ++ag)
     for (int e = 0; e < a->E; ++e) {
       double p, r;
-      pgw::agent_step(a->agents[ag], a->comps, io, e, p, r);
+      if (pgw::is_house(a->agents[ag], a->comps))
+        pgw::house_step(a->agents[ag], a->comps, io, e, p, r);
+      else
+        pgw::agent_step(a->agents[ag], a->comps, io, e, p, r);
       a->agent_p[(size_t)ag * a->E + e] = p;
       a->rew[(size_t)ag * a->E + e] = r;
     }

@@ -68,6 +68,7 @@ class EmulatedEnv:
         self.vbus = np.ones((self.A, self.E))
         self.vmag = None
         self.t = 0
+        self.resets = 0
 
     def _args(self, event, actions=None, init_soc=None):
         a = EmuArgs()
@@ -112,6 +113,8 @@ class EmulatedEnv:
     def reset(self, init_soc):
         self._powerflow(0, controllable=False)
         soc = np.ascontiguousarray(init_soc, dtype=np.float64) if init_soc is not None else None
+        self.lib.emu_set_first_reset(1 if self.resets == 0 else 0)
+        self.resets += 1
         self.lib.emu_reset(C.byref(self._args(0, init_soc=soc)))
         self.t = 0
         return self.obs.copy()

@@ -425,3 +425,92 @@ def test_der123_fp16_tensor_core_power_flow_matches_fp64_kernel():
     it = b_env.get_field(7)
     assert int(it.min()) > 0, "tensor-core solve did not converge"
     assert float(it.double().mean()) < 25
+
+
+# ------------------------------------------------------------------ Home-Steward house
+def _hs_batch(name, num_envs):
+    from powergridworld_b200.base_hs import house_agent_config
+    from tests import scenarios_hs as SH
+    from tests.product_hs_ns import PRODUCT_HS_NS as HNS
+    cfg = SH.VARIANTS[name](HNS)
+    return PNS.MultiAgentEnv(
+        common_config={"start_time": cfg["start_time"], "end_time": "01-01-2031 00:00:00",
+                       "control_timedelta": cfg["control_timedelta"]},
+        pf_config=None, num_envs=num_envs,
+        agents=[{"name": "house", "bus": None, "cls": HNS.HSMultiComponentEnv,
+                 "config": house_agent_config(cfg)}])
+
+
+@pytest.mark.parametrize("name", ["shipped", "two_vehicles", "raw_spaces"])
+def test_hs_house_golden_trace_on_gpu(name):
+    """The reference's HSMultiComponentEnv trace (recorded from the unmodified reference) through
+    the CUDA path, one house per env, every env fed the golden actions: observations 1e-12,
+    rewards 1e-12 relative, done flags and the house's real power."""
+    torch = _torch()
+    g = np.load(os.path.join(GOLD, f"hs_{name}.npz"))
+    E = 5
+    env = _hs_batch(name, E)
+    assert env.episode_length == 288
+    obs0 = env.reset_batch(np.repeat(g["init_soc"].reshape(1, 1), E, axis=1)).cpu().numpy()
+    for e in range(E):
+        np.testing.assert_allclose(obs0[:, e], g["obs0"], rtol=0, atol=1e-13)
+    for t in range(g["actions"].shape[0]):
+        act = torch.as_tensor(np.repeat(g["actions"][t].reshape(4, 1), E, axis=1)).cuda()
+        o, r, d, alld = env.step_batch(act)
+        o, r = o.cpu().numpy(), r.cpu().numpy()
+        for e in (0, E - 1):
+            np.testing.assert_allclose(o[:, e], g["obs"][t], rtol=0, atol=1e-12, err_msg=f"t={t}")
+            np.testing.assert_allclose(r[0, e], g["rew"][t], rtol=1e-12, atol=1e-13, err_msg=f"t={t}")
+        assert bool(d[0]) == bool(g["done"][t])
+        np.testing.assert_allclose(env.get_field(2).cpu().numpy()[0], g["real_power"][t],
+                                   rtol=1e-14, atol=0)
+
+
+def test_hs_house_batch_matches_oracle_per_env():
+    """Different actions and initial storage per env against the HS oracle, two episodes back to
+    back (the storage cost and the meta state survive the reset, as in the reference)."""
+    torch = _torch()
+    from tests import scenarios_hs as SH
+    from tests.oracle_hs_ns import ORACLE_HS_NS as OHS
+    E, T = 6, 60
+    env = _hs_batch("two_vehicles", E)
+    rng = np.random.default_rng(17)
+    refs = [OHS.HSMultiComponentEnv(**SH.two_vehicles(OHS)) for _ in range(E)]
+    flat = lambda h, ob: np.concatenate([np.asarray(ob[c.name], dtype=np.float64).ravel() for c in h.envs])
+    for episode in range(2):
+        soc = rng.uniform(3, 19, size=(1, E))
+        obs0 = env.reset_batch(soc).cpu().numpy()
+        for e in range(E):
+            np.testing.assert_allclose(obs0[:, e], flat(refs[e], refs[e].reset(init_storage=soc[0, e])),
+                                       rtol=0, atol=1e-12)
+        for t in range(T):
+            acts = rng.uniform(-1.2, 1.2, size=(4, E))
+            o, r, _, _ = env.step_batch(torch.as_tensor(acts).cuda())
+            o, r = o.cpu().numpy(), r.cpu().numpy()
+            for e in range(E):
+                ob, rw, _, _ = refs[e].step({c.name: acts[k:k + 1, e] for k, c in enumerate(refs[e].envs)})
+                np.testing.assert_allclose(o[:, e], flat(refs[e], ob), rtol=0, atol=1e-12)
+                np.testing.assert_allclose(r[0, e], rw, rtol=1e-12, atol=1e-13)
+
+
+def test_hs_house_object_protocol():
+    """HSMultiComponentEnv(**make_env_config()) stepped on its own like the reference object:
+    reset() -> obs dict, step(action dict) -> (obs, reward, done, meta_state)."""
+    from powergridworld_b200.base_hs import HSMultiComponentEnv
+    from powergridworld_b200.scenarios.heterogeneous_hs import make_env_config
+    g = np.load(os.path.join(GOLD, "hs_shipped.npz"))
+    house = HSMultiComponentEnv(**make_env_config())
+    obs = house.reset(init_storage=float(g["init_soc"][0]))
+    assert set(obs) == {"pv", "storage", "ev-charging", "other-devices"}
+    names = [e.name for e in house.envs]
+    for t in range(5):
+        a = g["actions"][t]
+        obs, rew, done, meta = house.step({n: a[k:k + 1] for k, n in enumerate(names)})
+        got = np.concatenate([np.asarray(obs[n]).ravel() for n in names])
+        np.testing.assert_allclose(got, g["obs"][t], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(rew, g["rew"][t], rtol=1e-12, atol=1e-13)
+        assert not done
+        # golden meta order: grid_cost, es_cost, grid_power, pv_power, es_power, pv_cost
+        np.testing.assert_allclose(
+            [meta[k] for k in ("grid_cost", "es_cost", "grid_power", "pv_power", "es_power", "pv_cost")],
+            g["meta"][t], rtol=1e-14, atol=0)

@@ -514,3 +514,73 @@ def test_hs_house_object_protocol():
         np.testing.assert_allclose(
             [meta[k] for k in ("grid_cost", "es_cost", "grid_power", "pv_power", "es_power", "pv_cost")],
             g["meta"][t], rtol=1e-14, atol=0)
+
+
+# ------------------------------------------------------------------ tc2 tile widths / stand-alone solve
+def _truncated_feeder(tmp_path, n_loads):
+    """The packaged 123-bus-class feeder with only its first ``n_loads`` spot loads."""
+    from powergridworld_b200 import assets
+    src = os.path.join(os.path.dirname(os.path.abspath(assets.__file__)), "data", "feeders",
+                       "synthetic123.dss")
+    out, seen = [], 0
+    for line in open(src):
+        if line.startswith("New Load."):
+            seen += 1
+            if seen > n_loads:
+                continue
+        out.append(line)
+    path = os.path.join(str(tmp_path), f"synthetic_{n_loads}.dss")
+    with open(path, "w") as fh:
+        fh.writelines(out)
+    return path
+
+
+@pytest.mark.parametrize("n_loads", [24, 50, 85])
+def test_tc2_every_tile_width_standalone_and_in_env(tmp_path, n_loads):
+    """24 / 50 / 85 load branches -> the NCH = 4 / 8 / 11 instantiations of pf_tc2_kernel, through
+    the stand-alone solve (pgw_pf_solve, its own instantiation) and inside a stepping env, against
+    the FP64 kernel: voltages within 1e-6 p.u."""
+    torch = _torch()
+    from powergridworld_b200 import _native as N
+    path = _truncated_feeder(tmp_path, n_loads)
+    shape = "ieee_13_dss/annual_hourly_load_profile.csv"
+    a, b = PNS.OpenDSSSolver(path, shape, 0.9), PNS.OpenDSSSolver(path, shape, 0.9)
+    assert a.feeder.nb == n_loads
+    for s_, k in ((a, 0), (b, 2)):
+        s_.calculate_power_flow(current_time="08-12-2021 12:00:00")
+        s_._env.set_option(N.OPT_PF_KERNEL, k)
+    names = a.feeder.load_names
+    ctrl = {names[0]: 150.0, names[3]: -80.0, names[n_loads - 1]: 40.0}
+    for s_ in (a, b):
+        s_.calculate_power_flow(current_time="08-12-2021 12:00:00", p_controllable_consumed=ctrl,
+                                q_controllable_consumed={names[0]: 20.0})
+    va, vb = a.get_bus_voltages(), b.get_bus_voltages()
+    np.testing.assert_allclose([vb[k] for k in va], list(va.values()), rtol=0, atol=1e-6)
+    assert min(va.values()) < 0.999                      # the loads did move the profile
+
+    import pandas as pd
+    def env(kernel):
+        agents = [{"name": f"s{i}", "bus": names[(7 * i) % n_loads], "cls": PNS.EnergyStorageEnv,
+                   "config": {"max_power": 40. + 10 * i, "storage_range": (3., 80.)}}
+                  for i in range(6)]
+        e = PNS.MultiAgentEnv(
+            common_config={"start_time": "08-12-2021 00:00:00", "end_time": "08-13-2021 00:00:00",
+                           "control_timedelta": pd.Timedelta(300, "s")},
+            pf_config={"cls": PNS.OpenDSSSolver, "config": {
+                "feeder_file": path, "loadshape_file": shape, "system_load_rescale_factor": 0.9}},
+            agents=agents, num_envs=200)
+        e.set_option(N.OPT_PF_KERNEL, kernel)
+        return e
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ea, eb = env(0), env(2)
+    rng = np.random.default_rng(n_loads)
+    soc = rng.uniform(10, 70, size=(6, 200))
+    ea.reset_batch(soc); eb.reset_batch(soc)
+    for t in range(6):
+        act = torch.as_tensor(rng.uniform(-1, 1, size=(ea.act_dim, 200))).cuda()
+        ea.step_batch(act); eb.step_batch(act)
+        np.testing.assert_allclose(eb.get_field(3).cpu().numpy(), ea.get_field(3).cpu().numpy(),
+                                   rtol=0, atol=1e-6, err_msg=f"t={t}")
+    assert int(eb.get_field(7).min()) > 0

@@ -34,8 +34,9 @@
 namespace pgw {
 
 constexpr int T2_M = 128;
-constexpr int T2_THREADS = 512;
-constexpr int T2_ISSUER = 15;               // warp that feeds the pipelined chains (fewest chunks)
+// A CTA is G groups of 128 threads (one thread per env row and group); group g owns the chunks
+// g, g + G, ...  Wide feeders use G = 4 and one CTA per SM (shared memory is full anyway); small
+// ones (NCH <= 4) use G = 2 with two CTAs per SM, so that every thread has a chunk to work on.
 
 __device__ __forceinline__ uint64_t t2_smem_desc(uint32_t saddr, uint32_t sbo) {
   // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
@@ -175,9 +176,12 @@ __device__ __forceinline__ void t2_current(float4 c, float2 gh, float dr, float 
 // STANDALONE: the solve of pgw_pf_solve (total kW / kvar per load given per env) instead of the
 // step / reset solve (base load of the event + the agents' powers).
 template <int NCH, bool ANY_M5, bool STANDALONE>
-__global__ void __launch_bounds__(T2_THREADS, 1)
+__global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, NCH <= 4 ? 2 : 1)
     pf_tc2_kernel(const PfParams p, const __grid_constant__ Tc2Consts kc) {
-  constexpr int SLOTS = (NCH + 3) / 4;                 // chunks per thread: c = grp + 4 * slot
+  constexpr int G = NCH <= 4 ? 2 : 4;                  // groups of 128 threads
+  constexpr int T2_THREADS = 128 * G;
+  constexpr int T2_ISSUER = 4 * G - 1;                 // warp that feeds the pipelined chains
+  constexpr int SLOTS = (NCH + G - 1) / G;             // chunks per thread: c = grp + G * slot
   constexpr int N = 16 * NCH;
   constexpr uint32_t SBO = 256u * NCH;                 // bytes between 8-row groups
   constexpr uint32_t PB = (uint32_t)(N / 8) * SBO;     // one B image: N rows
@@ -185,13 +189,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
   extern __shared__ __align__(1024) unsigned char t2_smem[];
   __shared__ __align__(8) uint64_t mbar_tab, mbar_b, mbar_mma, mbar_wave[SLOTS];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_dpart[2][4][T2_M];                // per-group partial max |d drop|, 2 phases
+  __shared__ float s_dpart[2][G][T2_M];                // per-group partial max |d drop|, 2 phases
   float (*s_vmn)[T2_M] = s_dpart[0], (*s_vmx)[T2_M] = s_dpart[1];   // reused after the solve
   const Tc2Params& t = p.tc2;
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // provably warp-uniform
   const int row = tid & (T2_M - 1);                    // env row in the tile = TMEM lane
-  const int grp = warp >> 2;                           // chunk group 0..3
+  const int grp = warp >> 2;                           // chunk group 0..G-1
   const int hdr = 2 + 2 * p.nl;
 
   unsigned char* sB = t2_smem;                         // B_hi | B_lo (iteration) or a Znb chunk
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
     mbar_init(&mbar_b, 1);
     mbar_init(&mbar_mma, 1);
     for (int w = 0; w < SLOTS; ++w)                    // one arrival per warp that owns a chunk of wave w
-      mbar_init(&mbar_wave[w], 4u * (uint32_t)(NCH - 4 * w < 4 ? NCH - 4 * w : 4));
+      mbar_init(&mbar_wave[w], 4u * (uint32_t)(NCH - G * w < G ? NCH - G * w : G));
     mbar_expect_tx(&mbar_tab, (uint32_t)t.tab_bytes + (uint32_t)hdr * 8u);
     tma_bulk_g2s(sT, t.blob + t.off_tab, (uint32_t)t.tab_bytes, &mbar_tab);
     mbar_expect_tx(&mbar_b, (uint32_t)(1 + nres) * 2 * PB);
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
     float sr[SLOTS][8], si[SLOTS][8];
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
-      const int c = grp + 4 * s;
+      const int c = grp + G * s;
       if (c < NCH) {
         float d0[16], x[8], y[8];
 #pragma unroll
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
       float dpart = 0.f;
 #pragma unroll
       for (int s = 0; s < SLOTS; ++s) {
-        const int c = grp + 4 * s;
+        const int c = grp + G * s;
         if (c < NCH) {                                 // warp-uniform: tcgen05.ld is collective
           float dn[16], dold[16];
           t2_ld16(t_lane + cur * N + 16 * c, dn);
@@ -425,8 +429,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
           __syncthreads_and((conv || dpart < tol_s || it >= p.max_iter) ? 1 : 0) != 0;
       const bool frozen = conv;                        // converged before this iteration
       if (!conv) {                                     // per-env convergence mask
-        const float d = fmaxf(fmaxf(s_dpart[it & 1][0][row], s_dpart[it & 1][1][row]),
-                              fmaxf(s_dpart[it & 1][2][row], s_dpart[it & 1][3][row]));
+        float d = s_dpart[it & 1][0][row];
+#pragma unroll
+        for (int q = 1; q < G; ++q) d = fmaxf(d, s_dpart[it & 1][q][row]);
         conv_ok = d < tol_s;
         conv = conv_ok || it >= p.max_iter;
         my_it = it;
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
 
 #pragma unroll
       for (int s = 0; s < SLOTS; ++s) {
-        const int c = grp + 4 * s;
+        const int c = grp + G * s;
         if (c < NCH) {
           float dn[16], x[8], y[8];
           t2_ld16(t_lane + cur * N + 16 * c, dn);
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
             const uint64_t a_hi = t2_smem_desc(sA_u, SBO), a_lo = t2_smem_desc(sA_u + APB, SBO);
             const uint64_t b_hi = t2_smem_desc(sB_u, SBO), b_lo = t2_smem_desc(sB_u + PB, SBO);
 #pragma unroll
-            for (int kk = 4 * s; kk < 4 * s + 4 && kk < NCH; ++kk) {
+            for (int kk = G * s; kk < G * s + G && kk < NCH; ++kk) {
               t2_umma_f16(tmem + d_col, a_lo + 16u * kk, b_hi + 16u * kk, idesc, kk > 0 ? 1u : 0u);
               t2_umma_f16(tmem + d_col, a_hi + 16u * kk, b_lo + 16u * kk, idesc, 1u);
               t2_umma_f16(tmem + d_col, a_hi + 16u * kk, b_hi + 16u * kk, idesc, 1u);
@@ -493,7 +498,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
     float vmn = 3.0e38f, vmx = -3.0e38f;
 #pragma unroll 1                                       // executed once per tile: keep the code small
     for (int s = 0; s < SLOTS; ++s) {
-      const int c = grp + 4 * s;
+      const int c = grp + G * s;
       if (c < NCH) {                                   // warp-uniform: tcgen05.ld is collective
         float dn[16];
         t2_ld16(t_lane + last * N + 16 * c, dn);
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
       }
 #pragma unroll 1
       for (int s = 0; s < SLOTS; ++s) {
-        const int c = grp + 4 * s;
+        const int c = grp + G * s;
         if (c < NCH) {
           const int s0 = 8 * (cc * NCH + c);           // expanded slots s0 .. s0 + 7
           if (s0 < t.nx) {
@@ -575,8 +580,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
     __syncthreads();                        // vmag / partial min-max of the other groups visible
 
     if (valid && grp == 0) {
-      p.vmin[e] = (double)fminf(fminf(s_vmn[0][row], s_vmn[1][row]), fminf(s_vmn[2][row], s_vmn[3][row]));
-      p.vmax[e] = (double)fmaxf(fmaxf(s_vmx[0][row], s_vmx[1][row]), fmaxf(s_vmx[2][row], s_vmx[3][row]));
+      float mn = s_vmn[0][row], mx = s_vmx[0][row];
+#pragma unroll
+      for (int q = 1; q < G; ++q) { mn = fminf(mn, s_vmn[q][row]); mx = fmaxf(mx, s_vmx[q][row]); }
+      p.vmin[e] = (double)mn;
+      p.vmax[e] = (double)mx;
       p.iters[e] = conv_ok ? my_it : -my_it;
     }
     if (valid) {
@@ -588,13 +596,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
       }
       if (grp == 0) p.viol[e] = viol;
       if (p.reward_hook) {
-        // every agent: bus voltage + the shared penalty.  Agents a = grp, grp + 4, ... in
+        // every agent: bus voltage + the shared penalty.  Agents a = grp, grp + G, ... in
         // batches of 4 so that the loads of a batch are in flight together.
-        for (int a0 = grp; a0 < p.A; a0 += 16) {
+        for (int a0 = grp; a0 < p.A; a0 += 4 * G) {
           double vb[4], rw[4], er[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int a = a0 + 4 * q;
+            const int a = a0 + G * q;
             vb[q] = 1.0; rw[q] = 0.0; er[q] = 0.0;
             if (a < p.A) {
               const int node = anode[a];
@@ -606,7 +614,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int a = a0 + 4 * q;
+            const int a = a0 + G * q;
             if (a < p.A) {
               const size_t ae = (size_t)a * p.E + e;
               const double r = rw[q] - pen_share;
@@ -619,7 +627,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
         }
       } else {
         // the agents whose bus is not a wye-load node (none in the shipped scenarios)
-        for (int q = grp; q < t.ntail; q += 4) {
+        for (int q = grp; q < t.ntail; q += G) {
           const int a = vtail[q], node = anode[a];
           p.vbus[(size_t)a * p.E + e] = node >= 0 ? p.vmag[(size_t)node * p.E + e] : 1.0;
         }
@@ -655,7 +663,7 @@ static cudaError_t launch_tc2_t(const PfParams& p, int grid, size_t smem, cudaSt
   if (err != cudaSuccess) return err;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(T2_THREADS);
+  cfg.blockDim = dim3(NCH <= 4 ? 256 : 512);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -668,7 +676,8 @@ static cudaError_t launch_tc2_t(const PfParams& p, int grid, size_t smem, cudaSt
 
 cudaError_t launch_powerflow_tc2(const PfParams& p, cudaStream_t s) {
   const int tiles = (p.E + T2_M - 1) / T2_M;
-  int grid = tiles < 148 ? tiles : 148;
+  const int per_sm = p.tc2.nch <= 4 ? 2 : 1;
+  int grid = tiles < 148 * per_sm ? tiles : 148 * per_sm;
   if (grid < 1) grid = 1;
   const size_t smem = tc2_smem_bytes(p);
   switch (p.tc2.nch) {

@@ -74,7 +74,8 @@ struct pgw_env {
   // device tables
   unsigned char* comp_blob = nullptr;   // [agents | comps | dpar | ipar]
   int comp_blob_bytes = 0, off_comps = 0, off_dpar = 0, off_ipar = 0;
-  pgw::AgentSlice* slices = nullptr;    // per-agent staging ranges
+  pgw::CtaWork* work = nullptr;         // CTA -> (agent, env blocks, staging ranges)
+  int num_ctas = 0;
   int max_cn = 0, max_dn = 0, max_in = 0;
   double* dtab = nullptr;
   int32_t* itab = nullptr;
@@ -259,7 +260,60 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       env->max_dn = std::max(env->max_dn, s.d_n);
       env->max_in = std::max(env->max_in, s.i_n);
     }
-    PGW_TRY(upload(&env->slices, sl.data(), sl.size())); env->own(env->slices);
+    // CTA budget of ~16 per SM, split over the agents in proportion to a cost estimate of their
+    // components (rough time per 64-env block), every agent between 1 CTA and one CTA per
+    // 64-env block.  Agents are emitted interleaved, heavy ones first within a round.
+    {
+      const int blocks = (env->E + 63) / 64, budget = 148 * 16;
+      std::vector<double> w(env->A, 0.5);            // ~us per env block: loop + latency floor
+      double wsum = 0.0;
+      for (int a = 0; a < env->A; ++a) {
+        for (int c = spec->agents[a].comp_begin; c < spec->agents[a].comp_end; ++c) {
+          const pgw_component& k = spec->components[c];
+          switch (k.type) {
+            case PGW_BUILDING: w[a] += 5.0; break;
+            case PGW_EV: case PGW_HS_EV: w[a] += 2.0 + 0.04 * spec->ipar[k.ipar_off]; break;
+            case PGW_STORAGE: w[a] += 0.8; break;
+            case PGW_HS_BEGIN: case PGW_HS_STORAGE: case PGW_HS_DEVICES: w[a] += 1.0; break;
+            default: w[a] += 0.5; break;
+          }
+        }
+        wsum += w[a];
+      }
+      // water-filling: agents that reach one CTA per block give their surplus to the others
+      std::vector<int> n(env->A, 0);
+      {
+        std::vector<char> capped(env->A, 0);
+        double left = budget, wleft = wsum;
+        for (bool again = true; again;) {
+          again = false;
+          for (int a = 0; a < env->A; ++a)
+            if (!capped[a] && left * w[a] / wleft >= blocks) {
+              capped[a] = 1; n[a] = blocks; left -= blocks; wleft -= w[a]; again = true;
+            }
+        }
+        for (int a = 0; a < env->A; ++a)
+          if (!capped[a])
+            n[a] = std::max(1, std::min(blocks, (int)std::ceil(left * w[a] / wleft)));
+      }
+      std::vector<int> order(env->A);
+      for (int a = 0; a < env->A; ++a) order[a] = a;
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return w[x] > w[y]; });
+      std::vector<pgw::CtaWork> work;
+      for (int j = 0;; ++j) {                        // round j: the j-th CTA of every agent that has one
+        bool any = false;
+        for (int a : order)
+          if (j < n[a]) {
+            pgw::CtaWork cw{};
+            cw.agent = a; cw.j = j; cw.n = n[a]; cw.sl = sl[a];
+            work.push_back(cw);
+            any = true;
+          }
+        if (!any) break;
+      }
+      env->num_ctas = (int)work.size();
+      PGW_TRY(upload(&env->work, work.data(), work.size())); env->own(env->work);
+    }
     if (env->max_cn * (int)sizeof(pgw_component) + env->max_dn * 8 + env->max_in * 4 +
             spec->dtab_stride * 8 + spec->itab_stride * 4 > 160 * 1024) {
       delete env;
@@ -631,7 +685,7 @@ static pgw::CompParams comp_params(pgw_env* env) {
   p.E = env->E; p.A = env->A;
   p.blob = env->comp_blob; p.blob_bytes = env->comp_blob_bytes;
   p.off_comps = env->off_comps; p.off_dpar = env->off_dpar; p.off_ipar = env->off_ipar;
-  p.slices = env->slices; p.max_cn = env->max_cn; p.max_dn = env->max_dn; p.max_in = env->max_in;
+  p.work = env->work; p.num_ctas = env->num_ctas; p.max_cn = env->max_cn; p.max_dn = env->max_dn; p.max_in = env->max_in;
   p.dtab = env->dtab; p.itab = env->itab; p.dstride = env->dstride; p.istride = env->istride;
   p.sd = env->sd; p.si = env->si; p.rew_copy = env->rew_last;
   p.vmin = env->vmin; p.vmax = env->vmax; p.vbus = env->vbus;

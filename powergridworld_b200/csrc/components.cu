@@ -36,8 +36,9 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
       smem_raw + static_bytes + (size_t)p.dstride * 8 + (size_t)p.istride * 4);
 
   // the three independent global reads of the prologue, issued back to back
-  const int a = blockIdx.y;
-  const AgentSlice sl = p.slices[a];
+  const CtaWork wk = p.work[blockIdx.x];
+  const int a = wk.agent;
+  const AgentSlice sl = wk.sl;
   const pgw_agent ag = reinterpret_cast<const pgw_agent*>(p.blob)[a];
   const int ev = p.event_mode == 0 ? 0 : (*p.clock + 1);
   // Two staging phases so that the latency of reading the device clock (which selects the
@@ -82,8 +83,8 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
 
   // Persistent CTA: the tables are staged once, then the CTA walks env blocks of its agent.
   bool first = true;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e - (int)threadIdx.x < p.E;
-       e += gridDim.x * blockDim.x) {
+  for (int e = wk.j * blockDim.x + threadIdx.x; e - (int)threadIdx.x < p.E;
+       e += wk.n * blockDim.x) {
     if (e < p.E && p.event_mode != 0) {
       // pull this thread's action and (small) state rows towards the SM early
       for (int ci = ag.comp_begin; ci < ag.comp_end; ++ci) {
@@ -123,16 +124,12 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
       }
     }
   }
-  if (p.advance_clock) publish_clock_last_cta(p.ticket, p.clock, event, gridDim.x * gridDim.y);
+  if (p.advance_clock) publish_clock_last_cta(p.ticket, p.clock, event, gridDim.x);
 }
 
 cudaError_t launch_components(const CompParams& p, int smem_bytes, cudaStream_t s) {
   const int threads = 64;      // small CTAs: a 4096-env batch still reaches every SM
-  const int blocks = (p.E + threads - 1) / threads;
-  // persistent for big batches: ~16 CTAs per SM in total, each walking several env blocks
-  int per_agent = (148 * 16 + p.A - 1) / p.A;
-  if (per_agent < 1) per_agent = 1;
-  dim3 grid(blocks < per_agent ? blocks : per_agent, p.A);
+  dim3 grid(p.num_ctas);       // the CTA -> (agent, env blocks) table is built in pgw_create
   auto kern = p.has_house ? component_kernel<true> : component_kernel<false>;
   if (smem_bytes > 48 * 1024) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

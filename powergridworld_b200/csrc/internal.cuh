@@ -16,6 +16,14 @@ struct AgentSlice {
   int pad0, pad1;
 };
 
+// One CTA of the component kernel: agent `agent`, env blocks j, j + n, j + 2n, ...  Heavy agents
+// (buildings, EV stations) get more CTAs than light ones (PV, storage), so that the persistent
+// CTAs of a launch finish together.  The agent's slice rides along: one 48-byte read per CTA.
+struct CtaWork {
+  int agent, j, n, pad;
+  AgentSlice sl;
+};
+
 struct CompParams {
   int E, A;
   int event_mode;          // 0 = reset (event row 0), 1 = step (event row clock+1)
@@ -27,7 +35,8 @@ struct CompParams {
   // static tables, one contiguous 16-byte aligned blob: [agents | comps | dpar | ipar]
   const unsigned char* blob;
   int blob_bytes, off_comps, off_dpar, off_ipar;
-  const AgentSlice* slices;   // [A] (device)
+  const CtaWork* work;        // [num_ctas] (device)
+  int num_ctas;
   int max_cn, max_dn, max_in; // largest slice of any agent = the CTA's staging area
   const double* dtab;
   const int32_t* itab;

@@ -50,6 +50,11 @@ SURVEY_BYTES = {"c1": 3 * (264 + 28 + 40) + 1, "c2": (16 * 100 + 72 + 8 * 4) + 2
 _PF_NAMES = {"fp64": "fp64-simt", "tc": "tcgen05 split-tf32", "tc2": "tcgen05 split-fp16, Z-bus in smem"}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of component_kernel per launch, from the committed
+# `ncu --set full` captures (profiles/r1s3_ncu_full_raw_*.csv); keyed by (workload, envs per GPU)
+NCU_TRAFFIC = {("c1", 4096): 1.557e6, ("c1", 262144): 202.3e6, ("c3", 16384): 151.96e6}
+
+
 def _config(n_gpus):
     if WORKLOAD == "c2":
         return {"workload": "C2: component-only EV station (100 vehicles) + PV + storage, "
@@ -426,7 +431,10 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"kernel": "component_kernel", "bound": "hbm", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": NCU_TRAFFIC.get((WORKLOAD, E)),
+                         "traffic_source": "profiles/r1s3_ncu_full_raw_*.csv (ncu --set full, one "
+                                           "capture)" if (WORKLOAD, E) in NCU_TRAFFIC else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "survey_bytes_per_launch": survey_bytes,
                          "frac_survey_bytes": (survey_bytes / (comp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])

@@ -113,6 +113,8 @@ struct pgw_env {
   // staging for the *_host entry points
   double *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_soc = nullptr;
   uint8_t* h_done = nullptr;
+  cudaStream_t copy_stream = nullptr;   // pgw_step_host: observation copy-out behind the power flow
+  cudaEvent_t ev_comp = nullptr, ev_copy = nullptr;
   std::vector<void*> owned;
   // optional per-kernel timing (pgw_set_timing)
   bool timing = false;
@@ -124,6 +126,9 @@ struct pgw_env {
     for (void* p : owned) cudaFree(p);
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    if (ev_comp) cudaEventDestroy(ev_comp);
+    if (ev_copy) cudaEventDestroy(ev_copy);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
   cudaEvent_t next_event() {
     if (ev_used == ev_pool.size()) {
@@ -756,23 +761,33 @@ int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stre
 }
 
 // The kernels of one step, enqueued on `s` (directly, or while `s` is being captured).
-static int enqueue_step(pgw_env* env, const double* actions, double* obs, double* rew,
-                        uint8_t* done, cudaStream_t s, bool timed) {
+static int enqueue_components(pgw_env* env, const double* actions, double* obs, double* rew,
+                              uint8_t* done, cudaStream_t s) {
   pgw::CompParams cp = comp_params(env);
   const bool hook = env->has_feeder && env->punit != 0.0;   // power flow finishes the rewards
   cp.event_mode = 1; cp.advance_clock = env->has_feeder ? 0 : 1; cp.owns_reward = hook ? 0 : 1;
   cp.actions = actions; cp.obs = obs; cp.rew = rew; cp.done = done;
-  if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
   PGW_CUDA(pgw::launch_components(cp, smem_for_events(env), s));
+  return PGW_OK;
+}
+
+static int enqueue_powerflow(pgw_env* env, double* rew, cudaStream_t s, bool timed) {
+  pgw::PfParams pf = pf_params(env);
+  pf.event_mode = 1; pf.advance_clock = 1; pf.agent_p = env->agent_p; pf.rew = rew;
+  pf.reward_hook = (env->punit != 0.0) ? 1 : 0;
+  pf.pdl = (env->use_pdl && !timed) ? 1 : 0;
+  pf.warm_start = env->warm_start ? 1 : 0;
+  PGW_CUDA(launch_pf(env, pf, s));
+  return PGW_OK;
+}
+
+static int enqueue_step(pgw_env* env, const double* actions, double* obs, double* rew,
+                        uint8_t* done, cudaStream_t s, bool timed) {
   if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
-  if (env->has_feeder) {
-    pgw::PfParams pf = pf_params(env);
-    pf.event_mode = 1; pf.advance_clock = 1; pf.agent_p = env->agent_p; pf.rew = rew;
-    pf.reward_hook = hook ? 1 : 0;
-    pf.pdl = (env->use_pdl && !timed) ? 1 : 0;
-    pf.warm_start = env->warm_start ? 1 : 0;
-    PGW_CUDA(launch_pf(env, pf, s));
-  }
+  int rc = enqueue_components(env, actions, obs, rew, done, s);
+  if (rc) return rc;
+  if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
+  if (env->has_feeder && (rc = enqueue_powerflow(env, rew, s, timed))) return rc;
   if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
   return PGW_OK;
 }
@@ -857,12 +872,39 @@ int pgw_step_host(pgw_env* env, const double* actions, double* obs, double* rew,
   const size_t E = (size_t)env->E;
   PGW_CUDA(cudaMemcpyAsync(env->h_act, actions, (size_t)env->act_dim * E * 8,
                            cudaMemcpyHostToDevice, s));
-  rc = pgw_step(env, env->h_act, env->h_obs, env->h_rew, env->h_done, s);
-  if (rc) return rc;
-  PGW_CUDA(cudaMemcpyAsync(obs, env->h_obs, (size_t)env->obs_dim * E * 8, cudaMemcpyDeviceToHost, s));
+  if (!env->has_feeder || env->timing) {
+    rc = pgw_step(env, env->h_act, env->h_obs, env->h_rew, env->h_done, s);
+    if (rc) return rc;
+    PGW_CUDA(cudaMemcpyAsync(obs, env->h_obs, (size_t)env->obs_dim * E * 8, cudaMemcpyDeviceToHost, s));
+    PGW_CUDA(cudaMemcpyAsync(rew, env->h_rew, (size_t)env->A * E * 8, cudaMemcpyDeviceToHost, s));
+    PGW_CUDA(cudaMemcpyAsync(done, env->h_done, E, cudaMemcpyDeviceToHost, s));
+    PGW_CUDA(cudaStreamSynchronize(s));
+    return PGW_OK;
+  }
+  // With a feeder the observations and done flags are final after the component kernel (the
+  // power flow only touches rewards and the voltages the NEXT step observes): their copy to
+  // the host runs on a second stream while the power flow is solved.
+  if (env->clock < 0) return fail(PGW_ERR_STATE, "pgw_step before pgw_reset");
+  if (env->clock + 1 >= env->num_events)
+    return fail(PGW_ERR_STATE, "episode is over: call pgw_reset");
+  if (!env->copy_stream) {
+    PGW_CUDA(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
+    PGW_CUDA(cudaEventCreateWithFlags(&env->ev_comp, cudaEventDisableTiming));
+    PGW_CUDA(cudaEventCreateWithFlags(&env->ev_copy, cudaEventDisableTiming));
+  }
+  if ((rc = enqueue_components(env, env->h_act, env->h_obs, env->h_rew, env->h_done, s))) return rc;
+  PGW_CUDA(cudaEventRecord(env->ev_comp, s));
+  PGW_CUDA(cudaStreamWaitEvent(env->copy_stream, env->ev_comp, 0));
+  PGW_CUDA(cudaMemcpyAsync(obs, env->h_obs, (size_t)env->obs_dim * E * 8, cudaMemcpyDeviceToHost,
+                           env->copy_stream));
+  PGW_CUDA(cudaMemcpyAsync(done, env->h_done, E, cudaMemcpyDeviceToHost, env->copy_stream));
+  PGW_CUDA(cudaEventRecord(env->ev_copy, env->copy_stream));
+  if ((rc = enqueue_powerflow(env, env->h_rew, s, false))) return rc;
   PGW_CUDA(cudaMemcpyAsync(rew, env->h_rew, (size_t)env->A * E * 8, cudaMemcpyDeviceToHost, s));
-  PGW_CUDA(cudaMemcpyAsync(done, env->h_done, E, cudaMemcpyDeviceToHost, s));
+  PGW_CUDA(cudaStreamWaitEvent(s, env->ev_copy, 0));
   PGW_CUDA(cudaStreamSynchronize(s));
+  env->launches += 2;
+  ++env->clock;
   return PGW_OK;
 }
 

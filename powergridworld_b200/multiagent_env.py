@@ -114,7 +114,6 @@ class MultiAgentEnv:
         self.num_envs = int(num_envs)
         self.record_history = record_history
         self.episode_step = None
-        self.time = None
         self.history = None
 
         # ---- agents (same constructor call as multiagent_env.py:57-70)
@@ -152,6 +151,14 @@ class MultiAgentEnv:
         self._h = None
         if not _dry_run:        # tests inspect the compiled tables without a GPU
             self._open(device)
+
+    @property
+    def time(self):
+        """Simulation time of the current step (multiagent_env.py:129, :160), derived from the
+        step counter so that the hot loop does no pandas arithmetic."""
+        if self.episode_step is None:
+            return None
+        return self.start_time + self.episode_step * self.control_timedelta
 
     # ------------------------------------------------------------------ spec compiler
     def _compile(self):
@@ -361,7 +368,6 @@ class MultiAgentEnv:
             N.check(self._lib.pgw_reset(self._h, soc_ptr, C.c_void_p(self.obs.data_ptr()),
                                         self._stream()))
         self.episode_step = 0
-        self.time = self.start_time
         self._needs_reset = False
         if self.record_history:
             self.history = {"timestamp": [], "voltage": [], "agent_power_p": []}
@@ -382,7 +388,6 @@ class MultiAgentEnv:
         if rc:
             N.check(rc)
         self.episode_step += 1
-        self.time += self.control_timedelta
         all_done = self.episode_step >= self.episode_length
         if all_done:
             self._needs_reset = True
@@ -411,7 +416,6 @@ class MultiAgentEnv:
             N.check(self._lib.pgw_reset_host(self._h, soc_ptr, C.c_void_p(pin["obs"].data_ptr()),
                                              self._stream()))
         self.episode_step = 0
-        self.time = self.start_time
         self._needs_reset = False
         return pin["obs"].numpy()
 
@@ -424,15 +428,19 @@ class MultiAgentEnv:
         pin = self._pinned()
         src = actions if isinstance(actions, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(actions, dtype=np.float64))
-        if src.data_ptr() != pin["act"].data_ptr():
+        if src.numel() != self.act_dim * self.num_envs:
+            raise ValueError(f"actions must be [{self.act_dim}, {self.num_envs}]")
+        if src.is_pinned() and src.is_contiguous() and src.dtype == torch.float64:
+            act_ptr = src.data_ptr()                # already page-locked: the DMA reads it in place
+        else:
             pin["act"].copy_(src.reshape(self.act_dim, self.num_envs))
+            act_ptr = pin["act"].data_ptr()
         with torch.cuda.device(self.device):
             N.check(self._lib.pgw_step_host(
-                self._h, C.c_void_p(pin["act"].data_ptr()), C.c_void_p(pin["obs"].data_ptr()),
+                self._h, C.c_void_p(act_ptr), C.c_void_p(pin["obs"].data_ptr()),
                 C.c_void_p(pin["rew"].data_ptr()), C.c_void_p(pin["done"].data_ptr()),
                 self._stream()))
         self.episode_step += 1
-        self.time += self.control_timedelta
         if self.episode_step >= self.episode_length:
             self._needs_reset = True
         return pin["obs"].numpy(), pin["rew"].numpy(), pin["done"].numpy()
@@ -490,7 +498,6 @@ class MultiAgentEnv:
                                           t.numel() * t.element_size(), self._stream()))
         N.check(self._lib.pgw_set_clock(self._h, int(state["episode_step"]), self._stream()))
         self.episode_step = int(state["episode_step"])
-        self.time = self.start_time + self.episode_step * self.control_timedelta
         self.obs.copy_(state["obs"])
         self._needs_reset = bool(state["needs_reset"])
 

@@ -1,9 +1,9 @@
-// K6, tensor-core form for 123-bus-class feeders (up to 88 load branches): the Z-bus fixed
-// point  u <- u0 - Zbb i(u)  as a dense FP16 contraction on tcgen05 with FP32 accumulation in
-// TMEM, one CTA per tile of 128 envs, Zbb resident in shared memory for the whole solve.
+// K6, tensor-core form for feeders with up to 88 load branches (IEEE-13 ... 123-bus class): the
+// Z-bus fixed point  u <- u0 - Zbb i(u)  as a dense FP16 contraction on tcgen05 with FP32
+// accumulation in TMEM, one CTA per tile of 128 envs, Zbb resident in shared memory.
 //
-//   D[env, :] = X[env, :] * B^T       M = 128 envs (TMEM lanes),  N = K = 16 * nch,
-//                                      nch = ceil(nb / 8) chunks of 8 branches
+//   D[env, :] = X[env, :] * B^T       M = 128 envs (TMEM lanes),  N = K = 16 * NCH,
+//                                      NCH = chunks of 8 branches (instantiated: 2, 4, 8, 11)
 //
 // * Real-ified complex product, interleaved by chunks of 8 branches: columns 16c..16c+7 hold
 //   Re, 16c+8..16c+15 hold Im of branches 8c..8c+7 - on the K side (currents) as well as on
@@ -11,19 +11,26 @@
 //   tcgen05.ld hands a thread the complex drops of the 8 branches it owns.
 // * Split FP16: x = x_hi + x_lo, B = B_hi + B_lo (each part 11 significant bits, both operands
 //   pre-scaled by powers of two into the FP16 range).  The three significant products
-//   x_lo B_hi + x_hi B_lo + x_hi B_hi are ONE accumulation chain of 3 * nch MMAs that re-uses
+//   x_lo B_hi + x_hi B_lo + x_hi B_hi are ONE accumulation chain of 3 * NCH MMAs that re-uses
 //   the two resident images of each operand (no tripled K).  Error of a drop: ~1e-8 p.u.
-// * Shared memory (nch = 11): B_hi | B_lo 121 kB, A_hi | A_lo 88 kB, tables 8 kB.  All images
+// * Shared memory (NCH = 11): B_hi | B_lo 121 kB, A_hi | A_lo 88 kB, tables 8 kB.  All images
 //   are canonical K-major no-swizzle UMMA tiles (8-row x 16-byte core matrices, LBO 128 B,
-//   SBO 256 * nch B); B images are prepared on the host and staged by TMA bulk copies, A is
-//   written by the epilogue threads (16-byte st.shared + fence.proxy.async).
+//   SBO 256 * NCH B); B images are prepared on the host and staged by TMA bulk copies, A is
+//   written by the epilogue threads (16-byte st.shared + fence.proxy.async).  Per-branch
+//   constants come through the constant bank (a __grid_constant__ parameter), because the MMA
+//   operand reads alone need ~110 of the 128 B/clk of shared-memory bandwidth.
 // * TMEM: two accumulators D[0], D[1] of N columns used alternately, so the previous drop is
 //   still there for the per-env convergence test max|du| < tol and nothing but the nominal
 //   powers lives in registers across iterations.  Converged envs stop rewriting their row of
 //   A (convergence mask): their drop reproduces itself.
-// * Expansion v = w - Znb i for all nodes: the same chain against ceil(2 nn / N) row chunks
-//   of Znb streamed from L2 over the B images by TMA (prefetch of chunk c+1 overlaps the
-//   epilogue of chunk c), then |v|, min/max, agent bus voltages and the reward hook.
+// * Iteration = pass 1 (max|du| over my chunks, CTA barrier, mask) + pass 2 (currents at the new
+//   voltages, chunk by chunk).  As soon as the G chunks of a wave are written by all warps
+//   (mbarrier) the issuer warp feeds those K steps of the NEXT chain into the other
+//   accumulator: the tensor core runs while the remaining chunks are evaluated.
+// * Expansion v = w - Znb i: nodes that ARE a load-branch voltage up to a real factor (wye
+//   loads) come from u directly; the rest go through the same chain against row chunks of Znb,
+//   streamed from L2 over the B images by TMA (next chunk prefetched during the epilogue) or
+//   kept resident for small feeders; then |v|, min/max, agent bus voltages, the reward hook.
 //
 // Same inputs/outputs as pf_fixed_point_kernel (powerflow.cu).
 #include <cuda_fp16.h>

@@ -41,6 +41,8 @@
 namespace pgw {
 
 constexpr int T2_M = 128;
+// resident CTAs per SM
+constexpr int t2_ctas_per_sm(int nch) { return nch <= 4 ? 2 : 1; }
 // A CTA is G groups of 128 threads (one thread per env row and group); group g owns the chunks
 // g, g + G, ...  Wide feeders use G = 4 and one CTA per SM (shared memory is full anyway); small
 // ones (NCH <= 4) use G = 2 with two CTAs per SM, so that every thread has a chunk to work on.
@@ -182,8 +184,11 @@ __device__ __forceinline__ void t2_current(float4 c, float2 gh, float dr, float 
 
 // STANDALONE: the solve of pgw_pf_solve (total kW / kvar per load given per env) instead of the
 // step / reset solve (base load of the event + the agents' powers).
-template <int NCH, bool ANY_M5, bool STANDALONE>
-__global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, NCH <= 4 ? 2 : 1)
+// OCC: resident CTAs per SM the kernel is compiled for.  Small feeders (NCH <= 2, one chunk per
+// thread) also come in a 64-register build that runs four CTAs per SM: slower for a single wave
+// of tiles (spills, latency) but ~12 % faster once the batch is several waves deep.
+template <int NCH, bool ANY_M5, bool STANDALONE, int OCC = t2_ctas_per_sm(NCH)>
+__global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
     pf_tc2_kernel(const PfParams p, const __grid_constant__ Tc2Consts kc) {
   constexpr int G = NCH <= 4 ? 2 : 4;                  // groups of 128 threads
   constexpr int T2_THREADS = 128 * G;
@@ -661,11 +666,11 @@ int tc2_padded_chunks(int nch) {            // instantiated tile widths
   return nch <= 2 ? 2 : nch <= 4 ? 4 : nch <= 8 ? 8 : nch <= 11 ? 11 : 0;
 }
 
-template <int NCH>
+template <int NCH, int OCC>
 static cudaError_t launch_tc2_t(const PfParams& p, int grid, size_t smem, cudaStream_t s) {
   auto kern = p.load_kw != nullptr
-                  ? (p.tc2.any_m5 ? pf_tc2_kernel<NCH, true, true> : pf_tc2_kernel<NCH, false, true>)
-                  : (p.tc2.any_m5 ? pf_tc2_kernel<NCH, true, false> : pf_tc2_kernel<NCH, false, false>);
+                  ? (p.tc2.any_m5 ? pf_tc2_kernel<NCH, true, true, OCC> : pf_tc2_kernel<NCH, false, true, OCC>)
+                  : (p.tc2.any_m5 ? pf_tc2_kernel<NCH, true, false, OCC> : pf_tc2_kernel<NCH, false, false, OCC>);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   cudaLaunchConfig_t cfg{};
@@ -683,15 +688,17 @@ static cudaError_t launch_tc2_t(const PfParams& p, int grid, size_t smem, cudaSt
 
 cudaError_t launch_powerflow_tc2(const PfParams& p, cudaStream_t s) {
   const int tiles = (p.E + T2_M - 1) / T2_M;
-  const int per_sm = p.tc2.nch <= 4 ? 2 : 1;
+  // the dense build pays off when the tiles do not fit one wave of the regular one
+  const bool dense = p.tc2.nch == 2 && tiles > 148 * t2_ctas_per_sm(2) && p.tc2.tmem_cols <= 128;
+  const int per_sm = dense ? 4 : t2_ctas_per_sm(p.tc2.nch);
   int grid = tiles < 148 * per_sm ? tiles : 148 * per_sm;
   if (grid < 1) grid = 1;
   const size_t smem = tc2_smem_bytes(p);
   switch (p.tc2.nch) {
-    case 2: return launch_tc2_t<2>(p, grid, smem, s);
-    case 4: return launch_tc2_t<4>(p, grid, smem, s);
-    case 8: return launch_tc2_t<8>(p, grid, smem, s);
-    case 11: return launch_tc2_t<11>(p, grid, smem, s);
+    case 2: return dense ? launch_tc2_t<2, 4>(p, grid, smem, s) : launch_tc2_t<2, 2>(p, grid, smem, s);
+    case 4: return launch_tc2_t<4, 2>(p, grid, smem, s);
+    case 8: return launch_tc2_t<8, 1>(p, grid, smem, s);
+    case 11: return launch_tc2_t<11, 1>(p, grid, smem, s);
     default: return cudaErrorInvalidValue;
   }
 }

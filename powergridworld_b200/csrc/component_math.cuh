@@ -155,6 +155,8 @@ PGW_HD void pv_step(const pgw_component& c, const AgentIO& io, int e, double& p_
 // One pass over the vehicles parked at the event's time (the roster is shared by
 // all envs, so the window is a per-event list; only the "energy > 0" part of the
 // reference's charging set is per-env).  kwh = energy one vehicle may take now.
+constexpr int kEvBatch = 8;   // vehicles whose energies are in flight together
+
 struct EvTotals {
   double consumed, demand, deficit_sum, unserved;
   int active, n_deficit;
@@ -183,19 +185,19 @@ PGW_HD EvTotals ev_charge_pass(const pgw_component& c, const AgentIO& io, int e,
   uint32_t word = 0;
   int cur_word = 0;
   for (int w = 0; w < words; ++w) mask[(size_t)w * io.E] = 0u;
-  // Ascending vehicle index, four vehicles per trip: their energies are loaded up front so
-  // that four independent HBM/L2 requests are in flight per thread (a vehicle's store can
+  // Ascending vehicle index, kEvBatch vehicles per trip: their energies are loaded up front so
+  // that as many independent HBM/L2 requests are in flight per thread (a vehicle's store can
   // never alias another vehicle's load, which the compiler cannot know).
-  for (int k0 = 0; k0 < n_win; k0 += 4) {
-    int idx[4];
-    double need4[4];
+  for (int k0 = 0; k0 < n_win; k0 += kEvBatch) {
+    int idx[kEvBatch];
+    double need4[kEvBatch];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kEvBatch; ++j) {
       idx[j] = k0 + j < n_win ? win[k0 + j] : -1;
       need4[j] = idx[j] >= 0 ? energy[(size_t)idx[j] * io.E] : 0.0;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kEvBatch; ++j) {
       const int i = idx[j];
       const double need = need4[j];
       if (i < 0 || !(need > 0.0)) continue;             // :191

@@ -53,6 +53,8 @@ _PF_NAMES = {"fp64": "fp64-simt", "tc": "tcgen05 split-tf32", "tc2": "tcgen05 sp
 # dram__bytes_read.sum + dram__bytes_write.sum of component_kernel per launch, from the committed
 # `ncu --set full` captures (profiles/r1s3_ncu_full_raw_*.csv); keyed by (workload, envs per GPU)
 NCU_TRAFFIC = {("c1", 4096): 1.557e6, ("c1", 262144): 202.3e6, ("c3", 16384): 151.96e6}
+# sm__pipe_tensor_cycles_active.max (% of elapsed, busy SMs) of pf_tc2_kernel in the same captures
+NCU_TENSOR_PCT = {("c1", 4096): 2.37, ("c1", 262144): 5.72, ("c3", 16384): 21.23}
 
 
 def _config(n_gpus):
@@ -446,6 +448,8 @@ def run_ours(args):
                             "achieved": flops / (pf_ms * 1e-3) / 1e12 if pf_ms > 0 else 0.0,
                             "peak": pf_peak, "unit": "TFLOP/s", "peak_source": pf_peak_src,
                             "algorithmic_flops_per_launch": flops, "avg_launch_ms": pf_ms,
+                            "tensor_pipe_active_pct_ncu": NCU_TENSOR_PCT.get((WORKLOAD, E))
+                            if PF_KERNEL == "tc2" else None,
                             "mean_iterations": iters_mean},
             "kernel_share": {"components": comp_ms / max(comp_ms + pf_ms, 1e-12),
                              "powerflow": pf_ms / max(comp_ms + pf_ms, 1e-12)},

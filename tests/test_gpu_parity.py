@@ -615,3 +615,28 @@ def test_tc2_is_bitwise_deterministic():
             for f in (3, 4, 5, 6, 7, 9):
                 assert torch.equal(envs[0].get_field(f), envs[1].get_field(f)), (t, f)
     stream.synchronize()
+
+
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+def test_power_flow_non_convergence_is_data(kernel):
+    """non-convergence is data, not an error.  With the iteration budget cut to 2 every
+    solver reports -2 iterations per env and pgw_stats counts the envs; with the default budget
+    the same batch converges (positive counts)."""
+    torch = _torch()
+    from powergridworld_b200 import _native as N
+    E = 200
+    rng = np.random.default_rng(2)
+    for budget, ok in ((2, False), (None, True)):
+        env = PNS.CoordinatedMultiBuildingControlEnv(
+            **S.buildings_scenario(PNS, PNS.OpenDSSSolver, 1.2), num_envs=E, pf_max_iter=budget)
+        env.set_option(N.OPT_PF_KERNEL, kernel)
+        env.reset_batch(rng.uniform(10, 40, size=(env.num_storage, E)))
+        env.step_batch(torch.as_tensor(rng.uniform(-1, 1, size=(env.act_dim, E))).cuda())
+        it = env.get_field(7).cpu().numpy()
+        st = env.stats().cpu().numpy()
+        if ok:
+            assert (it > 0).all() and st[4] == 0
+        else:
+            assert (it == -2).all() and st[4] == E
+        v = env.get_field(3).cpu().numpy()
+        assert np.isfinite(v).all() and v.min() > 0.8 and v.max() < 1.1

@@ -87,7 +87,7 @@ typedef enum pgw_component_type {
  *                 peak_threshold, reward_scale, obs_high[6], 1/obs_high[6], 1/reward_scale,
  *                 1/60, end_park_min[n], e0_kwh[n]
  *           ipar: n, words(=ceil(n/32)), list capacity m
- *           dtab: time_now, time_next
+ *           dtab: time_now, time_next, hours_left[m], 1/hours_left[m] (per window slot)
  *           itab: n_window, n_left, window[m], left[m]
  *           state: n double rows (remaining kWh), words uint32 rows (charging set)
  *                                                          action 1, obs 6
@@ -109,7 +109,7 @@ typedef enum pgw_component_type {
  *                 initial cost, max_storage_cost     ipar: storage ordinal
  *            state: 2 double rows (SOC, current cost)                    action 1, obs 2
  *  HS_EV     dpar: the EV layout, then max_charge_cost, 60 / minutes_per_step
- *            dtab: evaluation time, new time    itab: as EV
+ *            dtab: evaluation time, new time, hours_left[m], 1/hours_left[m]    itab: as EV
  *            state: n + 1 double rows (remaining kWh, current cost), words uint32 rows
  *                                                                        action 1, obs 7
  *  HS_DEVICES dpar: minutes_per_step / 60, obs_high[k]    ipar: k

@@ -99,9 +99,15 @@ class EVChargingEnv(ComponentEnv):
         cap = max(1, max(len(w) for w in wins), max(len(l) for l in lefts))
         words = (n + 31) // 32
 
+        end_raw = self._roster_end[:n]
+
         def dtab_fn(r):
             k = min(r, n_ev - 1)
-            return [times[k], times[k + 1]]
+            left = np.zeros(cap)
+            left[:len(wins[k])] = (end_raw[wins[k]] - times[k]) / 60.             # :216
+            with np.errstate(divide="ignore"):
+                inv = np.where(left > 0, 1.0 / left, 0.0)
+            return [times[k], times[k + 1]] + list(left) + list(inv)
 
         def itab_fn(r):
             k = min(r, n_ev - 1)
@@ -119,4 +125,4 @@ class EVChargingEnv(ComponentEnv):
         b.add_component(self, N.EV, agent_index,
                         flags=N.F_RESCALE if self.rescale_spaces else 0,
                         dpar=dpar, ipar=[n, words, cap], sd_rows=n, si_rows=words,
-                        dtab_width=2, dtab_fn=dtab_fn, itab_width=2 + 2 * cap, itab_fn=itab_fn)
+                        dtab_width=2 + 2 * cap, dtab_fn=dtab_fn, itab_width=2 + 2 * cap, itab_fn=itab_fn)

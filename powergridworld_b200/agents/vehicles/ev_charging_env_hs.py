@@ -95,9 +95,15 @@ class HSEVChargingEnv(ComponentEnv):
         cap = max(1, max(len(w) for w in wins), max(len(l) for l in lefts))
         words = (n + 31) // 32
 
+        end_raw = self._roster_end
+
         def dtab_fn(r):
             r = min(r, n_ev - 1)
-            return [t_eval(r), times[min(r, last)]]
+            left = np.zeros(cap)
+            left[:len(wins[r])] = (end_raw[wins[r]] - t_eval(r)) / 60.            # :240
+            with np.errstate(divide="ignore"):
+                inv = np.where(left > 0, 1.0 / left, 0.0)
+            return [t_eval(r), times[min(r, last)]] + list(left) + list(inv)
 
         def itab_fn(r):
             r = min(r, n_ev - 1)
@@ -117,4 +123,4 @@ class HSEVChargingEnv(ComponentEnv):
         b.add_component(self, N.HS_EV, agent_index,
                         flags=N.F_RESCALE if self.rescale_spaces else 0,
                         dpar=dpar, ipar=[n, words, cap], sd_rows=n + 1, si_rows=words,
-                        dtab_width=2, dtab_fn=dtab_fn, itab_width=2 + 2 * cap, itab_fn=itab_fn)
+                        dtab_width=2 + 2 * cap, dtab_fn=dtab_fn, itab_width=2 + 2 * cap, itab_fn=itab_fn)

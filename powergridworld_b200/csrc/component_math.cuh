@@ -165,13 +165,13 @@ struct EvTotals {
 // The charging pass shared by the stock station and the Home-Steward charger: window of the
 // event's evaluation time t_now, per-vehicle energy update, charging-set mask, unserved energy
 // of the vehicles that left the window.
-PGW_HD EvTotals ev_charge_pass(const pgw_component& c, const AgentIO& io, int e, double kwh,
-                               double t_now) {
+PGW_HD EvTotals ev_charge_pass(const pgw_component& c, const AgentIO& io, int e, double kwh) {
   const double* dp = io.dpar + c.dpar_off;
   const int32_t* ip = io.ipar + c.ipar_off;
   const int words = ip[1], cap = ip[2];
   const double rate = dp[0];
-  const double* end_park = dp + 21;
+  const double* lh = io.drow + c.dtab_off + 2;         // [cap] hours left, by window slot
+  const double* ilh = lh + cap;                        // [cap] 1 / hours left
   const int32_t* ir = io.irow + c.itab_off;
   const int n_win = ir[0], n_left = ir[1];
   const int32_t* win = ir + 2;
@@ -209,9 +209,11 @@ PGW_HD EvTotals ev_charge_pass(const pgw_component& c, const AgentIO& io, int e,
       word |= 1u << (i & 31);
       ++t.active;
       t.demand += need;                                 // :210
-      const double left_h = div_by(end_park[i] - t_now, 60.0, dp[20]);
+      // hours left until the vehicle departs and the correctly rounded reciprocal, both compiled
+      // per window slot into the event row: need / left_h becomes a multiply + FMA correction
+      const double left_h = lh[k0 + j];
       if (left_h <= 0.0) continue;                      // :218-220
-      t.deficit_sum += fmax(0.0, rate - need / left_h); // :221-223
+      t.deficit_sum += fmax(0.0, rate - div_by(need, left_h, ilh[k0 + j]));   // :221-223
       ++t.n_deficit;
       const double delta = fmin(kwh, need);             // :226-228
       energy[(size_t)i * io.E] = need - delta;
@@ -231,7 +233,7 @@ PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double 
   const double* obs_high = dp + 7;
   const double* inv_high = dp + 13;
   const double t_now = io.drow[c.dtab_off], t_next = io.drow[c.dtab_off + 1];
-  const EvTotals t = ev_charge_pass(c, io, e, kwh, t_now);
+  const EvTotals t = ev_charge_pass(c, io, e, kwh);
   const double unserved = t.unserved;
 
   const double s_consumed = mult * t.consumed;
@@ -679,7 +681,7 @@ PGW_HD void hs_ev_advance(const pgw_component& c, const AgentIO& io, int e, doub
   const double t_eval = io.drow[c.dtab_off], t_new = io.drow[c.dtab_off + 1];
   double* cost_p = io.sd + (size_t)(c.sd_off + n) * io.E + e;
   const double kwh = (a_raw * dp[0]) * dp[1];          // ev_charging_env_hs.py:203-204
-  const EvTotals t = ev_charge_pass(c, io, e, kwh, t_eval);
+  const EvTotals t = ev_charge_pass(c, io, e, kwh);
   const double real_power = mult * t.consumed;         // :281
   const double power = real_power * per_hour;          // :285
   double cost = *cost_p;                               // kept across episodes, 0 at creation

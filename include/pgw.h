@@ -104,15 +104,16 @@ typedef enum pgw_component_type {
 /*  HS_BEGIN  dpar: max_grid_power      dtab: grid cost of the event
  *            state: 5 double rows (pv_power, es_power, es_cost, pv_cost, grid_power = the
  *            reference's meta state, kept from step to step and across resets)
- *  HS_PV     dpar: obs_low, obs_high    dtab: scaled profile value       action 1, obs 1
+ *  HS_PV     dpar: obs_low, obs_high, 1/(high-low)    dtab: scaled profile value   action 1, obs 1
  *  HS_STORAGE dpar: lo, hi, eta_charge, eta_discharge, max_power, dt_hours, initial mean,
- *                 initial cost, max_storage_cost     ipar: storage ordinal
+ *                 initial cost, max_storage_cost, 1/(hi-lo), 1/max_storage_cost,
+ *                 1/eta_discharge, 1/dt_hours, 1/eta_charge     ipar: storage ordinal
  *            state: 2 double rows (SOC, current cost)                    action 1, obs 2
- *  HS_EV     dpar: the EV layout, then max_charge_cost, 60 / minutes_per_step
+ *  HS_EV     dpar: the EV layout, then max_charge_cost, 60 / minutes_per_step, 1/max_charge_cost
  *            dtab: evaluation time, new time, hours_left[m], 1/hours_left[m]    itab: as EV
  *            state: n + 1 double rows (remaining kWh, current cost), words uint32 rows
  *                                                                        action 1, obs 7
- *  HS_DEVICES dpar: minutes_per_step / 60, obs_high[k]    ipar: k
+ *  HS_DEVICES dpar: minutes_per_step / 60, obs_high[k], 1/obs_high[k]    ipar: k
  *            dtab: scaled row[k], unscaled row[k]                        action 1, obs k
  */
 #define PGW_HS_MAX_COMPONENTS 8  /* components of one house, HS_BEGIN not counted */

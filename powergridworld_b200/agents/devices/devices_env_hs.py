@@ -58,6 +58,7 @@ class HSDevicesEnv(ComponentEnv):
         row = lambda r: min(max(r - 1, 0), last)
         b.add_component(self, N.HS_DEVICES, agent_index,
                         flags=N.F_RESCALE if self.rescale_spaces else 0,
-                        dpar=[self.minutes_per_step / 60.0] + list(self._observation_space.high),
+                        dpar=[self.minutes_per_step / 60.0] + list(self._observation_space.high)
+                        + list(1.0 / self._observation_space.high),
                         ipar=[k], dtab_width=2 * k,
                         dtab_fn=lambda r: list(data[row(r)]) + list(frame[row(r)]))

@@ -52,7 +52,10 @@ class HSEnergyStorageEnv(ComponentEnv):
             raise NotImplementedError("HS components are stepped inside an HSMultiComponentEnv")
         dpar = [self.storage_range[0], self.storage_range[1], self.charge_efficiency,
                 self.discharge_efficiency, self.max_power, self.control_interval_in_hr,
-                self.initial_storage_mean, self.initial_storage_cost, self.max_storage_cost]
+                self.initial_storage_mean, self.initial_storage_cost, self.max_storage_cost,
+                1.0 / (self.storage_range[1] - self.storage_range[0]), 1.0 / self.max_storage_cost,
+                1.0 / self.discharge_efficiency, 1.0 / self.control_interval_in_hr,
+                1.0 / self.charge_efficiency]
         b.add_component(self, N.HS_STORAGE, agent_index,
                         flags=N.F_RESCALE if self.rescale_spaces else 0,
                         dpar=dpar, ipar=[b.next_storage_ordinal(self)], sd_rows=2)

@@ -119,7 +119,7 @@ class HSEVChargingEnv(ComponentEnv):
         with np.errstate(divide="ignore"):
             dpar += list(hi[:6]) + list(1.0 / hi[:6]) + [1.0 / self.reward_scale, 1.0 / 60.0]
         dpar += list(self._roster_end) + list(self._roster_energy)
-        dpar += [self.max_charge_cost, 60.0 / self.minutes_per_step]
+        dpar += [self.max_charge_cost, 60.0 / self.minutes_per_step, 1.0 / self.max_charge_cost]
         b.add_component(self, N.HS_EV, agent_index,
                         flags=N.F_RESCALE if self.rescale_spaces else 0,
                         dpar=dpar, ipar=[n, words, cap], sd_rows=n + 1, si_rows=words,

@@ -521,20 +521,15 @@ PGW_HD void building_step_fast(const pgw_component& c, const AgentIO& io, int e,
 // gridworld/base_hs.py:12-199 + agents/*/*_hs.py: the components of a house are stepped in
 // order and share the step's available solar / battery / grid power through a "meta state"
 // that also survives from step to step.  On the device that state is a small per-thread record
-// loaded by the leading HS_BEGIN pseudo-component and stored by the trailing HS_END one.
-// Divisions are plain IEEE float64 divisions, as in the reference.
+// loaded by the leading HS_BEGIN pseudo-component and stored at the end of the house's step.
+// Divisions by per-env quantities (the blended costs) are plain IEEE float64 divisions; divisions
+// by constants use the host-computed reciprocal + FMA correction of div_by (same quotient).
 struct HsMeta {
   double pv_power, es_power, grid_power, pv_cost, es_cost, grid_cost;
   double r[PGW_HS_MAX_COMPONENTS];        // per-component reward terms, summed in order at the end
   double es_pen[PGW_HS_MAX_COMPONENTS];   // storage: pending penalty (needs the FINAL meta), or 0
   int n;
 };
-
-// to_scaled / to_raw with a real division (the HS bounds come without host reciprocals)
-PGW_HD double hs_scaled(double x, double lo, double hi) {
-  x = clip(x, lo, hi);
-  return (2.0 * x - (lo + hi)) / (hi - lo);
-}
 
 // HS_BEGIN  dpar: max_grid_power   dtab: grid_cost of the event
 //           state: pv_power, es_power, es_cost, pv_cost, grid_power (5 rows, the meta state)
@@ -573,14 +568,14 @@ PGW_HD void hs_end(const pgw_component& c, const AgentIO& io, int e, const HsMet
   r_agent = r;
 }
 
-// HS_PV  dpar: obs_low, obs_high   dtab: scaled profile value of the event
+// HS_PV  dpar: obs_low, obs_high, 1/(high-low)   dtab: scaled profile value of the event
 PGW_HD void hs_pv_step(const pgw_component& c, const AgentIO& io, int e, HsMeta& m, bool reset,
                        double& p_out) {
   const double* dp = io.dpar + c.dpar_off;
   const bool rs = (c.flags & PGW_F_RESCALE) != 0;
   const double data = io.drow[c.dtab_off];
   const double raw = -data;                            // pv_profile_env_hs.py:110
-  io.obs[(size_t)c.obs_off * io.E + e] = rs ? hs_scaled(raw, dp[0], dp[1]) : raw;
+  io.obs[(size_t)c.obs_off * io.E + e] = rs ? to_scaled(raw, dp[0], dp[1], dp[2]) : raw;
   if (reset) {
     m.pv_power = -raw;                                 // only the reset chain sees it (:121-124)
     p_out = 0.0;
@@ -595,13 +590,14 @@ PGW_HD void hs_pv_step(const pgw_component& c, const AgentIO& io, int e, HsMeta&
 }
 
 // HS_STORAGE  dpar: lo, hi, eta_c, eta_d, max_power, dt_hours, initial mean, initial cost,
-//                   max_storage_cost      ipar: storage ordinal
+//                   max_storage_cost, 1/(hi-lo), 1/max_storage_cost, 1/eta_d, 1/dt, 1/eta_c
+//             ipar: storage ordinal
 //             state: SOC, current_cost
 PGW_HD void hs_storage_obs(const pgw_component& c, const AgentIO& io, int e, double soc, double cost) {
   const double* dp = io.dpar + c.dpar_off;
   const bool rs = (c.flags & PGW_F_RESCALE) != 0;
-  io.obs[(size_t)c.obs_off * io.E + e] = rs ? hs_scaled(soc, dp[0], dp[1]) : soc;
-  io.obs[(size_t)(c.obs_off + 1) * io.E + e] = rs ? hs_scaled(cost, 0.0, dp[8]) : cost;
+  io.obs[(size_t)c.obs_off * io.E + e] = rs ? to_scaled(soc, dp[0], dp[1], dp[9]) : soc;
+  io.obs[(size_t)(c.obs_off + 1) * io.E + e] = rs ? to_scaled(cost, 0.0, dp[8], dp[10]) : cost;
 }
 
 PGW_HD void hs_storage_reset(const pgw_component& c, const AgentIO& io, int e, bool first_reset) {
@@ -625,14 +621,15 @@ PGW_HD void hs_storage_step(const pgw_component& c, const AgentIO& io, int e, Hs
   if (c.flags & PGW_F_RESCALE) a = to_raw(a, -1.0, 1.0);
   double power = a * pmax;
   // validate_power :111-143
+  const double inv_eta_d = dp[11], inv_dt = dp[12], inv_eta_c = dp[13];
   if (power > 0.0) {
-    const double delta = power * dt / eta_d;
+    const double delta = div_by(power * dt, eta_d, inv_eta_d);
     if (soc <= lo) power = 0.0;
-    else if (soc - delta < lo) power = (soc - lo) / dt * eta_d;
+    else if (soc - delta < lo) power = div_by(soc - lo, dt, inv_dt) * eta_d;
   } else if (power < 0.0) {
     const double delta = -(power * dt * eta_c);
     if (soc >= hi) power = 0.0;
-    else if (soc + delta > hi) power = -((hi - soc) / dt / eta_c);
+    else if (soc + delta > hi) power = -div_by(div_by(hi - soc, dt, inv_dt), eta_c, inv_eta_c);
   }
   double delta_cost = 0.0;
   if (power == 0.0) {                                  // :215-217
@@ -649,7 +646,7 @@ PGW_HD void hs_storage_step(const pgw_component& c, const AgentIO& io, int e, Hs
     m.grid_power = fmax(0.0, m.grid_power - grid_used);
     m.es_power = 0.0;
   } else {                                             // discharging :248-253
-    const double delta_storage = power * dt / eta_d;
+    const double delta_storage = div_by(power * dt, eta_d, inv_eta_d);
     soc = fmax(soc - delta_storage, lo);
     m.es_power = power;
   }
@@ -668,7 +665,8 @@ PGW_HD void hs_storage_step(const pgw_component& c, const AgentIO& io, int e, Hs
   p_out = real_power;
 }
 
-// HS_EV  dpar: as the stock station up to e0[n], then max_charge_cost, 60 / minutes_per_step
+// HS_EV  dpar: as the stock station up to e0[n], then max_charge_cost, 60 / minutes_per_step,
+//              1 / max_charge_cost
 //        dtab: evaluation time, new time      itab: as the stock station
 //        state: n energy rows + current_cost; words of the charging set
 PGW_HD void hs_ev_advance(const pgw_component& c, const AgentIO& io, int e, double a_raw, HsMeta& m,
@@ -713,7 +711,8 @@ PGW_HD void hs_ev_advance(const pgw_component& c, const AgentIO& io, int e, doub
 #pragma unroll
   for (int j = 0; j < 7; ++j) {
     const double hi = j < 6 ? obs_high[j] : max_cost;
-    io.obs[(size_t)(c.obs_off + j) * io.E + e] = rs ? hs_scaled(raw[j], 0.0, hi) : raw[j];
+    const double inv = j < 6 ? dp[13 + j] : dp[23 + 2 * n];
+    io.obs[(size_t)(c.obs_off + j) * io.E + e] = rs ? to_scaled(raw[j], 0.0, hi, inv) : raw[j];
   }
   if (!reset) {
     m.pv_power = loc.pv_power; m.es_power = loc.es_power; m.grid_power = loc.grid_power;
@@ -736,7 +735,7 @@ PGW_HD void hs_ev_reset(const pgw_component& c, const AgentIO& io, int e, HsMeta
   hs_ev_advance(c, io, e, a, m, true, p);
 }
 
-// HS_DEVICES  dpar: minutes_per_step / 60, obs_high[k]     ipar: k (columns)
+// HS_DEVICES  dpar: minutes_per_step / 60, obs_high[k], 1/obs_high[k]     ipar: k (columns)
 //             dtab: scaled row [k] (observation), unscaled row [k] (demand)
 PGW_HD void hs_devices_step(const pgw_component& c, const AgentIO& io, int e, HsMeta& m, bool reset,
                             double& p_out) {
@@ -745,7 +744,8 @@ PGW_HD void hs_devices_step(const pgw_component& c, const AgentIO& io, int e, Hs
   const bool rs = (c.flags & PGW_F_RESCALE) != 0;
   const double* row = io.drow + c.dtab_off;
   for (int j = 0; j < k; ++j)
-    io.obs[(size_t)(c.obs_off + j) * io.E + e] = rs ? hs_scaled(row[j], 0.0, dp[1 + j]) : row[j];
+    io.obs[(size_t)(c.obs_off + j) * io.E + e] =
+        rs ? to_scaled(row[j], 0.0, dp[1 + j], dp[1 + k + j]) : row[j];
   p_out = 0.0;
   if (reset) return;
   double a = io.actions[(size_t)c.act_off * io.E + e];

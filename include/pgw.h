@@ -68,6 +68,11 @@ typedef enum pgw_component_type {
 #define PGW_F_PV_VOLT_REWARD 4u /* ThisPVEnv.step_reward, gridworld/scenarios/heterogeneous.py:46-52   */
 #define PGW_F_BUILDING_FAST 16u /* building with the shipped model's input pattern and the default
                                    15-entry observation set: straight-line register code path   */
+#define PGW_F_TELEMETRY 32u     /* Home-Steward component: PGW_HS_TEL_ROWS extra double state rows behind
+                                   its own state receive the numbers of the reference's step_meta record
+                                   (cost, reward, raw action, solar / battery / grid power consumed,
+                                   device_custom_info entries)                                         */
+#define PGW_HS_TEL_ROWS 13
 #define PGW_F_STALE_REWARD 8u   /* stand-alone building agent: reward from the pre-step state
                                    (five_zone_rom_env.py:215 precedes :223)                            */
 

@@ -18,6 +18,7 @@ NUM_STATS = 8
 STORAGE, PV, EV, BUILDING = 1, 2, 3, 4
 HS_BEGIN, HS_PV, HS_STORAGE, HS_EV, HS_DEVICES = 5, 6, 7, 8, 9
 HS_MAX_COMPONENTS = 8
+F_TELEMETRY, HS_TEL_ROWS = 32, 13
 F_RESCALE, F_GRID_AWARE, F_PV_VOLT_REWARD, F_STALE_REWARD, F_BUILDING_FAST = 1, 2, 4, 8, 16
 
 OPT_PF_KERNEL, OPT_WARM_START, OPT_GRAPHS, OPT_PDL = 0, 1, 2, 3

@@ -57,8 +57,10 @@ class HSDevicesEnv(ComponentEnv):
         data, frame, last = self.data, self._frame, len(self.data) - 1
         row = lambda r: min(max(r - 1, 0), last)
         b.add_component(self, N.HS_DEVICES, agent_index,
-                        flags=N.F_RESCALE if self.rescale_spaces else 0,
+                        flags=(N.F_RESCALE if self.rescale_spaces else 0)
+                        | (N.F_TELEMETRY if getattr(self, "_telemetry", False) else 0),
                         dpar=[self.minutes_per_step / 60.0] + list(self._observation_space.high)
                         + list(1.0 / self._observation_space.high),
                         ipar=[k], dtab_width=2 * k,
-                        dtab_fn=lambda r: list(data[row(r)]) + list(frame[row(r)]))
+                        dtab_fn=lambda r: list(data[row(r)]) + list(frame[row(r)]),
+                        sd_rows=N.HS_TEL_ROWS if getattr(self, "_telemetry", False) else 0)

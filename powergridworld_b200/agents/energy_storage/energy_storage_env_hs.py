@@ -57,5 +57,7 @@ class HSEnergyStorageEnv(ComponentEnv):
                 1.0 / self.discharge_efficiency, 1.0 / self.control_interval_in_hr,
                 1.0 / self.charge_efficiency]
         b.add_component(self, N.HS_STORAGE, agent_index,
-                        flags=N.F_RESCALE if self.rescale_spaces else 0,
-                        dpar=dpar, ipar=[b.next_storage_ordinal(self)], sd_rows=2)
+                        flags=(N.F_RESCALE if self.rescale_spaces else 0)
+                        | (N.F_TELEMETRY if getattr(self, "_telemetry", False) else 0),
+                        dpar=dpar, ipar=[b.next_storage_ordinal(self)],
+                        sd_rows=2 + (N.HS_TEL_ROWS if getattr(self, "_telemetry", False) else 0))

@@ -61,6 +61,8 @@ class HSPVEnv(ComponentEnv):
         last = len(data) - 1
         # event 0 (reset) shows row 0; step t acts on row t
         b.add_component(self, N.HS_PV, agent_index,
-                        flags=N.F_RESCALE if self.rescale_spaces else 0,
+                        flags=(N.F_RESCALE if self.rescale_spaces else 0)
+                        | (N.F_TELEMETRY if getattr(self, "_telemetry", False) else 0),
                         dpar=[lo[0], hi[0], 1.0 / (hi[0] - lo[0])],
-                        dtab_width=1, dtab_fn=lambda r: [data[min(max(r - 1, 0), last)]])
+                        dtab_width=1, dtab_fn=lambda r: [data[min(max(r - 1, 0), last)]],
+                        sd_rows=N.HS_TEL_ROWS if getattr(self, "_telemetry", False) else 0)

@@ -94,6 +94,8 @@ class HSEVChargingEnv(ComponentEnv):
         lefts = [np.array([], dtype=int)] + [np.setdiff1d(wins[r - 1], wins[r]) for r in range(1, n_ev)]
         cap = max(1, max(len(w) for w in wins), max(len(l) for l in lefts))
         words = (n + 31) // 32
+        if getattr(self, "_telemetry", False) and words > 4:
+            raise NotImplementedError("step_meta telemetry supports up to 128 vehicles per charger")
 
         end_raw = self._roster_end
 
@@ -121,6 +123,9 @@ class HSEVChargingEnv(ComponentEnv):
         dpar += list(self._roster_end) + list(self._roster_energy)
         dpar += [self.max_charge_cost, 60.0 / self.minutes_per_step, 1.0 / self.max_charge_cost]
         b.add_component(self, N.HS_EV, agent_index,
-                        flags=N.F_RESCALE if self.rescale_spaces else 0,
-                        dpar=dpar, ipar=[n, words, cap], sd_rows=n + 1, si_rows=words,
+                        flags=(N.F_RESCALE if self.rescale_spaces else 0)
+                        | (N.F_TELEMETRY if getattr(self, "_telemetry", False) else 0),
+                        dpar=dpar, ipar=[n, words, cap],
+                        sd_rows=n + 1 + (N.HS_TEL_ROWS if getattr(self, "_telemetry", False) else 0),
+                        si_rows=words,
                         dtab_width=2 + 2 * cap, dtab_fn=dtab_fn, itab_width=2 + 2 * cap, itab_fn=itab_fn)

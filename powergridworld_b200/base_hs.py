@@ -35,7 +35,11 @@ class HSMultiComponentEnv(MultiComponentEnv):
     def __init__(self, name: str = None, components: List[dict] = None, start_time: str = '',
                  end_time: str = '', control_timedelta=pd.Timedelta(300, "s"),
                  max_grid_power: float = 48, max_episode_steps: int = None,
-                 rescale_spaces: bool = True, **kwargs):
+                 rescale_spaces: bool = True, step_meta: bool = None, **kwargs):
+        # step_meta: produce the per-device telemetry records of the reference's meta_state
+        # (13 extra state rows per component).  None = only when the house is stepped on its
+        # own through reset()/step(); batches leave it off unless asked.
+        self._step_meta = step_meta
         self.max_grid_power = max_grid_power
         super().__init__(name=name, components=components)
         if len(self.envs) > N.HS_MAX_COMPONENTS:
@@ -54,7 +58,14 @@ class HSMultiComponentEnv(MultiComponentEnv):
         self.time_index = 0
 
     # ---- spec compiler
+    def _runner(self):
+        if self._standalone is None and self._step_meta is None:
+            self._step_meta = True
+        return super()._runner()
+
     def _emit(self, b, agent_index, standalone):
+        for e in self.envs:
+            e._telemetry = bool(self._step_meta)
         cost, last = self._grid_cost_data, len(self._grid_cost_data) - 1
         b.add_component(self._begin, N.HS_BEGIN, agent_index, dpar=[self.max_grid_power],
                         sd_rows=5, dtab_width=1,
@@ -71,7 +82,43 @@ class HSMultiComponentEnv(MultiComponentEnv):
         self.meta_state.update({key: float(v) for key, v in zip(META_KEYS, rows)})
         self.meta_state["grid_cost"] = self._grid_cost_data[k]
         self.meta_state["timestamp"] = self._timestamps[k] if k < len(self._timestamps) else None
-        self.meta_state["step_meta"] = []           # the per-device telemetry is not produced
+        self.meta_state["step_meta"] = self._step_meta_records(r, self.meta_state["timestamp"]) \
+            if self._step_meta else []
+
+    _CUSTOM = {
+        "HSPVEnv": (0, ("pv_available_power", "pv_actionable_power")),
+        "HSEnergyStorageEnv": (2, ("current_storage", "power_ask", "solar_power_available",
+                                   "grid_power_available", "es_power_available")),
+        "HSEVChargingEnv": (None, ("power_ask", "power_unserved", "charging_vehicle",
+                                   "vehicle_charged", "solar_power_available", "es_power_available",
+                                   "grid_power_available")),
+        "HSDevicesEnv": (0, ("power_ask", "solar_power_available", "es_power_available",
+                             "grid_power_available"))}
+
+    def telemetry_rows(self, comp) -> tuple:
+        """(first row, count) of ``comp``'s telemetry block in the double state (FIELD_STATE_D)."""
+        own, _ = self._CUSTOM[type(comp).__name__]
+        if own is None:
+            own = len(comp._roster_energy) + 1
+        return comp._slot["sd"][0] + own, N.HS_TEL_ROWS
+
+    def _step_meta_records(self, runner, timestamp, env_index: int = 0):
+        """The reference's per-device records (base_hs.py:158-164) from the telemetry rows."""
+        sd = runner.get_field(N.FIELD_STATE_D)[:, env_index].cpu().numpy()
+        out = []
+        for comp in self.envs:
+            off, _ = self.telemetry_rows(comp)
+            t = sd[off:off + N.HS_TEL_ROWS]
+            names = self._CUSTOM[type(comp).__name__][1]
+            custom = {k: float(t[6 + i]) for i, k in enumerate(names)}
+            for k in ("charging_vehicle", "vehicle_charged"):
+                if k in custom:
+                    custom[k] = int(custom[k])
+            out.append({"device_id": comp.name, "timestamp": timestamp, "cost": float(t[0]),
+                        "reward": float(t[1]), "action": [float(t[2])],
+                        "solar_power_consumed": float(t[3]), "es_power_consumed": float(t[4]),
+                        "grid_power_consumed": float(t[5]), "device_custom_info": custom})
+        return out
 
     def reset(self, **kwargs):
         obs, _ = super().reset(**kwargs)

@@ -69,7 +69,7 @@ struct pgw_env {
   int pf_kernel = 0;
   int clock = -1;             // host mirror
   long long resets = 0;
-  bool has_house = false;
+  int has_house = 0;          // 1 = houses, 2 = houses with step_meta telemetry
   long long launches = 0;
   // device tables
   unsigned char* comp_blob = nullptr;   // [agents | comps | dpar | ipar]
@@ -195,7 +195,10 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
   env->num_storage = spec->num_storage; env->num_events = spec->num_events;
   env->dstride = spec->dtab_stride; env->istride = spec->itab_stride;
   for (int c = 0; c < spec->num_components; ++c)
-    if (spec->components[c].type == PGW_HS_BEGIN) env->has_house = true;
+    if (spec->components[c].type == PGW_HS_BEGIN) env->has_house = std::max(env->has_house, 1);
+  for (int c = 0; c < spec->num_components; ++c)
+    if (spec->components[c].type >= PGW_HS_PV && (spec->components[c].flags & PGW_F_TELEMETRY))
+      env->has_house = 2;
   for (int c = 0; c < spec->num_components; ++c)
     if (spec->components[c].type == PGW_BUILDING) {
       env->need_scratch_reset = true;                // reset always takes the table-driven path
@@ -696,7 +699,7 @@ static pgw::CompParams comp_params(pgw_env* env) {
   p.vmin = env->vmin; p.vmax = env->vmax; p.vbus = env->vbus;
   p.agent_p = env->agent_p; p.ep_ret = env->ep_ret;
   p.clock = env->d_clock; p.ticket = env->d_ticket;
-  p.has_house = env->has_house ? 1 : 0;
+  p.has_house = env->has_house;
   return p;
 }
 

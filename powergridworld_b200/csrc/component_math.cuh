@@ -24,6 +24,11 @@
 #define PGW_HD inline
 #endif
 #define PGW_RESTRICT __restrict__
+#if defined(__CUDA_ARCH__)
+#define PGW_POPC(x) __popc(x)
+#else
+#define PGW_POPC(x) __builtin_popcount(x)
+#endif
 #if defined(__CUDACC__)
 #define PGW_NO_UNROLL _Pragma("unroll 1")
 #else
@@ -531,6 +536,24 @@ struct HsMeta {
   int n;
 };
 
+// Optional per-component telemetry (PGW_F_TELEMETRY): the numbers of the reference's
+// ``step_meta`` records, kPgwTelRows state rows behind the component's own state:
+//   0 cost, 1 reward (as evaluated inside the component's step), 2 raw action,
+//   3 solar / 4 battery / 5 grid power consumed, 6.. device_custom_info entries
+struct HsTel {
+  double* p;
+  int E;
+  PGW_HD void put(int r, double v) const { if (p) p[(size_t)r * E] = v; }
+};
+template <bool TEL>
+PGW_HD HsTel hs_tel(const pgw_component& c, const AgentIO& io, int e, int own_rows) {
+  HsTel t;
+  t.E = io.E;
+  t.p = (TEL && (c.flags & PGW_F_TELEMETRY)) ? io.sd + (size_t)(c.sd_off + own_rows) * io.E + e
+                                             : nullptr;
+  return t;
+}
+
 // HS_BEGIN  dpar: max_grid_power   dtab: grid_cost of the event
 //           state: pv_power, es_power, es_cost, pv_cost, grid_power (5 rows, the meta state)
 PGW_HD void hs_begin(const pgw_component& c, const AgentIO& io, int e, HsMeta& m, bool first_reset) {
@@ -569,6 +592,7 @@ PGW_HD void hs_end(const pgw_component& c, const AgentIO& io, int e, const HsMet
 }
 
 // HS_PV  dpar: obs_low, obs_high, 1/(high-low)   dtab: scaled profile value of the event
+template <bool TEL>
 PGW_HD void hs_pv_step(const pgw_component& c, const AgentIO& io, int e, HsMeta& m, bool reset,
                        double& p_out) {
   const double* dp = io.dpar + c.dpar_off;
@@ -586,6 +610,9 @@ PGW_HD void hs_pv_step(const pgw_component& c, const AgentIO& io, int e, HsMeta&
   const double p = a * (-raw);                         // :149
   m.pv_power = p;                                      // :153
   m.r[m.n] = 0.0; m.es_pen[m.n] = 0.0; ++m.n;
+  const HsTel t = hs_tel<TEL>(c, io, e, 0);                 // :154-158
+  t.put(0, 0.0); t.put(1, 0.0); t.put(2, a); t.put(3, -raw); t.put(4, 0.0); t.put(5, 0.0);
+  t.put(6, -raw); t.put(7, p);
   p_out = p;
 }
 
@@ -611,6 +638,7 @@ PGW_HD void hs_storage_reset(const pgw_component& c, const AgentIO& io, int e, b
   hs_storage_obs(c, io, e, soc, sd[(size_t)1 * io.E]);
 }
 
+template <bool TEL>
 PGW_HD void hs_storage_step(const pgw_component& c, const AgentIO& io, int e, HsMeta& m,
                             double& p_out) {
   const double* dp = io.dpar + c.dpar_off;
@@ -631,7 +659,8 @@ PGW_HD void hs_storage_step(const pgw_component& c, const AgentIO& io, int e, Hs
     if (soc >= hi) power = 0.0;
     else if (soc + delta > hi) power = -div_by(div_by(hi - soc, dt, inv_dt), eta_c, inv_eta_c);
   }
-  double delta_cost = 0.0;
+  double delta_cost = 0.0, solar_taken = 0.0, grid_taken = 0.0;
+  const double solar_cap = m.pv_power, grid_cap = m.grid_power;
   if (power == 0.0) {                                  // :215-217
     m.es_power = 0.0;
   } else if (power < 0.0) {                            // charging :219-245
@@ -645,6 +674,8 @@ PGW_HD void hs_storage_step(const pgw_component& c, const AgentIO& io, int e, Hs
     m.pv_power = fmax(0.0, m.pv_power - solar_used);
     m.grid_power = fmax(0.0, m.grid_power - grid_used);
     m.es_power = 0.0;
+    solar_taken = solar_used;
+    grid_taken = grid_used;
   } else {                                             // discharging :248-253
     const double delta_storage = div_by(power * dt, eta_d, inv_eta_d);
     soc = fmax(soc - delta_storage, lo);
@@ -661,6 +692,15 @@ PGW_HD void hs_storage_step(const pgw_component& c, const AgentIO& io, int e, Hs
   const double smax = fmax(lo, hi);
   m.r[m.n] = -step_cost;
   m.es_pen[m.n] = soc < smax ? dp[8] * (smax - soc) : 0.0;
+  const HsTel t = hs_tel<TEL>(c, io, e, 2);                 // :262-271
+  if (t.p) {
+    double rew = -step_cost;                           // reward as seen inside the step (:264)
+    if (m.pv_power > 0.0 && m.es_power > 0.0 && m.es_pen[m.n] != 0.0) rew -= m.es_pen[m.n];
+    t.put(0, step_cost); t.put(1, rew); t.put(2, a);
+    t.put(3, solar_taken); t.put(4, 0.0); t.put(5, grid_taken);
+    t.put(6, soc); t.put(7, power); t.put(8, solar_cap - solar_taken);
+    t.put(9, grid_cap - grid_taken); t.put(10, m.es_power);
+  }
   ++m.n;
   p_out = real_power;
 }
@@ -669,6 +709,7 @@ PGW_HD void hs_storage_step(const pgw_component& c, const AgentIO& io, int e, Hs
 //              1 / max_charge_cost
 //        dtab: evaluation time, new time      itab: as the stock station
 //        state: n energy rows + current_cost; words of the charging set
+template <bool TEL>
 PGW_HD void hs_ev_advance(const pgw_component& c, const AgentIO& io, int e, double a_raw, HsMeta& m,
                           bool reset, double& p_out) {
   const double* dp = io.dpar + c.dpar_off;
@@ -679,16 +720,23 @@ PGW_HD void hs_ev_advance(const pgw_component& c, const AgentIO& io, int e, doub
   const double t_eval = io.drow[c.dtab_off], t_new = io.drow[c.dtab_off + 1];
   double* cost_p = io.sd + (size_t)(c.sd_off + n) * io.E + e;
   const double kwh = (a_raw * dp[0]) * dp[1];          // ev_charging_env_hs.py:203-204
+  const HsTel tel = hs_tel<TEL>(c, io, e, n + 1);
+  const int words = io.ipar[c.ipar_off + 1];
+  uint32_t* mask = io.si + (size_t)c.si_off * io.E + e;
+  uint32_t old_mask[4] = {0u, 0u, 0u, 0u};             // telemetry: vehicles that stop charging
+  if (tel.p && !reset)
+    for (int w = 0; w < words && w < 4; ++w) old_mask[w] = mask[(size_t)w * io.E];
   const EvTotals t = ev_charge_pass(c, io, e, kwh);
   const double real_power = mult * t.consumed;         // :281
   const double power = real_power * per_hour;          // :285
   double cost = *cost_p;                               // kept across episodes, 0 at creation
   HsMeta loc = m;                                      // the hidden step of reset discards these
+  const double cap_pv = m.pv_power, cap_es = m.es_power, cap_grid = m.grid_power;
+  double solar_used = 0.0, battery_used = 0.0, grid_used = 0.0;
   if (power == 0.0 || a_raw == 0.0) {                  // :292-293
     cost = 0.0;
   } else {
-    const double solar_used = fmin(power, loc.pv_power);
-    double battery_used, grid_used;
+    solar_used = fmin(power, loc.pv_power);
     if (loc.es_cost < loc.grid_cost) {                 // :304-309
       battery_used = fmin(loc.es_power, power - solar_used);
       grid_used = fmin(loc.grid_power, power - solar_used - battery_used);
@@ -717,13 +765,25 @@ PGW_HD void hs_ev_advance(const pgw_component& c, const AgentIO& io, int e, doub
   if (!reset) {
     m.pv_power = loc.pv_power; m.es_power = loc.es_power; m.grid_power = loc.grid_power;
     // :178-191
-    m.r[m.n] = -(cost * real_power + dp[3] * (t.unserved * t.unserved));
+    const double step_cost = cost * real_power;
+    m.r[m.n] = -(step_cost + dp[3] * (t.unserved * t.unserved));
     m.es_pen[m.n] = 0.0;
+    if (tel.p) {                                       // :318-323
+      int departed = 0;
+      for (int w = 0; w < words && w < 4; ++w)
+        departed += PGW_POPC(old_mask[w] & ~mask[(size_t)w * io.E]);
+      tel.put(0, step_cost); tel.put(1, m.r[m.n]); tel.put(2, a_raw);
+      tel.put(3, solar_used); tel.put(4, battery_used); tel.put(5, grid_used);
+      tel.put(6, power); tel.put(7, t.unserved); tel.put(8, (double)t.active);
+      tel.put(9, (double)departed); tel.put(10, cap_pv - solar_used);
+      tel.put(11, cap_es - battery_used); tel.put(12, cap_grid - grid_used);
+    }
     ++m.n;
   }
   p_out = real_power;
 }
 
+template <bool TEL>
 PGW_HD void hs_ev_reset(const pgw_component& c, const AgentIO& io, int e, HsMeta& m) {
   const double* dp = io.dpar + c.dpar_off;
   const int n = io.ipar[c.ipar_off];
@@ -732,11 +792,12 @@ PGW_HD void hs_ev_reset(const pgw_component& c, const AgentIO& io, int e, HsMeta
   for (int i = 0; i < n; ++i) energy[(size_t)i * io.E] = e0[i];
   double a = 0.0, p;                                   // hidden step, action = space low (:151, :199)
   if (c.flags & PGW_F_RESCALE) a = to_raw(a, 0.0, 1.0);
-  hs_ev_advance(c, io, e, a, m, true, p);
+  hs_ev_advance<TEL>(c, io, e, a, m, true, p);
 }
 
 // HS_DEVICES  dpar: minutes_per_step / 60, obs_high[k], 1/obs_high[k]     ipar: k (columns)
 //             dtab: scaled row [k] (observation), unscaled row [k] (demand)
+template <bool TEL>
 PGW_HD void hs_devices_step(const pgw_component& c, const AgentIO& io, int e, HsMeta& m, bool reset,
                             double& p_out) {
   const double* dp = io.dpar + c.dpar_off;
@@ -753,19 +814,25 @@ PGW_HD void hs_devices_step(const pgw_component& c, const AgentIO& io, int e, Hs
   double total = 0.0;
   for (int j = 0; j < k; ++j) total += row[k + j];     // :165
   const double p = a * total;
-  double cost = 0.0;
+  double cost = 0.0, solar_used = 0.0, battery_used = 0.0, grid_used = 0.0;
   if (rint(p * 1000.0) != 0.0) {                       // round(p, 3) == 0.0 (:174)
-    const double solar_used = fmin(p, m.pv_power);
-    const double battery_used = fmin(m.es_power, p - solar_used);
-    const double grid_used = fmin(m.grid_power, p - solar_used - battery_used);
+    solar_used = fmin(p, m.pv_power);
+    battery_used = fmin(m.es_power, p - solar_used);
+    grid_used = fmin(m.grid_power, p - solar_used - battery_used);
     cost = (m.pv_cost * solar_used + m.grid_cost * grid_used + m.es_cost * battery_used) /
            (solar_used + grid_used + battery_used);
     // the reference hands back the meta it copied BEFORE this allocation (:163, :201):
     // what the devices consume never reaches the meta state
   }
-  m.r[m.n] = -(cost * p * dp[0]);                      // :128-131
+  const double step_cost = cost * p * dp[0];           // :128-131
+  m.r[m.n] = -step_cost;
   m.es_pen[m.n] = 0.0;
   ++m.n;
+  const HsTel t = hs_tel<TEL>(c, io, e, 0);                 // :194-198
+  t.put(0, step_cost); t.put(1, -step_cost); t.put(2, a);
+  t.put(3, solar_used); t.put(4, battery_used); t.put(5, grid_used);
+  t.put(6, p); t.put(7, m.pv_power - solar_used); t.put(8, m.es_power - battery_used);
+  t.put(9, m.grid_power - grid_used);
   p_out = p;
 }
 
@@ -779,6 +846,7 @@ PGW_HD bool is_house(const pgw_agent& ag, const pgw_component* comps) {
 
 // Home-Steward house (base_hs.py:120-178).  Kept apart from agent_step so that kernels of
 // scenarios without a house do not carry its code and stack frame.
+template <bool TEL>
 PGW_HD void house_step(const pgw_agent& ag, const pgw_component* comps, const AgentIO& io, int e,
                        double& p_agent, double& r_agent) {
   p_agent = 0.0;
@@ -788,15 +856,15 @@ PGW_HD void house_step(const pgw_agent& ag, const pgw_component* comps, const Ag
     const pgw_component c = comps[ci];
     double p = 0.0;
     switch (c.type) {
-      case PGW_HS_PV: hs_pv_step(c, io, e, m, false, p); break;
-      case PGW_HS_STORAGE: hs_storage_step(c, io, e, m, p); break;
+      case PGW_HS_PV: hs_pv_step<TEL>(c, io, e, m, false, p); break;
+      case PGW_HS_STORAGE: hs_storage_step<TEL>(c, io, e, m, p); break;
       case PGW_HS_EV: {
         double a = io.actions[(size_t)c.act_off * io.E + e];
         if (c.flags & PGW_F_RESCALE) a = to_raw(a, 0.0, 1.0);
-        hs_ev_advance(c, io, e, a, m, false, p);
+        hs_ev_advance<TEL>(c, io, e, a, m, false, p);
         break;
       }
-      case PGW_HS_DEVICES: hs_devices_step(c, io, e, m, false, p); break;
+      case PGW_HS_DEVICES: hs_devices_step<TEL>(c, io, e, m, false, p); break;
       default: break;
     }
     p_agent += p;
@@ -805,6 +873,7 @@ PGW_HD void house_step(const pgw_agent& ag, const pgw_component* comps, const Ag
 }
 
 // base_hs.py:67-92; the meta state itself is not reset
+template <bool TEL>
 PGW_HD void house_reset(const pgw_agent& ag, const pgw_component* comps, const AgentIO& io, int e,
                         bool first_reset) {
   HsMeta m;
@@ -813,10 +882,10 @@ PGW_HD void house_reset(const pgw_agent& ag, const pgw_component* comps, const A
     const pgw_component c = comps[ci];
     double p;
     switch (c.type) {
-      case PGW_HS_PV: hs_pv_step(c, io, e, m, true, p); break;
+      case PGW_HS_PV: hs_pv_step<TEL>(c, io, e, m, true, p); break;
       case PGW_HS_STORAGE: hs_storage_reset(c, io, e, first_reset); break;
-      case PGW_HS_EV: hs_ev_reset(c, io, e, m); break;
-      case PGW_HS_DEVICES: hs_devices_step(c, io, e, m, true, p); break;
+      case PGW_HS_EV: hs_ev_reset<TEL>(c, io, e, m); break;
+      case PGW_HS_DEVICES: hs_devices_step<TEL>(c, io, e, m, true, p); break;
       default: break;
     }
   }

@@ -18,8 +18,9 @@
 
 namespace pgw {
 
-// HOUSE: the scenario contains Home-Steward houses (their code stays out of the other kernel).
-template <bool HOUSE>
+// HOUSE: the scenario contains Home-Steward houses (their code stays out of the other kernel);
+// TEL: some of their components record step_meta telemetry.
+template <bool HOUSE, bool TEL>
 __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t mbar[2];
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
     if (e < p.E) {
       const size_t ae = (size_t)a * p.E + e;
       if (p.event_mode == 0) {
-        if (HOUSE && is_house(ag, comps)) house_reset(ag, comps, io, e, p.first_reset != 0);
+        if (HOUSE && is_house(ag, comps)) house_reset<TEL>(ag, comps, io, e, p.first_reset != 0);
         else agent_reset(ag, comps, io, e);
         p.agent_p[ae] = 0.0;
         p.ep_ret[ae] = 0.0;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
         double pw, rw, er = 0.0;
         if (p.owns_reward)                      // issued early: its latency hides behind the step
           asm volatile("ld.global.f64 %0, [%1];" : "=d"(er) : "l"(p.ep_ret + ae));
-        if (HOUSE && is_house(ag, comps)) house_step(ag, comps, io, e, pw, rw);
+        if (HOUSE && is_house(ag, comps)) house_step<TEL>(ag, comps, io, e, pw, rw);
         else agent_step(ag, comps, io, e, pw, rw);
         p.agent_p[ae] = pw;
         p.rew[ae] = rw;
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
 cudaError_t launch_components(const CompParams& p, int smem_bytes, cudaStream_t s) {
   const int threads = 64;      // small CTAs: a 4096-env batch still reaches every SM
   dim3 grid(p.num_ctas);       // the CTA -> (agent, env blocks) table is built in pgw_create
-  auto kern = p.has_house ? component_kernel<true> : component_kernel<false>;
+  auto kern = p.has_house ? (p.has_house > 1 ? component_kernel<true, true> : component_kernel<true, false>)
+                          : component_kernel<false, false>;
   if (smem_bytes > 48 * 1024) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (err != cudaSuccess) return err;

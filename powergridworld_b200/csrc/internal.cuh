@@ -29,7 +29,8 @@ struct CompParams {
   int event_mode;          // 0 = reset (event row 0), 1 = step (event row clock+1)
   int advance_clock;       // 1 when this kernel is the last one of the step (no feeder)
   int owns_reward;         // 1 when no later kernel changes the reward (no feeder / no penalty)
-  int has_house;           // the scenario contains Home-Steward houses (kernel variant)
+  int has_house;           // 1: the scenario contains Home-Steward houses, 2: with telemetry
+                           // (kernel variants)
   int first_reset;         // reset only: first reset of the handle (state that the reference keeps
                            // across episodes gets its constructor value)
   // static tables, one contiguous 16-byte aligned blob: [agents | comps | dpar | ipar]

@@ -48,7 +48,7 @@ void emu_reset(const EmuArgs* a) {
   for (int ag = 0; ag < a->A; ++ag)
     for (int e = 0; e < a->E; ++e) {
       if (pgw::is_house(a->agents[ag], a->comps))
-        pgw::house_reset(a->agents[ag], a->comps, io, e, g_first_reset != 0);
+        pgw::house_reset<true>(a->agents[ag], a->comps, io, e, g_first_reset != 0);
       else
         pgw::agent_reset(a->agents[ag], a->comps, io, e);
       a->agent_p[(size_t)ag * a->E + e] = 0.0;
@@ -61,7 +61,7 @@ void emu_step(const EmuArgs* a) {
     for (int e = 0; e < a->E; ++e) {
       double p, r;
       if (pgw::is_house(a->agents[ag], a->comps))
-        pgw::house_step(a->agents[ag], a->comps, io, e, p, r);
+        pgw::house_step<true>(a->agents[ag], a->comps, io, e, p, r);
       else
         pgw::agent_step(a->agents[ag], a->comps, io, e, p, r);
       a->agent_p[(size_t)ag * a->E + e] = p;

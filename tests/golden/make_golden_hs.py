@@ -12,6 +12,9 @@ Builds the reference's ``HSMultiComponentEnv`` (gridworld/base_hs.py) from its o
   actions[T, 4]   one action per component, component order
   obs0[obs_dim], obs[T, obs_dim], rew[T], done[T], real_power[T]
   meta[T, 6]      grid_cost, es_cost, grid_power, pv_power, es_power, pv_cost after the step
+  telemetry[T, 4, 13]  the numbers of the per-device step_meta records (base_hs.py:158-164):
+                  cost, reward, raw action, solar / es / grid power consumed, then the
+                  device_custom_info values in their dict order (nan-padded)
   init_soc        the storage level the reference started from
 """
 import io
@@ -68,7 +71,7 @@ def record(name, ns, seed):
     storage = [e for e in env.envs if hasattr(e, "current_storage")]
     init_soc = np.array([storage[0].current_storage if storage else np.nan])
     rng = np.random.default_rng(seed)
-    A, O, R, D, P, M = [], [], [], [], [], []
+    A, O, R, D, P, M, TL = [], [], [], [], [], [], []
     done = False
     while not done:
         a = np.array([SH.draw_action(e, rng) for e in env.envs])
@@ -76,10 +79,18 @@ def record(name, ns, seed):
             ob, rew, done, meta = env.step({e.name: a[k:k + 1] for k, e in enumerate(env.envs)})
         A.append(a); O.append(flat(env, ob)); R.append(rew); D.append(done)
         P.append(env.real_power); M.append([float(meta[k]) for k in META_KEYS])
+        tel = np.full((len(env.envs), 13), np.nan)
+        for k, rec in enumerate(meta["step_meta"]):
+            vals = [rec["cost"], rec["reward"], np.asarray(rec["action"]).ravel()[0],
+                    rec["solar_power_consumed"], rec["es_power_consumed"], rec["grid_power_consumed"]]
+            vals += [float(v) for v in rec["device_custom_info"].values()]
+            tel[k, :len(vals)] = vals
+            assert rec["device_id"] == env.envs[k].name
+        TL.append(tel)
     np.savez_compressed(os.path.join(HERE, f"hs_{name}.npz"), actions=np.array(A),
                         obs0=flat(env, obs0), obs=np.array(O), rew=np.array(R, dtype=np.float64),
                         done=np.array(D), real_power=np.array(P, dtype=np.float64),
-                        meta=np.array(M), init_soc=init_soc)
+                        meta=np.array(M), init_soc=init_soc, telemetry=np.array(TL))
     print(f"hs_{name}: T={len(A)} obs_dim={len(O[0])} total reward {np.sum(R):.6f} "
           f"min grid_power {np.min(np.array(M)[:, 2]):.3f}")
 

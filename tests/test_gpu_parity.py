@@ -514,6 +514,15 @@ def test_hs_house_object_protocol():
         np.testing.assert_allclose(
             [meta[k] for k in ("grid_cost", "es_cost", "grid_power", "pv_power", "es_power", "pv_cost")],
             g["meta"][t], rtol=1e-14, atol=0)
+        # the per-device telemetry records of base_hs.py:158-164
+        assert [r["device_id"] for r in meta["step_meta"]] == names
+        for k, rec in enumerate(meta["step_meta"]):
+            vals = [rec["cost"], rec["reward"], rec["action"][0], rec["solar_power_consumed"],
+                    rec["es_power_consumed"], rec["grid_power_consumed"]]
+            vals += [float(v) for v in rec["device_custom_info"].values()]
+            want = g["telemetry"][t, k]
+            np.testing.assert_allclose(vals, want[:len(vals)], rtol=1e-12, atol=1e-13)
+            assert np.isnan(want[len(vals):]).all()
 
 
 # ------------------------------------------------------------------ tc2 tile widths / stand-alone solve

@@ -16,8 +16,8 @@ from tests.product_hs_ns import PRODUCT_HS_NS as PNS
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def house_batch(name, num_envs=1, **kw):
-    cfg = SH.VARIANTS[name](PNS)
+def house_batch(name, num_envs=1, step_meta=None, **kw):
+    cfg = dict(SH.VARIANTS[name](PNS), step_meta=step_meta)
     return pgw.MultiAgentEnv(
         common_config={"start_time": cfg["start_time"], "end_time": "01-01-2031 00:00:00",
                        "control_timedelta": cfg["control_timedelta"]},
@@ -65,3 +65,26 @@ def test_hs_second_episode_keeps_storage_cost_and_meta():
     assert cost != 0.25847
     emu.reset(g["init_soc"].reshape(1, 1))
     assert emu.sd[es + 1, 0] == cost and emu.sd[es, 0] == 8.1 != soc
+
+
+@pytest.mark.parametrize("name", ["shipped", "two_vehicles"])
+def test_hs_telemetry_rows_match_reference_step_meta(name):
+    """PGW_F_TELEMETRY: the numbers of the reference's per-device step_meta records (cost, reward,
+    raw action, solar / battery / grid power consumed, device_custom_info) against the golden."""
+    g = np.load(os.path.join(GOLD, f"hs_{name}.npz"))
+    env = house_batch(name, step_meta=True, _dry_run=True)
+    plain = house_batch(name, _dry_run=True)
+    assert env._b.sd_rows == plain._b.sd_rows + 4 * 13
+    emu = EmulatedEnv(env)
+    emu.reset(g["init_soc"].reshape(1, 1))
+    house = env.agents[0]
+    for t in range(g["actions"].shape[0]):
+        obs, rew, _ = emu.step(g["actions"][t].reshape(4, 1))
+        np.testing.assert_allclose(obs[:, 0], g["obs"][t], rtol=0, atol=1e-14)
+        for k, comp in enumerate(house.envs):
+            off, n = house.telemetry_rows(comp)
+            want = g["telemetry"][t, k]
+            have = emu.sd[off:off + n, 0]
+            m = ~np.isnan(want)
+            np.testing.assert_allclose(have[m], want[m], rtol=1e-13, atol=1e-13,
+                                       err_msg=f"t={t} {comp.name}")

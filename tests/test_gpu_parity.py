@@ -649,3 +649,37 @@ def test_power_flow_non_convergence_is_data(kernel):
             assert (it == -2).all() and st[4] == E
         v = env.get_field(3).cpu().numpy()
         assert np.isfinite(v).all() and v.min() > 0.8 and v.max() < 1.1
+
+
+@pytest.mark.parametrize("kernel", [0, 2])
+def test_runtime_options_do_not_change_results(kernel):
+    """PGW_OPT_WARM_START = 0 (every solve from the no-load voltages) and PGW_OPT_PDL = 1
+    (power flow as a programmatic dependent launch) give the same voltages as the defaults
+    within the solver's own tolerance; cold starts need more iterations."""
+    torch = _torch()
+    from powergridworld_b200 import _native as N
+    E, T = 260, 5
+    rng = np.random.default_rng(8)
+    soc = rng.uniform(10, 40, size=(3, E))
+    acts = [torch.as_tensor(rng.uniform(-1, 1, size=(24, E))).cuda() for _ in range(T)]
+    out = {}
+    for label, opts in (("default", {}), ("cold", {N.OPT_WARM_START: 0}), ("pdl", {N.OPT_PDL: 1})):
+        env = PNS.CoordinatedMultiBuildingControlEnv(
+            **S.buildings_scenario(PNS, PNS.OpenDSSSolver, 1.2), num_envs=E)
+        env.set_option(N.OPT_PF_KERNEL, kernel)
+        for k, v in opts.items():
+            env.set_option(k, v)
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            env.reset_batch(soc)
+            for a in acts:
+                env.step_batch(a)
+            out[label] = (env.get_field(3).cpu().numpy(), env.get_field(7).cpu().numpy(),
+                          env.rew.cpu().numpy().copy())
+        stream.synchronize()
+    tol = 2e-9 if kernel == 0 else 3e-7
+    for label in ("cold", "pdl"):
+        np.testing.assert_allclose(out[label][0], out["default"][0], rtol=0, atol=tol, err_msg=label)
+        np.testing.assert_allclose(out[label][2], out["default"][2], rtol=1e-6, atol=1e4 * tol)
+    assert (out["pdl"][1] == out["default"][1]).all()
+    assert out["cold"][1].mean() > out["default"][1].mean()

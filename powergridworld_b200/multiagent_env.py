@@ -97,8 +97,8 @@ class MultiAgentEnv:
     def __init__(self, common_config: dict = {}, pf_config: dict = None, agents: list = None,
                  max_episode_steps: int = None, rescale_spaces: bool = True,
                  num_envs: int = 1, device=None, record_history: bool = False,
-                 pf_tol: float = None, pf_max_iter: int = None, _dry_run: bool = False,
-                 **kwargs):
+                 pf_tol: float = None, pf_max_iter: int = None, pf_kernel: str = "fp64",
+                 _dry_run: bool = False, **kwargs):
         if type(self).get_external_obs_vars is not MultiAgentEnv.get_external_obs_vars:
             raise NotImplementedError(
                 "overriding get_external_obs_vars is not supported: grid variables are "
@@ -149,8 +149,25 @@ class MultiAgentEnv:
 
         self._compile()
         self._h = None
+        if pf_kernel not in self._PF_KERNELS:
+            raise ValueError(f"pf_kernel must be one of {sorted(self._PF_KERNELS)}")
         if not _dry_run:        # tests inspect the compiled tables without a GPU
             self._open(device)
+            if self.pf_solver is not None and pf_kernel != "fp64":
+                self._select_pf_kernel(pf_kernel)
+
+    # power-flow kernels (PGW_OPT_PF_KERNEL): "fp64" = FP64 SIMT fixed point (default, agrees with
+    # the oracle to ~1e-9 p.u.), "tc" / "tc2" = tcgen05 solvers (1e-6 p.u., what bench.py runs),
+    # "auto" = tc2 when the feeder fits it (<= 88 load branches), else fp64
+    _PF_KERNELS = {"fp64": 0, "tc": 1, "tc2": 2, "auto": 2}
+
+    def _select_pf_kernel(self, name: str):
+        try:
+            self.set_option(N.OPT_PF_KERNEL, self._PF_KERNELS[name])
+        except N.NativeError:
+            if name != "auto":
+                raise
+            self.set_option(N.OPT_PF_KERNEL, 0)
 
     @property
     def time(self):

@@ -211,3 +211,29 @@ def test_random_component_configurations_match_oracle():
                                            err_msg=f"case {case} env {e} t={t}")
                 np.testing.assert_allclose(R[t][:, e], [r[a.name] for a in ref.agents],
                                            rtol=1e-5, atol=2e-5, err_msg=f"case {case} env {e} t={t}")
+
+
+@pytest.mark.gpu
+def test_pf_kernel_keyword_and_house_readme_example():
+    """MultiAgentEnv(pf_kernel=...) selects the solver ("auto" = tc2 where the feeder fits);
+    the README's Home-Steward snippet runs as written."""
+    import numpy as np
+    import powergridworld_b200 as pgw
+    from tests import scenarios as S
+    from tests.product_ns import PRODUCT_NS as PNS
+    envs = {k: PNS.CoordinatedMultiBuildingControlEnv(
+        **S.buildings_scenario(PNS, PNS.OpenDSSSolver, 1.2), num_envs=64, pf_kernel=k)
+        for k in ("fp64", "auto")}
+    soc = np.full((3, 64), 25.0)
+    v = {k: (e.reset_batch(soc), e.get_field(3).cpu().numpy())[1] for k, e in envs.items()}
+    assert 0 < np.abs(v["auto"] - v["fp64"]).max() < 1e-6        # a different (fp32) solver ran
+    with pytest.raises(ValueError):
+        PNS.CoordinatedMultiBuildingControlEnv(
+            **S.buildings_scenario(PNS, PNS.OpenDSSSolver, 1.2), pf_kernel="fastest", _dry_run=True)
+    from powergridworld_b200.scenarios.heterogeneous_hs import make_env_config
+    house = pgw.HSMultiComponentEnv(**make_env_config())
+    obs = house.reset()
+    obs, reward, done, meta = house.step(
+        {name: space.sample() for name, space in house.action_space.items()})
+    assert set(obs) == {"pv", "storage", "ev-charging", "other-devices"} and not done
+    assert len(meta["step_meta"]) == 4 and np.isfinite(reward)

@@ -624,9 +624,11 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
         const int l = blp[k], cnt = lptr[l + 1] - lptr[l];
         bag[k] = cnt == 0 ? -1 : (cnt == 1 ? lidx[lptr[l]] : -2);
       }
-      for (int k = 0; k < NBP; ++k) {
-        env->tc2c.cst[k] = make_float4(cst[4 * k], cst[4 * k + 1], cst[4 * k + 2], cst[4 * k + 3]);
-        env->tc2c.gh[k] = make_float2(gh[2 * k], gh[2 * k + 1]);
+      for (int q = 0; q < NBP / 2; ++q) {            // pairs of branches (2q, 2q + 1)
+        const int k0 = 2 * q, k1 = 2 * q + 1;
+        env->tc2c.pa[q] = make_float4(cst[4 * k0], cst[4 * k1], cst[4 * k0 + 1], cst[4 * k1 + 1]);
+        env->tc2c.pb[q] = make_float4(cst[4 * k0 + 2], cst[4 * k1 + 2], cst[4 * k0 + 3], cst[4 * k1 + 3]);
+        env->tc2c.pc[q] = make_float4(gh[2 * k0], gh[2 * k1], gh[2 * k0 + 1], gh[2 * k1 + 1]);
       }
       t.consts = &env->tc2c;
       t.t_share = put(shf.data(), shf.size() * 4);

@@ -62,10 +62,13 @@ struct CompParams {
 
 // Operand images + fp32 tables of the FP16 tensor-core power flow (powerflow_tc2.cu).
 // blob: [B_hi | B_lo] (2 x part_bytes) | ncc x [Zn_hi | Zn_lo] at off_zn | tables at off_tab.
-// Per-branch constants of the tc2 kernel, passed as a __grid_constant__ kernel parameter.
+// Per-branch constants of the tc2 kernel, passed as a __grid_constant__ kernel parameter, laid
+// out by PAIRS of branches (2q, 2q + 1) for the packed f32x2 arithmetic of the hot loop.
 struct Tc2Consts {
-  float4 cst[8 * 11];      // {Re u0, Im u0, vlo^2, vhi^2}
-  float2 gh[8 * 11];       // (1, 0): 1 / clamp(|u|^2);  (0, 1): 1 / |u| (constant-current load)
+  float4 pa[4 * 11];       // {Re u0 (2q), Re u0 (2q+1), Im u0 (2q), Im u0 (2q+1)}
+  float4 pb[4 * 11];       // {vlo^2 (2q), vlo^2 (2q+1), vhi^2 (2q), vhi^2 (2q+1)}
+  float4 pc[4 * 11];       // {g (2q), g (2q+1), h (2q), h (2q+1)}: (1, 0) = 1 / clamp(|u|^2),
+                           // (0, 1) = 1 / |u| (constant-current load)
 };
 
 struct Tc2Params {

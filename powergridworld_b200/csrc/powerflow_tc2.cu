@@ -187,6 +187,37 @@ __device__ __forceinline__ void t2_current(float4 c, float2 gh, float dr, float 
 // OCC: resident CTAs per SM the kernel is compiled for.  Small feeders (NCH <= 2, one chunk per
 // thread) also come in a 64-register build that runs four CTAs per SM: slower for a single wave
 // of tiles (spills, latency) but ~12 % faster once the batch is several waves deep.
+// The same for the branch pair (2q, 2q + 1) in packed f32x2 arithmetic (FFMA2 / FMUL2): half the
+// issue slots for the multiply-add part.  Lane-wise identical to t2_current.
+template <bool ANY_M5>
+__device__ __forceinline__ void t2_current2(float4 a, float4 b, float4 c, float2 dr, float2 di, float ds,
+                                            float2 sr, float2 si, float2& x, float2& y) {
+  const float2 ds2 = make_float2(ds, ds);
+  const float2 ur = __ffma2_rn(dr, ds2, make_float2(a.x, a.y));
+  const float2 ui = __ffma2_rn(di, ds2, make_float2(a.z, a.w));
+  const float2 m2 = __ffma2_rn(ur, ur, __fmul2_rn(ui, ui));
+  const float2 r = make_float2(t2_rsqrt(fminf(fmaxf(m2.x, b.x), b.z)),
+                               t2_rsqrt(fminf(fmaxf(m2.y, b.y), b.w)));
+  const float2 kf = ANY_M5 ? __fmul2_rn(r, __ffma2_rn(r, make_float2(c.x, c.y), make_float2(c.z, c.w)))
+                           : __fmul2_rn(r, r);
+  const float2 tr = __fmul2_rn(ur, kf), ti = __fmul2_rn(ui, kf);
+  x = __ffma2_rn(sr, tr, __fmul2_rn(si, ti));          // conj(s) u k
+  const float2 m = __fmul2_rn(si, tr);
+  y = __ffma2_rn(sr, ti, make_float2(-m.x, -m.y));
+}
+
+// scalar views of the pair-packed constants (cold paths)
+__device__ __forceinline__ float4 t2_cst(const Tc2Consts& kc, int k) {
+  const float* a = &kc.pa[k >> 1].x;
+  const float* b = &kc.pb[k >> 1].x;
+  const int o = k & 1;
+  return make_float4(a[o], a[2 + o], b[o], b[2 + o]);
+}
+__device__ __forceinline__ float2 t2_gh(const Tc2Consts& kc, int k) {
+  const float* c = &kc.pc[k >> 1].x;
+  return make_float2(c[k & 1], c[2 + (k & 1)]);
+}
+
 template <int NCH, bool ANY_M5, bool STANDALONE, int OCC = t2_ctas_per_sm(NCH)>
 __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
     pf_tc2_kernel(const PfParams p, const __grid_constant__ Tc2Consts kc) {
@@ -272,8 +303,6 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
 
   // per-branch constants come through the constant bank (kernel parameter), not shared memory:
   // the tensor core's operand reads already take most of the shared-memory bandwidth
-  const float4* cst = kc.cst;
-  const float2* ghp = kc.gh;
   const float* share = reinterpret_cast<const float*>(sT + t.t_share);
   const int32_t* bload = reinterpret_cast<const int32_t*>(sT + t.t_bload);
   const int32_t* bagent = reinterpret_cast<const int32_t*>(sT + t.t_bagent);
@@ -367,7 +396,8 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
             } else if (p.agent_p != nullptr && ag[j] >= 0) {
               kwd[j] = p.agent_p[(size_t)ag[j] * p.E + e];
             }
-            up[j] = make_double2((double)cst[k].x, (double)cst[k].y);
+            const float4 c0 = t2_cst(kc, k);
+            up[j] = make_double2((double)c0.x, (double)c0.y);
             if (p.warm_start && k < p.nb) up[j] = p.u_state[(size_t)k * p.E + e];
           }
 #pragma unroll
@@ -385,10 +415,10 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
             const float sh = share[k] * xs;            // 0 for the padded branches
             sr[s][jj] = (float)kwd[j] * sh;
             si[s][jj] = (float)kvd[j] * sh;
-            const float4 cc = cst[k];
+            const float4 cc = t2_cst(kc, k);
             d0[jj] = ((float)up[j].x - cc.x) * (1.f / ds1);        // initial guess: fp32 is plenty
             d0[8 + jj] = ((float)up[j].y - cc.y) * (1.f / ds1);
-            t2_current<ANY_M5>(cc, ANY_M5 ? ghp[k] : make_float2(1.f, 0.f), d0[jj], d0[8 + jj], ds1,
+            t2_current<ANY_M5>(cc, ANY_M5 ? t2_gh(kc, k) : make_float2(1.f, 0.f), d0[jj], d0[8 + jj], ds1,
                                sr[s][jj], si[s][jj], x[jj], y[jj]);
           }
         }
@@ -457,10 +487,16 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
           t2_ld16(t_lane + cur * N + 16 * c, dn);
           if (!frozen) {                               // the env's last write holds x(u_final)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int k = 8 * c + j;
-              t2_current<ANY_M5>(cst[k], ANY_M5 ? ghp[k] : make_float2(1.f, 0.f), dn[j], dn[8 + j],
-                                 ds1, sr[s][j], si[s][j], x[j], y[j]);
+            for (int jp = 0; jp < 4; ++jp) {           // branch pairs 8c + 2jp, 8c + 2jp + 1
+              const int q = 4 * c + jp;
+              float2 x2, y2;
+              t2_current2<ANY_M5>(kc.pa[q], kc.pb[q], ANY_M5 ? kc.pc[q] : make_float4(1.f, 1.f, 0.f, 0.f),
+                                  make_float2(dn[2 * jp], dn[2 * jp + 1]),
+                                  make_float2(dn[8 + 2 * jp], dn[9 + 2 * jp]), ds1,
+                                  make_float2(sr[s][2 * jp], sr[s][2 * jp + 1]),
+                                  make_float2(si[s][2 * jp], si[s][2 * jp + 1]), x2, y2);
+              x[2 * jp] = x2.x; x[2 * jp + 1] = x2.y;
+              y[2 * jp] = y2.x; y[2 * jp + 1] = y2.y;
             }
             uint4 hi, lo;
             t2_split8(x, hi, lo);
@@ -517,7 +553,8 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int k = 8 * c + j;
-          const float ur = fmaf(dn[j], ds1, cst[k].x), ui = fmaf(dn[8 + j], ds1, cst[k].y);
+          const float4 c0 = t2_cst(kc, k);
+          const float ur = fmaf(dn[j], ds1, c0.x), ui = fmaf(dn[8 + j], ds1, c0.y);
           if (valid && k < p.nb)
             p.u_state[(size_t)k * p.E + e] = make_double2((double)ur, (double)ui);
           const int n = dnode[k];

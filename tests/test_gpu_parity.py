@@ -683,3 +683,73 @@ def test_runtime_options_do_not_change_results(kernel):
         np.testing.assert_allclose(out[label][2], out["default"][2], rtol=1e-6, atol=1e4 * tol)
     assert (out["pdl"][1] == out["default"][1]).all()
     assert out["cold"][1].mean() > out["default"][1].mean()
+
+
+def test_full_size_c3_shard_invariance_with_tc2():
+    """BASELINE C3 at its full size (16 384 envs, 100 agents, tc2 solver): an env's trajectory does
+    not depend on the batch it sits in -- the first 384 envs of the big batch agree with a 384-env
+    batch fed the same inputs (component state bit for bit, voltages within the solver tolerance:
+    a tile iterates until its slowest env has converged); every solve converges."""
+    import warnings
+    torch = _torch()
+    from powergridworld_b200 import _native as N
+    E, S_, T = 16384, 384, 6
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        big = PNS.MultiAgentEnv(**S.der123_scenario(PNS, PNS.OpenDSSSolver), num_envs=E, pf_kernel="tc2")
+        small = PNS.MultiAgentEnv(**S.der123_scenario(PNS, PNS.OpenDSSSolver), num_envs=S_, pf_kernel="tc2")
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(4)
+    soc = 10 + 40 * torch.rand((big.num_storage, E), generator=gen, device="cuda", dtype=torch.float64)
+    ob, os_ = big.reset_batch(soc), small.reset_batch(soc[:, :S_].contiguous())
+    assert torch.equal(ob[:, :S_], os_)
+    for t in range(T):
+        act = 2 * torch.rand((big.act_dim, E), generator=gen, device="cuda", dtype=torch.float64) - 1
+        ob, rb, _, _ = big.step_batch(act)
+        os_, rs, _, _ = small.step_batch(act[:, :S_].contiguous())
+        vb, vs = big.get_field(3)[:, :S_], small.get_field(3)
+        assert float((vb - vs).abs().max()) < 5e-7, t
+        assert float((ob[:, :S_] - os_).abs().max()) < 1e-5          # lagged voltages in the obs
+        assert torch.equal(big.get_field(0)[:, :S_], small.get_field(0))   # component state
+        torch.testing.assert_close(rb[:, :S_], rs, rtol=1e-6, atol=1e-4)
+    it = big.get_field(7)
+    assert int(it.min()) > 0 and int(it.max()) < 20
+    st = big.stats().cpu().numpy()
+    assert st[0] == E * T and st[4] == 0
+
+
+def test_full_size_c2_and_house_replicas_and_integer_state():
+    """BASELINE C2 (65 536 envs, EV station of 100 vehicles + PV + storage) and 65 536 Home-Steward
+    houses: replicas fed identical inputs stay bit-identical; the charging-set bitmask agrees with
+    the num_active_vehicles observation; energies never go negative."""
+    torch = _torch()
+    E, T = 65536, 12
+    half = E // 2
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(9)
+    env = PNS.MultiAgentEnv(**S.ev_pv_storage_scenario(PNS), num_envs=E)
+    soc_h = 10 + 30 * torch.rand((env.num_storage, half), generator=gen, device="cuda", dtype=torch.float64)
+    env.reset_batch(torch.cat([soc_h, soc_h], dim=1))
+    for t in range(T):
+        a_h = 2 * torch.rand((env.act_dim, half), generator=gen, device="cuda", dtype=torch.float64) - 1
+        obs, rew, _, _ = env.step_batch(torch.cat([a_h, a_h], dim=1))
+    assert torch.equal(obs[:, :half], obs[:, half:]) and torch.equal(rew[:, :half], rew[:, half:])
+    ev = [a for a in env.agents if hasattr(a, "num_vehicles")][0]
+    o_off, _ = ev._slot["obs"]
+    s_off, n = ev._slot["sd"]
+    m_off, words = ev._slot["si"]
+    energy = env.get_field(0)[s_off:s_off + n]
+    assert float(energy.min()) >= 0.0
+    mask = env.get_field(1)[m_off:m_off + words].to(torch.int64) & 0xFFFFFFFF
+    pop = sum(((mask >> b) & 1) for b in range(32)).sum(dim=0)
+    raw_active = (obs[o_off + 1] + 1) / 2 * ev._observation_space.high[1] if ev.rescale_spaces else obs[o_off + 1]
+    torch.testing.assert_close(raw_active, pop.double() * ev.vehicle_multiplier, rtol=0, atol=1e-9)
+
+    house = _hs_batch("two_vehicles", E)
+    soc_h = 3 + 16 * torch.rand((1, half), generator=gen, device="cuda", dtype=torch.float64)
+    house.reset_batch(torch.cat([soc_h, soc_h], dim=1))
+    for t in range(T):
+        a_h = 2.4 * torch.rand((4, half), generator=gen, device="cuda", dtype=torch.float64) - 1.2
+        obs, rew, _, _ = house.step_batch(torch.cat([a_h, a_h], dim=1))
+    assert torch.equal(obs[:, :half], obs[:, half:]) and torch.equal(rew[:, :half], rew[:, half:])
+    assert bool(torch.isfinite(rew).all())

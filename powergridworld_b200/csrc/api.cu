@@ -270,7 +270,7 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
     }
     // CTA budget of ~16 per SM, split over the agents in proportion to a cost estimate of their
     // components (rough time per 64-env block), every agent between 1 CTA and one CTA per
-    // 64-env block.  Agents are emitted interleaved, heavy ones first within a round.
+    // 64-env block.
     {
       const int blocks = (env->E + 63) / 64, budget = 148 * 16;
       std::vector<double> w(env->A, 0.5);            // ~us per env block: loop + latency floor
@@ -307,18 +307,16 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       std::vector<int> order(env->A);
       for (int a = 0; a < env->A; ++a) order[a] = a;
       std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return w[x] > w[y]; });
+      // longest-processing-time-first: every CTA of the heaviest agent, then the next agent, ...
+      // so that the long-running CTAs are all resident from the start and the light ones fill in
+      // behind them (with round-robin emission half of an EV station's CTAs started a wave late)
       std::vector<pgw::CtaWork> work;
-      for (int j = 0;; ++j) {                        // round j: the j-th CTA of every agent that has one
-        bool any = false;
-        for (int a : order)
-          if (j < n[a]) {
-            pgw::CtaWork cw{};
-            cw.agent = a; cw.j = j; cw.n = n[a]; cw.sl = sl[a];
-            work.push_back(cw);
-            any = true;
-          }
-        if (!any) break;
-      }
+      for (int a : order)
+        for (int j = 0; j < n[a]; ++j) {
+          pgw::CtaWork cw{};
+          cw.agent = a; cw.j = j; cw.n = n[a]; cw.sl = sl[a];
+          work.push_back(cw);
+        }
       env->num_ctas = (int)work.size();
       PGW_TRY(upload(&env->work, work.data(), work.size())); env->own(env->work);
     }

@@ -279,8 +279,8 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
         for (int c = spec->agents[a].comp_begin; c < spec->agents[a].comp_end; ++c) {
           const pgw_component& k = spec->components[c];
           switch (k.type) {
-            case PGW_BUILDING: w[a] += 5.0; break;
-            case PGW_EV: case PGW_HS_EV: w[a] += 2.0 + 0.04 * spec->ipar[k.ipar_off]; break;
+            case PGW_BUILDING: w[a] += 2.0; break;
+            case PGW_EV: case PGW_HS_EV: w[a] += 1.0 + 0.04 * spec->ipar[k.ipar_off]; break;
             case PGW_STORAGE: w[a] += 0.8; break;
             case PGW_HS_BEGIN: case PGW_HS_STORAGE: case PGW_HS_DEVICES: w[a] += 1.0; break;
             default: w[a] += 0.5; break;

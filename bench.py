@@ -52,9 +52,9 @@ _PF_NAMES = {"fp64": "fp64-simt", "tc": "tcgen05 split-tf32", "tc2": "tcgen05 sp
 
 # dram__bytes_read.sum + dram__bytes_write.sum of component_kernel per launch, from the committed
 # `ncu --set full` captures (profiles/r1s3_ncu_full_raw_*.csv); keyed by (workload, envs per GPU)
-NCU_TRAFFIC = {("c1", 4096): 1.557e6, ("c1", 262144): 202.3e6, ("c3", 16384): 151.96e6}
+NCU_TRAFFIC = {("c1", 4096): 1.557e6, ("c1", 262144): 202.3e6, ("c3", 16384): 152.85e6}
 # sm__pipe_tensor_cycles_active.max (% of elapsed, busy SMs) of pf_tc2_kernel in the same captures
-NCU_TENSOR_PCT = {("c1", 4096): 2.37, ("c1", 262144): 5.72, ("c3", 16384): 21.23}
+NCU_TENSOR_PCT = {("c1", 4096): 2.37, ("c1", 262144): 5.72, ("c3", 16384): 21.49}
 
 
 def _config(n_gpus):

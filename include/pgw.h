@@ -271,6 +271,16 @@ int pgw_get(pgw_env* env, int field, void* dst, size_t bytes, void* cuda_stream)
 int pgw_set(pgw_env* env, int field, const void* src, size_t bytes, void* cuda_stream);
 int pgw_set_clock(pgw_env* env, int steps, void* cuda_stream);
 
+/* Replace the VALUES of the parameter block and of both event tables (host pointers; the
+ * sizes and the component layout are those of pgw_create and cannot change; a NULL pointer
+ * leaves that table alone).  Stream-ordered before the next pgw_reset / pgw_step; returns
+ * after the host buffers have been consumed.  Replaces the roster re-sampling that
+ * EVChargingEnv(randomize=True) does on every reset
+ * (gridworld/agents/vehicles/ev_charging_env.py:154-157): the host draws the new roster,
+ * rebuilds that station's parameter and event columns and calls this before pgw_reset. */
+int pgw_update_tables(pgw_env* env, const double* dpar, int dpar_len, const double* dtab,
+                      const int32_t* itab, void* cuda_stream);
+
 /* Episode statistics (see PGW_NUM_STATS) reduced on the device into out[8] (device
  * pointer); the caller all-reduces it across ranks (one NCCL call per report). */
 int pgw_stats(pgw_env* env, double* out, void* cuda_stream);

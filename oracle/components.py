@@ -263,8 +263,7 @@ class EVChargingEnv(ComponentEnv):
                  peak_threshold=10.0, reward_scale=1e5, name=None, randomize=False,
                  vehicle_csv=None, vehicle_multiplier=1, rescale_spaces=True, **kwargs):
         super().__init__(name=name)
-        if randomize:
-            raise NotImplementedError("oracle covers the deterministic roster only")
+        self.randomize = randomize
         self.n = num_vehicles
         self.rate = max_charge_rate_kw
         self.minutes_per_step = minutes_per_step
@@ -325,9 +324,13 @@ class EVChargingEnv(ComponentEnv):
         self.time = self.simulation_times[0]
         self.charging_vehicles = []
         self.departed_vehicles = []
-        self.energy = self._e0[:self.n].copy()
-        self.start = self._start[:self.n]
-        self.end = self._end[:self.n]
+        # :154-157  df.sample(n) draws np.random.choice(len(df), n, replace=False) on NumPy's global
+        # RNG (pandas' random_state=None) and keeps the rows in drawn order
+        rows = np.random.choice(len(self._e0), size=self.n, replace=False) if self.randomize \
+            else np.arange(self.n)
+        self.energy = self._e0[rows].copy()
+        self.start = self._start[rows]
+        self.end = self._end[rows]
         self._real_power = 0.0
         self.step(**kwargs)
         obs, _ = self.get_obs()

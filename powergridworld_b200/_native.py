@@ -76,6 +76,7 @@ SYMBOLS = {
     "pgw_get": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _vp]),
     "pgw_set": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _vp]),
     "pgw_set_clock": (C.c_int, [_vp, C.c_int, _vp]),
+    "pgw_update_tables": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "pgw_stats": (C.c_int, [_vp, _vp, _vp]),
     "pgw_clock": (C.c_int, [_vp]),
     "pgw_launch_count": (C.c_longlong, [_vp]),

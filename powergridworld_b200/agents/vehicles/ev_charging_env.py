@@ -4,6 +4,11 @@ Dynamics: csrc/component_math.cuh ev_advance / ev_step / ev_reset.
 The vehicle roster (arrival, departure, energy) is shared by every env, so the
 "who is parked at minute t" half of the reference's charging set is a static
 per-step list compiled here; only the "still needs energy" half is per-env state.
+
+``randomize=True`` (:154-157): every reset draws ``num_vehicles`` rows of the table without
+replacement -- NumPy's global RNG, the draw ``DataFrame.sample`` makes -- and the station's
+parameter and event columns are rebuilt and pushed to the device (pgw_update_tables).  The
+drawn roster is shared by all envs of the batch.
 """
 from collections import OrderedDict
 
@@ -31,10 +36,6 @@ class EVChargingEnv(ComponentEnv):
                  randomize: bool = False, vehicle_csv: str = None, vehicle_multiplier: int = 1,
                  rescale_spaces: bool = True, **kwargs):
         super().__init__(name=name)
-        if randomize:
-            raise NotImplementedError(
-                "randomize=True (a different roster sample per reset, :155-156) is not "
-                "supported: all envs of a batch share one roster")
         self.num_vehicles = num_vehicles
         self.max_charge_rate_kw = max_charge_rate_kw
         self.minutes_per_step = minutes_per_step
@@ -82,10 +83,20 @@ class EVChargingEnv(ComponentEnv):
         # reset leaves time_index == 1 (hidden step, :163); terminal at max_episode_steps - 1
         return self.max_episode_steps - 2
 
-    def _emit(self, b, agent_index, standalone):
+    _rows = None
+
+    def _draw_roster(self):
+        """df.sample(n) (:155): np.random.choice(len(df), n, replace=False), rows kept in drawn
+        order (the order fixes the index each vehicle gets after reset_index, :157)."""
+        self._rows = np.random.choice(len(self._roster_energy), size=self.num_vehicles,
+                                      replace=False)
+
+    def _retable(self):
+        """(dpar, dtab_fn, itab_fn) of the current roster; widths do not depend on the draw."""
         n = self.num_vehicles
-        start = np.floor(self._roster_start[:n])
-        end = np.floor(self._roster_end[:n])
+        rows = self._rows if (self.randomize and self._rows is not None) else np.arange(n)
+        start = np.floor(self._roster_start[rows])
+        end = np.floor(self._roster_end[rows])
         times = self.simulation_times
         idx = np.arange(n)
 
@@ -96,10 +107,12 @@ class EVChargingEnv(ComponentEnv):
         n_ev = len(times) - 1                               # events 0 .. len-2 have a "next" time
         wins = [window(k) for k in range(n_ev)]
         lefts = [np.array([], dtype=int)] + [np.setdiff1d(wins[k - 1], wins[k]) for k in range(1, n_ev)]
-        cap = max(1, max(len(w) for w in wins), max(len(l) for l in lefts))
-        words = (n + 31) // 32
+        # a randomised station sizes its lists for the worst draw (everyone parked at once)
+        cap = n if self.randomize else \
+            max(1, max(len(w) for w in wins), max(len(l) for l in lefts))
+        self._cap = cap
 
-        end_raw = self._roster_end[:n]
+        end_raw = self._roster_end[rows]
 
         def dtab_fn(r):
             k = min(r, n_ev - 1)
@@ -121,7 +134,13 @@ class EVChargingEnv(ComponentEnv):
         dpar = [self.max_charge_rate_kw, self.minutes_per_step / 60., float(self.vehicle_multiplier),
                 self.unserved_penalty, self.peak_penalty, self.peak_threshold, self.reward_scale]
         dpar += list(hi) + list(1.0 / hi) + [1.0 / self.reward_scale, 1.0 / 60.0]
-        dpar += list(self._roster_end[:n]) + list(self._roster_energy[:n])
+        dpar += list(self._roster_end[rows]) + list(self._roster_energy[rows])
+        return dpar, dtab_fn, itab_fn
+
+    def _emit(self, b, agent_index, standalone):
+        n = self.num_vehicles
+        dpar, dtab_fn, itab_fn = self._retable()
+        cap, words = self._cap, (n + 31) // 32
         b.add_component(self, N.EV, agent_index,
                         flags=N.F_RESCALE if self.rescale_spaces else 0,
                         dpar=dpar, ipar=[n, words, cap], sd_rows=n, si_rows=words,

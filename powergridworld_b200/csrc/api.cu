@@ -73,7 +73,7 @@ struct pgw_env {
   long long launches = 0;
   // device tables
   unsigned char* comp_blob = nullptr;   // [agents | comps | dpar | ipar]
-  int comp_blob_bytes = 0, off_comps = 0, off_dpar = 0, off_ipar = 0;
+  int comp_blob_bytes = 0, off_comps = 0, off_dpar = 0, off_ipar = 0, dpar_len = 0;
   pgw::CtaWork* work = nullptr;         // CTA -> (agent, env blocks, staging ranges)
   int num_ctas = 0;
   int max_cn = 0, max_dn = 0, max_in = 0;
@@ -222,6 +222,7 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
     const size_t b_co = (size_t)env->C * sizeof(pgw_component);
     const size_t b_dp = (size_t)spec->dpar_len * sizeof(double);
     const size_t b_ip = (size_t)spec->ipar_len * sizeof(int32_t);
+    env->dpar_len = spec->dpar_len;
     env->off_comps = round_up((int)b_ag, 16);
     env->off_dpar = round_up(env->off_comps + (int)b_co, 16);
     env->off_ipar = round_up(env->off_dpar + (int)b_dp, 16);
@@ -971,6 +972,26 @@ int pgw_set_clock(pgw_env* env, int steps, void* cuda_stream) {
                            static_cast<cudaStream_t>(cuda_stream)));
   PGW_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
   env->clock = steps;
+  return PGW_OK;
+}
+
+int pgw_update_tables(pgw_env* env, const double* dpar, int dpar_len, const double* dtab,
+                      const int32_t* itab, void* cuda_stream) {
+  if (!env) return fail(PGW_ERR_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  if (dpar) {
+    if (dpar_len != env->dpar_len) return fail(PGW_ERR_INVALID, "parameter block length changed");
+    if (dpar_len)
+      PGW_CUDA(cudaMemcpyAsync(env->comp_blob + env->off_dpar, dpar, (size_t)dpar_len * sizeof(double),
+                               cudaMemcpyHostToDevice, s));
+  }
+  if (dtab)
+    PGW_CUDA(cudaMemcpyAsync(env->dtab, dtab, (size_t)env->num_events * env->dstride * sizeof(double),
+                             cudaMemcpyHostToDevice, s));
+  if (itab && env->istride)
+    PGW_CUDA(cudaMemcpyAsync(env->itab, itab, (size_t)env->num_events * env->istride * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, s));
+  PGW_CUDA(cudaStreamSynchronize(s));
   return PGW_OK;
 }
 

@@ -83,7 +83,9 @@ class SpecBuilder:
         if max_events is not None:
             self.max_events = min(self.max_events, max_events)
         obj._slot = {"act": (c.act_off, obj._act_dim), "obs": (c.obs_off, obj._obs_dim),
-                     "sd": (c.sd_off, sd_rows), "si": (c.si_off, si_rows)}
+                     "sd": (c.sd_off, sd_rows), "si": (c.si_off, si_rows),
+                     "dpar": (c.dpar_off, len(dpar)), "ipar": (c.ipar_off, len(ipar)),
+                     "dtab": (c.dtab_off, dtab_width), "itab": (c.itab_off, itab_width)}
         self.comps.append(c)
         self.objs.append(obj)
 
@@ -233,6 +235,7 @@ class MultiAgentEnv:
 
         self._b = b
         self._agent_recs = agent_recs
+        self._dpar = np.asarray(b.dpar if b.dpar else [0.0], dtype=np.float64)
         self._dtab, self._itab = dtab, itab
         self._dstride, self._istride = dstride, istride
         self.act_dim, self.obs_dim = b.act_dim, b.obs_dim
@@ -265,15 +268,17 @@ class MultiAgentEnv:
         spec.num_events = self._dtab.shape[0]
         spec.dtab_stride, spec.itab_stride = self._dstride, self._istride
         comps = (N.Component * len(b.comps))(*b.comps)
-        dpar = np.asarray(b.dpar if b.dpar else [0.0], dtype=np.float64)
+        dpar = self._dpar
         ipar = np.asarray(b.ipar if b.ipar else [0], dtype=np.int32)
         spec.dpar_len, spec.ipar_len = len(b.dpar), len(b.ipar)
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
         ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
         spec.agents, spec.components = self._agent_recs, comps
         spec.dpar, spec.ipar = dp(dpar), ip(ipar)
-        dtab = np.ascontiguousarray(self._dtab)
+        dtab = self._dtab = np.ascontiguousarray(self._dtab)
         itab = np.ascontiguousarray(self._itab if self._istride else np.zeros((1, 4), np.int32))
+        if self._istride:
+            self._itab = itab
         spec.dtab, spec.itab = dp(dtab), ip(itab)
         keep = [comps, dpar, ipar, dtab, itab]
         if self.pf_solver is not None:
@@ -357,6 +362,53 @@ class MultiAgentEnv:
     def _stream(self):
         return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
 
+    def _randomised(self):
+        return [o for o in self._b.objs if getattr(o, "randomize", False) and hasattr(o, "_retable")]
+
+    def _rebuild_roster_tables(self):
+        """Rewrite (host side, in place) the parameter and event columns of every randomised
+        charging station from its current roster draw; widths never change."""
+        n_events = self._dtab.shape[0]
+        for o in self._randomised():
+            dpar, dtab_fn, itab_fn = o._retable()
+            off, n = o._slot["dpar"]
+            assert len(dpar) == n
+            self._dpar[off:off + n] = dpar
+            doff, dw = o._slot["dtab"]
+            ioff, iw = o._slot["itab"]
+            for r in range(n_events):
+                self._dtab[r, doff:doff + dw] = dtab_fn(r)
+                self._itab[r, ioff:ioff + iw] = itab_fn(r)
+
+    def _reset_draws(self, init_storage):
+        """Host-side randomness of a reset in the reference's order -- agents in turn, their
+        components in turn (multiagent_env.py:131-137): a storage draws its initial SOC
+        (energy_storage_env.py:82-84), an EVChargingEnv(randomize=True) its roster
+        (ev_charging_env.py:154-157; NumPy's global RNG, shared by all envs of the batch).  New
+        rosters are pushed to the device with pgw_update_tables before the reset kernel runs.
+        Returns the [num_storage, E] initial SOCs (or ``init_storage`` when given)."""
+        rand = self._randomised()
+        draw_soc = self.num_storage and init_storage is None
+        if not rand:
+            return self.draw_initial_storage() if draw_soc else init_storage
+        soc = []
+        for o in self._b.objs:
+            if any(o is r for r in rand):
+                o._draw_roster()
+            elif draw_soc and any(o is s for s in self._b.storages):
+                x = o.draw_initial_storage() if self.num_envs == 1 \
+                    else o.draw_initial_storage(size=self.num_envs)
+                soc.append(np.broadcast_to(np.asarray(x, dtype=np.float64), (self.num_envs,)))
+        self._rebuild_roster_tables()
+        if self._h is not None:
+            dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+            with _torch().cuda.device(self.device):
+                N.check(self._lib.pgw_update_tables(
+                    self._h, dp(self._dpar), len(self._b.dpar), dp(self._dtab),
+                    self._itab.ctypes.data_as(C.POINTER(C.c_int32)) if self._istride else None,
+                    self._stream()))
+        return np.stack(soc) if draw_soc else init_storage
+
     def draw_initial_storage(self) -> np.ndarray:
         """[num_storage, E] initial SOC drawn like the reference does on reset
         (energy_storage_env.py:82-84): one scalar truncnorm draw per storage in agent /
@@ -371,9 +423,8 @@ class MultiAgentEnv:
         """Reset all envs; returns the observation tensor ``[obs_dim, E]`` (reused buffer)."""
         torch = _torch()
         soc_ptr = None
+        init_storage = self._reset_draws(init_storage)
         if self.num_storage:
-            if init_storage is None:
-                init_storage = self.draw_initial_storage()
             if not isinstance(init_storage, torch.Tensor):
                 init_storage = torch.as_tensor(np.ascontiguousarray(init_storage, dtype=np.float64))
             soc = init_storage.to(self.device, dtype=torch.float64).contiguous()
@@ -424,9 +475,8 @@ class MultiAgentEnv:
         torch = _torch()
         pin = self._pinned()
         soc_ptr = None
+        init_storage = self._reset_draws(init_storage)
         if self.num_storage:
-            if init_storage is None:
-                init_storage = self.draw_initial_storage()
             pin["soc"][:self.num_storage].copy_(torch.as_tensor(np.asarray(init_storage, dtype=np.float64)))
             soc_ptr = C.c_void_p(pin["soc"].data_ptr())
         with torch.cuda.device(self.device):

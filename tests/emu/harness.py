@@ -56,7 +56,7 @@ class EmulatedEnv:
         b = env._b
         self.E, self.A = env.num_envs, len(env.agents)
         self.comps = (N.Component * len(b.comps))(*b.comps)
-        self.dpar = np.asarray(b.dpar if b.dpar else [0.0], dtype=np.float64)
+        self.dpar = env._dpar          # shared: roster re-draws rewrite it in place
         self.ipar = np.asarray(b.ipar if b.ipar else [0], dtype=np.int32)
         self.sd = np.zeros((max(b.sd_rows, 1), self.E))
         self.si = np.zeros((max(b.si_rows, 1), self.E), dtype=np.uint32)

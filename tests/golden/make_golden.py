@@ -118,6 +118,44 @@ def record(name, env_cls, cfg, ref, seed=1234):
           f"vmin={out['volt'].min():.4f} vmax={out['volt'].max():.4f}")
 
 
+def record_randomized(ref, ns, pf, episodes=2, seed=4321):
+    """Two episodes of tests/scenarios.py::randomized_ev_scenario.  np.random.seed(100 + ep) is
+    set right before each reset; the file keeps what the reference then drew (storage SOCs,
+    and -- through the trace -- the rosters), so a replay checks the draws themselves and
+    their order, not only the dynamics."""
+    with quiet_stdout():
+        env = ns.MultiAgentEnv(**S.randomized_ev_scenario(ns, pf))
+    layout = action_layout(env)
+    rng = np.random.default_rng(seed)
+    out = {}
+    for ep in range(episodes):
+        np.random.seed(100 + ep)
+        with quiet_stdout():
+            obs0 = env.reset()
+        socs = storage_socs(ref, env)               # what this reset drew
+        A, O, R, P = [], [], [], []
+        done = False
+        while not done:
+            a = draw_actions(layout, rng)
+            with quiet_stdout():
+                ob, rew, dn, _ = env.step(unflatten_action(env, a))
+            A.append(a)
+            O.append(flat_obs(env, ob))
+            R.append(np.array([rew[ag.name] for ag in env.agents], dtype=np.float64))
+            P.append(np.array(env.history["agent_power_p"][-1], dtype=np.float64))
+            done = dn["__all__"]
+        rosters = [np.asarray(e.df["index"].values) for a in env.agents
+                   for e in getattr(a, "envs", [a]) if isinstance(e, ref.EVChargingEnv)]
+        out.update({f"init_soc{ep}": socs, f"obs0_{ep}": flat_obs(env, obs0),
+                    f"actions{ep}": np.array(A), f"obs{ep}": np.array(O), f"rew{ep}": np.array(R),
+                    f"agent_p{ep}": np.array(P)})
+        for k, r in enumerate(rosters):
+            out[f"roster{ep}_{k}"] = r
+    np.savez_compressed(os.path.join(HERE, "ev_randomized.npz"), episodes=episodes, **out)
+    print(f"ev_randomized: {episodes} episodes, T={len(A)}, rosters "
+          f"{[out[f'roster0_{k}'][:4].tolist() for k in range(len(rosters))]}")
+
+
 def ev_totals(ref):
     cfg = {"num_vehicles": 100, "minutes_per_step": 5, "max_charge_rate_kw": 7.,
            "peak_threshold": 250., "vehicle_multiplier": 5., "rescale_spaces": False}
@@ -150,6 +188,7 @@ def main():
     record("heterogeneous_max250", ns.MultiAgentEnv,
            S.heterogeneous_scenario(ns, pf, 0.6, max_episode_steps=250), ref)
     record("test_heterogeneous", ns.MultiAgentEnv, S.test_heterogeneous_scenario(ns, pf), ref)
+    record_randomized(ref, ns, pf)
     ev_totals(ref)
 
 

@@ -10,6 +10,7 @@ the CPU oracle and the product.  They restate the reference's shipped scenarios:
                           examples/marl/openai/train.py:165-188  (BASELINE C0/C1)
   heterogeneous_scenario  gridworld/scenarios/heterogeneous.py:13-112
   ev_pv_storage_scenario  BASELINE C2 (component-only)
+  randomized_ev_scenario  charging stations that re-draw their roster on every reset
   test_* fixtures         tests/conftest.py:99-148, tests/agents/conftest.py
 """
 import pandas as pd
@@ -96,6 +97,32 @@ def ev_pv_storage_scenario(ns, pf_cls=None, rescale_spaces=True):
         ],
     }
     return cfg
+
+
+def randomized_ev_scenario(ns, pf_cls):
+    """EVChargingEnv(randomize=True) (ev_charging_env.py:154-157) standalone and inside a
+    MultiComponentEnv, between storages so that the order of the host RNG draws of a reset
+    (storage SOC, roster, storage SOC, roster) is part of what is compared."""
+    ev = lambda n, mult, rescale: {"num_vehicles": n, "minutes_per_step": 5,
+                                   "max_charge_rate_kw": 7., "peak_threshold": 60.,
+                                   "vehicle_multiplier": mult, "rescale_spaces": rescale,
+                                   "randomize": True}
+    depot = [
+        {"name": "storage", "cls": ns.EnergyStorageEnv, "config": {"max_power": 20.}},
+        {"name": "chargers", "cls": ns.EVChargingEnv, "config": ev(20, 3., True)},
+    ]
+    return {
+        "common_config": {"start_time": "08-12-2020 00:00:00",
+                          "end_time": "08-13-2020 00:00:00",
+                          "control_timedelta": pd.Timedelta(300, "s")},
+        "pf_config": _pf(pf_cls, 0.7),
+        "agents": [
+            {"name": "storage", "bus": "675c", "cls": ns.EnergyStorageEnv, "config": {}},
+            {"name": "depot", "bus": "634a", "cls": ns.MultiComponentEnv,
+             "config": {"components": depot}},
+            {"name": "ev", "bus": "675a", "cls": ns.EVChargingEnv, "config": ev(45, 2., False)},
+        ],
+    }
 
 
 def test_multicomponent_components(ns):

@@ -753,3 +753,69 @@ def test_full_size_c2_and_house_replicas_and_integer_state():
         obs, rew, _, _ = house.step_batch(torch.cat([a_h, a_h], dim=1))
     assert torch.equal(obs[:, :half], obs[:, half:]) and torch.equal(rew[:, :half], rew[:, half:])
     assert bool(torch.isfinite(rew).all())
+
+
+def test_randomized_rosters_replay_reference_trace_on_gpu():
+    """EVChargingEnv(randomize=True) (ev_charging_env.py:154-157), dict API, two episodes: every
+    reset draws new rosters on the host (same RNG stream as the reference), pushes them with
+    pgw_update_tables and the cached step graphs keep running on the new tables."""
+    from tests.test_oracle_golden import _replay_randomized
+
+    def step(env, a):
+        ob, rew, dn, _ = env.step(unflatten_action(env, a))
+        return flat_obs(env, ob), np.array([rew[x.name] for x in env.agents]), dn["__all__"]
+
+    _replay_randomized(
+        lambda: PNS.MultiAgentEnv(**S.randomized_ev_scenario(PNS, PNS.OpenDSSSolver)),
+        lambda env: flat_obs(env, env.reset()), step, exact=False)
+
+
+def test_randomized_station_standalone_and_batched_vs_oracle():
+    """Per-object protocol and a ragged batch: the roster drawn at reset is shared by all envs
+    of the batch, every env replays the oracle station that drew the same roster; the host-
+    buffer entry points go through the same draw."""
+    torch = _torch()
+    cfg = dict(num_vehicles=37, minutes_per_step=5, max_charge_rate_kw=7., peak_threshold=40.,
+               vehicle_multiplier=2., rescale_spaces=True, randomize=True)
+    rng = np.random.default_rng(5)
+    # (a) station on its own, three resets
+    dev, ora = PNS.EVChargingEnv(**cfg), ONS.EVChargingEnv(**cfg)
+    for ep in range(3):
+        np.random.seed(9 + ep)
+        od, _ = dev.reset()
+        np.random.seed(9 + ep)
+        oo, _ = ora.reset()
+        np.testing.assert_allclose(od, oo, rtol=0, atol=1e-12)
+        for t in range(120):
+            a = rng.uniform(-1.1, 1.1, size=1)
+            rd, ro = dev.step(a), ora.step(a)
+            np.testing.assert_allclose(rd[0], ro[0], rtol=0, atol=1e-9, err_msg=f"ep={ep} t={t}")
+            np.testing.assert_allclose(rd[1], ro[1], rtol=1e-9, atol=1e-12)
+    # (b) batch of 70 envs, device and host entry points
+    E = 70
+    common = {"start_time": "08-12-2020 00:00:00", "end_time": "08-13-2020 00:00:00",
+              "control_timedelta": __import__("pandas").Timedelta(300, "s")}
+    env = PNS.MultiAgentEnv(common_config=common, pf_config=None, num_envs=E, agents=[
+        {"name": "ev", "bus": None, "cls": PNS.EVChargingEnv, "config": cfg}])
+    for ep, host in enumerate([False, True, False]):
+        np.random.seed(30 + ep)
+        obs0 = env.reset_host() if host else env.reset_batch().cpu().numpy()
+        np.random.seed(30 + ep)
+        refs = [ONS.EVChargingEnv(**cfg) for _ in range(3)]
+        state = np.random.get_state()
+        for r in refs:                               # same draw for every replica
+            np.random.set_state(state)
+            o, _ = r.reset()
+            np.testing.assert_allclose(obs0[:, 0], o, rtol=0, atol=1e-12)
+        acts = rng.uniform(-1.1, 1.1, size=(100, 1, E))
+        for t in range(100):
+            if host:
+                obs, rew, _ = env.step_host(acts[t])
+            else:
+                o_, r_, _, _ = env.step_batch(torch.as_tensor(acts[t]).cuda())
+                obs, rew = o_.cpu().numpy(), r_.cpu().numpy()
+            for k, e in enumerate([0, 33, 69]):
+                ro = refs[k].step(acts[t][:, e])
+                np.testing.assert_allclose(obs[:, e], ro[0], rtol=0, atol=1e-9,
+                                           err_msg=f"ep={ep} t={t} env={e}")
+                np.testing.assert_allclose(rew[0, e], ro[1], rtol=1e-9, atol=1e-12)

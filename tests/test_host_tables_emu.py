@@ -88,3 +88,32 @@ def test_der123_scenario_tables_and_arithmetic_vs_oracle():
         np.testing.assert_allclose(o[:, 0], flat_obs(ref, ro), rtol=0, atol=1e-12)
         np.testing.assert_allclose(r[:, 0], [rr[x.name] for x in ref.agents], rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(emu.vmag[:, 0], [ref.voltages[n] for n in names], rtol=0, atol=1e-10)
+
+
+def test_randomized_rosters_host_draws_and_tables_vs_reference_trace():
+    """EVChargingEnv(randomize=True): the product's host side draws the rosters and the
+    storage SOCs of a reset in the reference's RNG order and rebuilds the station tables in
+    place; with the device arithmetic emulated this replays the reference's two episodes."""
+    from tests.test_oracle_golden import _replay_randomized
+    state = {}
+
+    def make():
+        env = NS.MultiAgentEnv(**S.randomized_ev_scenario(NS, NS.OpenDSSSolver), _dry_run=True)
+        state["emu"] = EmulatedEnv(env)
+        return env
+
+    def reset(env):
+        soc = env._reset_draws(None)                 # what reset_batch / reset_host do first
+        assert soc.shape == (2, 1)
+        return state["emu"].reset(soc)[:, 0]
+
+    def step(env, a):
+        obs, rew, done = state["emu"].step(a.reshape(-1, 1))
+        return obs[:, 0], rew[:, 0], bool(done)
+
+    _replay_randomized(make, reset, step, exact=False)
+    env = state["emu"].env
+    g = np.load(os.path.join(GOLD, "ev_randomized.npz"))
+    rosters = [o._rows for o in env._b.objs if getattr(o, "randomize", False)]
+    for k, r in enumerate(rosters):                  # last episode's draw, row for row
+        np.testing.assert_array_equal(r, g[f"roster1_{k}"])

@@ -79,3 +79,32 @@ def test_storage_episode_is_287_steps():
         _, _, done, _ = env.step(np.array([0.3]))
         n += 1
     assert n == 287
+
+
+def _replay_randomized(make_env, reset, step, exact):
+    """Shared by the oracle (here) and the product tiers: two episodes of
+    tests/golden/ev_randomized.npz, np.random.seed(100 + ep) before each reset like the
+    recording; the storages' drawn SOCs and the rosters must come out of the same RNG stream."""
+    g = np.load(os.path.join(GOLD, "ev_randomized.npz"))
+    env = make_env()
+    cmp = np.testing.assert_array_equal if exact else \
+        (lambda a, b, err_msg="": np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-7, err_msg=err_msg))
+    for ep in range(int(g["episodes"])):
+        np.random.seed(100 + ep)
+        cmp(reset(env), g[f"obs0_{ep}"], err_msg=f"obs0 ep={ep}")
+        A = g[f"actions{ep}"]
+        for t in range(A.shape[0]):
+            ob, rew, done = step(env, A[t])
+            cmp(ob, g[f"obs{ep}"][t], err_msg=f"obs ep={ep} t={t}")
+            cmp(rew, g[f"rew{ep}"][t], err_msg=f"rew ep={ep} t={t}")
+        assert done
+
+
+def test_oracle_replays_randomized_rosters():
+    """EVChargingEnv(randomize=True): pandas' df.sample(n) == np.random.choice(N, n, False)."""
+    def step(env, a):
+        ob, rew, dn, _ = env.step(unflatten_action(env, a))
+        return flat_obs(env, ob), np.array([rew[x.name] for x in env.agents]), dn["__all__"]
+    _replay_randomized(
+        lambda: NS.MultiAgentEnv(**S.randomized_ev_scenario(NS, NS.OpenDSSSolver)),
+        lambda env: flat_obs(env, env.reset()), step, exact=True)

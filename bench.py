@@ -421,6 +421,54 @@ def run_ours(args):
             pf_peak_src = "measured bf16 (= fp16 dense), " + peak_src
         else:
             pf_peak, pf_peak_src = 37.0, "nominal B200 FP64 (no measured FP64 peak)"
+        rf_comp = {"kernel": "component_kernel", "bound": "hbm", "achieved": achieved,
+                   "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                   "frac": achieved / peaks["hbm_gbs"],
+                   "traffic": NCU_TRAFFIC.get((WORKLOAD, E)),
+                   "traffic_source": "profiles/r1s3_ncu_full_raw_*.csv (ncu --set full, one "
+                                     "capture)" if (WORKLOAD, E) in NCU_TRAFFIC else None,
+                   "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                   "survey_bytes_per_launch": survey_bytes,
+                   "frac_survey_bytes": (survey_bytes / (comp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
+                   if comp_ms > 0 else 0.0,
+                   "avg_launch_ms": comp_ms}
+        rf_pf = None
+        if has_pf:
+            # Power-flow kernel, both roofs: per env it reads the agents'
+            # power (A x 8 B), the warm-start branch voltages (nb x 16 B) and -- with a reward
+            # hook -- the rewards (A x 8 B); it writes the branch voltages (nb x 16 B), the node
+            # magnitudes (nn x 8 B), min/max (16 B), the agents' bus voltages (A x 8 B), the
+            # rewards (A x 8 B, hook only) and the iteration count (4 B).  Shared tables (Z-bus
+            # images, event row) are staged in shared memory and not counted.  The roof that
+            # binds is the one with the larger time at peak.
+            hook = 1 if getattr(env, "_penalty", None) is not None else 0
+            pf_bytes = (8.0 * A + 16.0 * f.nb + 8.0 * A * hook + 16.0 * f.nb + 8.0 * f.nn + 16.0 +
+                        8.0 * A + 8.0 * A * hook + 4.0) * E
+            t_hbm = pf_bytes / (peaks["hbm_gbs"] * 1e9)
+            t_tensor = flops / (pf_peak * 1e12)
+            gbs = pf_bytes / (pf_ms * 1e-3) / 1e9 if pf_ms > 0 else 0.0
+            tfs = flops / (pf_ms * 1e-3) / 1e12 if pf_ms > 0 else 0.0
+            hbm_bound = t_hbm >= t_tensor
+            rf_pf = {"kernel": {"tc": "pf_tc_kernel", "tc2": "pf_tc2_kernel"}.get(
+                         PF_KERNEL, "pf_fixed_point_kernel"),
+                     "bound": "hbm" if hbm_bound else ("tensor" if PF_KERNEL != "fp64" else "fp64-fma"),
+                     "achieved": gbs if hbm_bound else tfs,
+                     "peak": peaks["hbm_gbs"] if hbm_bound else pf_peak,
+                     "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                     "frac": (gbs / peaks["hbm_gbs"]) if hbm_bound else (tfs / pf_peak),
+                     "traffic": None,
+                     "peak_source": peak_src if hbm_bound else pf_peak_src,
+                     "algorithmic_bytes_per_launch": pf_bytes,
+                     "algorithmic_flops_per_launch": flops,
+                     "arithmetic_intensity_flop_per_byte": flops / pf_bytes,
+                     "ridge_flop_per_byte": pf_peak * 1e12 / (peaks["hbm_gbs"] * 1e9),
+                     "hbm": {"achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"]},
+                     "tensor": {"achieved_tflops": tfs, "peak_tflops": pf_peak, "frac": tfs / pf_peak,
+                                "peak_source": pf_peak_src,
+                                "pipe_active_pct_ncu": NCU_TENSOR_PCT.get((WORKLOAD, E))
+                                if PF_KERNEL == "tc2" else None},
+                     "avg_launch_ms": pf_ms, "mean_iterations": iters_mean}
+        dominant = rf_pf if (rf_pf is not None and pf_ms > comp_ms) else rf_comp
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
@@ -431,33 +479,16 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / ke, "steps": ke},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "component_kernel", "bound": "hbm", "achieved": achieved,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": NCU_TRAFFIC.get((WORKLOAD, E)),
-                         "traffic_source": "profiles/r1s3_ncu_full_raw_*.csv (ncu --set full, one "
-                                           "capture)" if (WORKLOAD, E) in NCU_TRAFFIC else None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "survey_bytes_per_launch": survey_bytes,
-                         "frac_survey_bytes": (survey_bytes / (comp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
-                         if comp_ms > 0 else 0.0,
-                         "avg_launch_ms": comp_ms},
-            "roofline_pf": {"kernel": {"tc": "pf_tc_kernel", "tc2": "pf_tc2_kernel"}.get(
-                                PF_KERNEL, "pf_fixed_point_kernel"),
-                            "bound": "tensor" if PF_KERNEL != "fp64" else "fp64-fma",
-                            "achieved": flops / (pf_ms * 1e-3) / 1e12 if pf_ms > 0 else 0.0,
-                            "peak": pf_peak, "unit": "TFLOP/s", "peak_source": pf_peak_src,
-                            "algorithmic_flops_per_launch": flops, "avg_launch_ms": pf_ms,
-                            "tensor_pipe_active_pct_ncu": NCU_TENSOR_PCT.get((WORKLOAD, E))
-                            if PF_KERNEL == "tc2" else None,
-                            "mean_iterations": iters_mean},
+            # `roofline` = the kernel with the larger share of the step; both are always listed
+            "roofline": dominant,
+            "roofline_components": rf_comp,
+            "roofline_pf": rf_pf,
             "kernel_share": {"components": comp_ms / max(comp_ms + pf_ms, 1e-12),
                              "powerflow": pf_ms / max(comp_ms + pf_ms, 1e-12)},
             "warm_l2": {"ms_per_step": warm_ms, "value": E * world / (warm_ms * 1e-3)},
             "stats": [float(x) for x in stats.cpu()],
             "wall_s_timed_region": wall,
         }
-        line["roofline_pf"]["frac"] = line["roofline_pf"]["achieved"] / pf_peak
         if not has_pf:
             del line["roofline_pf"]
         if cpu_base is not None:

@@ -278,9 +278,9 @@ def run_ours(args):
     if PF_KERNEL != "fp64" and has_pf:
         from powergridworld_b200 import _native as N
         env.set_option(N.OPT_PF_KERNEL, {"tc": 1, "tc2": 2}[PF_KERNEL])
-    if args.pdl:
+    if not args.pdl:
         from powergridworld_b200 import _native as N
-        env.set_option(N.OPT_PDL, 1)
+        env.set_option(N.OPT_PDL, 0)
     A = len(env.agents)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -655,8 +655,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pdl", action="store_true",
-                    help="power flow as a programmatic dependent launch of the component kernel")
+    ap.add_argument("--pdl", type=int, default=1, choices=[0, 1],
+                    help="power flow as a programmatic dependent launch of the component kernel "
+                         "(library default 1; applies to feeders whose solver CTA leaves room on the SM)")
     ap.add_argument("--envs", type=int, default=None,
                     help="envs per GPU (default: 4096 for C1, 65536 for C2, 16384 for C3)")
     ap.add_argument("--pf-kernel", default=PF_KERNEL, choices=["fp64", "tc", "tc2"])

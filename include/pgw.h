@@ -298,9 +298,10 @@ long long pgw_launch_count(const pgw_env* env);
 #define PGW_OPT_WARM_START 1  /* 1 (default): each solve starts from the env's previous solution */
 #define PGW_OPT_GRAPHS 2      /* 1 (default): pgw_step replays a captured CUDA graph per distinct
                                  (actions, obs, rew, done) pointer set; needs a non-default stream */
-#define PGW_OPT_PDL 3         /* 1: the tcgen05 power-flow kernel of a step is launched as a programmatic
-                                 dependent of the component kernel (its prologue overlaps the
-                                 component kernel's tail).  Default 0: measured gain < 1 % on B200 */
+#define PGW_OPT_PDL 3         /* 1 (default): the tcgen05 power-flow kernel of a step is launched as a
+                                 programmatic dependent of the component kernel, which releases it
+                                 early (griddepcontrol.launch_dependents): the power-flow prologue
+                                 overlaps the component kernel */
 int pgw_set_option(pgw_env* env, int option, int value);
 
 /* Per-kernel device timing for benchmarks: when enabled, every launch of pgw_step is

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgw_b200.so")
+# PGW_B200_LIB: an instrumented build of the same library (tools/phase_probe.py)
+LIB_PATH = os.environ.get("PGW_B200_LIB") or os.path.join(_HERE, "libpgw_b200.so")
 
 ABI_VERSION = 1
 NUM_STATS = 8

@@ -101,7 +101,7 @@ struct pgw_env {
   };
   std::vector<StepGraph> graphs;
   bool use_graphs = true;
-  bool use_pdl = false;
+  bool use_pdl = true;
   // device state
   double* sd = nullptr;
   uint32_t* si = nullptr;
@@ -110,6 +110,7 @@ struct pgw_env {
   int32_t* iters = nullptr;
   int* d_clock = nullptr;
   unsigned int* d_ticket = nullptr;
+  long long* phase_clk = nullptr;       // PGW_PHASE_TIMERS builds (tools/phase_probe.py)
   // staging for the *_host entry points
   double *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_soc = nullptr;
   uint8_t* h_done = nullptr;
@@ -339,6 +340,9 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
   PGW_TRY(alloc_zero(&env->rew_last, A * E)); env->own(env->rew_last);
   PGW_TRY(alloc_zero(&env->d_clock, 1)); env->own(env->d_clock);
   PGW_TRY(alloc_zero(&env->d_ticket, 1)); env->own(env->d_ticket);
+#ifdef PGW_PHASE_TIMERS
+  PGW_TRY(alloc_zero(&env->phase_clk, (size_t)4096 * 16 + (size_t)4096 * 2)); env->own(env->phase_clk);
+#endif
 
   if (spec->feeder) {
     const pgw_feeder& f = *spec->feeder;
@@ -701,6 +705,9 @@ static pgw::CompParams comp_params(pgw_env* env) {
   p.agent_p = env->agent_p; p.ep_ret = env->ep_ret;
   p.clock = env->d_clock; p.ticket = env->d_ticket;
   p.has_house = env->has_house;
+#ifdef PGW_PHASE_TIMERS
+  p.phase_clk = env->phase_clk + (size_t)4096 * 16;
+#endif
   return p;
 }
 
@@ -726,6 +733,9 @@ static pgw::PfParams pf_params(pgw_env* env) {
   p.iters = env->iters; p.ep_ret = env->ep_ret; p.viol = env->viol;
   p.penalty_node = env->penalty_node; p.pvlo = env->pvlo; p.pvhi = env->pvhi; p.punit = env->punit;
   p.clock = env->d_clock; p.ticket = env->d_ticket;
+#ifdef PGW_PHASE_TIMERS
+  p.phase_clk = env->phase_clk;
+#endif
   return p;
 }
 
@@ -766,20 +776,35 @@ int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stre
 
 // The kernels of one step, enqueued on `s` (directly, or while `s` is being captured).
 static int enqueue_components(pgw_env* env, const double* actions, double* obs, double* rew,
-                              uint8_t* done, cudaStream_t s) {
+                              uint8_t* done, cudaStream_t s, int pdl_trigger = 0) {
   pgw::CompParams cp = comp_params(env);
   const bool hook = env->has_feeder && env->punit != 0.0;   // power flow finishes the rewards
   cp.event_mode = 1; cp.advance_clock = env->has_feeder ? 0 : 1; cp.owns_reward = hook ? 0 : 1;
   cp.actions = actions; cp.obs = obs; cp.rew = rew; cp.done = done;
+  cp.pdl_trigger = pdl_trigger;
   PGW_CUDA(pgw::launch_components(cp, smem_for_events(env), s));
   return PGW_OK;
+}
+
+// Programmatic dependent launch of the tcgen05 power-flow kernel behind the component kernel.
+// Used when a power-flow CTA leaves room on its SM (<= 64 kB of shared memory: IEEE-13 class
+// feeders); a CTA that fills the SM's shared memory gains nothing from starting early and was
+// measured 2 us slower per step at C3.  The component kernel releases the dependent right after
+// its clock read when both grids fit on the GPU side by side (1), else at the end of each CTA (2).
+// Measured (C1, cold L2): 27.5 -> 25.6 us per step at 4096 envs, 40.1 -> 37.9 us at 32 768.
+static int pdl_trigger_mode(const pgw_env* env, bool timed) {
+  if (!env->use_pdl || timed || !env->has_feeder || env->pf_kernel != 2) return 0;
+  pgw::PfParams pf{};
+  pf.tc2 = env->tc2; pf.nl = env->nl;
+  if (pgw::tc2_smem_bytes(pf) > 64 * 1024) return 0;
+  return env->num_ctas <= 148 * 4 ? 1 : 2;
 }
 
 static int enqueue_powerflow(pgw_env* env, double* rew, cudaStream_t s, bool timed) {
   pgw::PfParams pf = pf_params(env);
   pf.event_mode = 1; pf.advance_clock = 1; pf.agent_p = env->agent_p; pf.rew = rew;
   pf.reward_hook = (env->punit != 0.0) ? 1 : 0;
-  pf.pdl = (env->use_pdl && !timed) ? 1 : 0;
+  pf.pdl = pdl_trigger_mode(env, timed) != 0 ? 1 : 0;
   pf.warm_start = env->warm_start ? 1 : 0;
   PGW_CUDA(launch_pf(env, pf, s));
   return PGW_OK;
@@ -788,7 +813,7 @@ static int enqueue_powerflow(pgw_env* env, double* rew, cudaStream_t s, bool tim
 static int enqueue_step(pgw_env* env, const double* actions, double* obs, double* rew,
                         uint8_t* done, cudaStream_t s, bool timed) {
   if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
-  int rc = enqueue_components(env, actions, obs, rew, done, s);
+  int rc = enqueue_components(env, actions, obs, rew, done, s, pdl_trigger_mode(env, timed));
   if (rc) return rc;
   if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
   if (env->has_feeder && (rc = enqueue_powerflow(env, rew, s, timed))) return rc;
@@ -1048,6 +1073,26 @@ int pgw_get_timing(pgw_env* env, double* out3, void* cuda_stream) {
 }
 
 int pgw_clock(const pgw_env* env) { return env ? env->clock : -1; }
+
+#ifdef PGW_PHASE_TIMERS
+// instrumented builds only: SM-clock stamps of the power-flow kernel's phases, [ctas][16]
+int pgw_debug_phases(pgw_env* env, long long* host_out, int ctas) {
+  if (!env || !host_out || ctas > 4096) return PGW_ERR_INVALID;
+  PGW_CUDA(cudaDeviceSynchronize());
+  PGW_CUDA(cudaMemcpy(host_out, env->phase_clk, (size_t)ctas * 16 * sizeof(long long),
+                      cudaMemcpyDeviceToHost));
+  return PGW_OK;
+}
+// globaltimer at entry / exit of the component kernel's CTAs, [ctas][2]
+int pgw_debug_comp_span(pgw_env* env, long long* host_out, int ctas) {
+  if (!env || !host_out || ctas > 4096) return PGW_ERR_INVALID;
+  PGW_CUDA(cudaDeviceSynchronize());
+  PGW_CUDA(cudaMemcpy(host_out, env->phase_clk + (size_t)4096 * 16,
+                      (size_t)ctas * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return PGW_OK;
+}
+int pgw_debug_num_comp_ctas(pgw_env* env) { return env ? env->num_ctas : 0; }
+#endif
 long long pgw_launch_count(const pgw_env* env) { return env ? env->launches : 0; }
 
 int pgw_set_option(pgw_env* env, int option, int value) {

@@ -41,7 +41,12 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
   const int a = wk.agent;
   const AgentSlice sl = wk.sl;
   const pgw_agent ag = reinterpret_cast<const pgw_agent*>(p.blob)[a];
-  const int ev = p.event_mode == 0 ? 0 : (*p.clock + 1);
+#ifdef PGW_PHASE_TIMERS
+  if (p.phase_clk != nullptr && threadIdx.x == 0) p.phase_clk[(size_t)blockIdx.x * 2] = (long long)global_timer_ns();
+#endif
+  const int clk = p.event_mode == 0 ? -1 : *p.clock;
+  unsigned int my_ticket = 0u;                        // thread 0, when this kernel advances the clock
+  const int ev = clk + 1;
   // Two staging phases so that the latency of reading the device clock (which selects the
   // event row) overlaps the copy of the static tables and the threads' own prefetches.
   // A CTA serves one agent, so only that agent's slice of the tables is staged.
@@ -58,8 +63,17 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
     mbar_expect_tx(&mbar[1], dbytes + ibytes);
     tma_bulk_g2s(drow, p.dtab + (size_t)ev * p.dstride, dbytes, &mbar[1]);
     if (ibytes) tma_bulk_g2s(irow, p.itab + (size_t)ev * p.istride, ibytes, &mbar[1]);
+    if (p.advance_clock) my_ticket = clock_take_ticket(p.ticket, clk);
   }
-  __syncthreads();
+  // Programmatic dependent launch of the power-flow kernel (pdl_trigger 1): its CTAs may start
+  // their prologue (tables, TMEM, prefetches) now and block in griddepcontrol.wait until this
+  // grid has completed.  They advance the clock, hence only after this whole CTA has read it:
+  // the barrier's predicate makes it wait for every thread's clock value.
+  if (p.pdl_trigger == 1) {
+    if (!__syncthreads_or(ev < 0)) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
   mbar_wait(&mbar[0], 0);
 
   const int event = ev;
@@ -125,7 +139,12 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
       }
     }
   }
-  if (p.advance_clock) publish_clock_last_cta(p.ticket, p.clock, event, gridDim.x);
+  if (p.pdl_trigger == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (p.advance_clock && threadIdx.x == 0)
+    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, gridDim.x);
+#ifdef PGW_PHASE_TIMERS
+  if (p.phase_clk != nullptr && threadIdx.x == 0) p.phase_clk[(size_t)blockIdx.x * 2 + 1] = (long long)global_timer_ns();
+#endif
 }
 
 cudaError_t launch_components(const CompParams& p, int smem_bytes, cudaStream_t s) {

@@ -28,6 +28,8 @@ struct CompParams {
   int E, A;
   int event_mode;          // 0 = reset (event row 0), 1 = step (event row clock+1)
   int advance_clock;       // 1 when this kernel is the last one of the step (no feeder)
+  int pdl_trigger;         // griddepcontrol.launch_dependents: 0 never, 1 after the clock read, 2 at the end
+  long long* phase_clk;    // PGW_PHASE_TIMERS builds only: [CTA][2] globaltimer at entry / exit
   int owns_reward;         // 1 when no later kernel changes the reward (no feeder / no penalty)
   int has_house;           // 1: the scenario contains Home-Steward houses, 2: with telemetry
                            // (kernel variants)
@@ -89,6 +91,7 @@ struct PfParams {
                            // (rew -= share, rew_copy, ep_ret); otherwise the component kernel did
   int warm_start;          // start from the previous solution kept in u_state
   int pdl;                 // launch as a programmatic dependent of the component kernel
+  long long* phase_clk;    // PGW_PHASE_TIMERS builds only: [CTA][16] SM-clock stamps, else null
   // static tables, one contiguous 16-byte aligned blob (staged to shared memory by TMA
   // when it fits):  zbbT [nb][nbp] double2 (zbbT[j*nbp+k] = Zbb[k][j]) | u0 [nbp] double2 |
   // znbT [nb][nnp] double2 (znbT[k*nnp+n] = Znb[n][k]) | w [nnp] double2 |

@@ -93,12 +93,15 @@ __global__ void __launch_bounds__(256, 2) pf_fixed_point_kernel(const PfParams p
   const unsigned gmask =
       TPE == 32 ? 0xffffffffu : (((1u << TPE) - 1u) << (TPE * ((threadIdx.x & 31) / TPE)));
 
-  const int event = p.event_mode == 0 ? 0 : (*p.clock + 1);
+  const int clk = p.event_mode == 0 ? -1 : *p.clock;
+  unsigned int my_ticket = 0u;                        // thread 0, when this kernel advances the clock
+  const int event = clk + 1;
   if (threadIdx.x == 0) {
     mbar_init(&mbar, 1);
     mbar_expect_tx(&mbar, (uint32_t)blob_smem + (uint32_t)hdr * 8u);
     if (p.stage_blob) tma_bulk_g2s(pf_smem, p.blob, (uint32_t)p.blob_bytes, &mbar);
     tma_bulk_g2s(drow, p.dtab + (size_t)event * p.dstride, (uint32_t)hdr * 8u, &mbar);
+    if (p.advance_clock) my_ticket = clock_take_ticket(p.ticket, clk);
   }
   __syncthreads();
   mbar_wait(&mbar, 0);
@@ -289,8 +292,8 @@ __global__ void __launch_bounds__(256, 2) pf_fixed_point_kernel(const PfParams p
     }
     __syncthreads();
   }
-
-  if (p.advance_clock) publish_clock_last_cta(p.ticket, p.clock, event, gridDim.x);
+  if (p.advance_clock && threadIdx.x == 0)
+    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, gridDim.x);
 }
 
 template <int TPE, int R, bool ZREG>

@@ -113,13 +113,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) pf_tc_kernel(const PfParams p) 
   unsigned char* sT = tc_smem + TC_A_BYTES;                      // staged blob: B1' | B2' | tables
   double* drow = reinterpret_cast<double*>(sT + p.tc_blob_bytes);
 
-  const int event = p.event_mode == 0 ? 0 : (*p.clock + 1);
+  const int clk = p.event_mode == 0 ? -1 : *p.clock;
+  unsigned int my_ticket = 0u;                        // thread 0, when this kernel advances the clock
+  const int event = clk + 1;
   if (tid == 0) {
     mbar_init(&mbar_tma, 1);
     mbar_init(&mbar_mma, 1);
     mbar_expect_tx(&mbar_tma, (uint32_t)p.tc_blob_bytes + (uint32_t)hdr * 8u);
     tma_bulk_g2s(sT, p.tc_blob, (uint32_t)p.tc_blob_bytes, &mbar_tma);
     tma_bulk_g2s(drow, p.dtab + (size_t)event * p.dstride, (uint32_t)hdr * 8u, &mbar_tma);
+    if (p.advance_clock) my_ticket = clock_take_ticket(p.ticket, clk);
   }
   if (warp == 0) {                                               // one warp owns TMEM alloc / free
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -351,7 +354,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) pf_tc_kernel(const PfParams p) 
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_COLS)
                  : "memory");
-  if (p.advance_clock) publish_clock_last_cta(p.ticket, p.clock, event, gridDim.x);
+  if (p.advance_clock && tid == 0)
+    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, gridDim.x);
 }
 
 cudaError_t launch_powerflow_tc(const PfParams& p, cudaStream_t s) {

@@ -218,6 +218,18 @@ __device__ __forceinline__ float2 t2_gh(const Tc2Consts& kc, int k) {
   return make_float2(c[k & 1], c[2 + (k & 1)]);
 }
 
+// Phase stamps of tools/phase_probe.py (instrumented build only, -DPGW_PHASE_TIMERS): thread 0 of
+// every CTA records the SM clock at the phase boundaries of its FIRST tile.
+#ifdef PGW_PHASE_TIMERS
+#define T2_STAMP(k)                                                          \
+  do {                                                                       \
+    if (p.phase_clk != nullptr && threadIdx.x == 0 && stamp_tile)            \
+      p.phase_clk[(size_t)blockIdx.x * 16 + (k)] = clock64();                \
+  } while (0)
+#else
+#define T2_STAMP(k) do { } while (0)
+#endif
+
 template <int NCH, bool ANY_M5, bool STANDALONE, int OCC = t2_ctas_per_sm(NCH)>
 __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
     pf_tc2_kernel(const PfParams p, const __grid_constant__ Tc2Consts kc) {
@@ -249,7 +261,16 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
   unsigned char* sT = sA + 2 * APB;                    // tables
   double* drow = reinterpret_cast<double*>(sT + t.tab_bytes);
 
-  const int event = p.event_mode == 0 ? 0 : (*p.clock + 1);
+  [[maybe_unused]] bool stamp_tile = true;
+  [[maybe_unused]] int it_stamp = 0;
+#ifdef PGW_PHASE_TIMERS
+  if (p.phase_clk != nullptr && threadIdx.x == 0) p.phase_clk[(size_t)blockIdx.x * 16 + 12] = (long long)global_timer_ns();
+#endif
+  T2_STAMP(0);
+  const int clk = p.event_mode == 0 ? -1 : *p.clock;
+  unsigned int my_ticket = 0u;                        // thread 0, when this kernel advances the clock
+  const int event = clk + 1;
+  T2_STAMP(1);
   if (tid == 0) {
     mbar_init(&mbar_tab, 1);
     mbar_init(&mbar_b, 1);
@@ -262,6 +283,7 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
     tma_bulk_g2s(sB, t.blob, (uint32_t)(1 + nres) * 2 * PB, &mbar_b);   // chunks follow in the blob
     // last: the event row's address waits for the device clock
     tma_bulk_g2s(drow, p.dtab + (size_t)event * p.dstride, (uint32_t)hdr * 8u, &mbar_tab);
+    if (p.advance_clock) my_ticket = clock_take_ticket(p.ticket, clk);
   }
   // Pull the tile's per-env inputs (warm-start voltages, agent powers) towards L2 while the
   // tables, the operand images and the TMEM allocation are in flight: 32-byte sectors of
@@ -296,7 +318,9 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
+  T2_STAMP(2);
   mbar_wait(&mbar_tab, 0);
+  T2_STAMP(3);
   // Programmatic dependent launch: everything above overlapped the tail of the component kernel;
   // its outputs (agent powers, rewards) are visible from here on.
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -440,10 +464,12 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
     //           of a wave are written by all warps, the issuer warp feeds the K steps of those
     //           chunks of the NEXT chain into D[cur^1] (free since the barrier), so the tensor
     //           core works while the remaining chunks are still being evaluated.
+    T2_STAMP(4);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // st.shared -> tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     issue_chain(0u, b_fresh);                          // first chain; the Zbb images have landed
+    T2_STAMP(5);
     int it = 0, my_it = 0, cur = 0;                    // D[cur] = newest drop once its chain is done
     bool conv = !valid, conv_ok = true;
     while (true) {
@@ -534,6 +560,8 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
       wave_phase ^= 1u;
       cur ^= 1;
     }
+    T2_STAMP(6);
+    if (stamp_tile) it_stamp = it;
     const int last = cur;                              // D[last] = final drop
     cur ^= 1;                                          // the expansion starts in the older buffer
 
@@ -575,6 +603,7 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
         }
       }
     }
+    T2_STAMP(7);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                                   // D[last] may be overwritten from chunk 1 on
 
@@ -626,6 +655,7 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
     }
     s_vmn[grp][row] = vmn;
     s_vmx[grp][row] = vmx;
+    T2_STAMP(8);
     __syncthreads();                        // vmag / partial min-max of the other groups visible
 
     if (valid && grp == 0) {
@@ -683,6 +713,8 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
       }
     }
     __syncthreads();                        // s_* and A are reused by the next tile
+    T2_STAMP(9);
+    stamp_tile = false;
   }
 
   __syncthreads();
@@ -690,7 +722,15 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
                  "r"((uint32_t)t.tmem_cols)
                  : "memory");
-  if (p.advance_clock) publish_clock_last_cta(p.ticket, p.clock, event, gridDim.x);
+  if (p.advance_clock && tid == 0)
+    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, gridDim.x);
+#ifdef PGW_PHASE_TIMERS
+  if (p.phase_clk != nullptr && threadIdx.x == 0) {
+    p.phase_clk[(size_t)blockIdx.x * 16 + 10] = clock64();
+    p.phase_clk[(size_t)blockIdx.x * 16 + 11] = (long long)it_stamp;
+    p.phase_clk[(size_t)blockIdx.x * 16 + 13] = (long long)global_timer_ns();
+  }
+#endif
 }
 
 size_t tc2_smem_bytes(const PfParams& p) {

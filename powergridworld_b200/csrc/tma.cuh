@@ -42,20 +42,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
       : "memory");
 }
 
-// Last CTA of the last kernel of a step publishes the new episode clock, so that a step
-// has constant launch parameters (CUDA-graph replayable).
-__device__ __forceinline__ void publish_clock_last_cta(unsigned int* ticket, int* clock,
-                                                       int value, unsigned int num_ctas) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int t = atomicAdd(ticket, 1u);
-    if (t == num_ctas - 1) {
-      *ticket = 0u;
-      *clock = value;
-      __threadfence();
-    }
+// The last kernel of a step advances the episode clock on the device, so that a step has
+// constant launch parameters (CUDA-graph replayable).  Every CTA reads the clock at entry and
+// then takes a ticket (one thread); the CTA that took the LAST ticket knows that all the others
+// have read the old value, and writes the new one when it is done.  The ticket is taken at
+// entry -- its round trip to L2 hides behind the kernel's work, nothing waits for it until
+// the very end -- and its increment carries a data dependence on the value read, so that the
+// read is performed before the ticket is taken.
+__device__ __forceinline__ unsigned int clock_take_ticket(unsigned int* ticket, int clock_read) {
+  const unsigned int inc = 1u + ((unsigned int)clock_read >> 31);   // 1: the clock is never negative
+  return atomicAdd(ticket, inc);
+}
+__device__ __forceinline__ void clock_advance_if_last(unsigned int my_ticket, unsigned int* ticket,
+                                                      int* clock, int clock_read,
+                                                      unsigned int num_ctas) {
+  if (my_ticket == num_ctas - 1) {
+    *ticket = 0u;
+    *clock = clock_read + 1;
   }
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 }  // namespace pgw

@@ -400,6 +400,10 @@ class MultiAgentEnv:
                 x = o.draw_initial_storage() if self.num_envs == 1 \
                     else o.draw_initial_storage(size=self.num_envs)
                 soc.append(np.broadcast_to(np.asarray(x, dtype=np.float64), (self.num_envs,)))
+        self._push_roster_tables()
+        return np.stack(soc) if draw_soc else init_storage
+
+    def _push_roster_tables(self):
         self._rebuild_roster_tables()
         if self._h is not None:
             dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
@@ -408,7 +412,6 @@ class MultiAgentEnv:
                     self._h, dp(self._dpar), len(self._b.dpar), dp(self._dtab),
                     self._itab.ctypes.data_as(C.POINTER(C.c_int32)) if self._istride else None,
                     self._stream()))
-        return np.stack(soc) if draw_soc else init_storage
 
     def draw_initial_storage(self) -> np.ndarray:
         """[num_storage, E] initial SOC drawn like the reference does on reset
@@ -574,11 +577,23 @@ class MultiAgentEnv:
                                                 N.FIELD_VBUS, N.FIELD_PF_ITERS, N.FIELD_PF_STATE):
                 continue
             fields[f] = self.get_field(f).clone()
-        return {"fields": fields, "episode_step": self.episode_step, "obs": self.obs.clone(),
-                "needs_reset": self._needs_reset}
+        state = {"fields": fields, "episode_step": self.episode_step, "obs": self.obs.clone(),
+                 "needs_reset": self._needs_reset}
+        rand = self._randomised()
+        if rand:                                    # the rosters drawn at the last reset
+            state["rosters"] = [None if o._rows is None else np.array(o._rows) for o in rand]
+        return state
 
     def load_state_dict(self, state: dict):
         torch = _torch()
+        rand = self._randomised()
+        if rand:
+            rosters = state.get("rosters")
+            if rosters is None or len(rosters) != len(rand):
+                raise ValueError("checkpoint holds no rosters for the randomised charging stations")
+            for o, rows in zip(rand, rosters):
+                o._rows = None if rows is None else np.array(rows)
+            self._push_roster_tables()
         for f, t in state["fields"].items():
             t = t.to(self.device).contiguous()
             if t.numel():

@@ -237,3 +237,34 @@ def test_pf_kernel_keyword_and_house_readme_example():
         {name: space.sample() for name, space in house.action_space.items()})
     assert set(obs) == {"pv", "storage", "ev-charging", "other-devices"} and not done
     assert len(meta["step_meta"]) == 4 and np.isfinite(reward)
+
+
+def test_update_tables_abi_and_checkpoint_of_randomised_rosters():
+    """pgw_update_tables: sizes are those of pgw_create (a changed parameter length is refused,
+    null tables are left alone); a checkpoint of a batch with EVChargingEnv(randomize=True)
+    carries the drawn rosters, so a fresh env resumes it bit for bit."""
+    import ctypes as C
+    from powergridworld_b200 import _native as N
+    torch = _torch()
+    E = 40
+    mk = lambda: PNS.MultiAgentEnv(**S.randomized_ev_scenario(PNS, PNS.OpenDSSSolver), num_envs=E)
+    a, b = mk(), mk()
+    dp = a._dpar.ctypes.data_as(C.POINTER(C.c_double))
+    assert a._lib.pgw_update_tables(a._h, dp, len(a._b.dpar) - 1, None, None, a._stream()) != 0
+    with pytest.raises(N.NativeError, match="length changed"):
+        N.check(a._lib.pgw_update_tables(a._h, dp, len(a._b.dpar) + 2, None, None, a._stream()))
+    assert a._lib.pgw_update_tables(a._h, None, 0, None, None, a._stream()) == 0
+    rng = np.random.default_rng(3)
+    acts = [torch.as_tensor(rng.uniform(-1, 1, size=(a.act_dim, E))).cuda() for _ in range(140)]
+    np.random.seed(77)
+    a.reset_batch()
+    for t in range(100):                             # well into the day: vehicles are parked
+        a.step_batch(acts[t])
+    np.random.seed(78)
+    b.reset_batch()                                  # another draw, overwritten by the checkpoint
+    b.load_state_dict(a.state_dict())
+    for t in range(100, 140):
+        oa, ra, _, _ = a.step_batch(acts[t])
+        ob, rb, _, _ = b.step_batch(acts[t])
+        assert torch.equal(oa, ob) and torch.equal(ra, rb)
+    assert torch.equal(a.get_field(0), b.get_field(0)) and torch.equal(a.get_field(1), b.get_field(1))

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -274,7 +275,13 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
     // components (rough time per 64-env block), every agent between 1 CTA and one CTA per
     // 64-env block.
     {
-      const int blocks = (env->E + 63) / 64, budget = 148 * 16;
+      // 16 CTAs per SM (10 are resident: 96 registers x 64 threads) lets the hardware scheduler
+      // even out the rough cost estimates of a many-agent scenario (C3: 134 us at 16 per SM,
+      // 150 us at 10); with a single agent there is nothing to even out and a second round of
+      // CTAs only adds a partial wave (262 144 houses: 42.3 us at 16 per SM, 35.8 us at 10).
+      int budget = env->A == 1 ? 148 * 10 : 148 * 16;
+      if (const char* b = getenv("PGW_CTA_BUDGET")) budget = std::max(1, atoi(b));   // tuning knob
+      const int blocks = (env->E + 63) / 64;
       std::vector<double> w(env->A, 0.5);            // ~us per env block: loop + latency floor
       double wsum = 0.0;
       for (int a = 0; a < env->A; ++a) {

@@ -52,9 +52,10 @@ _PF_NAMES = {"fp64": "fp64-simt", "tc": "tcgen05 split-tf32", "tc2": "tcgen05 sp
 
 # dram__bytes_read.sum + dram__bytes_write.sum of component_kernel per launch, from the committed
 # `ncu --set full` captures (profiles/r1s3_ncu_full_raw_*.csv); keyed by (workload, envs per GPU)
-NCU_TRAFFIC = {("c1", 4096): 1.557e6, ("c1", 262144): 202.3e6, ("c3", 16384): 152.85e6}
+NCU_TRAFFIC = {("c1", 4096): 1.557e6, ("c1", 262144): 202.3e6, ("c3", 16384): 151.65e6}
+NCU_TRAFFIC_PF = {("c1", 4096): 1.294e6, ("c3", 16384): 49.78e6}     # pf_tc2_kernel, same captures
 # sm__pipe_tensor_cycles_active.max (% of elapsed, busy SMs) of pf_tc2_kernel in the same captures
-NCU_TENSOR_PCT = {("c1", 4096): 2.37, ("c1", 262144): 5.72, ("c3", 16384): 21.49}
+NCU_TENSOR_PCT = {("c1", 4096): 2.45, ("c1", 262144): 5.72, ("c3", 16384): 22.47}
 
 
 def _config(n_gpus):
@@ -425,8 +426,8 @@ def run_ours(args):
                    "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": achieved / peaks["hbm_gbs"],
                    "traffic": NCU_TRAFFIC.get((WORKLOAD, E)),
-                   "traffic_source": "profiles/r1s3_ncu_full_raw_*.csv (ncu --set full, one "
-                                     "capture)" if (WORKLOAD, E) in NCU_TRAFFIC else None,
+                   "traffic_source": "profiles/r1s4_ncu_full_raw_c1.csv / _c3.csv, r1s3_..._c1x64.csv "
+                                     "(ncu --set full, one capture)" if (WORKLOAD, E) in NCU_TRAFFIC else None,
                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                    "survey_bytes_per_launch": survey_bytes,
                    "frac_survey_bytes": (survey_bytes / (comp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
@@ -456,7 +457,7 @@ def run_ours(args):
                      "peak": peaks["hbm_gbs"] if hbm_bound else pf_peak,
                      "unit": "GB/s" if hbm_bound else "TFLOP/s",
                      "frac": (gbs / peaks["hbm_gbs"]) if hbm_bound else (tfs / pf_peak),
-                     "traffic": None,
+                     "traffic": NCU_TRAFFIC_PF.get((WORKLOAD, E)) if PF_KERNEL == "tc2" else None,
                      "peak_source": peak_src if hbm_bound else pf_peak_src,
                      "algorithmic_bytes_per_launch": pf_bytes,
                      "algorithmic_flops_per_launch": flops,

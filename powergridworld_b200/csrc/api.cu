@@ -597,7 +597,7 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       while (t.tmem_cols < (t.resident ? 2 + ncc : 2) * N) t.tmem_cols *= 2;
       // cst = {Re u0, Im u0, vlo^2, vhi^2}, gh = (1, 0) -> 1/clamp(|u|^2), (0, 1) -> 1/|u| (model 5)
       std::vector<float> cst(4 * (size_t)NBP, 1.f), gh(2 * (size_t)NBP, 0.f), shf(NBP, 0.f), wf(2 * xnode.size(), 0.f);
-      std::vector<int32_t> blp(NBP, 0), bag(2 * (size_t)NBP, -1), lptr(f.nl + 1, 0), lidx(env->A, 0), node(env->A);
+      std::vector<int32_t> blp(NBP, 0), bag(NBP, -1), lptr(f.nl + 1, 0), lidx(env->A, 0), node(env->A);
       for (int k = 0; k < NBP; ++k) { cst[4 * k + 1] = 0.f; gh[2 * k] = 1.f; }
       for (int k = 0; k < nb; ++k) {
         cst[4 * k] = (float)f.u0[2 * k]; cst[4 * k + 1] = (float)f.u0[2 * k + 1];
@@ -630,12 +630,9 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
         if (bytes) memcpy(blob.data() + off, src, bytes);
         return (int)(off - (size_t)t.off_tab);
       };
-      // the (up to two) agents on the branch's load, in agent order; (-2, -1): more than two,
-      // summed from the lptr / lidx list
-      for (int k = 0; k < nb; ++k) {
+      for (int k = 0; k < nb; ++k) {                  // the one agent on the branch's load, or -2
         const int l = blp[k], cnt = lptr[l + 1] - lptr[l];
-        bag[2 * k] = cnt == 0 ? -1 : (cnt <= 2 ? lidx[lptr[l]] : -2);
-        bag[2 * k + 1] = cnt == 2 ? lidx[lptr[l] + 1] : -1;
+        bag[k] = cnt == 0 ? -1 : (cnt == 1 ? lidx[lptr[l]] : -2);
       }
       for (int q = 0; q < NBP / 2; ++q) {            // pairs of branches (2q, 2q + 1)
         const int k0 = 2 * q, k1 = 2 * q + 1;

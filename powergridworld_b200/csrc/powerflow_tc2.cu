@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
   // the tensor core's operand reads already take most of the shared-memory bandwidth
   const float* share = reinterpret_cast<const float*>(sT + t.t_share);
   const int32_t* bload = reinterpret_cast<const int32_t*>(sT + t.t_bload);
-  const int2* bagent = reinterpret_cast<const int2*>(sT + t.t_bagent);   // agents on the branch's load
+  const int32_t* bagent = reinterpret_cast<const int32_t*>(sT + t.t_bagent);
   const float2* wx = reinterpret_cast<const float2*>(sT + t.t_w);        // w of the expanded slots
   const int32_t* xnode = reinterpret_cast<const int32_t*>(sT + t.t_xnode);  // slot -> node or -1
   const int32_t* dnode = reinterpret_cast<const int32_t*>(sT + t.t_dnode);  // branch -> node or -1
@@ -399,10 +399,9 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
         float d0[16], x[8], y[8];
 #pragma unroll
         for (int h = 0; h < 8; h += 4) {               // half chunks: 12 loads in flight per thread
-          double kwd[4], kw2[4], kvd[4];
+          double kwd[4], kvd[4];
           double2 up[4];
-          int ld[4];
-          int2 ag[4];
+          int ld[4], ag[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             ld[j] = bload[8 * c + h + j];
@@ -412,16 +411,14 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
           for (int j = 0; j < 4; ++j) {
             const int k = 8 * c + h + j;
             kwd[j] = 0.0;
-            kw2[j] = 0.0;
             kvd[j] = 0.0;
             if (STANDALONE) {
               if (k < p.nb) {
                 kwd[j] = p.load_kw[(size_t)ld[j] * p.E + e];
                 kvd[j] = p.load_kvar[(size_t)ld[j] * p.E + e];
               }
-            } else if (p.agent_p != nullptr) {
-              if (ag[j].x >= 0) kwd[j] = p.agent_p[(size_t)ag[j].x * p.E + e];
-              if (ag[j].y >= 0) kw2[j] = p.agent_p[(size_t)ag[j].y * p.E + e];
+            } else if (p.agent_p != nullptr && ag[j] >= 0) {
+              kwd[j] = p.agent_p[(size_t)ag[j] * p.E + e];
             }
             const float4 c0 = t2_cst(kc, k);
             up[j] = make_double2((double)c0.x, (double)c0.y);
@@ -431,13 +428,12 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
           for (int j = 0; j < 4; ++j) {
             const int k = 8 * c + h + j, jj = h + j;
             if (!STANDALONE) {
+              double kw = base_kw[ld[j]];
               // multiagent_env.py:171-181: P summed per load name in agent order, then added to
-              // the scaled base load (opendss.py:128); one or two agents came with the batch of
-              // loads above, ag.x == -2: more than two on this load
-              double psum = kwd[j] + kw2[j];
-              if (p.agent_p != nullptr && ag[j].x == -2)
-                psum = t2_shared_load_kw(p.agent_p, lidx, lptr[ld[j]], lptr[ld[j] + 1], p.E, e);
-              kwd[j] = base_kw[ld[j]] + psum;
+              // the scaled base load (opendss.py:128); ag == -2: several agents on this load
+              if (p.agent_p != nullptr && ag[j] == -2)
+                kw += t2_shared_load_kw(p.agent_p, lidx, lptr[ld[j]], lptr[ld[j] + 1], p.E, e);
+              kwd[j] += kw;
               kvd[j] = base_kvar[ld[j]];
             }
             const float sh = share[k] * xs;            // 0 for the padded branches

@@ -302,6 +302,10 @@ long long pgw_launch_count(const pgw_env* env);
                                  programmatic dependent of the component kernel, which releases it
                                  early (griddepcontrol.launch_dependents): the power-flow prologue
                                  overlaps the component kernel */
+#define PGW_OPT_CLIP_INIT_SOC 4  /* 1 (default): pgw_reset clips init_soc to each storage's range, what the
+                                 reference does with an explicit init_storage (energy_storage_env.py:
+                                 88-89); 0: used as given -- the reference does NOT clip the value it
+                                 draws itself (:82-84), so a host that replays that draw turns it off */
 int pgw_set_option(pgw_env* env, int option, int value);
 
 /* Per-kernel device timing for benchmarks: when enabled, every launch of pgw_step is

@@ -103,6 +103,7 @@ struct pgw_env {
   std::vector<StepGraph> graphs;
   bool use_graphs = true;
   bool use_pdl = true;
+  bool clip_init_soc = true;
   // device state
   double* sd = nullptr;
   uint32_t* si = nullptr;
@@ -773,6 +774,7 @@ int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stre
   }
   pgw::CompParams cp = comp_params(env);
   cp.event_mode = 0; cp.advance_clock = 0; cp.init_soc = init_soc; cp.obs = obs;
+  cp.clip_init_soc = env->clip_init_soc ? 1 : 0;
   cp.first_reset = env->resets == 0 ? 1 : 0;
   ++env->resets;
   PGW_CUDA(pgw::launch_components(cp, smem_for_events(env, true), s));
@@ -1105,6 +1107,10 @@ int pgw_debug_num_comp_ctas(pgw_env* env) { return env ? env->num_ctas : 0; }
 long long pgw_launch_count(const pgw_env* env) { return env ? env->launches : 0; }
 
 int pgw_set_option(pgw_env* env, int option, int value) {
+  if (env && option == PGW_OPT_CLIP_INIT_SOC) {      // a reset parameter: the step graphs stay valid
+    env->clip_init_soc = value != 0;
+    return PGW_OK;
+  }
   if (!env) return fail(PGW_ERR_INVALID, "null argument");
   switch (option) {
     case PGW_OPT_PF_KERNEL:

@@ -56,6 +56,9 @@ struct AgentIO {
   double* PGW_RESTRICT sd;              // [sd_rows][E]
   uint32_t* PGW_RESTRICT si;            // [si_rows][E]
   const double* PGW_RESTRICT init_soc;  // [num_storage][E] or nullptr (reset only)
+  int clip_init_soc;                    // 1: an explicit init_storage, clipped to the storage range
+                                        // (energy_storage_env.py:88-89); 0: the values are the
+                                        // reference's own draw, which it does not clip (:82-84)
   const double* PGW_RESTRICT vmin;      // [E]    lagged grid variables (previous solve) or nullptr
   const double* PGW_RESTRICT vmax;      // [E]
   const double* PGW_RESTRICT vbus;      // [A][E]
@@ -98,7 +101,7 @@ PGW_HD void storage_reset(const pgw_component& c, const AgentIO& io, int e) {
   double* soc = io.sd + (size_t)c.sd_off * io.E + e;
   const int ord = io.ipar[c.ipar_off];
   const double init = io.init_soc != nullptr ? io.init_soc[(size_t)ord * io.E + e] : dp[6];
-  *soc = clip(init, dp[0], dp[1]);                                     // :88-89
+  *soc = (io.init_soc != nullptr && !io.clip_init_soc) ? init : clip(init, dp[0], dp[1]);   // :82-89
   io.obs[(size_t)c.obs_off * io.E + e] = storage_obs(c, dp, *soc);
 }
 
@@ -632,7 +635,8 @@ PGW_HD void hs_storage_reset(const pgw_component& c, const AgentIO& io, int e, b
   double* sd = io.sd + (size_t)c.sd_off * io.E + e;
   const int ord = io.ipar[c.ipar_off];
   const double init = io.init_soc != nullptr ? io.init_soc[(size_t)ord * io.E + e] : dp[6];
-  const double soc = clip(init, dp[0], dp[1]);         // energy_storage_env_hs.py:93-96
+  // energy_storage_env_hs.py:84-96: a drawn SOC is used as is, an explicit one is clipped
+  const double soc = (io.init_soc != nullptr && !io.clip_init_soc) ? init : clip(init, dp[0], dp[1]);
   sd[0] = soc;
   if (first_reset) sd[(size_t)1 * io.E] = dp[7];       // current_cost is never reset (:39)
   hs_storage_obs(c, io, e, soc, sd[(size_t)1 * io.E]);

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
   io.sd = p.sd;
   io.si = p.si;
   io.init_soc = p.init_soc;
+  io.clip_init_soc = p.clip_init_soc;
   io.vmin = p.vmin;
   io.vmax = p.vmax;
   io.vbus = p.vbus;

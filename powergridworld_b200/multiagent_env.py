@@ -390,6 +390,11 @@ class MultiAgentEnv:
         Returns the [num_storage, E] initial SOCs (or ``init_storage`` when given)."""
         rand = self._randomised()
         draw_soc = self.num_storage and init_storage is None
+        # the reference clips an explicit init_storage to the storage range but not the value it
+        # draws itself (energy_storage_env.py:82-89): tell the reset kernel which one this is
+        if self.num_storage and self._h is not None:
+            self.set_option(N.OPT_CLIP_INIT_SOC, 0 if draw_soc else 1)
+        self._soc_drawn = bool(draw_soc)
         if not rand:
             return self.draw_initial_storage() if draw_soc else init_storage
         soc = []

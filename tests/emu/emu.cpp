@@ -23,6 +23,7 @@ struct EmuArgs {
   double* sd;
   uint32_t* si;
   const double* init_soc;
+  int clip_init_soc;
   const double* vmin;
   const double* vmax;
   const double* vbus;
@@ -35,7 +36,7 @@ static pgw::AgentIO make_io(const EmuArgs* a) {
   io.scr.p = g_scratch;
   io.scr.stride = 1;
   io.E = a->E; io.actions = a->actions; io.obs = a->obs; io.sd = a->sd; io.si = a->si;
-  io.init_soc = a->init_soc; io.vmin = a->vmin; io.vmax = a->vmax; io.vbus = a->vbus;
+  io.init_soc = a->init_soc; io.clip_init_soc = a->clip_init_soc; io.vmin = a->vmin; io.vmax = a->vmax; io.vbus = a->vbus;
   io.dpar = a->dpar; io.ipar = a->ipar; io.drow = a->drow; io.irow = a->irow;
   return io;
 }

@@ -26,7 +26,8 @@ def build():
 class EmuArgs(C.Structure):
     _fields_ = [("E", C.c_int), ("A", C.c_int)] + [(n, C.c_void_p) for n in (
         "agents", "comps", "dpar", "ipar", "drow", "irow", "actions", "obs", "rew", "agent_p",
-        "sd", "si", "init_soc", "vmin", "vmax", "vbus")]
+        "sd", "si", "init_soc")] + [("clip_init_soc", C.c_int)] + [
+        (n, C.c_void_p) for n in ("vmin", "vmax", "vbus")]
 
 
 def zbus_solve(f, kw, kvar, tol=1e-12, max_iter=200):
@@ -70,8 +71,9 @@ class EmulatedEnv:
         self.t = 0
         self.resets = 0
 
-    def _args(self, event, actions=None, init_soc=None):
+    def _args(self, event, actions=None, init_soc=None, drawn=False):
         a = EmuArgs()
+        a.clip_init_soc = 0 if drawn else 1
         a.E, a.A = self.E, self.A
         p = lambda x: x.ctypes.data if x is not None else None
         a.agents = C.addressof(self.env._agent_recs)
@@ -110,12 +112,14 @@ class EmulatedEnv:
             n = env._agent_recs[ai].bus_node
             self.vbus[ai] = self.vmag[n] if n >= 0 else 1.0
 
-    def reset(self, init_soc):
+    def reset(self, init_soc, drawn=False):
+        """``drawn``: the SOCs are the reference's own (unclipped) draw, not an explicit
+        init_storage (PGW_OPT_CLIP_INIT_SOC = 0)."""
         self._powerflow(0, controllable=False)
         soc = np.ascontiguousarray(init_soc, dtype=np.float64) if init_soc is not None else None
         self.lib.emu_set_first_reset(1 if self.resets == 0 else 0)
         self.resets += 1
-        self.lib.emu_reset(C.byref(self._args(0, init_soc=soc)))
+        self.lib.emu_reset(C.byref(self._args(0, init_soc=soc, drawn=drawn)))
         self.t = 0
         return self.obs.copy()
 

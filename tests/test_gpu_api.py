@@ -268,3 +268,24 @@ def test_update_tables_abi_and_checkpoint_of_randomised_rosters():
         ob, rb, _, _ = b.step_batch(acts[t])
         assert torch.equal(oa, ob) and torch.equal(ra, rb)
     assert torch.equal(a.get_field(0), b.get_field(0)) and torch.equal(a.get_field(1), b.get_field(1))
+
+
+def test_drawn_initial_storage_is_not_clipped_but_explicit_is():
+    """energy_storage_env.py:82-89: the SOC the reference draws itself is used as is (here:
+    mean 30 +- 5 against a 0..20 kWh range), an explicit init_storage is clipped to the range."""
+    cfg = dict(storage_range=(0., 20.), rescale_spaces=False)
+    dev, ora = PNS.EnergyStorageEnv(name="s", **cfg), ONS.EnergyStorageEnv(name="s", **cfg)
+    np.random.seed(5)
+    od, _ = dev.reset()
+    np.random.seed(5)
+    oo, _ = ora.reset()
+    assert oo[0] > 20.0
+    np.testing.assert_array_equal(od, oo)
+    for t in range(5):                               # discharging brings it back into the range
+        a = np.array([0.9])
+        rd, ro = dev.step(a), ora.step(a)
+        np.testing.assert_allclose(rd[0], ro[0], rtol=0, atol=1e-12)
+    od, _ = dev.reset(init_storage=33.0)
+    oo, _ = ora.reset(init_storage=33.0)
+    np.testing.assert_array_equal(od, oo)
+    assert od[0] == 20.0

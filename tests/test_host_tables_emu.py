@@ -105,7 +105,7 @@ def test_randomized_rosters_host_draws_and_tables_vs_reference_trace():
     def reset(env):
         soc = env._reset_draws(None)                 # what reset_batch / reset_host do first
         assert soc.shape == (2, 1)
-        return state["emu"].reset(soc)[:, 0]
+        return state["emu"].reset(soc, drawn=True)[:, 0]
 
     def step(env, a):
         obs, rew, done = state["emu"].step(a.reshape(-1, 1))

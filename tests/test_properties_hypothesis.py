@@ -82,6 +82,37 @@ def test_components_match_oracle_on_random_parameters_and_actions(s_cfg, p_cfg, 
             break
 
 
+@settings(max_examples=8, deadline=None, suppress_health_check=list(HealthCheck))
+@given(e_cfg=ev_cfg, s_cfg=storage_cfg, seed=st.integers(0, 2 ** 31 - 1), roster_seed=st.integers(0, 2 ** 31 - 1))
+def test_randomized_station_matches_oracle_over_two_draws(e_cfg, s_cfg, seed, roster_seed):
+    """EVChargingEnv(randomize=True): the host draws (roster and storage SOC, in the reference's
+    order), the rebuilt station tables and the device arithmetic against the oracle, for two
+    consecutive resets = two different rosters, through the busy part of the day."""
+    e_cfg = dict(e_cfg, randomize=True)
+    mk = lambda ns: {"common_config": COMMON, "pf_config": None, "agents": [
+        {"name": "station", "bus": None, "cls": ns.EVChargingEnv, "config": dict(e_cfg)},
+        {"name": "battery", "bus": None, "cls": ns.EnergyStorageEnv, "config": dict(s_cfg)}]}
+    env = PNS.MultiAgentEnv(**mk(PNS), _dry_run=True)
+    oscn = mk(ONS)
+    oscn["pf_config"] = {"cls": _NoPF, "config": {}}
+    ref = ONS.MultiAgentEnv(**oscn)
+    emu = EmulatedEnv(env)
+    rng = np.random.default_rng(seed)
+    for ep in range(2):
+        np.random.seed((roster_seed + ep) % 2 ** 32)
+        o0 = emu.reset(env._reset_draws(None), drawn=True)
+        np.random.seed((roster_seed + ep) % 2 ** 32)
+        r0 = ref.reset()
+        np.testing.assert_allclose(o0[:, 0], flat_obs(ref, r0), rtol=0, atol=1e-12)
+        for t in range(170):
+            a = rng.uniform(-1.2, 1.2, size=(env.act_dim, 1))
+            o, r, d = emu.step(a)
+            ro, rr, rd, _ = ref.step(unflatten_action(ref, a[:, 0]))
+            np.testing.assert_allclose(o[:, 0], flat_obs(ref, ro), rtol=1e-12, atol=1e-12,
+                                       err_msg=f"ep={ep} t={t}")
+            np.testing.assert_allclose(r[:, 0], [rr[x.name] for x in ref.agents], rtol=1e-11, atol=1e-14)
+
+
 # ------------------------------------------------------------------ Home-Steward house
 house_params = st.fixed_dictionaries({
     "pv_scale": st.floats(0.3, 3.0), "max_power": st.floats(2.0, 12.0),

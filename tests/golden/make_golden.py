@@ -189,6 +189,8 @@ def main():
            S.heterogeneous_scenario(ns, pf, 0.6, max_episode_steps=250), ref)
     record("test_heterogeneous", ns.MultiAgentEnv, S.test_heterogeneous_scenario(ns, pf), ref)
     record_randomized(ref, ns, pf)
+    for v in S.TIME_BASE_VARIANTS:
+        record("timebase_" + v, ns.MultiAgentEnv, S.time_base_scenario(ns, pf, v), ref)
     ev_totals(ref)
 
 

@@ -99,6 +99,27 @@ def ev_pv_storage_scenario(ns, pf_cls=None, rescale_spaces=True):
     return cfg
 
 
+TIME_BASE_VARIANTS = {
+    # control_timedelta [s], start, end, max_episode_steps: the same heterogeneous scenario on
+    # other clocks (the storage's dt, the feeder's hourly load shape, the episode length and who
+    # ends the episode all depend on them)
+    "dt600_day": (600, "08-12-2020 06:00:00", "08-12-2020 18:00:00", None),
+    "dt60_night": (60, "08-12-2020 00:00:00", "08-12-2020 03:00:00", None),
+    "dt900_max50": (900, "08-12-2020 00:00:00", "08-13-2020 00:00:00", 50),
+    "dt300_from_noon": (300, "08-12-2020 12:00:00", "08-13-2020 12:00:00", None),
+}
+
+
+def time_base_scenario(ns, pf_cls, variant):
+    dt, start, end, mes = TIME_BASE_VARIANTS[variant]
+    cfg = heterogeneous_scenario(ns, pf_cls, 0.65)
+    cfg["common_config"] = {"start_time": start, "end_time": end,
+                            "control_timedelta": pd.Timedelta(dt, "s")}
+    if mes:
+        cfg["max_episode_steps"] = mes
+    return cfg
+
+
 def randomized_ev_scenario(ns, pf_cls):
     """EVChargingEnv(randomize=True) (ev_charging_env.py:154-157) standalone and inside a
     MultiComponentEnv, between storages so that the order of the host RNG draws of a reset

@@ -37,6 +37,34 @@ def _torch():
     return torch
 
 
+TIMEBASE = {"timebase_" + v: (lambda v: lambda ns, **k: ns.MultiAgentEnv(
+    **S.time_base_scenario(ns, ns.OpenDSSSolver, v), **k))(v) for v in S.TIME_BASE_VARIANTS}
+
+
+@pytest.mark.parametrize("name", list(TIMEBASE))
+def test_other_time_bases_replay_reference_trace(name):
+    """The heterogeneous scenario on other clocks (10-minute, 1-minute and 15-minute control
+    intervals, day windows that do not start at midnight, max_episode_steps): batch of 5 replicas
+    through the batched API, every column against the trace recorded from the reference."""
+    torch = _torch()
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    E = 5
+    env = TIMEBASE[name](PNS, num_envs=E)
+    T = g["actions"].shape[0]
+    assert env.episode_length == T
+    obs0 = env.reset_batch(np.repeat(g["init_soc"].reshape(-1, 1), E, axis=1)).cpu().numpy()
+    np.testing.assert_allclose(obs0, np.repeat(g["obs0"][:, None], E, 1), rtol=0, atol=OBS_ATOL)
+    for t in range(T):
+        a = torch.as_tensor(np.repeat(g["actions"][t][:, None], E, 1)).cuda()
+        obs, rew, done, all_done = env.step_batch(a)
+        np.testing.assert_allclose(obs.cpu().numpy(), np.repeat(g["obs"][t][:, None], E, 1),
+                                   rtol=0, atol=OBS_ATOL, err_msg=f"t={t}")
+        np.testing.assert_allclose(rew.cpu().numpy(), np.repeat(g["rew"][t][:, None], E, 1),
+                                   rtol=REW_RTOL, atol=REW_ATOL)
+        assert bool(done.cpu().numpy().all()) == bool(g["done"][t])
+    assert all_done
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_dict_api_replays_reference_trace(name):
     """num_envs == 1 through the reference's dict API."""

@@ -23,6 +23,9 @@ CASES = {
     "test_heterogeneous": lambda **k: NS.MultiAgentEnv(
         **S.test_heterogeneous_scenario(NS, NS.OpenDSSSolver), **k),
 }
+for _v in S.TIME_BASE_VARIANTS:                     # other control intervals / day windows
+    CASES["timebase_" + _v] = (lambda v: lambda **k: NS.MultiAgentEnv(
+        **S.time_base_scenario(NS, NS.OpenDSSSolver, v), **k))(_v)
 # tolerances of BASELINE.json north_star: voltages 1e-4 p.u., states 1e-6 rel, rewards 1e-5 rel;
 # what is asserted here is much tighter because both sides are float64.
 # The shared voltage penalty multiplies a ~3e-9 p.u. solver difference (two formulations of the

@@ -23,6 +23,11 @@ CASES = {
 }
 
 
+for _v in S.TIME_BASE_VARIANTS:                     # other control intervals / day windows
+    CASES["timebase_" + _v] = (lambda v: lambda: (NS.MultiAgentEnv, S.time_base_scenario(
+        NS, NS.OpenDSSSolver, v)))(_v)
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_oracle_replays_reference_trace(name):
     g = np.load(os.path.join(GOLD, name + ".npz"))

@@ -289,3 +289,26 @@ def test_drawn_initial_storage_is_not_clipped_but_explicit_is():
     oo, _ = ora.reset(init_storage=33.0)
     np.testing.assert_array_equal(od, oo)
     assert od[0] == 20.0
+
+
+def test_per_object_protocol_on_random_configurations_vs_reference_traces():
+    """tests/golden/component_configs.npz, the cases that need no grid input, through the
+    reference's per-object protocol (component.reset() / component.step(action)) on the GPU."""
+    from tests.component_cases import build_component
+    from tests.test_host_tables_emu import _standalone_cases
+    g, cases = _standalone_cases()
+    for ci, m in cases[::2]:                         # every second case: a device handle each
+        dev = build_component(getattr(PNS, m["cls"]), m["cfg"])
+        np.random.seed(m["seed"])
+        r0 = dev.reset(**m["reset_kw"])
+        o0 = r0[0] if isinstance(r0, tuple) else r0
+        if g[f"obs0_{ci}"].size and o0 is not None:
+            np.testing.assert_allclose(np.asarray(o0, float), g[f"obs0_{ci}"], rtol=1e-13, atol=1e-13,
+                                       err_msg=f"case {ci} ({m['cls']}) reset")
+        A = g[f"act_{ci}"]
+        for t in range(min(A.shape[0], 120)):
+            ob, rew, done, _ = dev.step(A[t])
+            np.testing.assert_allclose(np.asarray(ob, float), g[f"obs_{ci}"][t], rtol=1e-12, atol=1e-12,
+                                       err_msg=f"case {ci} ({m['cls']}) t={t}")
+            np.testing.assert_allclose(rew, g[f"rew_{ci}"][t], rtol=1e-11, atol=1e-14)
+            assert bool(done) == bool(g[f"done_{ci}"][t])

@@ -120,3 +120,47 @@ def test_randomized_rosters_host_draws_and_tables_vs_reference_trace():
     rosters = [o._rows for o in env._b.objs if getattr(o, "randomize", False)]
     for k, r in enumerate(rosters):                  # last episode's draw, row for row
         np.testing.assert_array_equal(r, g[f"roster1_{k}"])
+
+
+def _standalone_cases():
+    from tests.component_cases import load_cases
+    g, meta = load_cases()
+    # a component on its own has no feeder: cases with voltage inputs or an injected set point are
+    # covered inside full envs (tests/test_gpu_api.py::test_random_component_configurations_match_oracle)
+    return g, [(ci, m) for ci, m in enumerate(meta)
+               if not m["ext_keys"] and "p_setpoint" not in m["reset_kw"]]
+
+
+def test_standalone_components_on_random_configurations_vs_reference_traces():
+    """tests/golden/component_configs.npz (recorded from the unmodified reference): the spec
+    compiler's tables + the device arithmetic for every case that needs no grid input --
+    1..30-minute EV steps, episode caps, storage ranges / efficiencies / control intervals with
+    drawn and explicit initial SOC, the three PV profiles, building observation subsets."""
+    import pandas as pd
+    from tests.component_cases import build_component
+    g, cases = _standalone_cases()
+    assert len(cases) >= 28
+    common = {"start_time": "01-01-2021 00:00:00", "end_time": "01-01-2031 00:00:00",
+              "control_timedelta": pd.Timedelta(300, "s")}
+    for ci, m in cases:
+        me = build_component(getattr(NS, m["cls"]), m["cfg"])
+        me.name = me.name or "x"
+        env = NS.MultiAgentEnv(common_config=common, pf_config=None, _dry_run=True, agents=[
+            {"name": me.name, "bus": None, "cls": lambda name, me=me, **kw: me, "config": {}}])
+        emu = EmulatedEnv(env)
+        np.random.seed(m["seed"])
+        if "init_storage" in m["reset_kw"]:
+            o0 = emu.reset(np.array([[m["reset_kw"]["init_storage"]]]))
+        else:
+            o0 = emu.reset(env._reset_draws(None), drawn=True)
+        if g[f"obs0_{ci}"].size:                     # PVEnv.reset returns nothing in the reference
+            np.testing.assert_allclose(o0[:, 0], g[f"obs0_{ci}"], rtol=1e-13, atol=1e-13,
+                                       err_msg=f"case {ci} ({m['cls']}) reset")
+        A = g[f"act_{ci}"]
+        assert env.episode_length >= A.shape[0] or not g[f"done_{ci}"][-1]
+        for t in range(A.shape[0]):
+            o, r, d = emu.step(A[t].reshape(-1, 1))
+            np.testing.assert_allclose(o[:, 0], g[f"obs_{ci}"][t], rtol=1e-12, atol=1e-12,
+                                       err_msg=f"case {ci} ({m['cls']}) {m['cfg']} t={t}")
+            np.testing.assert_allclose(r[0, 0], g[f"rew_{ci}"][t], rtol=1e-11, atol=1e-14)
+            assert bool(d) == bool(g[f"done_{ci}"][t]), (ci, t)

@@ -113,3 +113,28 @@ def test_oracle_replays_randomized_rosters():
     _replay_randomized(
         lambda: NS.MultiAgentEnv(**S.randomized_ev_scenario(NS, NS.OpenDSSSolver)),
         lambda env: flat_obs(env, env.reset()), step, exact=True)
+
+
+def test_oracle_matches_reference_on_random_component_configurations():
+    """tests/golden/component_configs.npz: 40 seeded random configurations of the four component
+    classes recorded from the unmodified reference (tests/golden/make_golden_configs.py), each
+    stepped on its own with out-of-range actions and external voltage / set-point inputs."""
+    from tests.component_cases import build_component, load_cases
+    g, meta = load_cases()
+    assert len(meta) == 40
+    for ci, m in enumerate(meta):
+        env = build_component(getattr(NS, m["cls"]), m["cfg"])
+        np.random.seed(m["seed"])
+        r0 = env.reset(**m["reset_kw"], **m["ext0"])
+        o0 = r0[0] if isinstance(r0, tuple) else r0
+        if o0 is None:
+            assert g[f"obs0_{ci}"].size == 0
+        else:
+            np.testing.assert_array_equal(np.asarray(o0, float), g[f"obs0_{ci}"], err_msg=f"case {ci} reset")
+        fixed = {k: v for k, v in m["reset_kw"].items() if k == "p_setpoint"}
+        A = g[f"act_{ci}"]
+        for t in range(A.shape[0]):
+            ob, rew, done, _ = env.step(A[t], **dict(zip(m["ext_keys"], g[f"ext_{ci}"][t])), **fixed)
+            np.testing.assert_array_equal(np.asarray(ob, float), g[f"obs_{ci}"][t],
+                                          err_msg=f"case {ci} ({m['cls']}) t={t}")
+            assert float(rew) == g[f"rew_{ci}"][t] and bool(done) == bool(g[f"done_{ci}"][t]), (ci, t)

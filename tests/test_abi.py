@@ -47,3 +47,21 @@ def test_no_cpu_fallback_without_gpu():
     from tests.product_ns import PRODUCT_NS as NS
     with pytest.raises(N.NativeError):
         NS.MultiAgentEnv(**S.ev_pv_storage_scenario(NS))
+
+
+def test_constants_of_the_binding_match_the_header():
+    """Every PGW_* enumerator / #define the Python binding mirrors has the header's value."""
+    text = open(os.path.join(ROOT, "include", "pgw.h")).read()
+    defs = {m.group(1): int(m.group(2).rstrip("u"), 0)
+            for m in re.finditer(r"#define\s+PGW_([A-Z0-9_]+)\s+(\d+u?)\b", text)}
+    enums = {m.group(1): int(m.group(2)) for m in re.finditer(r"\bPGW_([A-Z0-9_]+)\s*=\s*(-?\d+)", text)}
+    known = {**defs, **enums}
+    checked = 0
+    for name in ("STORAGE", "PV", "EV", "BUILDING", "HS_BEGIN", "HS_PV", "HS_STORAGE", "HS_EV", "HS_DEVICES",
+                 "HS_MAX_COMPONENTS", "F_TELEMETRY", "HS_TEL_ROWS", "F_RESCALE", "F_GRID_AWARE",
+                 "F_PV_VOLT_REWARD", "F_STALE_REWARD", "F_BUILDING_FAST", "OPT_PF_KERNEL", "OPT_WARM_START",
+                 "OPT_GRAPHS", "OPT_PDL", "OPT_CLIP_INIT_SOC", "ABI_VERSION", "NUM_STATS"):
+        assert name in known, f"PGW_{name} not found in pgw.h"
+        assert getattr(N, name) == known[name], (name, getattr(N, name), known[name])
+        checked += 1
+    assert checked == 24

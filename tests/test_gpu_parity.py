@@ -679,19 +679,20 @@ def test_power_flow_non_convergence_is_data(kernel):
         assert np.isfinite(v).all() and v.min() > 0.8 and v.max() < 1.1
 
 
-@pytest.mark.parametrize("kernel", [0, 2])
-def test_runtime_options_do_not_change_results(kernel):
-    """PGW_OPT_WARM_START = 0 (every solve from the no-load voltages) and PGW_OPT_PDL = 1
-    (power flow as a programmatic dependent launch) give the same voltages as the defaults
-    within the solver's own tolerance; cold starts need more iterations."""
+@pytest.mark.parametrize("kernel,E", [(0, 260), (2, 260), (2, 13000)])
+def test_runtime_options_do_not_change_results(kernel, E):
+    """PGW_OPT_WARM_START = 0 (every solve from the no-load voltages) gives the same voltages as
+    the default within the solver's own tolerance and needs more iterations; PGW_OPT_PDL = 0
+    (no programmatic dependent launch of the power flow; default on: released after the clock
+    read at 260 envs, at the end of the component CTAs at 13 000) changes nothing at all."""
     torch = _torch()
     from powergridworld_b200 import _native as N
-    E, T = 260, 5
+    T = 5
     rng = np.random.default_rng(8)
     soc = rng.uniform(10, 40, size=(3, E))
     acts = [torch.as_tensor(rng.uniform(-1, 1, size=(24, E))).cuda() for _ in range(T)]
     out = {}
-    for label, opts in (("default", {}), ("cold", {N.OPT_WARM_START: 0}), ("pdl", {N.OPT_PDL: 1})):
+    for label, opts in (("default", {}), ("cold", {N.OPT_WARM_START: 0}), ("pdl", {N.OPT_PDL: 0})):
         env = PNS.CoordinatedMultiBuildingControlEnv(
             **S.buildings_scenario(PNS, PNS.OpenDSSSolver, 1.2), num_envs=E)
         env.set_option(N.OPT_PF_KERNEL, kernel)
@@ -709,7 +710,8 @@ def test_runtime_options_do_not_change_results(kernel):
     for label in ("cold", "pdl"):
         np.testing.assert_allclose(out[label][0], out["default"][0], rtol=0, atol=tol, err_msg=label)
         np.testing.assert_allclose(out[label][2], out["default"][2], rtol=1e-6, atol=1e4 * tol)
-    assert (out["pdl"][1] == out["default"][1]).all()
+    for k in range(3):                               # same arithmetic, another launch order
+        np.testing.assert_array_equal(out["pdl"][k], out["default"][k])
     assert out["cold"][1].mean() > out["default"][1].mean()
 
 

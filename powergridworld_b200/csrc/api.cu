@@ -349,7 +349,7 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
   PGW_TRY(alloc_zero(&env->d_clock, 1)); env->own(env->d_clock);
   PGW_TRY(alloc_zero(&env->d_ticket, 1)); env->own(env->d_ticket);
 #ifdef PGW_PHASE_TIMERS
-  PGW_TRY(alloc_zero(&env->phase_clk, (size_t)4096 * 16 + (size_t)4096 * 2)); env->own(env->phase_clk);
+  PGW_TRY(alloc_zero(&env->phase_clk, (size_t)4096 * 16 + (size_t)4096 * 8)); env->own(env->phase_clk);
 #endif
 
   if (spec->feeder) {
@@ -1094,12 +1094,12 @@ int pgw_debug_phases(pgw_env* env, long long* host_out, int ctas) {
                       cudaMemcpyDeviceToHost));
   return PGW_OK;
 }
-// globaltimer at entry / exit of the component kernel's CTAs, [ctas][2]
+// component kernel CTAs, [ctas][8]: globaltimer at entry / exit, then SM-clock phase stamps
 int pgw_debug_comp_span(pgw_env* env, long long* host_out, int ctas) {
   if (!env || !host_out || ctas > 4096) return PGW_ERR_INVALID;
   PGW_CUDA(cudaDeviceSynchronize());
   PGW_CUDA(cudaMemcpy(host_out, env->phase_clk + (size_t)4096 * 16,
-                      (size_t)ctas * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+                      (size_t)ctas * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
   return PGW_OK;
 }
 int pgw_debug_num_comp_ctas(pgw_env* env) { return env ? env->num_ctas : 0; }

@@ -42,8 +42,15 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
   const AgentSlice sl = wk.sl;
   const pgw_agent ag = reinterpret_cast<const pgw_agent*>(p.blob)[a];
 #ifdef PGW_PHASE_TIMERS
-  if (p.phase_clk != nullptr && threadIdx.x == 0) p.phase_clk[(size_t)blockIdx.x * 2] = (long long)global_timer_ns();
+#define C_STAMP(k)                                                                        \
+  do {                                                                                    \
+    if (p.phase_clk != nullptr && threadIdx.x == 0) p.phase_clk[(size_t)blockIdx.x * 8 + (k)] = clock64(); \
+  } while (0)
+  if (p.phase_clk != nullptr && threadIdx.x == 0) p.phase_clk[(size_t)blockIdx.x * 8] = (long long)global_timer_ns();
+#else
+#define C_STAMP(k) do { } while (0)
 #endif
+  C_STAMP(2);
   const int clk = p.event_mode == 0 ? -1 : *p.clock;
   unsigned int my_ticket = 0u;                        // thread 0, when this kernel advances the clock
   const int ev = clk + 1;
@@ -74,7 +81,9 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
   } else {
     __syncthreads();
   }
+  C_STAMP(3);
   mbar_wait(&mbar[0], 0);
+  C_STAMP(4);
 
   const int event = ev;
   const pgw_component* comps = s_comps - sl.c_lo;      // indexed by absolute component number
@@ -116,6 +125,7 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
     if (first) {
       mbar_wait(&mbar[1], 0);                  // event row has landed
       first = false;
+      C_STAMP(5);
     }
     if (e < p.E) {
       const size_t ae = (size_t)a * p.E + e;
@@ -140,11 +150,12 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
       }
     }
   }
+  C_STAMP(6);
   if (p.pdl_trigger == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (p.advance_clock && threadIdx.x == 0)
     clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, gridDim.x);
 #ifdef PGW_PHASE_TIMERS
-  if (p.phase_clk != nullptr && threadIdx.x == 0) p.phase_clk[(size_t)blockIdx.x * 2 + 1] = (long long)global_timer_ns();
+  if (p.phase_clk != nullptr && threadIdx.x == 0) p.phase_clk[(size_t)blockIdx.x * 8 + 1] = (long long)global_timer_ns();
 #endif
 }
 

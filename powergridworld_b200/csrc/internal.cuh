@@ -30,7 +30,7 @@ struct CompParams {
   int advance_clock;       // 1 when this kernel is the last one of the step (no feeder)
   int clip_init_soc;       // reset: clip init_soc to each storage's range (PGW_OPT_CLIP_INIT_SOC)
   int pdl_trigger;         // griddepcontrol.launch_dependents: 0 never, 1 after the clock read, 2 at the end
-  long long* phase_clk;    // PGW_PHASE_TIMERS builds only: [CTA][2] globaltimer at entry / exit
+  long long* phase_clk;    // PGW_PHASE_TIMERS builds only: [CTA][8] globaltimer at entry / exit + SM-clock stamps
   int owns_reward;         // 1 when no later kernel changes the reward (no feeder / no penalty)
   int has_house;           // 1: the scenario contains Home-Steward houses, 2: with telemetry
                            // (kernel variants)

@@ -58,7 +58,7 @@ def main():
     for pdl in (1, 0):
         env.set_option(N.OPT_PDL, pdl)
         env.reset_batch(soc)
-        spans = []
+        spans, cphase = [], []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev_ms = []
         for t in range(60):
@@ -68,17 +68,21 @@ def main():
             e1.record()
             if t >= 20:
                 pf = np.zeros((ctas, 16), dtype=np.int64)
-                cp = np.zeros((nc, 2), dtype=np.int64)
+                cp = np.zeros((nc, 8), dtype=np.int64)
                 N.check(lib.pgw_debug_phases(env._h, pf.ctypes.data_as(C.c_void_p), ctas))
                 N.check(lib.pgw_debug_comp_span(env._h, cp.ctypes.data_as(C.c_void_p), nc))
                 t0 = cp[:, 0].min()
                 spans.append([cp[:, 1].max() - t0, pf[:, 12].min() - t0, pf[:, 13].max() - t0,
                               pf[:, 12].max() - t0])
                 ev_ms.append(e0.elapsed_time(e1) * 1e3)
+                cphase.append(np.diff(cp[:, 2:7], axis=1) / mhz)
         sp = np.array(spans, dtype=np.float64).mean(axis=0) / 1e3
         print(f"--- {wl} E={E} PDL={pdl} cold L2 (globaltimer, us from the first component CTA's entry): "
               f"components end {sp[0]:.2f}, power flow first entry {sp[1]:.2f} / last entry {sp[3]:.2f}, "
               f"power flow end {sp[2]:.2f}; step by CUDA events {np.mean(ev_ms):.2f} us")
+        cph = np.stack(cphase).mean(axis=(0, 1))
+        print("    component kernel CTA phases (mean, us): entry -> TMA issued + barrier %.2f | static slice landed %.2f | "
+              "event row landed (first block's prefetches issued) %.2f | agent steps of all blocks %.2f" % tuple(cph))
     env.set_option(N.OPT_PDL, 1)
     for cold in (True, False):
         env.reset_batch(soc)

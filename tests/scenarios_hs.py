@@ -70,3 +70,20 @@ def clone(cfg):
     out = copy.copy(cfg)
     out["components"] = [dict(c, config=copy.deepcopy(c["config"])) for c in cfg["components"]]
     return out
+
+
+def parametrised(ns, hp):
+    """two_vehicles with the numeric knobs of ``hp`` (pv_scale, max_power, lo, hi, eta_c, eta_d,
+    init_cost, mult, rate, grid, rescale[4]) -- shared by the property test, the random-config
+    goldens (tests/golden/make_golden_hs_configs.py) and their replays."""
+    cfg = two_vehicles(ns)
+    cfg["max_grid_power"] = hp["grid"]
+    by = {c["name"]: c["config"] for c in cfg["components"]}
+    by["pv"].update(scaling_factor=hp["pv_scale"], rescale_spaces=bool(hp["rescale"][0]))
+    by["storage"].update(max_power=hp["max_power"], storage_range=[hp["lo"], hp["hi"]],
+                         charge_efficiency=hp["eta_c"], discharge_efficiency=hp["eta_d"],
+                         initial_storage_cost=hp["init_cost"], rescale_spaces=bool(hp["rescale"][1]))
+    by["ev-charging"].update(vehicle_multiplier=hp["mult"], max_charge_rate_kw=hp["rate"],
+                             rescale_spaces=bool(hp["rescale"][2]))
+    by["other-devices"].update(rescale_spaces=bool(hp["rescale"][3]))
+    return cfg

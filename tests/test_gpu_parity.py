@@ -494,6 +494,32 @@ def test_hs_house_golden_trace_on_gpu(name):
                                    rtol=1e-14, atol=0)
 
 
+@pytest.mark.parametrize("case", [0, 3, 5])
+def test_hs_random_houses_two_episodes_on_gpu(case):
+    """tests/golden/hs_random_configs.npz (six random houses x two consecutive episodes recorded
+    from the unmodified reference): the house through the reference's own per-object API
+    (house.reset() draws the SOC from the same RNG stream; house.step(dict))."""
+    import json
+    from tests import scenarios_hs as SH
+    from tests.product_hs_ns import PRODUCT_HS_NS as HNS
+    g = np.load(os.path.join(GOLD, "hs_random_configs.npz"))
+    m = json.loads(str(g["meta"]))[case]
+    house = HNS.HSMultiComponentEnv(**SH.parametrised(HNS, m["hp"]))
+    names = [e.name for e in house.envs]
+    flat = lambda obs: np.concatenate([np.asarray(obs[n], dtype=np.float64).ravel() for n in names])
+    for ep in range(2):
+        key = f"{case}_{ep}"
+        np.random.seed(m["seed"] + ep)
+        obs0 = house.reset()
+        np.testing.assert_allclose(flat(obs0), g["obs0_" + key], rtol=0, atol=1e-13, err_msg=key)
+        A = g["act_" + key]
+        for t in range(A.shape[0]):
+            ob, rew, done, _ = house.step({n: A[t][k:k + 1] for k, n in enumerate(names)})
+            np.testing.assert_allclose(flat(ob), g["obs_" + key][t], rtol=0, atol=1e-12, err_msg=f"{key} t={t}")
+            np.testing.assert_allclose(rew, g["rew_" + key][t], rtol=1e-12, atol=1e-13, err_msg=f"{key} t={t}")
+        assert done
+
+
 def test_hs_house_batch_matches_oracle_per_env():
     """Different actions and initial storage per env against the HS oracle, two episodes back to
     back (the storage cost and the meta state survive the reset, as in the reference)."""

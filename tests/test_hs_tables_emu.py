@@ -88,3 +88,36 @@ def test_hs_telemetry_rows_match_reference_step_meta(name):
             m = ~np.isnan(want)
             np.testing.assert_allclose(have[m], want[m], rtol=1e-13, atol=1e-13,
                                        err_msg=f"t={t} {comp.name}")
+
+
+def test_hs_device_arithmetic_replays_random_houses_over_two_episodes():
+    """tests/golden/hs_random_configs.npz: the reference's house on six random parameter sets,
+    two consecutive episodes each (what survives a reset: storage cost, meta state; the initial
+    SOC is the reference's own unclipped draw, fed through the drawn-SOC path)."""
+    import json
+    g = np.load(os.path.join(GOLD, "hs_random_configs.npz"))
+    for i, m in enumerate(json.loads(str(g["meta"]))):
+        cfg = dict(SH.parametrised(PNS, m["hp"]), step_meta=None)
+        env = pgw.MultiAgentEnv(
+            common_config={"start_time": cfg["start_time"], "end_time": "01-01-2031 00:00:00",
+                           "control_timedelta": cfg["control_timedelta"]},
+            pf_config=None, num_envs=1, _dry_run=True,
+            agents=[{"name": "house", "bus": None, "cls": PNS.HSMultiComponentEnv,
+                     "config": house_agent_config(cfg)}])
+        emu = EmulatedEnv(env)
+        for ep in range(2):
+            key = f"{i}_{ep}"
+            np.random.seed(m["seed"] + ep)
+            soc = env._reset_draws(None)                       # the product's own draw ...
+            np.testing.assert_array_equal(soc[:, 0], g["soc_" + key])   # ... is the reference's
+            obs0 = emu.reset(soc, drawn=True)
+            np.testing.assert_allclose(obs0[:, 0], g["obs0_" + key], rtol=0, atol=1e-14, err_msg=key)
+            A = g["act_" + key]
+            for t in range(A.shape[0]):
+                obs, rew, done = emu.step(A[t].reshape(4, 1))
+                np.testing.assert_allclose(obs[:, 0], g["obs_" + key][t], rtol=0, atol=1e-13,
+                                           err_msg=f"{key} obs t={t}")
+                np.testing.assert_allclose(rew[0, 0], g["rew_" + key][t], rtol=1e-13, atol=1e-13,
+                                           err_msg=f"{key} rew t={t}")
+                np.testing.assert_allclose(emu.agent_p[0, 0], g["p_" + key][t], rtol=1e-14, atol=1e-14)
+            assert done

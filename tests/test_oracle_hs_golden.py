@@ -49,3 +49,28 @@ def test_hs_second_episode_keeps_costs_and_meta():
     cost = env.envs[1].current_cost
     env.reset(init_storage=8.1)
     assert env.envs[1].current_cost == cost
+
+
+def test_hs_oracle_replays_random_houses_over_two_episodes():
+    """tests/golden/hs_random_configs.npz (tests/golden/make_golden_hs_configs.py): six houses with
+    random PV / storage / charger parameters and rescale flags, two consecutive episodes each
+    recorded from the unmodified reference -- the initial SOC is the reference's own draw
+    (np.random.seed before the reset), storage cost and meta state survive the reset."""
+    import json
+    g = np.load(os.path.join(GOLD, "hs_random_configs.npz"))
+    meta = json.loads(str(g["meta"]))
+    assert len(meta) == 6
+    for i, m in enumerate(meta):
+        env = ONS.HSMultiComponentEnv(**SH.parametrised(ONS, m["hp"]))
+        for ep in range(2):
+            key = f"{i}_{ep}"
+            np.random.seed(m["seed"] + ep)
+            obs0 = env.reset()
+            np.testing.assert_array_equal(flat(env, obs0), g["obs0_" + key], err_msg=key)
+            A = g["act_" + key]
+            for t in range(A.shape[0]):
+                ob, rew, done, mt = env.step({e.name: A[t][k:k + 1] for k, e in enumerate(env.envs)})
+                np.testing.assert_array_equal(flat(env, ob), g["obs_" + key][t], err_msg=f"{key} t={t}")
+                assert rew == g["rew_" + key][t] and env.real_power == g["p_" + key][t], (key, t)
+                np.testing.assert_array_equal([float(mt[k]) for k in META_KEYS], g["meta_" + key][t])
+            assert done

@@ -125,17 +125,7 @@ house_params = st.fixed_dictionaries({
 
 def house_config(ns, hp):
     from tests import scenarios_hs as SH
-    cfg = SH.two_vehicles(ns)
-    cfg["max_grid_power"] = hp["grid"]
-    by = {c["name"]: c["config"] for c in cfg["components"]}
-    by["pv"].update(scaling_factor=hp["pv_scale"], rescale_spaces=hp["rescale"][0])
-    by["storage"].update(max_power=hp["max_power"], storage_range=[hp["lo"], hp["hi"]],
-                         charge_efficiency=hp["eta_c"], discharge_efficiency=hp["eta_d"],
-                         initial_storage_cost=hp["init_cost"], rescale_spaces=hp["rescale"][1])
-    by["ev-charging"].update(vehicle_multiplier=hp["mult"], max_charge_rate_kw=hp["rate"],
-                             rescale_spaces=hp["rescale"][2])
-    by["other-devices"].update(rescale_spaces=hp["rescale"][3])
-    return cfg
+    return SH.parametrised(ns, hp)
 
 
 @settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))

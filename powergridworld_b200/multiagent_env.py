@@ -193,8 +193,17 @@ class MultiAgentEnv:
             rec.load_slot, rec.bus_node = -1, -1
             if feeder is not None:
                 bus = self.agent_name_bus_map[ag.name]
-                rec.load_slot = feeder.load_index(bus)
-                if feeder.load_model[rec.load_slot] != 1:
+                try:
+                    rec.load_slot = feeder.load_index(bus)
+                except ValueError:
+                    # the reference only walks the feeder's own load names (opendss.py:115-129):
+                    # power reported under any other name silently never reaches the circuit
+                    import warnings
+                    warnings.warn(f"agent {ag.name!r}: the feeder has no load named {bus!r} "
+                                  f"(loads: {', '.join(feeder.load_names)}); its power is ignored "
+                                  "by the power flow, as in the reference")
+                    rec.load_slot = -1
+                if rec.load_slot >= 0 and feeder.load_model[rec.load_slot] != 1:
                     # the reference only manipulates Model=1 (PQ) loads (opendss.py:54-77,
                     # :115-129): power of an agent on any other load never reaches the feeder
                     import warnings

@@ -164,3 +164,33 @@ def test_standalone_components_on_random_configurations_vs_reference_traces():
                                        err_msg=f"case {ci} ({m['cls']}) {m['cfg']} t={t}")
             np.testing.assert_allclose(r[0, 0], g[f"rew_{ci}"][t], rtol=1e-11, atol=1e-14)
             assert bool(d) == bool(g[f"done_{ci}"][t]), (ci, t)
+
+
+def test_agent_on_unknown_load_name_is_ignored_by_the_power_flow_like_the_reference():
+    """opendss.py:115-129 walks the feeder's own load names: an agent whose ``bus`` is not one of
+    them still steps, but its power never reaches the circuit.  Same here (with a warning); the
+    trajectories agree with the oracle, which follows the reference."""
+    from tests.flatten import flat_obs, unflatten_action
+    from tests.oracle_ns import ORACLE_NS as ONS, storage_socs_to_dict
+
+    def scen(ns):
+        cfg = S.heterogeneous_scenario(ns, ns.OpenDSSSolver, 0.65)
+        cfg["agents"][2]["bus"] = "nowhere"          # the EV station
+        return cfg
+    with pytest.warns(UserWarning, match="no load named 'nowhere'"):
+        env = NS.MultiAgentEnv(**scen(NS), _dry_run=True)
+    assert env._agent_recs[2].load_slot == -1 and env._agent_recs[0].load_slot >= 0
+    ref = ONS.MultiAgentEnv(**scen(ONS))
+    emu = EmulatedEnv(env)
+    soc = np.array([[30.0]])
+    o0 = emu.reset(soc)
+    r0 = ref.reset(init_storage=storage_socs_to_dict(ref, soc[:, 0]))
+    np.testing.assert_allclose(o0[:, 0], flat_obs(ref, r0), rtol=0, atol=OBS_ATOL)
+    rng = np.random.default_rng(3)
+    for t in range(140):                             # into the hours when vehicles charge
+        a = rng.uniform(-1, 1, size=(env.act_dim, 1))
+        o, r, _ = emu.step(a)
+        ro, rr, _, _ = ref.step(unflatten_action(ref, a[:, 0]))
+        np.testing.assert_allclose(o[:, 0], flat_obs(ref, ro), rtol=0, atol=OBS_ATOL, err_msg=f"t={t}")
+        np.testing.assert_allclose(r[:, 0], [rr[x.name] for x in ref.agents], rtol=REW_RTOL, atol=REW_ATOL)
+    assert emu.agent_p[2, 0] > 0.0                   # the station does draw power

@@ -272,7 +272,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        _init_nccl(dev)
     E = ENVS_PER_GPU
     env = _make_env(NS, num_envs=E, device=dev)
     has_pf = env.pf_solver is not None
@@ -503,6 +503,25 @@ def run_ours(args):
 C4_MIX = (("c1", 65536), ("c3", 16384), ("c2", 49152))   # 131 072 envs per GPU, 1 048 576 on 8
 
 
+def _init_nccl(dev):
+    """init_process_group with eager communicator creation.  NCCL announces its version on the
+    process's stdout when NCCL_DEBUG is set (the GPU boxes set it): stdout carries the one JSON
+    line of the contract and nothing else, so file descriptor 1 points at stderr meanwhile."""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def run_mix(args):
     """BASELINE configs[4]: heterogeneous scenario mix, ~1 M env instances over 8 GPUs.  Every GPU
     holds three env batches (IEEE-13 buildings, 123-bus DER feeder, component-only EV station),
@@ -522,7 +541,7 @@ def run_mix(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        _init_nccl(dev)
     scale = args.envs / 131072.0 if args.envs else 1.0
     parts = []
     gen = torch.Generator(device=dev)

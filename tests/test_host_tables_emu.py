@@ -194,3 +194,32 @@ def test_agent_on_unknown_load_name_is_ignored_by_the_power_flow_like_the_refere
         np.testing.assert_allclose(o[:, 0], flat_obs(ref, ro), rtol=0, atol=OBS_ATOL, err_msg=f"t={t}")
         np.testing.assert_allclose(r[:, 0], [rr[x.name] for x in ref.agents], rtol=REW_RTOL, atol=REW_ATOL)
     assert emu.agent_p[2, 0] > 0.0                   # the station does draw power
+
+
+def test_composite_on_its_own_replays_reference_trace():
+    """gridworld/base.py:108-172 -- a MultiComponentEnv stepped outside any MultiAgentEnv (the
+    reference's tests/conftest.py fixture: 6-entry building observation + PV + storage, raw
+    spaces, actions slightly outside the spaces): tests/golden/composite_standalone.npz through
+    the spec compiler and the device arithmetic; the storage SOC is the reference's own draw
+    (np.random.seed(3) before the constructor and reset, as in the recording)."""
+    import pandas as pd
+    g = np.load(os.path.join(GOLD, "composite_standalone.npz"))
+    np.random.seed(3)
+    me = NS.MultiComponentEnv(name="house", components=S.test_multicomponent_components(NS))
+    common = {"start_time": "01-01-2021 00:00:00", "end_time": "01-01-2031 00:00:00",
+              "control_timedelta": pd.Timedelta(300, "s")}
+    env = NS.MultiAgentEnv(common_config=common, pf_config=None, _dry_run=True, agents=[
+        {"name": "house", "bus": None, "cls": lambda name, **kw: me, "config": {}}])
+    emu = EmulatedEnv(env)
+    soc = env._reset_draws(None)
+    np.testing.assert_array_equal(soc[:, 0], g["init_soc"])
+    o0 = emu.reset(soc, drawn=True)
+    np.testing.assert_allclose(o0[:, 0], g["obs0"], rtol=0, atol=1e-13)
+    T = g["actions"].shape[0]
+    assert T == 285                                  # the building ends the episode first
+    for t in range(T):
+        o, r, d = emu.step(g["actions"][t].reshape(-1, 1))
+        np.testing.assert_allclose(o[:, 0], g["obs"][t], rtol=1e-12, atol=1e-12, err_msg=f"t={t}")
+        np.testing.assert_allclose(r[0, 0], g["rew"][t], rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(emu.agent_p[0, 0], g["real_power"][t], rtol=1e-13, atol=1e-13)
+        assert bool(d) == bool(g["done"][t])

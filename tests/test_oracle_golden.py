@@ -138,3 +138,24 @@ def test_oracle_matches_reference_on_random_component_configurations():
             np.testing.assert_array_equal(np.asarray(ob, float), g[f"obs_{ci}"][t],
                                           err_msg=f"case {ci} ({m['cls']}) t={t}")
             assert float(rew) == g[f"rew_{ci}"][t] and bool(done) == bool(g[f"done_{ci}"][t]), (ci, t)
+
+
+def test_oracle_composite_on_its_own_replays_reference_trace():
+    """tests/golden/composite_standalone.npz: MultiComponentEnv outside a MultiAgentEnv."""
+    g = np.load(os.path.join(GOLD, "composite_standalone.npz"))
+    np.random.seed(3)
+    env = NS.MultiComponentEnv(name="house", components=S.test_multicomponent_components(NS))
+    obs0, _ = env.reset()
+    flat = lambda o: np.concatenate([np.atleast_1d(np.asarray(o[e.name], float)) for e in env.envs])
+    np.testing.assert_array_equal(flat(obs0), g["obs0"])
+    k = 0
+    for t in range(g["actions"].shape[0]):
+        act, k = {}, 0
+        for e in env.envs:
+            n = int(np.prod(e.action_space.shape))
+            act[e.name] = g["actions"][t][k:k + n]
+            k += n
+        ob, rew, done, _ = env.step(act)
+        np.testing.assert_array_equal(flat(ob), g["obs"][t], err_msg=f"t={t}")
+        assert float(rew) == g["rew"][t] and float(env.real_power) == g["real_power"][t]
+        assert bool(done) == bool(g["done"][t])

@@ -156,6 +156,37 @@ def record_randomized(ref, ns, pf, episodes=2, seed=4321):
           f"{[out[f'roster0_{k}'][:4].tolist() for k in range(len(rosters))]}")
 
 
+def record_consecutive(ref, ns, pf, episodes=3, seed=77):
+    """Three consecutive 59-step episodes of the heterogeneous scenario on ONE env object: what a
+    reset keeps (the building's state vector is not zeroed, five_zone_rom_env.py:147-180) and
+    what it restores (EV energies, PV index, the storage SOC it draws: np.random.seed(10 + ep)
+    before each reset)."""
+    with quiet_stdout():
+        np.random.seed(0)
+        env = ns.MultiAgentEnv(**S.heterogeneous_scenario(ns, pf, 0.65, max_episode_steps=60))
+    layout = action_layout(env)
+    rng = np.random.default_rng(seed)
+    out = {}
+    for ep in range(episodes):
+        np.random.seed(10 + ep)
+        with quiet_stdout():
+            obs0 = env.reset()
+        socs = storage_socs(ref, env)
+        A, O, R = [], [], []
+        done = False
+        while not done:
+            a = draw_actions(layout, rng)
+            with quiet_stdout():
+                ob, rew, dn, _ = env.step(unflatten_action(env, a))
+            A.append(a); O.append(flat_obs(env, ob))
+            R.append(np.array([rew[ag.name] for ag in env.agents], dtype=np.float64))
+            done = dn["__all__"]
+        out.update({f"init_soc{ep}": socs, f"obs0_{ep}": flat_obs(env, obs0), f"actions{ep}": np.array(A),
+                    f"obs{ep}": np.array(O), f"rew{ep}": np.array(R)})
+    np.savez_compressed(os.path.join(HERE, "heterogeneous_3episodes.npz"), episodes=episodes, **out)
+    print(f"heterogeneous_3episodes: {episodes} x {len(A)} steps")
+
+
 def ev_totals(ref):
     cfg = {"num_vehicles": 100, "minutes_per_step": 5, "max_charge_rate_kw": 7.,
            "peak_threshold": 250., "vehicle_multiplier": 5., "rescale_spaces": False}
@@ -189,6 +220,7 @@ def main():
            S.heterogeneous_scenario(ns, pf, 0.6, max_episode_steps=250), ref)
     record("test_heterogeneous", ns.MultiAgentEnv, S.test_heterogeneous_scenario(ns, pf), ref)
     record_randomized(ref, ns, pf)
+    record_consecutive(ref, ns, pf)
     for v in S.TIME_BASE_VARIANTS:
         record("timebase_" + v, ns.MultiAgentEnv, S.time_base_scenario(ns, pf, v), ref)
     ev_totals(ref)

@@ -223,3 +223,21 @@ def test_composite_on_its_own_replays_reference_trace():
         np.testing.assert_allclose(r[0, 0], g["rew"][t], rtol=1e-11, atol=1e-13)
         np.testing.assert_allclose(emu.agent_p[0, 0], g["real_power"][t], rtol=1e-13, atol=1e-13)
         assert bool(d) == bool(g["done"][t])
+
+
+def test_three_consecutive_episodes_on_one_env_vs_reference_trace():
+    """tests/golden/heterogeneous_3episodes.npz through the spec compiler and the device
+    arithmetic: the building's state vector survives pgw_reset like the reference's does."""
+    g = np.load(os.path.join(GOLD, "heterogeneous_3episodes.npz"))
+    env = NS.MultiAgentEnv(**S.heterogeneous_scenario(NS, NS.OpenDSSSolver, 0.65, max_episode_steps=60),
+                           _dry_run=True)
+    emu = EmulatedEnv(env)
+    for ep in range(int(g["episodes"])):
+        o0 = emu.reset(g[f"init_soc{ep}"].reshape(-1, 1))
+        np.testing.assert_allclose(o0[:, 0], g[f"obs0_{ep}"], rtol=0, atol=OBS_ATOL, err_msg=f"ep={ep}")
+        A = g[f"actions{ep}"]
+        for t in range(A.shape[0]):
+            o, r, d = emu.step(A[t].reshape(-1, 1))
+            np.testing.assert_allclose(o[:, 0], g[f"obs{ep}"][t], rtol=0, atol=OBS_ATOL, err_msg=f"ep={ep} t={t}")
+            np.testing.assert_allclose(r[:, 0], g[f"rew{ep}"][t], rtol=REW_RTOL, atol=REW_ATOL)
+        assert bool(d)

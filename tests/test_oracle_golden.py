@@ -159,3 +159,21 @@ def test_oracle_composite_on_its_own_replays_reference_trace():
         np.testing.assert_array_equal(flat(ob), g["obs"][t], err_msg=f"t={t}")
         assert float(rew) == g["rew"][t] and float(env.real_power) == g["real_power"][t]
         assert bool(done) == bool(g["done"][t])
+
+
+def test_oracle_replays_three_consecutive_episodes_on_one_env():
+    """tests/golden/heterogeneous_3episodes.npz: what a reset keeps (the building's state vector,
+    five_zone_rom_env.py:147-180) and what it restores, on the reference itself."""
+    g = np.load(os.path.join(GOLD, "heterogeneous_3episodes.npz"))
+    env = NS.MultiAgentEnv(**S.heterogeneous_scenario(NS, NS.OpenDSSSolver, 0.65, max_episode_steps=60))
+    for ep in range(int(g["episodes"])):
+        obs0 = env.reset(init_storage=storage_socs_to_dict(env, g[f"init_soc{ep}"]))
+        np.testing.assert_array_equal(flat_obs(env, obs0), g[f"obs0_{ep}"], err_msg=f"ep={ep}")
+        A = g[f"actions{ep}"]
+        for t in range(A.shape[0]):
+            ob, rew, dn, _ = env.step(unflatten_action(env, A[t]))
+            np.testing.assert_array_equal(flat_obs(env, ob), g[f"obs{ep}"][t], err_msg=f"ep={ep} t={t}")
+            np.testing.assert_array_equal(np.array([rew[a.name] for a in env.agents]), g[f"rew{ep}"][t])
+        assert dn["__all__"] and A.shape[0] == 59
+    # the episodes differ although the scenario restarts at the same clock: carried-over state
+    assert not np.array_equal(g["obs0_0"], g["obs0_1"])

@@ -241,3 +241,43 @@ def test_three_consecutive_episodes_on_one_env_vs_reference_trace():
             np.testing.assert_allclose(o[:, 0], g[f"obs{ep}"][t], rtol=0, atol=OBS_ATOL, err_msg=f"ep={ep} t={t}")
             np.testing.assert_allclose(r[:, 0], g[f"rew{ep}"][t], rtol=REW_RTOL, atol=REW_ATOL)
         assert bool(d)
+
+
+def test_randomised_rosters_in_a_batch_are_shared_and_match_the_oracle_per_env():
+    """A batch of three envs with randomised stations: one roster draw per station and reset,
+    shared by the envs; with explicit per-env storage SOCs and per-env actions every env replays
+    an oracle env that was handed the same rosters (two resets = two draws)."""
+    from tests.flatten import flat_obs, unflatten_action
+    from tests.oracle_ns import ORACLE_NS as ONS, storage_socs_to_dict
+    E = 3
+    env = NS.MultiAgentEnv(**S.randomized_ev_scenario(NS, NS.OpenDSSSolver), num_envs=E, _dry_run=True)
+    emu = EmulatedEnv(env)
+    refs = [ONS.MultiAgentEnv(**S.randomized_ev_scenario(ONS, ONS.OpenDSSSolver)) for _ in range(E)]
+    rng = np.random.default_rng(0)
+    seen = []
+    for ep in range(2):
+        soc = rng.uniform(10, 45, size=(env.num_storage, E))
+        np.random.seed(40 + ep)
+        assert env._reset_draws(soc) is soc          # explicit SOCs: only the rosters are drawn
+        o0 = emu.reset(soc)
+        rosters = [np.array(o._rows) for o in env._b.objs if getattr(o, "randomize", False)]
+        seen.append(rosters)
+        orig = np.random.choice
+        for e, r in enumerate(refs):
+            q = list(rosters)
+            np.random.choice = lambda n, size=None, replace=True: q.pop(0)
+            try:
+                r0 = r.reset(init_storage=storage_socs_to_dict(r, soc[:, e]))
+            finally:
+                np.random.choice = orig
+            np.testing.assert_allclose(o0[:, e], flat_obs(r, r0), rtol=0, atol=OBS_ATOL)
+        for t in range(150):
+            a = rng.uniform(-1, 1, size=(env.act_dim, E))
+            o, rew, _ = emu.step(a)
+            for e, r in enumerate(refs):
+                ro, rr, _, _ = r.step(unflatten_action(r, a[:, e]))
+                np.testing.assert_allclose(o[:, e], flat_obs(r, ro), rtol=0, atol=OBS_ATOL,
+                                           err_msg=f"ep={ep} t={t} env={e}")
+                np.testing.assert_allclose(rew[:, e], [rr[x.name] for x in r.agents],
+                                           rtol=REW_RTOL, atol=REW_ATOL)
+    assert not np.array_equal(seen[0][0], seen[1][0])           # a new draw per reset

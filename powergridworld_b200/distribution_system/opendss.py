@@ -98,5 +98,6 @@ class ZBusSolver(PowerFlowSolver):
         return None
 
 
-# the reference's class name, so that scenario configs read the same
-OpenDSSSolver = ZBusSolver
+class OpenDSSSolver(ZBusSolver):
+    """The reference's class name (gridworld/distribution_system/opendss.py:18), so that scenario
+    configs read -- and print -- the same."""

@@ -10,6 +10,11 @@ from powergridworld_b200.agents.vehicles import EVChargingEnv
 from powergridworld_b200.distribution_system import OpenDSSSolver
 
 
+class ThisPVEnv(GridAwarePVEnv):
+    """gridworld/scenarios/heterogeneous.py:46-52: the PV farm rewarded for voltage support
+    (the reward itself is evaluated on the device, see GridAwarePVEnv)."""
+
+
 def make_env_config(system_load_rescale_factor=0.65, rescale_spaces=True):
     building_components = [
         {"name": "building", "cls": FiveZoneROMThermalEnergyEnv,
@@ -30,7 +35,7 @@ def make_env_config(system_load_rescale_factor=0.65, rescale_spaces=True):
     agents = [
         {"name": "building", "bus": "675c", "cls": MultiComponentEnv,
          "config": {"components": building_components}},
-        {"name": "pv", "bus": "675c", "cls": GridAwarePVEnv,
+        {"name": "pv", "bus": "675c", "cls": ThisPVEnv,
          "config": {"profile_csv": "constant.csv", "scaling_factor": 400.,
                     "rescale_spaces": rescale_spaces, "grid_aware": True}},
         {"name": "ev-charging", "bus": "675c", "cls": EVChargingEnv,

@@ -281,3 +281,26 @@ def test_randomised_rosters_in_a_batch_are_shared_and_match_the_oracle_per_env()
                 np.testing.assert_allclose(rew[:, e], [rr[x.name] for x in r.agents],
                                            rtol=REW_RTOL, atol=REW_ATOL)
     assert not np.array_equal(seen[0][0], seen[1][0])           # a new draw per reset
+
+
+def test_scenario_factories_read_like_the_reference():
+    """gridworld/scenarios/{buildings,heterogeneous}.py: same signatures, same class names inside
+    the config dicts (``OpenDSSSolver``, ``ThisPVEnv``, ...), and the configs build."""
+    import inspect
+    from powergridworld_b200.scenarios import buildings as PB, heterogeneous as PH
+    assert str(inspect.signature(PB.make_env_config)) == \
+        "(building_config=None, pv_config=None, storage_config=None, system_load_rescale_factor=0.65, num_buildings=3)"
+    assert str(inspect.signature(PH.make_env_config)) == "(system_load_rescale_factor=0.65, rescale_spaces=True)"
+    cfg = PH.make_env_config()
+    assert cfg["pf_config"]["cls"].__name__ == "OpenDSSSolver"
+    assert [a["cls"].__name__ for a in cfg["agents"]] == ["MultiComponentEnv", "ThisPVEnv", "EVChargingEnv"]
+    assert [c["cls"].__name__ for c in cfg["agents"][0]["config"]["components"]] == \
+        ["FiveZoneROMThermalEnergyEnv", "PVEnv", "EnergyStorageEnv"]
+    env = NS.MultiAgentEnv(**cfg, _dry_run=True)
+    assert env.episode_length == 286 and (env.act_dim, env.obs_dim) == (10, 25)
+    cfg = PB.make_env_config(building_config={},     # (None fails in the reference too: cls(**None))
+                             pv_config={"profile_csv": "pv_profile.csv", "scaling_factor": 40.},
+                             storage_config={"max_power": 15., "storage_range": (3., 50.)})
+    assert cfg["pf_config"]["cls"].__name__ == "OpenDSSSolver" and len(cfg["agents"]) == 3
+    env = NS.CoordinatedMultiBuildingControlEnv(**cfg, _dry_run=True)
+    assert (env.act_dim, env.obs_dim) == (24, 51)

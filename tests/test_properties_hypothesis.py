@@ -54,7 +54,7 @@ class _NoPF:
         return 1.0
 
 
-@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
 @given(s_cfg=storage_cfg, p_cfg=pv_cfg, e_cfg=ev_cfg, seed=st.integers(0, 2 ** 31 - 1),
        wild=st.floats(1.0, 1.6))
 def test_components_match_oracle_on_random_parameters_and_actions(s_cfg, p_cfg, e_cfg, seed, wild):
@@ -82,7 +82,7 @@ def test_components_match_oracle_on_random_parameters_and_actions(s_cfg, p_cfg, 
             break
 
 
-@settings(max_examples=8, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=8, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
 @given(e_cfg=ev_cfg, s_cfg=storage_cfg, seed=st.integers(0, 2 ** 31 - 1), roster_seed=st.integers(0, 2 ** 31 - 1))
 def test_randomized_station_matches_oracle_over_two_draws(e_cfg, s_cfg, seed, roster_seed):
     """EVChargingEnv(randomize=True): the host draws (roster and storage SOC, in the reference's
@@ -128,7 +128,7 @@ def house_config(ns, hp):
     return SH.parametrised(ns, hp)
 
 
-@settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=20, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
 @given(hp=house_params, seed=st.integers(0, 2 ** 31 - 1))
 def test_house_matches_hs_oracle_on_random_parameters_and_actions(hp, seed):
     from powergridworld_b200.base_hs import house_agent_config

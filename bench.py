@@ -58,6 +58,15 @@ NCU_TRAFFIC_PF = {("c1", 4096): 1.294e6, ("c3", 16384): 49.78e6}     # pf_tc2_ke
 NCU_TENSOR_PCT = {("c1", 4096): 2.45, ("c1", 262144): 5.72, ("c3", 16384): 22.47}
 
 
+def _dtype_label(has_pf):
+    """The arithmetic the step computes in (not a precision claim)."""
+    if not has_pf or PF_KERNEL == "fp64":
+        return "f64"
+    if PF_KERNEL == "tc2":
+        return "f64 components; power flow: split-fp16 operands / fp32 accumulate (tcgen05) + f64 polish sweeps"
+    return "f64 components; power flow: split-tf32 operands / fp32 accumulate (tcgen05)"
+
+
 def _config(n_gpus):
     if WORKLOAD == "c2":
         return {"workload": "C2: component-only EV station (100 vehicles) + PV + storage, "
@@ -87,47 +96,34 @@ def _config(n_gpus):
 
 
 def _make_env(ns, workload=None, **kw):
-    """The benchmark scenario against a plugin namespace (product or oracle)."""
-    from tests import scenarios as S
-    WORKLOAD = workload or globals()["WORKLOAD"]
-    if WORKLOAD == "c2":
-        if ns.__dict__.get("_is_oracle"):
-            from oracle.multiagent import PowerFlowSolver
+    """The benchmark scenario (powergridworld_b200/scenarios/bench.py) against a plugin
+    namespace: None = the product, the oracle namespace for the CPU arm."""
+    from powergridworld_b200.scenarios import bench as SB
+    wl = workload or WORKLOAD
+    if ns is None:
+        return SB.make_env(wl, **kw)
+    # ---- CPU arm (oracle classes; the one place outside tests/ and smoke() that runs oracle/)
+    if wl == "c2":
+        from oracle.multiagent import PowerFlowSolver
 
-            class NoPF(PowerFlowSolver):
-                def __init__(self, **k):
-                    pass
+        class NoPF(PowerFlowSolver):
+            def __init__(self, **k):
+                pass
 
-                def calculate_power_flow(self, *a, **k):
-                    pass
+            def calculate_power_flow(self, *a, **k):
+                pass
 
-                def get_bus_voltages(self):
-                    return {}
+            def get_bus_voltages(self):
+                return {}
 
-                def get_bus_voltage_by_name(self, n):
-                    return 1.0
-            return ns.MultiAgentEnv(**S.ev_pv_storage_scenario(ns, NoPF), **kw)
-        return ns.MultiAgentEnv(**S.ev_pv_storage_scenario(ns), **kw)
-    if WORKLOAD == "hs":
-        from tests import scenarios_hs as SH
-        if ns.__dict__.get("_is_oracle"):
-            from tests.oracle_hs_ns import ORACLE_HS_NS as OHS
-            return _OracleHouse(OHS.HSMultiComponentEnv(**SH.shipped(OHS)))
-        from powergridworld_b200.base_hs import house_agent_config
-        from tests.product_hs_ns import PRODUCT_HS_NS as HNS
-        cfg = SH.shipped(HNS)
-        return ns.MultiAgentEnv(
-            common_config={"start_time": cfg["start_time"], "end_time": "01-01-2031 00:00:00",
-                           "control_timedelta": cfg["control_timedelta"]},
-            pf_config=None, agents=[{"name": "house", "bus": None, "cls": HNS.HSMultiComponentEnv,
-                                     "config": house_agent_config(cfg)}], **kw)
-    if WORKLOAD == "c3":
-        import warnings
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            return ns.MultiAgentEnv(**S.der123_scenario(ns, ns.OpenDSSSolver), **kw)
-    return ns.CoordinatedMultiBuildingControlEnv(
-        **S.buildings_scenario(ns, ns.OpenDSSSolver, LOAD_FACTOR), **kw)
+            def get_bus_voltage_by_name(self, n):
+                return 1.0
+        return SB.c2_env(ns, NoPF, **kw)
+    if wl == "hs":
+        from oracle.namespace import ORACLE_HS_NS as OHS
+        from powergridworld_b200.scenarios import catalog_hs as SH
+        return _OracleHouse(OHS.HSMultiComponentEnv(**SH.shipped(OHS)))
+    return SB.make_env(wl, ns, **kw)
 
 
 class _OracleHouse:
@@ -152,9 +148,8 @@ def _cpu_worker(args):
     seed, steps = args
     import numpy as np
 
-    from tests.flatten import action_layout, unflatten_action
-    from tests.oracle_ns import ORACLE_NS as NS
-    NS._is_oracle = True
+    from oracle.flatten import action_layout, unflatten_action
+    from oracle.namespace import ORACLE_NS as NS
     env = _make_env(NS)
     rng = np.random.default_rng(seed)
     np.random.seed(seed)
@@ -267,14 +262,12 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from tests.product_ns import PRODUCT_NS as NS
-
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
         _init_nccl(dev)
     E = ENVS_PER_GPU
-    env = _make_env(NS, num_envs=E, device=dev)
+    env = _make_env(None, num_envs=E, device=dev)
     has_pf = env.pf_solver is not None
     if PF_KERNEL != "fp64" and has_pf:
         from powergridworld_b200 import _native as N
@@ -473,7 +466,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": _dtype_label(has_pf), "data": "synthetic",
             "config": _config(world),
             "agent_steps_per_s": value * A,
             "clocks": sampler.summary(),
@@ -532,7 +525,6 @@ def run_mix(args):
     import torch.distributed as dist
 
     from powergridworld_b200 import _native as N
-    from tests.product_ns import PRODUCT_NS as NS
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -549,7 +541,7 @@ def run_mix(args):
     rng = np.random.default_rng(rank)
     for wl, n in C4_MIX:
         E = max(128, int(n * scale) // 128 * 128)
-        env = _make_env(NS, workload=wl, num_envs=E, device=dev)
+        env = _make_env(None, workload=wl, num_envs=E, device=dev)
         if env.pf_solver is not None and PF_KERNEL != "fp64":
             env.set_option(N.OPT_PF_KERNEL, {"tc": 1, "tc2": 2}[PF_KERNEL])
         stream = torch.cuda.Stream(dev)

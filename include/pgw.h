@@ -306,6 +306,15 @@ long long pgw_launch_count(const pgw_env* env);
                                  reference does with an explicit init_storage (energy_storage_env.py:
                                  88-89); 0: used as given -- the reference does NOT clip the value it
                                  draws itself (:82-84), so a host that replays that draw turns it off */
+#define PGW_OPT_PF_POLISH 5   /* full float64 sweeps of the fixed point run after the tcgen05 split-FP16
+                                 solver (kernel 2) has converged -- followed by one more sweep over the
+                                 rows the rewards and the agents read -- in the step solve of feeders with
+                                 <= 16 load branches whose rewards read the fresh voltages (shared-penalty
+                                 hook, examples/marl/openai/train.py:51-88).  Default 1: the penalty-node
+                                 and agent-bus voltages then agree with the float64 solver to ~1e-9 p.u.,
+                                 i.e. rewards within rtol 1e-5 / atol 2e-5.  0 = off (~5e-8 p.u.)       */
+#define PGW_OPT_PF_TC_TOL_NANO 6 /* convergence threshold max|du| of the tcgen05 solvers in units of
+                                 1e-9 p.u. (default 100 = 1e-7, the split-FP16 operands' floor)          */
 int pgw_set_option(pgw_env* env, int option, int value);
 
 /* Per-kernel device timing for benchmarks: when enabled, every launch of pgw_step is

@@ -95,6 +95,7 @@ struct pgw_env {
   unsigned char* tc2_blob = nullptr;
   pgw::Tc2Params tc2{};
   pgw::Tc2Consts tc2c{};
+  pgw::Tc2Polish tc2p{};
   // CUDA graphs of a step, keyed by the caller's buffer pointers
   struct StepGraph {
     const void *actions, *obs, *rew, *done;
@@ -523,6 +524,7 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       // of the two voltage bases) need no expansion: |v_n| = c |u_k|.
       std::vector<int32_t> dnode(NBP, -1), xnode;
       std::vector<float> dscale(NBP, 0.f);
+      std::vector<double> dscale64(NBP, 0.0);
       {
         std::vector<char> taken(nb, 0);
         for (int n = 0; n < nn; ++n) {
@@ -543,7 +545,7 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
             }
             if (err <= 1e-10 * ref) { hit = k; cr = c; }
           }
-          if (hit >= 0) { taken[hit] = 1; dnode[hit] = n; dscale[hit] = (float)cr; }
+          if (hit >= 0) { taken[hit] = 1; dnode[hit] = n; dscale[hit] = (float)cr; dscale64[hit] = cr; }
           else xnode.push_back(n);
         }
       }
@@ -649,6 +651,36 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       t.t_xnode = put(xnode.data(), xnode.size() * 4);
       t.t_dnode = put(dnode.data(), dnode.size() * 4);
       t.t_dscale = put(dscale.data(), dscale.size() * 4);
+      // FP64 polish (powerflow_tc2.cu): one full float64 sweep + one over the rows the rewards
+      // and the agents read, on by default where the rewards read the fresh voltages
+      t.polish_ok = nch == 2 ? 1 : 0;
+      t.polish = (t.polish_ok && env->punit != 0.0) ? 1 : 0;
+      t.polish_row = -1;
+      if (t.polish_ok) {
+        pgw::Tc2Polish& kp = env->tc2p;
+        for (int j = 0; j < 16; ++j)
+          for (int k = 0; k < 16; ++k)
+            kp.zT[j * 16 + k] = (j < nb && k < nb) ? Z(k, j) : make_double2(0.0, 0.0);
+        for (int k = 0; k < 16; ++k) {
+          const bool real = k < nb;
+          kp.u0[k] = real ? make_double2(f.u0[2 * k], f.u0[2 * k + 1]) : make_double2(1.0, 0.0);
+          kp.share[k] = real ? f.branch_share[k] * 1e-3 : 0.0;
+          kp.model[k] = real ? f.branch_model[k] : 1;
+          const bool z = real && f.branch_model[k] == 2;
+          kp.vlo2[k] = z ? 1.0 : (real ? f.vminpu[k] * f.vminpu[k] : 0.9025);
+          kp.vhi2[k] = z ? 1.0 : (real ? f.vmaxpu[k] * f.vmaxpu[k] : 1.1025);
+          kp.dscale[k] = real ? dscale64[k] : 0.0;
+        }
+        kp.rows = 0u;
+        auto mark = [&](int node) {
+          for (int k = 0; k < nb; ++k)
+            if (node >= 0 && dnode[k] == node) { kp.rows |= 1u << k; return true; }
+          return false;
+        };
+        for (int a = 0; a < env->A; ++a) mark(spec->agents[a].bus_node);
+        if (env->punit != 0.0 && !mark(env->penalty_node)) t.polish_row = env->penalty_node;
+        t.pconsts = &env->tc2p;
+      }
       t.t_lptr = put(lptr.data(), lptr.size() * 4);
       t.t_lidx = put(lidx.data(), lidx.size() * 4);
       t.t_anode = put(node.data(), node.size() * 4);
@@ -803,9 +835,9 @@ static int enqueue_components(pgw_env* env, const double* actions, double* obs, 
 // Measured (C1, cold L2): 27.5 -> 25.6 us per step at 4096 envs, 40.1 -> 37.9 us at 32 768.
 static int pdl_trigger_mode(const pgw_env* env, bool timed) {
   if (!env->use_pdl || timed || !env->has_feeder || env->pf_kernel != 2) return 0;
-  pgw::PfParams pf{};
-  pf.tc2 = env->tc2; pf.nl = env->nl;
-  if (pgw::tc2_smem_bytes(pf) > 64 * 1024) return 0;
+  pgw::PfParams pf = pf_params(const_cast<pgw_env*>(env));
+  pf.event_mode = 1; pf.reward_hook = (env->punit != 0.0) ? 1 : 0;
+  if (pgw::tc2_smem_bytes(pf) > 112 * 1024) return 0;   // two power-flow CTAs + component CTAs per SM
   return env->num_ctas <= 148 * 4 ? 1 : 2;
 }
 
@@ -1126,6 +1158,16 @@ int pgw_set_option(pgw_env* env, int option, int value) {
     case PGW_OPT_WARM_START: env->warm_start = value != 0; break;
     case PGW_OPT_GRAPHS: env->use_graphs = value != 0; break;
     case PGW_OPT_PDL: env->use_pdl = value != 0; break;
+    case PGW_OPT_PF_POLISH:
+      if (value < 0 || value > 8) return fail(PGW_ERR_INVALID, "polish sweeps out of range (0..8)");
+      if (value > 0 && !env->tc2.polish_ok)
+        return fail(PGW_ERR_INVALID, "the FP64 polish serves feeders with <= 16 load branches");
+      env->tc2.polish = value;
+      break;
+    case PGW_OPT_PF_TC_TOL_NANO:
+      if (value < 10 || value > 100000) return fail(PGW_ERR_INVALID, "tolerance out of range (1e-8..1e-4)");
+      env->tc2.tol = (float)(value * 1e-9);
+      break;
     default: return fail(PGW_ERR_INVALID, "unknown option");
   }
   // the captured graphs bake the options in

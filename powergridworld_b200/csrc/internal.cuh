@@ -74,12 +74,33 @@ struct Tc2Consts {
                            // (0, 1) = 1 / |u| (constant-current load)
 };
 
+// Float64 tables of the polish sweeps (powerflow_tc2.cu, POLISH instantiations), passed as a
+// __grid_constant__ kernel parameter: every entry is warp uniform, so the sweeps read them as
+// constant-bank operands and shared memory only carries the per-env currents.
+struct Tc2Polish {
+  double2 zT[16 * 16];     // zT[j * 16 + k] = Zbb[k][j], zero padded
+  double2 u0[16];
+  double share[16];        // branch share x 1e-3 (kVA -> p.u. on 1 MVA), 0 for the padded branches
+  double vlo2[16], vhi2[16];   // clamp band of |u|^2: model 1 [vmin^2, vmax^2], model 2 [1, 1]
+  double dscale[16];       // node voltage = dscale x branch voltage (wye loads), else 0
+  int model[16];
+  unsigned rows;           // branches whose voltage the reward hook / the agents read (bit k)
+  int pad;
+};
+
 struct Tc2Params {
   const unsigned char* blob;
   const Tc2Consts* consts; // host copy owned by the env handle
+  const Tc2Polish* pconsts; // host copy owned by the env handle (polish only)
   int nch, ncc, nx, ntail, resident, part_bytes, off_zn, off_tab, tab_bytes, tmem_cols, any_m5;
   int t_share, t_bload, t_bagent, t_w, t_xnode, t_dnode, t_dscale, t_lptr, t_lidx,
       t_anode, t_vag, t_vtail;
+  // FP64 polish of the converged branch voltages (feeders with <= 16 load branches, step solve
+  // with the shared-penalty hook): `polish` full sweeps u <- u0 - Zbb i(u) in float64 on the
+  // SIMT pipe after the tensor-core fixed point has converged, then one more sweep restricted to
+  // the rows the reward hook and the agents read (Tc2Polish.rows), so that those voltages meet
+  // the float64 tolerance (rewards 1e-5 relative / 2e-5 absolute).  0 = off.
+  int polish, polish_ok, polish_row;   // polish_row: penalty node if it is NOT a wye-load node, else -1
   float xscale, descale1, descale2, tol;
 };
 
@@ -147,6 +168,8 @@ cudaError_t launch_powerflow(const PfParams& p, cudaStream_t s);
 cudaError_t launch_powerflow_tc(const PfParams& p, cudaStream_t s);
 cudaError_t launch_powerflow_tc2(const PfParams& p, cudaStream_t s);
 size_t tc2_smem_bytes(const PfParams& p);
+size_t tc2_polish_bytes(const PfParams& p);
+bool tc2_polish_active(const PfParams& p);
 int tc2_padded_chunks(int nch);      // instantiated tile width for nch chunks of 8 branches (0 = none)
 constexpr int kTc2MaxChunks = 11;   // 88 load branches: B and A images fill shared memory
 constexpr int kTcNb = 16;      // branch slots of the tensor-core kernel (IEEE-13 class feeders)

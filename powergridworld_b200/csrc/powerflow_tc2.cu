@@ -35,6 +35,8 @@
 // Same inputs/outputs as pf_fixed_point_kernel (powerflow.cu).
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "internal.cuh"
 #include "tma.cuh"
 
@@ -218,6 +220,55 @@ __device__ __forceinline__ float2 t2_gh(const Tc2Consts& kc, int k) {
   return make_float2(c[k & 1], c[2 + (k & 1)]);
 }
 
+// ---- FP64 polish (POLISH instantiations): the load characteristic and one row of the sweep
+// u <- u0 - Zbb i(u) in float64, same model semantics as branch_current of powerflow.cu
+// (OpenDSS model 1 = constant PQ inside [vmin, vmax], constant Z outside; 2 = constant Z;
+// 5 = constant current magnitude).
+__device__ __forceinline__ double2 t2_current64(int model, double2 s, double2 u, double vlo2,
+                                                double vhi2) {
+  const double m2 = u.x * u.x + u.y * u.y;
+  double k;
+  if (model == 5) {
+    k = m2 > 0.0 ? rsqrt(m2) : 0.0;
+  } else {                                               // model 2: the band is [1, 1]
+    // 1 / c from the float32 reciprocal and two Newton steps (relative error ~1e-21 before
+    // rounding): the voltages are O(1), nothing here can overflow or go subnormal
+    const double c = fmin(fmax(m2, vlo2), vhi2);
+    double x = (double)__frcp_rn((float)c);
+    x = fma(x, fma(-c, x, 1.0), x);
+    k = fma(x, fma(-c, x, 1.0), x);
+  }
+  const double tr = s.x * u.x + s.y * u.y, ti = s.x * u.y - s.y * u.x;   // conj(s) u
+  return make_double2(tr * k, ti * k);
+}
+__device__ __forceinline__ void t2_cmac_sub64(double2& acc, double2 z, double2 i) {
+  acc.x = fma(-z.x, i.x, acc.x);
+  acc.x = fma(z.y, i.y, acc.x);
+  acc.y = fma(-z.x, i.y, acc.y);
+  acc.y = fma(-z.y, i.x, acc.y);
+}
+
+// One float64 sweep over the 8 branches of chunk c of env row `row`:
+// u_k <- u0_k - sum_j Zbb[k][j] i_j.  Z and u0 are warp-uniform constant-bank reads, the env's
+// currents come from shared memory, [branch][env row].  The loop over j stays rolled: the code
+// runs once per tile, and straight-line code would be paid for in instruction fetches.
+__device__ __forceinline__ void t2_sweep64(const Tc2Polish& kp, int nb, int c, const double2* sI,
+                                           int row, double2 (&u)[8]) {
+  double2 acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = kp.u0[8 * c + j];
+#pragma unroll 2
+  for (int jj = 0; jj < nb; ++jj) {
+    const double2 ij = sI[(size_t)jj * T2_M + row];
+    const double2* z = kp.zT + jj * 16 + 8 * c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t2_cmac_sub64(acc[j], z[j], ij);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (8 * c + j < nb) u[j] = acc[j];
+}
+
 // Phase stamps of tools/phase_probe.py (instrumented build only, -DPGW_PHASE_TIMERS): thread 0 of
 // every CTA records the SM clock at the phase boundaries of its FIRST tile.
 #ifdef PGW_PHASE_TIMERS
@@ -230,9 +281,18 @@ __device__ __forceinline__ float2 t2_gh(const Tc2Consts& kc, int k) {
 #define T2_STAMP(k) do { } while (0)
 #endif
 
-template <int NCH, bool ANY_M5, bool STANDALONE, int OCC = t2_ctas_per_sm(NCH)>
+// POLISH: after the tensor-core fixed point has converged, `t.polish` sweeps of the same fixed
+// point in float64 on the SIMT pipe (Zbb, u0 and the load tables in float64 from the FP64
+// solver's feeder blob, nominal powers kept in shared memory since the prologue, currents
+// exchanged through shared memory).  The tensor core has taken the solution to ~5e-8 p.u. (the
+// split-FP16 operands carry 22 bits); every float64 sweep multiplies that error by the
+// contraction factor of the iteration (~0.2 on IEEE-13), so two sweeps reach ~3e-9 and three
+// ~6e-10 -- what the shared-penalty hook (1e4 x violation) needs for rewards within 2e-5.
+template <int NCH, bool ANY_M5, bool STANDALONE, int OCC = t2_ctas_per_sm(NCH), bool POLISH = false>
 __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
-    pf_tc2_kernel(const PfParams p, const __grid_constant__ Tc2Consts kc) {
+    pf_tc2_kernel(const PfParams p, const __grid_constant__ Tc2Consts kc,
+                  const __grid_constant__ std::conditional_t<POLISH, Tc2Polish, int> kp) {
+  static_assert(!POLISH || (NCH == 2 && !STANDALONE), "FP64 polish: <= 16 load branches, step solve");
   constexpr int G = NCH <= 4 ? 2 : 4;                  // groups of 128 threads
   constexpr int T2_THREADS = 128 * G;
   constexpr int T2_ISSUER = 4 * G - 1;                 // warp that feeds the pipelined chains
@@ -260,6 +320,10 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
   unsigned char* sA = sB + (size_t)(1 + nres) * 2 * PB;   // A_hi | A_lo
   unsigned char* sT = sA + 2 * APB;                    // tables
   double* drow = reinterpret_cast<double*>(sT + t.tab_bytes);
+  // POLISH: nominal powers s64 [16][128] (thread private, kept since the prologue) and the
+  // currents of a sweep i64 [16][128], both float64 complex
+  double2* sS64 = reinterpret_cast<double2*>(drow + hdr);
+  double2* sI64 = sS64 + (size_t)16 * T2_M;
 
   [[maybe_unused]] bool stamp_tile = true;
   [[maybe_unused]] int it_stamp = 0;
@@ -439,6 +503,8 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
             const float sh = share[k] * xs;            // 0 for the padded branches
             sr[s][jj] = (float)kwd[j] * sh;
             si[s][jj] = (float)kvd[j] * sh;
+            if constexpr (POLISH)                      // nominal power in float64 for the polish
+              sS64[(size_t)k * T2_M + row] = make_double2(kwd[j] * kp.share[k], kvd[j] * kp.share[k]);
             const float4 cc = t2_cst(kc, k);
             d0[jj] = ((float)up[j].x - cc.x) * (1.f / ds1);        // initial guess: fp32 is plenty
             d0[8 + jj] = ((float)up[j].y - cc.y) * (1.f / ds1);
@@ -572,31 +638,127 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
     // Final branch voltages: warm-start state, and the magnitudes of the nodes that ARE a
     // load branch voltage up to a real factor (wye loads: v_node = dscale * u_branch).
     float vmn = 3.0e38f, vmx = -3.0e38f;
-#pragma unroll 1                                       // executed once per tile: keep the code small
-    for (int s = 0; s < SLOTS; ++s) {
-      const int c = grp + G * s;
-      if (c < NCH) {                                   // warp-uniform: tcgen05.ld is collective
-        float dn[16];
-        t2_ld16(t_lane + last * N + 16 * c, dn);
+    [[maybe_unused]] bool chains_issued = false;
+    const bool polish = POLISH && t.polish > 0;
+    if (polish) {
+      // (a) The currents at the final voltages are in A: the expansion chains of a small feeder
+      //     (every Znb chunk resident, accumulators of their own) start now and run on the tensor
+      //     core while the SIMT pipe polishes the branch voltages.
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (t.resident && t.ncc > 0) {
+        for (int cc = 0; cc < t.ncc; ++cc)
+          issue_chain((uint32_t)((2 + cc) * N), false, (uint32_t)(1 + cc) * 2 * PB, cc + 1 == t.ncc);
+        chains_issued = true;
+      }
+      // (b) float64 sweeps u <- u0 - Zbb i(u) over my chunk's branches (G == 2, one chunk per
+      //     thread): t.polish full sweeps, then one over the rows the rewards read.  The env's
+      //     currents go through shared memory, [branch][env row] (conflict-free 16-byte accesses).
+      if constexpr (POLISH) {
+        const int c = grp;
+        double2 u[8];
+        {
+          float dn[16];
+          t2_ld16(t_lane + last * N + 16 * c, dn);
+          const double dsd = (double)ds1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const double2 b = kp.u0[8 * c + j];
+            u[j] = make_double2(b.x + (double)dn[j] * dsd, b.y + (double)dn[8 + j] * dsd);
+          }
+        }
+        const int sweeps = t.polish + ((kp.rows != 0u || t.polish_row >= 0) ? 1 : 0);
+#pragma unroll 1
+        for (int sweep = 0; sweep < sweeps; ++sweep) {
+          if (sweep > 0) __syncthreads();              // everyone has read the previous currents
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = 8 * c + j;
+            if (k < p.nb)
+              sI64[(size_t)k * T2_M + row] = t2_current64(kp.model[k], sS64[(size_t)k * T2_M + row], u[j],
+                                                          kp.vlo2[k], kp.vhi2[k]);
+          }
+          __syncthreads();
+          if (sweep == 0) T2_STAMP(14);
+          if (sweep < t.polish) {
+            t2_sweep64(kp, p.nb, c, sI64, row, u);
+            if (sweep == 0) T2_STAMP(15);
+            if (sweep + 1 == t.polish) {               // warm-start state: after the full sweeps
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (valid && 8 * c + j < p.nb) p.u_state[(size_t)(8 * c + j) * p.E + e] = u[j];
+            }
+          } else if ((kp.rows >> (8 * c)) & 0xffu) {   // warp uniform; rolled loops (cold, few rows)
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+              const int k = 8 * c + j;
+              if (!((kp.rows >> k) & 1u)) continue;
+              double2 acc = kp.u0[k];
+#pragma unroll 2
+              for (int jj = 0; jj < p.nb; ++jj)
+                t2_cmac_sub64(acc, kp.zT[jj * 16 + k], sI64[(size_t)jj * T2_M + row]);
+#pragma unroll
+              for (int q = 0; q < 8; ++q)              // u stays in registers: no dynamic index
+                if (q == j) u[q] = acc;
+            }
+          }
+        }
+        // (c) the wye-load nodes from the polished voltages
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int k = 8 * c + j;
-          const float4 c0 = t2_cst(kc, k);
-          const float ur = fmaf(dn[j], ds1, c0.x), ui = fmaf(dn[8 + j], ds1, c0.y);
-          if (valid && k < p.nb)
-            p.u_state[(size_t)k * p.E + e] = make_double2((double)ur, (double)ui);
           const int n = dnode[k];
           if (n >= 0) {
-            const float m2 = fmaf(ur, ur, ui * ui);
-            const float mag = m2 * t2_rsqrt(fmaxf(m2, 1e-30f)) * dscale[k];
-            vmn = fminf(vmn, mag);
-            vmx = fmaxf(vmx, mag);
+            const double m2 = u[j].x * u[j].x + u[j].y * u[j].y;
+            double mag;
+            if ((kp.rows >> k) & 1u) {
+              mag = sqrt(m2) * kp.dscale[k];
+            } else {                                   // float32 rsqrt + one Newton step: ~1e-14
+              const double r = (double)t2_rsqrt((float)m2);
+              const double y = m2 * r;
+              mag = fma(fma(-y, y, m2), 0.5 * r, y) * kp.dscale[k];
+            }
+            vmn = fminf(vmn, (float)mag);
+            vmx = fmaxf(vmx, (float)mag);
             if (valid) {
-              p.vmag[(size_t)n * p.E + e] = (double)mag;
-              if (!p.reward_hook) {                    // bus voltage of the agents at this node
+              p.vmag[(size_t)n * p.E + e] = mag;
+              if (!p.reward_hook) {
                 const int2 ag2 = vag[k];
-                if (ag2.x >= 0) p.vbus[(size_t)ag2.x * p.E + e] = (double)mag;
-                if (ag2.y >= 0) p.vbus[(size_t)ag2.y * p.E + e] = (double)mag;
+                if (ag2.x >= 0) p.vbus[(size_t)ag2.x * p.E + e] = mag;
+                if (ag2.y >= 0) p.vbus[(size_t)ag2.y * p.E + e] = mag;
+              }
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll 1                                       // executed once per tile: keep the code small
+      for (int s = 0; s < SLOTS; ++s) {
+        const int c = grp + G * s;
+        if (c < NCH) {                                   // warp-uniform: tcgen05.ld is collective
+          float dn[16];
+          t2_ld16(t_lane + last * N + 16 * c, dn);
+  #pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = 8 * c + j;
+            const float4 c0 = t2_cst(kc, k);
+            const float ur = fmaf(dn[j], ds1, c0.x), ui = fmaf(dn[8 + j], ds1, c0.y);
+            if (valid && k < p.nb)
+              p.u_state[(size_t)k * p.E + e] = make_double2((double)ur, (double)ui);
+            const int n = dnode[k];
+            if (n >= 0) {
+              const float m2 = fmaf(ur, ur, ui * ui);
+              const float mag = m2 * t2_rsqrt(fmaxf(m2, 1e-30f)) * dscale[k];
+              vmn = fminf(vmn, mag);
+              vmx = fmaxf(vmx, mag);
+              if (valid) {
+                p.vmag[(size_t)n * p.E + e] = (double)mag;
+                if (!p.reward_hook) {                    // bus voltage of the agents at this node
+                  const int2 ag2 = vag[k];
+                  if (ag2.x >= 0) p.vbus[(size_t)ag2.x * p.E + e] = (double)mag;
+                  if (ag2.y >= 0) p.vbus[(size_t)ag2.y * p.E + e] = (double)mag;
+                }
               }
             }
           }
@@ -608,8 +770,9 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
     __syncthreads();                                   // D[last] may be overwritten from chunk 1 on
 
     if (t.resident && t.ncc > 0) {                     // accumulators 2 + cc, one commit for all
-      for (int cc = 0; cc < t.ncc; ++cc)
-        issue_chain((uint32_t)((2 + cc) * N), false, (uint32_t)(1 + cc) * 2 * PB, cc + 1 == t.ncc);
+      if (!chains_issued)
+        for (int cc = 0; cc < t.ncc; ++cc)
+          issue_chain((uint32_t)((2 + cc) * N), false, (uint32_t)(1 + cc) * 2 * PB, cc + 1 == t.ncc);
       mbar_wait(&mbar_mma, mma_phase);
       mma_phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -666,10 +829,23 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
       p.vmax[e] = (double)mx;
       p.iters[e] = conv_ok ? my_it : -my_it;
     }
+    // Penalty node that is not a wye-load node (delta load, or no load at all): its row of the
+    // last sweep, v = w - Znb[row] i(u), from the currents still in shared memory.
+    [[maybe_unused]] double v_row = 0.0;
+    const bool have_row = POLISH && polish && t.polish_row >= 0;
+    if (POLISH && have_row) {
+      const double2* wv = reinterpret_cast<const double2*>(p.blob + p.off_w);
+      const double2* zn = reinterpret_cast<const double2*>(p.blob + p.off_znbT);
+      double2 v = wv[t.polish_row];
+      for (int jj = 0; jj < p.nb; ++jj)
+        t2_cmac_sub64(v, zn[(size_t)jj * p.nnp + t.polish_row], sI64[(size_t)jj * T2_M + row]);
+      v_row = sqrt(v.x * v.x + v.y * v.y);
+      if (valid && grp == 0) p.vmag[(size_t)t.polish_row * p.E + e] = v_row;
+    }
     if (valid) {
       double pen_share = 0.0, viol = 0.0;
       if (p.punit != 0.0) {
-        const double v = p.vmag[(size_t)p.penalty_node * p.E + e];
+        const double v = have_row ? v_row : p.vmag[(size_t)p.penalty_node * p.E + e];
         viol = fmax(0.0, fmax(p.pvlo - v, v - p.pvhi));
         pen_share = (viol * p.punit) / (double)p.A;
       }
@@ -686,7 +862,7 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
             if (a < p.A) {
               const int node = anode[a];
               const size_t ae = (size_t)a * p.E + e;
-              if (node >= 0) vb[q] = p.vmag[(size_t)node * p.E + e];
+              if (node >= 0) vb[q] = (have_row && node == t.polish_row) ? v_row : p.vmag[(size_t)node * p.E + e];
               rw[q] = p.rew[ae];
               er[q] = p.ep_ret[ae];
             }
@@ -736,11 +912,41 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
 size_t tc2_smem_bytes(const PfParams& p) {
   return (size_t)(1 + (p.tc2.resident ? p.tc2.ncc : 0)) * 2 * p.tc2.part_bytes +
          (size_t)2 * 16 * 256 * p.tc2.nch + (size_t)p.tc2.tab_bytes +
-         (size_t)(2 + 2 * p.nl) * 8 + 16;
+         (size_t)(2 + 2 * p.nl) * 8 + 16 + tc2_polish_bytes(p);
+}
+
+// FP64 polish area: s64 and i64, [16][128] complex each
+size_t tc2_polish_bytes(const PfParams& p) {
+  if (!tc2_polish_active(p)) return 0;
+  return (size_t)2 * 16 * T2_M * sizeof(double2);
+}
+
+// the polish runs in the step solve of a feeder with <= 16 load branches whose rewards depend on
+// the fresh voltages (shared-penalty hook)
+bool tc2_polish_active(const PfParams& p) {
+  return p.tc2.polish > 0 && p.tc2.nch == 2 && p.reward_hook && p.load_kw == nullptr && p.event_mode == 1;
 }
 
 int tc2_padded_chunks(int nch) {            // instantiated tile widths
   return nch <= 2 ? 2 : nch <= 4 ? 4 : nch <= 8 ? 8 : nch <= 11 ? 11 : 0;
+}
+
+template <bool M5>
+static cudaError_t launch_tc2_polish(const PfParams& p, int grid, size_t smem, cudaStream_t s) {
+  auto kern = pf_tc2_kernel<2, M5, false, 2, true>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = p.pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p, *p.tc2.consts, *p.tc2.pconsts);
 }
 
 template <int NCH, int OCC>
@@ -760,17 +966,19 @@ static cudaError_t launch_tc2_t(const PfParams& p, int grid, size_t smem, cudaSt
   attr[0].val.programmaticStreamSerializationAllowed = p.pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, p, *p.tc2.consts);
+  return cudaLaunchKernelEx(&cfg, kern, p, *p.tc2.consts, 0);
 }
 
 cudaError_t launch_powerflow_tc2(const PfParams& p, cudaStream_t s) {
   const int tiles = (p.E + T2_M - 1) / T2_M;
   // the dense build pays off when the tiles do not fit one wave of the regular one
-  const bool dense = p.tc2.nch == 2 && tiles > 148 * t2_ctas_per_sm(2) && p.tc2.tmem_cols <= 128;
+  const bool polish = tc2_polish_active(p);
+  const bool dense = !polish && p.tc2.nch == 2 && tiles > 148 * t2_ctas_per_sm(2) && p.tc2.tmem_cols <= 128;
   const int per_sm = dense ? 4 : t2_ctas_per_sm(p.tc2.nch);
   int grid = tiles < 148 * per_sm ? tiles : 148 * per_sm;
   if (grid < 1) grid = 1;
   const size_t smem = tc2_smem_bytes(p);
+  if (polish) return p.tc2.any_m5 ? launch_tc2_polish<true>(p, grid, smem, s) : launch_tc2_polish<false>(p, grid, smem, s);
   switch (p.tc2.nch) {
     case 2: return dense ? launch_tc2_t<2, 4>(p, grid, smem, s) : launch_tc2_t<2, 2>(p, grid, smem, s);
     case 4: return launch_tc2_t<4, 2>(p, grid, smem, s);

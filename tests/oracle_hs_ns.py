@@ -1,9 +1,2 @@
-"""Oracle plugin namespace for tests/scenarios_hs.py builders."""
-import types
-
-import oracle.components_hs as oh
-
-ORACLE_HS_NS = types.SimpleNamespace(
-    HSPVEnv=oh.HSPVEnv, HSEnergyStorageEnv=oh.HSEnergyStorageEnv,
-    HSEVChargingEnv=oh.HSEVChargingEnv, HSDevicesEnv=oh.HSDevicesEnv,
-    HSMultiComponentEnv=oh.HSMultiComponentEnv)
+"""Oracle Home-Steward namespace (lives in oracle/namespace.py)."""
+from oracle.namespace import ORACLE_HS_NS  # noqa: F401

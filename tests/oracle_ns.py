@@ -1,30 +1,2 @@
-"""Oracle plugin namespace for tests/scenarios.py builders."""
-import types
-
-import oracle.components as oc
-import oracle.multiagent as om
-from oracle.powerflow import OracleOpenDSSSolver
-
-ORACLE_NS = types.SimpleNamespace(
-    MultiComponentEnv=oc.MultiComponentEnv,
-    FiveZoneROMThermalEnergyEnv=oc.FiveZoneROMThermalEnergyEnv,
-    PVEnv=oc.PVEnv, GridAwarePVEnv=oc.GridAwarePVEnv, EnergyStorageEnv=oc.EnergyStorageEnv,
-    EVChargingEnv=oc.EVChargingEnv, MultiAgentEnv=om.MultiAgentEnv,
-    CoordinatedMultiBuildingControlEnv=om.CoordinatedMultiBuildingControlEnv,
-    OpenDSSSolver=OracleOpenDSSSolver)
-
-
-def storage_socs_to_dict(env, socs):
-    """Flat SOC vector (agent order, component order) -> oracle ``init_storage`` dict."""
-    out, k = {}, 0
-    for a in env.agents:
-        comps = getattr(a, "envs", None)
-        for e in (comps if comps is not None else [a]):
-            if isinstance(e, oc.EnergyStorageEnv):
-                if comps is None:
-                    out[a.name] = socs[k]
-                else:
-                    out.setdefault(a.name, {})[e.name] = socs[k]
-                k += 1
-    assert k == len(socs)
-    return out
+"""Oracle plugin namespace (lives in oracle/namespace.py)."""
+from oracle.namespace import ORACLE_NS, storage_socs_to_dict  # noqa: F401

@@ -352,7 +352,10 @@ def test_tensor_core_power_flow_matches_fp64_kernel(name, E, kernel):
                                    a_env.get_field(3).cpu().numpy(), rtol=0, atol=1e-6,
                                    err_msg=f"voltages t={t}")
         np.testing.assert_allclose(ob.cpu().numpy(), oa.cpu().numpy(), rtol=0, atol=2e-5)
-        np.testing.assert_allclose(rb.cpu().numpy(), ra.cpu().numpy(), rtol=1e-5, atol=1e-2)
+        # kernel 2 = what bench.py runs: its float64 polish holds the rewards to the float64
+        # solver's bound; kernel 1 (split-TF32, no polish) keeps the 1e4 x voltage floor
+        np.testing.assert_allclose(rb.cpu().numpy(), ra.cpu().numpy(), rtol=1e-5,
+                                   atol=2e-5 if kernel == 2 else 1e-2, err_msg=f"rewards t={t}")
     it = b_env.get_field(7)
     assert int(it.min()) > 0, "tensor-core solve did not converge"
     assert float(it.double().mean()) < 25
@@ -373,7 +376,7 @@ def test_tensor_core_golden_trace_within_north_star_tolerances(kernel):
         ob, rew, dn, _ = env.step(unflatten_action(env, g["actions"][t]))
         np.testing.assert_allclose(flat_obs(env, ob), g["obs"][t], rtol=0, atol=1e-5)
         np.testing.assert_allclose([rew[a.name] for a in env.agents], g["rew"][t],
-                                   rtol=1e-5, atol=1e-2)
+                                   rtol=1e-5, atol=2e-5 if kernel == 2 else 1e-2)
         if t % 50 == 0:
             v = env.voltages
             np.testing.assert_allclose([v[k] for k in names], g["volt"][t + 1], rtol=0, atol=1e-4)

@@ -1,7 +1,7 @@
 import sys, time; sys.path.insert(0,'/root/repo')
 import numpy as np, torch
-from tests import scenarios as S
-from tests.product_ns import PRODUCT_NS as NS
+from powergridworld_b200.scenarios import catalog as S
+from powergridworld_b200.scenarios.namespace import PRODUCT_NS as NS
 E=4096
 env = NS.CoordinatedMultiBuildingControlEnv(**S.buildings_scenario(NS, NS.OpenDSSSolver, 1.2), num_envs=E, pf_kernel="tc2")
 soc = np.full((env.num_storage,E),30.0)

@@ -2,8 +2,8 @@
 import sys, os, warnings
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from tests import scenarios as S
-from tests.product_ns import PRODUCT_NS as NS
+from powergridworld_b200.scenarios import catalog as S
+from powergridworld_b200.scenarios.namespace import PRODUCT_NS as NS
 from powergridworld_b200 import _native as N
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 2

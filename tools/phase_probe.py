@@ -21,8 +21,8 @@ import torch  # noqa: E402
 from powergridworld_b200 import _native as N  # noqa: E402
 
 N.LIB_PATH = os.path.join(ROOT, "tools", "_build", "libpgw_b200_phases.so")
-from tests import scenarios as S  # noqa: E402
-from tests.product_ns import PRODUCT_NS as NS  # noqa: E402
+from powergridworld_b200.scenarios import catalog as S  # noqa: E402
+from powergridworld_b200.scenarios.namespace import PRODUCT_NS as NS  # noqa: E402
 
 PHASES = ["clock read", "barrier init + TMA issue + prefetch + TMEM alloc", "wait tables/event row",
           "tile inputs + first currents + A", "first chain issue", "fixed-point loop",
@@ -32,6 +32,7 @@ PHASES = ["clock read", "barrier init + TMA issue + prefetch + TMEM alloc", "wai
 
 def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "c1"
+    polish = int(os.environ.get("PGW_POLISH", "-1"))
     E = int(sys.argv[2]) if len(sys.argv) > 2 else (4096 if wl == "c1" else 16384)
     import warnings
     warnings.simplefilter("ignore")
@@ -40,6 +41,8 @@ def main():
             **S.buildings_scenario(NS, NS.OpenDSSSolver, 1.2), num_envs=E, pf_kernel="tc2")
     else:
         env = NS.MultiAgentEnv(**S.der123_scenario(NS, NS.OpenDSSSolver), num_envs=E, pf_kernel="tc2")
+    if polish >= 0:
+        env.set_option(N.OPT_PF_POLISH, polish)
     lib = env._lib
     lib.pgw_debug_phases.restype = C.c_int
     lib.pgw_debug_phases.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -101,6 +104,11 @@ def main():
               f"iterations of the stamped tile: mean {a[:, :, 11].mean():.2f}")
         for k, name in enumerate(PHASES):
             print(f"  {name:52s} mean {d[:, :, k].mean():7.2f} us   max-CTA mean {d[:, :, k].max(axis=1).mean():7.2f} us")
+        if (a[:, :, 14] > 0).all():                              # FP64 polish stamps (inside "branch state")
+            pol = np.stack([a[:, :, 14] - a[:, :, 6], a[:, :, 15] - a[:, :, 14], a[:, :, 7] - a[:, :, 15]], axis=2) / mhz
+            for k, name in enumerate(["  polish: chains + u64 + currents of sweep 0", "  polish: full sweep 0 (matvec)",
+                                      "  polish: remaining sweeps + magnitudes"]):
+                print(f"  {name:52s} mean {pol[:, :, k].mean():7.2f} us   max-CTA mean {pol[:, :, k].max(axis=1).mean():7.2f} us")
         tot = (a[:, :, 10] - a[:, :, 0]) / mhz
         print(f"  {'entry -> exit':52s} mean {tot.mean():7.2f} us   max-CTA mean {tot.max(axis=1).mean():7.2f} us")
 

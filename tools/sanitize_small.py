@@ -10,10 +10,10 @@ import numpy as np
 import torch
 
 from powergridworld_b200 import _native as N
-from tests import scenarios as S
-from tests import scenarios_hs as SH
-from tests.product_hs_ns import PRODUCT_HS_NS as HNS
-from tests.product_ns import PRODUCT_NS as PNS
+from powergridworld_b200.scenarios import catalog as S
+from powergridworld_b200.scenarios import catalog_hs as SH
+from powergridworld_b200.scenarios.namespace import PRODUCT_HS_NS as HNS
+from powergridworld_b200.scenarios.namespace import PRODUCT_NS as PNS
 from powergridworld_b200.base_hs import house_agent_config
 
 rng = np.random.default_rng(0)

@@ -315,6 +315,11 @@ long long pgw_launch_count(const pgw_env* env);
                                  i.e. rewards within rtol 1e-5 / atol 2e-5.  0 = off (~5e-8 p.u.)       */
 #define PGW_OPT_PF_TC_TOL_NANO 6 /* convergence threshold max|du| of the tcgen05 solvers in units of
                                  1e-9 p.u. (default 100 = 1e-7, the split-FP16 operands' floor)          */
+#define PGW_OPT_FUSED 7       /* the whole step in one kernel (component steps -> tcgen05 power flow ->
+                                 float64 polish -> rewards per 32-env tile), for feeders with <= 16 load
+                                 branches, stock components and power-flow kernel 2: 0 = off, 1 (default)
+                                 = when the batch is at most two tiles per SM (<= 9472 envs), 2 = always.
+                                 Returns PGW_ERR_INVALID for 2 when the scenario is not eligible.        */
 int pgw_set_option(pgw_env* env, int option, int value);
 
 /* Per-kernel device timing for benchmarks: when enabled, every launch of pgw_step is

@@ -104,6 +104,10 @@ struct pgw_env {
   std::vector<StepGraph> graphs;
   bool use_graphs = true;
   bool use_pdl = true;
+  // fused step kernel (step_fused.cu): eligible scenario, and PGW_OPT_FUSED (0 off, 1 auto: batches
+  // of at most two 32-env tiles per SM, 2 always)
+  bool fused_ok = false;
+  int fused_mode = 1, fused_tmem_cols = 0;
   bool clip_init_soc = true;
   // device state
   double* sd = nullptr;
@@ -708,6 +712,24 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       if (pgw::tc2_smem_bytes(probe) + 6 * 1024 <= 227 * 1024) {   // + the kernel's static arrays
         PGW_TRY(upload(&env->tc2_blob, blob.data(), blob.size())); env->own(env->tc2_blob);
         env->tc2.blob = env->tc2_blob;
+        // The fused step kernel serves feeders with <= 16 load branches whose Znb chunks stay
+        // resident, stock components on their straight-line paths, tables that fit shared memory.
+        bool ok = nch == 2 && t.resident && !env->has_house && !env->need_scratch &&
+                  32 * (1 + ncc) <= 512;
+        for (int c = 0; c < spec->num_components && ok; ++c) {
+          const pgw_component& k = spec->components[c];
+          ok = k.type >= PGW_STORAGE && k.type <= PGW_BUILDING &&
+               (k.type != PGW_BUILDING || (k.flags & PGW_F_BUILDING_FAST));
+        }
+        if (ok) {
+          env->fused_tmem_cols = 32;
+          while (env->fused_tmem_cols < 32 * (1 + ncc)) env->fused_tmem_cols *= 2;
+          pgw::FusedParams P{};
+          P.c.blob_bytes = env->comp_blob_bytes; P.c.dstride = env->dstride; P.c.istride = env->istride;
+          P.f.tc2 = t; P.C = env->C;
+          ok = pgw::step_fused_smem_bytes(P) + 2048 <= 200 * 1024;
+        }
+        env->fused_ok = ok;
       }
     }
     PGW_TRY(alloc_zero(&env->vmag, (size_t)nn * E)); env->own(env->vmag);
@@ -851,8 +873,41 @@ static int enqueue_powerflow(pgw_env* env, double* rew, cudaStream_t s, bool tim
   return PGW_OK;
 }
 
+static bool use_fused(const pgw_env* env) {
+  if (!env->fused_ok || env->pf_kernel != 2 || env->fused_mode == 0) return false;
+  return env->fused_mode == 2 || pgw::step_fused_tiles(env->E) <= 2 * 148;
+}
+
+// One launch of the fused step kernel over the envs [e_lo, e_hi); `tickets` = CTAs of all the
+// launches that make up the step (the one that takes the last ticket advances the clock).
+static int fused_grid(int envs) { return std::max(1, std::min(pgw::step_fused_tiles(envs), 148)); }
+
+static int enqueue_fused(pgw_env* env, const double* actions, double* obs, double* rew, uint8_t* done,
+                         int e_lo, int e_hi, unsigned int tickets, cudaStream_t s) {
+  pgw::FusedParams P{};
+  P.c = comp_params(env);
+  P.c.event_mode = 1; P.c.actions = actions; P.c.obs = obs; P.c.rew = rew; P.c.done = done;
+  P.f = pf_params(env);
+  P.f.event_mode = 1; P.f.advance_clock = 1; P.f.agent_p = env->agent_p; P.f.rew = rew;
+  P.f.reward_hook = (env->punit != 0.0) ? 1 : 0;
+  P.f.warm_start = env->warm_start ? 1 : 0;
+  P.C = env->C; P.e_lo = e_lo; P.e_hi = e_hi; P.tmem_cols = env->fused_tmem_cols; P.tickets = tickets;
+  PGW_CUDA(pgw::launch_step_fused(P, fused_grid(e_hi - e_lo), s));
+  return PGW_OK;
+}
+
 static int enqueue_step(pgw_env* env, const double* actions, double* obs, double* rew,
                         uint8_t* done, cudaStream_t s, bool timed) {
+  if (use_fused(env)) {
+    if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
+    int rc = enqueue_fused(env, actions, obs, rew, done, 0, env->E, (unsigned int)fused_grid(env->E), s);
+    if (rc) return rc;
+    if (timed) {                                       // one kernel: reported as the component slot
+      PGW_CUDA(cudaEventRecord(env->next_event(), s));
+      PGW_CUDA(cudaEventRecord(env->next_event(), s));
+    }
+    return PGW_OK;
+  }
   if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
   int rc = enqueue_components(env, actions, obs, rew, done, s, pdl_trigger_mode(env, timed));
   if (rc) return rc;
@@ -869,7 +924,7 @@ int pgw_step(pgw_env* env, const double* actions, double* obs, double* rew, uint
   if (env->clock + 1 >= env->num_events)
     return fail(PGW_ERR_STATE, "episode is over: call pgw_reset");
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-  const int kernels = env->has_feeder ? 2 : 1;
+  const int kernels = use_fused(env) ? 1 : (env->has_feeder ? 2 : 1);
 
   // Replay a captured graph of the step when one exists for these buffers (the episode
   // clock lives on the device, so the launch parameters of a step never change).
@@ -942,7 +997,7 @@ int pgw_step_host(pgw_env* env, const double* actions, double* obs, double* rew,
   const size_t E = (size_t)env->E;
   PGW_CUDA(cudaMemcpyAsync(env->h_act, actions, (size_t)env->act_dim * E * 8,
                            cudaMemcpyHostToDevice, s));
-  if (!env->has_feeder || env->timing) {
+  if (!env->has_feeder || env->timing || use_fused(env)) {
     rc = pgw_step(env, env->h_act, env->h_obs, env->h_rew, env->h_done, s);
     if (rc) return rc;
     PGW_CUDA(cudaMemcpyAsync(obs, env->h_obs, (size_t)env->obs_dim * E * 8, cudaMemcpyDeviceToHost, s));
@@ -1158,6 +1213,12 @@ int pgw_set_option(pgw_env* env, int option, int value) {
     case PGW_OPT_WARM_START: env->warm_start = value != 0; break;
     case PGW_OPT_GRAPHS: env->use_graphs = value != 0; break;
     case PGW_OPT_PDL: env->use_pdl = value != 0; break;
+    case PGW_OPT_FUSED:
+      if (value < 0 || value > 2) return fail(PGW_ERR_INVALID, "PGW_OPT_FUSED takes 0, 1 or 2");
+      if (value == 2 && !env->fused_ok)
+        return fail(PGW_ERR_INVALID, "the fused step kernel does not serve this scenario");
+      env->fused_mode = value;
+      break;
     case PGW_OPT_PF_POLISH:
       if (value < 0 || value > 8) return fail(PGW_ERR_INVALID, "polish sweeps out of range (0..8)");
       if (value > 0 && !env->tc2.polish_ok)

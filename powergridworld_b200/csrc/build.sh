@@ -13,6 +13,7 @@ mkdir -p "$BUILD"
 "$NVCC" $COMMON ${PTXAS_V:+-Xptxas -v} -c "$HERE/powerflow.cu" -o "$BUILD/powerflow.o"
 "$NVCC" $COMMON ${PTXAS_V:+-Xptxas -v} -c "$HERE/powerflow_tc.cu" -o "$BUILD/powerflow_tc.o"
 "$NVCC" $COMMON ${PTXAS_V:+-Xptxas -v} -c "$HERE/powerflow_tc2.cu" -o "$BUILD/powerflow_tc2.o"
+"$NVCC" $COMMON -fmad=false ${PTXAS_V:+-Xptxas -v} -c "$HERE/step_fused.cu" -o "$BUILD/step_fused.o"
 "$NVCC" $COMMON -c "$HERE/api.cu" -o "$BUILD/api.o"
-"$NVCC" -shared $ARCH -o "$OUT" "$BUILD/components.o" "$BUILD/powerflow.o" "$BUILD/powerflow_tc.o" "$BUILD/powerflow_tc2.o" "$BUILD/api.o" -lcudart
+"$NVCC" -shared $ARCH -o "$OUT" "$BUILD/components.o" "$BUILD/powerflow.o" "$BUILD/powerflow_tc.o" "$BUILD/powerflow_tc2.o" "$BUILD/step_fused.o" "$BUILD/api.o" -lcudart
 echo "built $OUT"

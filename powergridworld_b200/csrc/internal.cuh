@@ -151,6 +151,16 @@ struct PfParams {
   unsigned int* ticket;
 };
 
+// One launch of the fused step kernel (step_fused.cu) over the envs [e_lo, e_hi).
+struct FusedParams {
+  CompParams c;            // component side: tables, event rows, caller buffers, state
+  PfParams f;              // power-flow side: tc2 tables and images, voltages, penalty hook
+  int C;                   // components per env
+  int e_lo, e_hi;
+  int tmem_cols;           // 32 x (1 + Znb chunks), rounded up to a power of two
+  unsigned int tickets;    // CTAs of all launches of this step (the last one advances the clock)
+};
+
 struct StatsParams {
   int E, A, nn;
   const double* rew;
@@ -175,5 +185,8 @@ constexpr int kTc2MaxChunks = 11;   // 88 load branches: B and A images fill sha
 constexpr int kTcNb = 16;      // branch slots of the tensor-core kernel (IEEE-13 class feeders)
 constexpr int kTcK3 = 96;      // 3 x 32: [x_hi | x_lo | x_hi] against [B_hi ; B_hi ; B_lo]
 cudaError_t launch_stats(const StatsParams& p, cudaStream_t s);
+cudaError_t launch_step_fused(const FusedParams& P, int grid, cudaStream_t s);
+size_t step_fused_smem_bytes(const FusedParams& P);
+int step_fused_tiles(int envs);
 
 }  // namespace pgw

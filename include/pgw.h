@@ -247,8 +247,9 @@ int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stre
 int pgw_step(pgw_env* env, const double* actions, double* obs, double* rew,
              uint8_t* done, void* cuda_stream);
 
-/* Same two calls with HOST buffers (pinned memory recommended): copies in, runs,
- * copies out and synchronises the stream -- the end-to-end path. */
+/* Same two calls with HOST buffers: results are on the host when the call returns (the stream is
+ * synchronised) -- the end-to-end path.  Page-locked buffers are read and written in place by the
+ * kernels (PGW_OPT_HOST_ZERO_COPY); pageable ones are staged with copies. */
 int pgw_reset_host(pgw_env* env, const double* init_soc, double* obs, void* cuda_stream);
 int pgw_step_host(pgw_env* env, const double* actions, double* obs, double* rew,
                   uint8_t* done, void* cuda_stream);
@@ -296,8 +297,9 @@ long long pgw_launch_count(const pgw_env* env);
                                  point with the Z-bus resident in shared memory, feeders with
                                  <= 88 load branches (123-bus class)                          */
 #define PGW_OPT_WARM_START 1  /* 1 (default): each solve starts from the env's previous solution */
-#define PGW_OPT_GRAPHS 2      /* 1 (default): pgw_step replays a captured CUDA graph per distinct
-                                 (actions, obs, rew, done) pointer set; needs a non-default stream */
+#define PGW_OPT_GRAPHS 2      /* 1 (default): pgw_step replays ONE captured CUDA graph per handle, its kernel
+                                 nodes re-pointed (cudaGraphExecKernelNodeSetParams) whenever the caller's
+                                 (actions, obs, rew, done) pointers change; needs a non-default stream  */
 #define PGW_OPT_PDL 3         /* 1 (default): the tcgen05 power-flow kernel of a step is launched as a
                                  programmatic dependent of the component kernel, which releases it
                                  early (griddepcontrol.launch_dependents): the power-flow prologue
@@ -320,6 +322,14 @@ long long pgw_launch_count(const pgw_env* env);
                                  branches, stock components and power-flow kernel 2: 0 = off, 1 (default)
                                  = when the batch is at most two tiles per SM (<= 9472 envs), 2 = always.
                                  Returns PGW_ERR_INVALID for 2 when the scenario is not eligible.        */
+#define PGW_OPT_HOST_CHUNKS 8 /* env chunks the staged form of pgw_step_host pipelines (copy-in of chunk k+1 |
+                                 kernels of chunk k | copy-out of chunk k-1 on streams of their own):
+                                 0 (default) = automatic (4 once the observations of a step exceed 32 MB,
+                                 else 1: a copy costs ~8 us of fixed latency), up to 8                    */
+#define PGW_OPT_HOST_ZERO_COPY 9 /* 1 (default): when all four buffers of pgw_step_host are page-locked host
+                                 memory the GPU can address (cudaHostAlloc / cudaHostRegister, torch
+                                 pin_memory()), the step's kernels read and write them in place over PCIe;
+                                 0, or pageable buffers: staged through device buffers with copies         */
 int pgw_set_option(pgw_env* env, int option, int value);
 
 /* Per-kernel device timing for benchmarks: when enabled, every launch of pgw_step is

@@ -23,7 +23,7 @@ F_TELEMETRY, HS_TEL_ROWS = 32, 13
 F_RESCALE, F_GRID_AWARE, F_PV_VOLT_REWARD, F_STALE_REWARD, F_BUILDING_FAST = 1, 2, 4, 8, 16
 
 OPT_PF_KERNEL, OPT_WARM_START, OPT_GRAPHS, OPT_PDL, OPT_CLIP_INIT_SOC = 0, 1, 2, 3, 4
-OPT_PF_POLISH, OPT_PF_TC_TOL_NANO, OPT_FUSED = 5, 6, 7
+OPT_PF_POLISH, OPT_PF_TC_TOL_NANO, OPT_FUSED, OPT_HOST_CHUNKS, OPT_HOST_ZERO_COPY = 5, 6, 7, 8, 9
 
 (FIELD_STATE_D, FIELD_STATE_I, FIELD_AGENT_P, FIELD_VOLTAGES, FIELD_VMIN, FIELD_VMAX,
  FIELD_VBUS, FIELD_PF_ITERS, FIELD_EP_RETURN, FIELD_PF_STATE) = range(10)

@@ -96,12 +96,42 @@ struct pgw_env {
   pgw::Tc2Params tc2{};
   pgw::Tc2Consts tc2c{};
   pgw::Tc2Polish tc2p{};
-  // CUDA graphs of a step, keyed by the caller's buffer pointers
+  // The captured CUDA graph of a step: ONE per handle; its kernel nodes are re-pointed at the
+  // caller's buffers when those change (kind: 0 fused step, 1 components, 2 power flow)
   struct StepGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t nodes[2] = {nullptr, nullptr};
+    cudaKernelNodeParams params[2] = {};
+    int kind[2] = {0, 0}, nargs[2] = {1, 1}, num_nodes = 0, pdl = 0;
+    const void *actions = nullptr, *obs = nullptr, *rew = nullptr, *done = nullptr;
+    void destroy() {
+      if (exec) cudaGraphExecDestroy(exec);
+      if (graph) cudaGraphDestroy(graph);
+      exec = nullptr; graph = nullptr; num_nodes = 0;
+    }
+  };
+  StepGraph step_graph;
+  // graphs of the pipelined host-buffer step, keyed by the host pointers (memcpy nodes)
+  struct HostGraph {
     const void *actions, *obs, *rew, *done;
     cudaGraphExec_t exec;
   };
-  std::vector<StepGraph> graphs;
+  std::vector<HostGraph> host_graphs;
+  static constexpr int kMaxChunks = 8;
+  int host_chunks = 0;                  // PGW_OPT_HOST_CHUNKS: 0 = automatic
+  bool host_zero_copy = true;           // PGW_OPT_HOST_ZERO_COPY
+  // device views of the caller's host buffers (cudaPointerGetAttributes is a driver query:
+  // remembered per pointer; nullptr = not page-locked / not device accessible)
+  struct HostView { const void* host; void* dev; };
+  std::vector<HostView> host_views;
+  cudaStream_t chunk_stream[kMaxChunks] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {};
+  void drop_graphs() {
+    step_graph.destroy();
+    for (auto& g : host_graphs) cudaGraphExecDestroy(g.exec);
+    host_graphs.clear();
+  }
   bool use_graphs = true;
   bool use_pdl = true;
   // fused step kernel (step_fused.cu): eligible scenario, and PGW_OPT_FUSED (0 off, 1 auto: batches
@@ -121,8 +151,6 @@ struct pgw_env {
   // staging for the *_host entry points
   double *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_soc = nullptr;
   uint8_t* h_done = nullptr;
-  cudaStream_t copy_stream = nullptr;   // pgw_step_host: observation copy-out behind the power flow
-  cudaEvent_t ev_comp = nullptr, ev_copy = nullptr;
   std::vector<void*> owned;
   // optional per-kernel timing (pgw_set_timing)
   bool timing = false;
@@ -133,10 +161,12 @@ struct pgw_env {
   ~pgw_env() {
     for (void* p : owned) cudaFree(p);
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
-    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
-    if (ev_comp) cudaEventDestroy(ev_comp);
-    if (ev_copy) cudaEventDestroy(ev_copy);
-    if (copy_stream) cudaStreamDestroy(copy_stream);
+    drop_graphs();
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (int k = 0; k < kMaxChunks; ++k) {
+      if (ev_join[k]) cudaEventDestroy(ev_join[k]);
+      if (chunk_stream[k]) cudaStreamDestroy(chunk_stream[k]);
+    }
   }
   cudaEvent_t next_event() {
     if (ev_used == ev_pool.size()) {
@@ -726,7 +756,7 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
           while (env->fused_tmem_cols < 32 * (1 + ncc)) env->fused_tmem_cols *= 2;
           pgw::FusedParams P{};
           P.c.blob_bytes = env->comp_blob_bytes; P.c.dstride = env->dstride; P.c.istride = env->istride;
-          P.f.tc2 = t; P.C = env->C;
+          P.f.tc2 = t; P.C = env->C; P.act_dim = env->act_dim;
           ok = pgw::step_fused_smem_bytes(P) + 2048 <= 200 * 1024;
         }
         env->fused_ok = ok;
@@ -757,7 +787,7 @@ int pgw_destroy(pgw_env* env) {
 
 static pgw::CompParams comp_params(pgw_env* env) {
   pgw::CompParams p{};
-  p.E = env->E; p.A = env->A;
+  p.E = env->E; p.A = env->A; p.e_lo = 0; p.e_hi = env->E; p.tickets = (unsigned int)env->num_ctas;
   p.blob = env->comp_blob; p.blob_bytes = env->comp_blob_bytes;
   p.off_comps = env->off_comps; p.off_dpar = env->off_dpar; p.off_ipar = env->off_ipar;
   p.work = env->work; p.num_ctas = env->num_ctas; p.max_cn = env->max_cn; p.max_dn = env->max_dn; p.max_in = env->max_in;
@@ -775,6 +805,7 @@ static pgw::CompParams comp_params(pgw_env* env) {
 
 static pgw::PfParams pf_params(pgw_env* env) {
   pgw::PfParams p{};
+  p.e_lo = 0; p.e_hi = env->E;
   p.E = env->E; p.A = env->A; p.nb = env->nb; p.nn = env->nn; p.nl = env->nl;
   p.nbp = env->nbp; p.nnp = env->nnp; p.max_iter = env->max_iter; p.tol = env->tol;
   p.blob = env->pf_blob; p.blob_bytes = env->pf_blob_bytes; p.stage_blob = env->pf_stage;
@@ -801,7 +832,14 @@ static pgw::PfParams pf_params(pgw_env* env) {
   return p;
 }
 
-static cudaError_t launch_pf(const pgw_env* env, const pgw::PfParams& pf, cudaStream_t s) {
+static int pf_grid(const pgw_env* env, const pgw::PfParams& pf) {
+  if (env->pf_kernel == 2) return pgw::tc2_grid(pf);
+  return env->pf_kernel == 1 ? pgw::tc_grid(pf) : pgw::fp64_grid(pf);
+}
+
+// pf.tickets == 0: this launch is the only one of its kind in the step
+static cudaError_t launch_pf(const pgw_env* env, pgw::PfParams pf, cudaStream_t s) {
+  if (pf.tickets == 0u) pf.tickets = (unsigned int)pf_grid(env, pf);
   if (env->pf_kernel == 2) return pgw::launch_powerflow_tc2(pf, s);
   return env->pf_kernel == 1 ? pgw::launch_powerflow_tc(pf, s) : pgw::launch_powerflow(pf, s);
 }
@@ -837,23 +875,23 @@ int pgw_reset(pgw_env* env, const double* init_soc, double* obs, void* cuda_stre
   return PGW_OK;
 }
 
-// The kernels of one step, enqueued on `s` (directly, or while `s` is being captured).
-static int enqueue_components(pgw_env* env, const double* actions, double* obs, double* rew,
-                              uint8_t* done, cudaStream_t s, int pdl_trigger = 0) {
+// ---- launch parameters of the kernels of one step over the envs [e_lo, e_hi)
+static pgw::CompParams step_comp_params(pgw_env* env, const double* actions, double* obs, double* rew,
+                                        uint8_t* done, int e_lo, int e_hi, int chunks, int pdl_trigger) {
   pgw::CompParams cp = comp_params(env);
   const bool hook = env->has_feeder && env->punit != 0.0;   // power flow finishes the rewards
   cp.event_mode = 1; cp.advance_clock = env->has_feeder ? 0 : 1; cp.owns_reward = hook ? 0 : 1;
   cp.actions = actions; cp.obs = obs; cp.rew = rew; cp.done = done;
   cp.pdl_trigger = pdl_trigger;
-  PGW_CUDA(pgw::launch_components(cp, smem_for_events(env), s));
-  return PGW_OK;
+  cp.e_lo = e_lo; cp.e_hi = e_hi; cp.tickets = (unsigned int)(env->num_ctas * chunks);
+  return cp;
 }
 
 // Programmatic dependent launch of the tcgen05 power-flow kernel behind the component kernel.
-// Used when a power-flow CTA leaves room on its SM (<= 64 kB of shared memory: IEEE-13 class
-// feeders); a CTA that fills the SM's shared memory gains nothing from starting early and was
-// measured 2 us slower per step at C3.  The component kernel releases the dependent right after
-// its clock read when both grids fit on the GPU side by side (1), else at the end of each CTA (2).
+// Used when a power-flow CTA leaves room on its SM (IEEE-13 class feeders); a CTA that fills the
+// SM's shared memory gains nothing from starting early and was measured 2 us slower per step at
+// C3.  The component kernel releases the dependent right after its clock read when both grids fit
+// on the GPU side by side (1), else at the end of each CTA (2).
 // Measured (C1, cold L2): 27.5 -> 25.6 us per step at 4096 envs, 40.1 -> 37.9 us at 32 768.
 static int pdl_trigger_mode(const pgw_env* env, bool timed) {
   if (!env->use_pdl || timed || !env->has_feeder || env->pf_kernel != 2) return 0;
@@ -863,14 +901,16 @@ static int pdl_trigger_mode(const pgw_env* env, bool timed) {
   return env->num_ctas <= 148 * 4 ? 1 : 2;
 }
 
-static int enqueue_powerflow(pgw_env* env, double* rew, cudaStream_t s, bool timed) {
+static pgw::PfParams step_pf_params(pgw_env* env, double* rew, int e_lo, int e_hi, unsigned int tickets,
+                                    bool pdl) {
   pgw::PfParams pf = pf_params(env);
   pf.event_mode = 1; pf.advance_clock = 1; pf.agent_p = env->agent_p; pf.rew = rew;
   pf.reward_hook = (env->punit != 0.0) ? 1 : 0;
-  pf.pdl = pdl_trigger_mode(env, timed) != 0 ? 1 : 0;
+  pf.pdl = pdl ? 1 : 0;
   pf.warm_start = env->warm_start ? 1 : 0;
-  PGW_CUDA(launch_pf(env, pf, s));
-  return PGW_OK;
+  pf.e_lo = e_lo; pf.e_hi = e_hi;
+  pf.tickets = tickets ? tickets : (unsigned int)pf_grid(env, pf);
+  return pf;
 }
 
 static bool use_fused(const pgw_env* env) {
@@ -878,42 +918,133 @@ static bool use_fused(const pgw_env* env) {
   return env->fused_mode == 2 || pgw::step_fused_tiles(env->E) <= 2 * 148;
 }
 
-// One launch of the fused step kernel over the envs [e_lo, e_hi); `tickets` = CTAs of all the
-// launches that make up the step (the one that takes the last ticket advances the clock).
 static int fused_grid(int envs) { return std::max(1, std::min(pgw::step_fused_tiles(envs), 148)); }
 
-static int enqueue_fused(pgw_env* env, const double* actions, double* obs, double* rew, uint8_t* done,
-                         int e_lo, int e_hi, unsigned int tickets, cudaStream_t s) {
+// `tickets` = CTAs of all the launches that make up the step (the CTA that takes the last ticket
+// advances the clock); 0 = this launch is the whole step.
+static pgw::FusedParams step_fused_params(pgw_env* env, const double* actions, double* obs, double* rew,
+                                          uint8_t* done, int e_lo, int e_hi, unsigned int tickets,
+                                          int stagger = 0) {
   pgw::FusedParams P{};
-  P.c = comp_params(env);
-  P.c.event_mode = 1; P.c.actions = actions; P.c.obs = obs; P.c.rew = rew; P.c.done = done;
-  P.f = pf_params(env);
-  P.f.event_mode = 1; P.f.advance_clock = 1; P.f.agent_p = env->agent_p; P.f.rew = rew;
-  P.f.reward_hook = (env->punit != 0.0) ? 1 : 0;
-  P.f.warm_start = env->warm_start ? 1 : 0;
-  P.C = env->C; P.e_lo = e_lo; P.e_hi = e_hi; P.tmem_cols = env->fused_tmem_cols; P.tickets = tickets;
-  PGW_CUDA(pgw::launch_step_fused(P, fused_grid(e_hi - e_lo), s));
-  return PGW_OK;
+  P.c = step_comp_params(env, actions, obs, rew, done, e_lo, e_hi, 1, 0);
+  P.f = step_pf_params(env, rew, e_lo, e_hi, 1u, false);
+  P.C = env->C; P.act_dim = env->act_dim; P.e_lo = e_lo; P.e_hi = e_hi; P.tmem_cols = env->fused_tmem_cols;
+  P.tickets = tickets ? tickets : (unsigned int)fused_grid(e_hi - e_lo);
+  P.stagger_cycles = stagger;
+  return P;
+}
+
+// The kernels of one step over [e_lo, e_hi), enqueued on `s` (directly, or while `s` is being
+// captured).  chunks = launches of this kind that make up the step (pgw_step_host pipelines
+// env chunks); their CTA counts add up to the clock tickets.
+static unsigned int step_pf_tickets(pgw_env* env, const int* bounds, int chunks) {
+  unsigned int n = 0;
+  for (int k = 0; k < chunks; ++k) {
+    if (use_fused(env)) {
+      n += (unsigned int)fused_grid(bounds[k + 1] - bounds[k]);
+    } else {
+      pgw::PfParams pf = pf_params(env);
+      pf.event_mode = 1; pf.reward_hook = (env->punit != 0.0) ? 1 : 0;
+      pf.e_lo = bounds[k]; pf.e_hi = bounds[k + 1];
+      n += (unsigned int)pf_grid(env, pf);
+    }
+  }
+  return n;
 }
 
 static int enqueue_step(pgw_env* env, const double* actions, double* obs, double* rew,
-                        uint8_t* done, cudaStream_t s, bool timed) {
+                        uint8_t* done, cudaStream_t s, bool timed, int e_lo = 0, int e_hi = -1,
+                        int chunks = 1, unsigned int pf_tickets = 0u, int stagger = 0) {
+  if (e_hi < 0) e_hi = env->E;
   if (use_fused(env)) {
     if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
-    int rc = enqueue_fused(env, actions, obs, rew, done, 0, env->E, (unsigned int)fused_grid(env->E), s);
-    if (rc) return rc;
-    if (timed) {                                       // one kernel: reported as the component slot
+    const pgw::FusedParams P = step_fused_params(env, actions, obs, rew, done, e_lo, e_hi, pf_tickets, stagger);
+    PGW_CUDA(pgw::launch_step_fused(P, fused_grid(e_hi - e_lo), s));
+    if (timed) {                                       // one kernel: reported in the component slot
       PGW_CUDA(cudaEventRecord(env->next_event(), s));
       PGW_CUDA(cudaEventRecord(env->next_event(), s));
     }
     return PGW_OK;
   }
+  const int pdl = chunks == 1 ? pdl_trigger_mode(env, timed) : 0;
   if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
-  int rc = enqueue_components(env, actions, obs, rew, done, s, pdl_trigger_mode(env, timed));
-  if (rc) return rc;
+  PGW_CUDA(pgw::launch_components(step_comp_params(env, actions, obs, rew, done, e_lo, e_hi, chunks, pdl),
+                                  smem_for_events(env), s));
   if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
-  if (env->has_feeder && (rc = enqueue_powerflow(env, rew, s, timed))) return rc;
+  if (env->has_feeder)
+    PGW_CUDA(launch_pf(env, step_pf_params(env, rew, e_lo, e_hi, pf_tickets, pdl != 0), s));
   if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
+  return PGW_OK;
+}
+
+static int step_kernels(const pgw_env* env) { return use_fused(env) ? 1 : (env->has_feeder ? 2 : 1); }
+
+// Re-point the kernel nodes of the captured step graph at another set of caller buffers
+// (cudaGraphExecKernelNodeSetParams: no re-capture, no re-instantiation; a policy loop that
+// hands in a fresh action tensor every step replays the same executable graph).
+static int retarget_step_graph(pgw_env* env, const double* actions, double* obs, double* rew,
+                               uint8_t* done) {
+  pgw_env::StepGraph& g = env->step_graph;
+  for (int i = 0; i < g.num_nodes; ++i) {
+    cudaKernelNodeParams np = g.params[i];
+    void* args[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int q = 1; q < g.nargs[i]; ++q) args[q] = g.params[i].kernelParams[q];
+    pgw::FusedParams fp;
+    pgw::CompParams cp;
+    pgw::PfParams pf;
+    if (g.kind[i] == 0) {
+      fp = step_fused_params(env, actions, obs, rew, done, 0, env->E, 0u);
+      args[0] = &fp;
+    } else if (g.kind[i] == 1) {
+      cp = step_comp_params(env, actions, obs, rew, done, 0, env->E, 1, g.pdl);
+      args[0] = &cp;
+    } else {
+      pf = step_pf_params(env, rew, 0, env->E, 0u, g.pdl != 0);
+      args[0] = &pf;
+    }
+    np.kernelParams = args;
+    np.extra = nullptr;
+    PGW_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.nodes[i], &np));
+  }
+  g.actions = actions; g.obs = obs; g.rew = rew; g.done = done;
+  return PGW_OK;
+}
+
+static int capture_step_graph(pgw_env* env, const double* actions, double* obs, double* rew,
+                              uint8_t* done, cudaStream_t s) {
+  pgw_env::StepGraph& g = env->step_graph;
+  g.destroy();
+  g.pdl = pdl_trigger_mode(env, false);
+  PGW_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_step(env, actions, obs, rew, done, s, false);
+  cudaError_t ce = cudaStreamEndCapture(s, &g.graph);
+  if (rc != PGW_OK) { g.destroy(); return rc; }
+  if (ce != cudaSuccess) {
+    g.destroy();
+    return fail(PGW_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+  }
+  ce = cudaGraphInstantiate(&g.exec, g.graph, 0);
+  if (ce != cudaSuccess) {
+    g.destroy();
+    return fail(PGW_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+  }
+  cudaGraphNode_t nodes[8];
+  size_t n = 8;
+  PGW_CUDA(cudaGraphGetNodes(g.graph, nodes, &n));
+  g.num_nodes = 0;
+  for (size_t i = 0; i < n; ++i) {
+    cudaGraphNodeType ty;
+    PGW_CUDA(cudaGraphNodeGetType(nodes[i], &ty));
+    if (ty != cudaGraphNodeTypeKernel) continue;
+    if (g.num_nodes == 2) { g.destroy(); return fail(PGW_ERR_CUDA, "unexpected step graph"); }
+    const int q = g.num_nodes++;
+    g.nodes[q] = nodes[i];
+    PGW_CUDA(cudaGraphKernelNodeGetParams(nodes[i], &g.params[q]));
+    if (pgw::is_step_fused_kernel(g.params[q].func)) { g.kind[q] = 0; g.nargs[q] = 3; }
+    else if (pgw::is_component_kernel(g.params[q].func)) { g.kind[q] = 1; g.nargs[q] = 1; }
+    else { g.kind[q] = 2; g.nargs[q] = env->pf_kernel == 2 ? 3 : 1; }
+  }
+  g.actions = actions; g.obs = obs; g.rew = rew; g.done = done;
   return PGW_OK;
 }
 
@@ -924,39 +1055,26 @@ int pgw_step(pgw_env* env, const double* actions, double* obs, double* rew, uint
   if (env->clock + 1 >= env->num_events)
     return fail(PGW_ERR_STATE, "episode is over: call pgw_reset");
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-  const int kernels = use_fused(env) ? 1 : (env->has_feeder ? 2 : 1);
 
-  // Replay a captured graph of the step when one exists for these buffers (the episode
-  // clock lives on the device, so the launch parameters of a step never change).
+  // Replay the captured graph of the step (the episode clock lives on the device, so the launch
+  // parameters of a step change only with the caller's buffers, and those are patched in place).
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   PGW_CUDA(cudaStreamIsCapturing(s, &cap));
   const bool graphable = env->use_graphs && !env->timing && cap == cudaStreamCaptureStatusNone &&
                          s != nullptr;
   if (graphable) {
-    cudaGraphExec_t exec = nullptr;
-    for (auto& g : env->graphs)
-      if (g.actions == actions && g.obs == obs && g.rew == rew && g.done == done) exec = g.exec;
-    if (!exec) {
-      cudaGraph_t graph = nullptr;
-      PGW_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      int rc = enqueue_step(env, actions, obs, rew, done, s, false);
-      cudaError_t ce = cudaStreamEndCapture(s, &graph);
-      if (rc != PGW_OK) return rc;
-      if (ce != cudaSuccess) return fail(PGW_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
-      PGW_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-      cudaGraphDestroy(graph);
-      if (env->graphs.size() >= 256) {               // bounded cache
-        cudaGraphExecDestroy(env->graphs.front().exec);
-        env->graphs.erase(env->graphs.begin());
-      }
-      env->graphs.push_back({actions, obs, rew, done, exec});
-    }
-    PGW_CUDA(cudaGraphLaunch(exec, s));
+    pgw_env::StepGraph& g = env->step_graph;
+    int rc = PGW_OK;
+    if (!g.exec) rc = capture_step_graph(env, actions, obs, rew, done, s);
+    else if (g.actions != actions || g.obs != obs || g.rew != rew || g.done != done)
+      rc = retarget_step_graph(env, actions, obs, rew, done);
+    if (rc != PGW_OK) return rc;
+    PGW_CUDA(cudaGraphLaunch(g.exec, s));
   } else {
     int rc = enqueue_step(env, actions, obs, rew, done, s, env->timing);
     if (rc != PGW_OK) return rc;
   }
-  env->launches += kernels;
+  env->launches += step_kernels(env);
   ++env->clock;
   return PGW_OK;
 }
@@ -988,49 +1106,204 @@ int pgw_reset_host(pgw_env* env, const double* init_soc, double* obs, void* cuda
   return PGW_OK;
 }
 
+// ---- end-to-end step with host buffers, pipelined over env chunks.
+// Chunk k: actions of its envs in (a strided copy over the rows x E pitch), the step's kernels on
+// that env range, observations / rewards / done flags out -- every chunk on a stream of its own,
+// so that the copy-in of chunk k+1, the kernels of chunk k and the copy-out of chunk k-1 overlap
+// (PCIe is full duplex, the copy engines are independent of the SMs).  The whole fork-join is
+// captured once per set of host buffers and replayed as one graph launch.
+static int host_chunks(const pgw_env* env) {
+  if (env->timing || (env->has_feeder && env->pf_kernel == 1)) return 1;   // kernel 1 has no env ranges
+  if (env->host_chunks > 0) return std::min(env->host_chunks, pgw_env::kMaxChunks);
+  // Every copy costs ~8 us of fixed latency on top of its bytes (measured, C1: 94 us per step
+  // with one chunk, 120 with four): chunks pay off only when a chunk's copy-out is several MB
+  const size_t out = (size_t)env->obs_dim * (size_t)env->E * 8;
+  return out >= ((size_t)32 << 20) ? 4 : 1;
+}
+
+// Device-side address of a host buffer if the GPU can access it in place (page-locked memory
+// under unified addressing: cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory()), else null.
+static void* device_view(pgw_env* env, const void* host) {
+  for (const auto& v : env->host_views)
+    if (v.host == host) return v.dev;
+  void* dev = nullptr;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost)
+    dev = at.devicePointer;
+  else
+    cudaGetLastError();                                // pageable memory: not an error of ours
+  if (env->host_views.size() < 64) env->host_views.push_back({host, dev});
+  return dev;
+}
+
+static int enqueue_host_step(pgw_env* env, const double* actions, double* obs, double* rew,
+                             uint8_t* done, cudaStream_t s) {
+  const int E = env->E, nch = host_chunks(env);
+  int bounds[pgw_env::kMaxChunks + 1];
+  const int per = ((E + nch - 1) / nch + 127) / 128 * 128;          // whole 128-env tiles
+  for (int k = 0; k <= nch; ++k) bounds[k] = std::min(E, k * per);
+  const unsigned int tickets = env->has_feeder ? step_pf_tickets(env, bounds, nch) : 0u;
+  const size_t pitch = (size_t)E * 8;
+  if (nch > 1) PGW_CUDA(cudaEventRecord(env->ev_fork, s));
+  for (int k = 0; k < nch; ++k) {
+    const int e0 = bounds[k], e1 = bounds[k + 1];
+    if (e1 <= e0) continue;
+    cudaStream_t ck = nch > 1 ? env->chunk_stream[k] : s;
+    if (nch > 1) PGW_CUDA(cudaStreamWaitEvent(ck, env->ev_fork, 0));
+    const size_t w8 = (size_t)(e1 - e0) * 8;
+    PGW_CUDA(cudaMemcpy2DAsync(env->h_act + e0, pitch, actions + e0, pitch, w8, (size_t)env->act_dim,
+                               cudaMemcpyHostToDevice, ck));
+    int rc = enqueue_step(env, env->h_act, env->h_obs, env->h_rew, env->h_done, ck, env->timing, e0, e1,
+                          nch, tickets);
+    if (rc) return rc;
+    PGW_CUDA(cudaMemcpy2DAsync(obs + e0, pitch, env->h_obs + e0, pitch, w8, (size_t)env->obs_dim,
+                               cudaMemcpyDeviceToHost, ck));
+    PGW_CUDA(cudaMemcpy2DAsync(rew + e0, pitch, env->h_rew + e0, pitch, w8, (size_t)env->A,
+                               cudaMemcpyDeviceToHost, ck));
+    PGW_CUDA(cudaMemcpyAsync(done + e0, env->h_done + e0, (size_t)(e1 - e0), cudaMemcpyDeviceToHost, ck));
+    if (nch > 1) {
+      PGW_CUDA(cudaEventRecord(env->ev_join[k], ck));
+      PGW_CUDA(cudaStreamWaitEvent(s, env->ev_join[k], 0));
+    }
+  }
+  return PGW_OK;
+}
+
+// The step on page-locked host buffers the GPU addresses in place.  With the fused kernel the
+// batch runs as a chain of env chunks on one stream, each launch a programmatic dependent of the
+// previous one that is released as soon as its predecessor has READ its actions: chunk k+1's
+// action reads (host -> GPU) then overlap chunk k's observation writes (GPU -> host); a single
+// launch does all its reads first and all its writes last (measured, C1 at 4096 envs: 66 us per
+// step in one launch = 18 compute + 17 reads + 27 writes, nothing overlapping).
+static int zero_copy_chunks(const pgw_env* env) {
+  if (!use_fused(env)) return 1;
+  // (measured: a chain of chunks pays ~10 us per link for its own reads; staggering the tiles of
+  // ONE launch gets the overlap without it.  The chain stays available as an option.)
+  return env->host_chunks > 0 ? std::min(env->host_chunks, pgw_env::kMaxChunks) : 1;
+}
+
+static int enqueue_zero_copy(pgw_env* env, const double* actions, double* obs, double* rew, uint8_t* done,
+                             cudaStream_t s) {
+  const int E = env->E, nch = zero_copy_chunks(env);
+  // one tile's actions (act_dim x 256 B) at ~48 GB/s of PCIe reads, in cycles of the 1.965 GHz SM clock
+  int per_row = 10;
+  if (const char* v = getenv("PGW_STAGGER_CYCLES_PER_ROW")) per_row = atoi(v);   // tuning knob
+  const int stagger = env->act_dim * per_row;
+  if (nch == 1) return enqueue_step(env, actions, obs, rew, done, s, false, 0, -1, 1, 0u, stagger);
+  int bounds[pgw_env::kMaxChunks + 1];
+  const int per = ((E + nch - 1) / nch + 31) / 32 * 32;             // whole 32-env tiles
+  for (int k = 0; k <= nch; ++k) bounds[k] = std::min(E, k * per);
+  unsigned int tickets = 0;
+  for (int k = 0; k < nch; ++k)
+    if (bounds[k + 1] > bounds[k]) tickets += (unsigned int)fused_grid(bounds[k + 1] - bounds[k]);
+  bool first = true;
+  for (int k = 0; k < nch; ++k) {
+    if (bounds[k + 1] <= bounds[k]) continue;
+    pgw::FusedParams P = step_fused_params(env, actions, obs, rew, done, bounds[k], bounds[k + 1], tickets);
+    P.pdl_trigger = 1;
+    PGW_CUDA(pgw::launch_step_fused(P, fused_grid(bounds[k + 1] - bounds[k]), s, !first));
+    first = false;
+  }
+  return PGW_OK;
+}
+
+static int zero_copy_step(pgw_env* env, const double* actions, double* obs, double* rew, uint8_t* done,
+                          cudaStream_t s) {
+  const int nch = zero_copy_chunks(env);
+  if (env->clock < 0) return fail(PGW_ERR_STATE, "pgw_step before pgw_reset");
+  if (env->clock + 1 >= env->num_events) return fail(PGW_ERR_STATE, "episode is over: call pgw_reset");
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  PGW_CUDA(cudaStreamIsCapturing(s, &cap));
+  cudaGraphExec_t exec = nullptr;
+  if (env->use_graphs && cap == cudaStreamCaptureStatusNone && s != nullptr) {
+    for (auto& g : env->host_graphs)
+      if (g.actions == actions && g.obs == obs && g.rew == rew && g.done == done) exec = g.exec;
+    if (!exec && env->host_graphs.size() < 8) {        // a few pinned buffer sets; beyond: direct
+      cudaGraph_t graph = nullptr;
+      PGW_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue_zero_copy(env, actions, obs, rew, done, s);
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc != PGW_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return fail(PGW_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) return fail(PGW_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+      env->host_graphs.push_back({actions, obs, rew, done, exec});
+    }
+  }
+  if (exec) {
+    PGW_CUDA(cudaGraphLaunch(exec, s));
+  } else {
+    int rc = enqueue_zero_copy(env, actions, obs, rew, done, s);
+    if (rc) return rc;
+  }
+  env->launches += nch * step_kernels(env);
+  ++env->clock;
+  return PGW_OK;
+}
+
 int pgw_step_host(pgw_env* env, const double* actions, double* obs, double* rew, uint8_t* done,
                   void* cuda_stream) {
   if (!env || !actions || !obs || !rew || !done) return fail(PGW_ERR_INVALID, "null argument");
-  int rc = ensure_staging(env);
-  if (rc) return rc;
-  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-  const size_t E = (size_t)env->E;
-  PGW_CUDA(cudaMemcpyAsync(env->h_act, actions, (size_t)env->act_dim * E * 8,
-                           cudaMemcpyHostToDevice, s));
-  if (!env->has_feeder || env->timing || use_fused(env)) {
-    rc = pgw_step(env, env->h_act, env->h_obs, env->h_rew, env->h_done, s);
-    if (rc) return rc;
-    PGW_CUDA(cudaMemcpyAsync(obs, env->h_obs, (size_t)env->obs_dim * E * 8, cudaMemcpyDeviceToHost, s));
-    PGW_CUDA(cudaMemcpyAsync(rew, env->h_rew, (size_t)env->A * E * 8, cudaMemcpyDeviceToHost, s));
-    PGW_CUDA(cudaMemcpyAsync(done, env->h_done, E, cudaMemcpyDeviceToHost, s));
-    PGW_CUDA(cudaStreamSynchronize(s));
-    return PGW_OK;
-  }
-  // With a feeder the observations and done flags are final after the component kernel (the
-  // power flow only touches rewards and the voltages the NEXT step observes): their copy to
-  // the host runs on a second stream while the power flow is solved.
   if (env->clock < 0) return fail(PGW_ERR_STATE, "pgw_step before pgw_reset");
   if (env->clock + 1 >= env->num_events)
     return fail(PGW_ERR_STATE, "episode is over: call pgw_reset");
-  if (!env->copy_stream) {
-    PGW_CUDA(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
-    PGW_CUDA(cudaEventCreateWithFlags(&env->ev_comp, cudaEventDisableTiming));
-    PGW_CUDA(cudaEventCreateWithFlags(&env->ev_copy, cudaEventDisableTiming));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  int rc;
+  if (env->host_zero_copy && !env->timing) {
+    // Page-locked host buffers: the kernels read the actions and write the observations,
+    // rewards and done flags in place over PCIe (coalesced 256-byte requests; reads and posted
+    // writes of different CTAs overlap in both directions of the link) -- no staging copies,
+    // none of their ~8 us of fixed latency each.
+    void* da = device_view(env, actions);
+    void* dobs = device_view(env, obs);
+    void* dr = device_view(env, rew);
+    void* dd = device_view(env, done);
+    if (da && dobs && dr && dd) {
+      rc = zero_copy_step(env, static_cast<const double*>(da), static_cast<double*>(dobs),
+                          static_cast<double*>(dr), static_cast<uint8_t*>(dd), s);
+      if (rc) return rc;
+      PGW_CUDA(cudaStreamSynchronize(s));
+      return PGW_OK;
+    }
   }
-  if ((rc = enqueue_components(env, env->h_act, env->h_obs, env->h_rew, env->h_done, s))) return rc;
-  PGW_CUDA(cudaEventRecord(env->ev_comp, s));
-  PGW_CUDA(cudaStreamWaitEvent(env->copy_stream, env->ev_comp, 0));
-  // (one copy: splitting the observations over two streams / copy engines was measured slower,
-  // 96 vs 90 us per step at C1)
-  PGW_CUDA(cudaMemcpyAsync(obs, env->h_obs, (size_t)env->obs_dim * E * 8, cudaMemcpyDeviceToHost,
-                           env->copy_stream));
-  PGW_CUDA(cudaMemcpyAsync(done, env->h_done, E, cudaMemcpyDeviceToHost, env->copy_stream));
-  PGW_CUDA(cudaEventRecord(env->ev_copy, env->copy_stream));
-  if ((rc = enqueue_powerflow(env, env->h_rew, s, false))) return rc;
-  PGW_CUDA(cudaMemcpyAsync(rew, env->h_rew, (size_t)env->A * E * 8, cudaMemcpyDeviceToHost, s));
-  PGW_CUDA(cudaStreamWaitEvent(s, env->ev_copy, 0));
+  rc = ensure_staging(env);
+  if (rc) return rc;
+  if (!env->ev_fork) {
+    PGW_CUDA(cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming));
+    for (int k = 0; k < pgw_env::kMaxChunks; ++k) {
+      PGW_CUDA(cudaStreamCreateWithFlags(&env->chunk_stream[k], cudaStreamNonBlocking));
+      PGW_CUDA(cudaEventCreateWithFlags(&env->ev_join[k], cudaEventDisableTiming));
+    }
+  }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  PGW_CUDA(cudaStreamIsCapturing(s, &cap));
+  const bool graphable = env->use_graphs && !env->timing && cap == cudaStreamCaptureStatusNone &&
+                         s != nullptr;
+  cudaGraphExec_t exec = nullptr;
+  if (graphable) {
+    for (auto& g : env->host_graphs)
+      if (g.actions == actions && g.obs == obs && g.rew == rew && g.done == done) exec = g.exec;
+    if (!exec && env->host_graphs.size() < 8) {        // a few pinned buffer sets; beyond: direct
+      cudaGraph_t graph = nullptr;
+      PGW_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      rc = enqueue_host_step(env, actions, obs, rew, done, s);
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc != PGW_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return fail(PGW_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) return fail(PGW_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+      env->host_graphs.push_back({actions, obs, rew, done, exec});
+    }
+  }
+  if (exec) {
+    PGW_CUDA(cudaGraphLaunch(exec, s));
+  } else if ((rc = enqueue_host_step(env, actions, obs, rew, done, s))) {
+    return rc;
+  }
   PGW_CUDA(cudaStreamSynchronize(s));
-  env->launches += 2;
+  env->launches += step_kernels(env) * host_chunks(env);
   ++env->clock;
   return PGW_OK;
 }
@@ -1213,6 +1486,11 @@ int pgw_set_option(pgw_env* env, int option, int value) {
     case PGW_OPT_WARM_START: env->warm_start = value != 0; break;
     case PGW_OPT_GRAPHS: env->use_graphs = value != 0; break;
     case PGW_OPT_PDL: env->use_pdl = value != 0; break;
+    case PGW_OPT_HOST_ZERO_COPY: env->host_zero_copy = value != 0; break;
+    case PGW_OPT_HOST_CHUNKS:
+      if (value < 0 || value > pgw_env::kMaxChunks) return fail(PGW_ERR_INVALID, "0 (automatic) .. 8 chunks");
+      env->host_chunks = value;
+      break;
     case PGW_OPT_FUSED:
       if (value < 0 || value > 2) return fail(PGW_ERR_INVALID, "PGW_OPT_FUSED takes 0, 1 or 2");
       if (value == 2 && !env->fused_ok)
@@ -1232,8 +1510,7 @@ int pgw_set_option(pgw_env* env, int option, int value) {
     default: return fail(PGW_ERR_INVALID, "unknown option");
   }
   // the captured graphs bake the options in
-  for (auto& g : env->graphs) cudaGraphExecDestroy(g.exec);
-  env->graphs.clear();
+  env->drop_graphs();
   return PGW_OK;
 }
 

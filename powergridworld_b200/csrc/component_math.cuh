@@ -51,7 +51,9 @@ struct AgentIO {
   int E;
   // The arrays never alias each other; telling the compiler lets it overlap the many
   // independent load -> divide -> store chains of one agent (the kernel is latency bound).
-  const double* PGW_RESTRICT actions;   // [act_dim][E]   (unused at reset)
+  const double* PGW_RESTRICT actions;   // [act_dim][aE], env e at column e - ae0 (unused at reset): the
+  int aE, ae0;                          // caller's [act_dim][E] array (aE = E, ae0 = 0) or a tile of it
+                                        // staged in shared memory (step_fused.cu)
   double* PGW_RESTRICT obs;             // [obs_dim][E]
   double* PGW_RESTRICT sd;              // [sd_rows][E]
   uint32_t* PGW_RESTRICT si;            // [si_rows][E]
@@ -69,6 +71,11 @@ struct AgentIO {
 };
 
 PGW_HD double clip(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+
+// action row `row` of env e
+PGW_HD double act_in(const AgentIO& io, int row, int e) {
+  return io.actions[(size_t)row * io.aE + (e - io.ae0)];
+}
 
 // x / d when r = RN(1/d) was computed on the host: one multiply plus one FMA-based
 // correction (Markstein) returns the correctly rounded IEEE quotient, i.e. the same bits
@@ -109,7 +116,7 @@ PGW_HD void storage_step(const pgw_component& c, const AgentIO& io, int e, doubl
   const double* dp = io.dpar + c.dpar_off;
   const double lo = dp[0], hi = dp[1], eta_c = dp[2], eta_d = dp[3], pmax = dp[4], dt = dp[5];
   const double inv_eta_d = dp[8], inv_dt = dp[9];
-  double a = io.actions[(size_t)c.act_off * io.E + e];
+  double a = act_in(io, c.act_off, e);
   if (c.flags & PGW_F_RESCALE) a = to_raw(a, -1.0, 1.0);
   double* soc_p = io.sd + (size_t)c.sd_off * io.E + e;
   double soc = *soc_p;
@@ -145,7 +152,7 @@ PGW_HD void pv_obs(const pgw_component& c, const AgentIO& io, int e, double raw_
 
 PGW_HD void pv_step(const pgw_component& c, const AgentIO& io, int e, double& p_out,
                     double& rew) {
-  double a = io.actions[(size_t)c.act_off * io.E + e];
+  double a = act_in(io, c.act_off, e);
   if (c.flags & PGW_F_RESCALE) a = to_raw(a, 0.0, 1.0);
   const double raw_power = -io.drow[c.dtab_off];      // obs of the PRE-increment row (:143)
   pv_obs(c, io, e, raw_power);
@@ -260,7 +267,7 @@ PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double 
 PGW_HD void ev_step(const pgw_component& c, const AgentIO& io, int e, double& p_out,
                     double& rew) {
   const double* dp = io.dpar + c.dpar_off;
-  double a = io.actions[(size_t)c.act_off * io.E + e];
+  double a = act_in(io, c.act_off, e);
   if (c.flags & PGW_F_RESCALE) a = to_raw(a, 0.0, 1.0);
   ev_advance(c, io, e, (a * dp[0]) * dp[1], p_out, rew);      // :182-183
 }
@@ -413,7 +420,7 @@ PGW_HD void building_step(const pgw_component& c, const AgentIO& io, int e, doub
   for (int i = 0; i < 6; ++i) {                         // action bounds :22-26
     const double lo = i < 4 ? 0.22 : (i == 4 ? 0.32 : 10.0);
     const double hi = i < 4 ? 2.2 : (i == 4 ? 3.2 : 16.0);
-    const double a = io.actions[(size_t)(c.act_off + i) * io.E + e];
+    const double a = act_in(io, c.act_off + i, e);
     const double raw = rs ? to_raw(a, lo, hi) : a;
     scr[BSCR_ACT + i] = raw;
     if (i < 5) flow = i == 0 ? raw : flow + raw;
@@ -470,12 +477,11 @@ PGW_HD void building_step_fast(const pgw_component& c, const AgentIO& io, int e,
   const double kLow[6] = {0.22, 0.22, 0.22, 0.22, 0.32, 10.0};      // action bounds :22-26
   const double kHigh[6] = {2.2, 2.2, 2.2, 2.2, 3.2, 16.0};
 
-  const double* ap = io.actions + (size_t)c.act_off * E + e;
   double* sp = io.sd + (size_t)c.sd_off * E + e;
   double act[6], x[5], T[5], Tn[5];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
-    const double a = ap[i * E];
+    const double a = act_in(io, c.act_off + i, e);
     act[i] = rs ? to_raw(a, kLow[i], kHigh[i]) : a;
   }
 #pragma unroll
@@ -608,7 +614,7 @@ PGW_HD void hs_pv_step(const pgw_component& c, const AgentIO& io, int e, HsMeta&
     p_out = 0.0;
     return;
   }
-  double a = io.actions[(size_t)c.act_off * io.E + e];
+  double a = act_in(io, c.act_off, e);
   if (rs) a = to_raw(a, 0.98, 1.0);                    // :100-101, :140-141
   const double p = a * (-raw);                         // :149
   m.pv_power = p;                                      // :153
@@ -649,7 +655,7 @@ PGW_HD void hs_storage_step(const pgw_component& c, const AgentIO& io, int e, Hs
   const double lo = dp[0], hi = dp[1], eta_c = dp[2], eta_d = dp[3], pmax = dp[4], dt = dp[5];
   double* sd = io.sd + (size_t)c.sd_off * io.E + e;
   double soc = sd[0], cost = sd[(size_t)1 * io.E];
-  double a = io.actions[(size_t)c.act_off * io.E + e];
+  double a = act_in(io, c.act_off, e);
   if (c.flags & PGW_F_RESCALE) a = to_raw(a, -1.0, 1.0);
   double power = a * pmax;
   // validate_power :111-143
@@ -813,7 +819,7 @@ PGW_HD void hs_devices_step(const pgw_component& c, const AgentIO& io, int e, Hs
         rs ? to_scaled(row[j], 0.0, dp[1 + j], dp[1 + k + j]) : row[j];
   p_out = 0.0;
   if (reset) return;
-  double a = io.actions[(size_t)c.act_off * io.E + e];
+  double a = act_in(io, c.act_off, e);
   if (rs) a = to_raw(a, 0.99, 1.0);                    // devices_env_hs.py:98-99
   double total = 0.0;
   for (int j = 0; j < k; ++j) total += row[k + j];     // :165
@@ -863,7 +869,7 @@ PGW_HD void house_step(const pgw_agent& ag, const pgw_component* comps, const Ag
       case PGW_HS_PV: hs_pv_step<TEL>(c, io, e, m, false, p); break;
       case PGW_HS_STORAGE: hs_storage_step<TEL>(c, io, e, m, p); break;
       case PGW_HS_EV: {
-        double a = io.actions[(size_t)c.act_off * io.E + e];
+        double a = act_in(io, c.act_off, e);
         if (c.flags & PGW_F_RESCALE) a = to_raw(a, 0.0, 1.0);
         hs_ev_advance<TEL>(c, io, e, a, m, false, p);
         break;

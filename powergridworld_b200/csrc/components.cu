@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
   io.scr.stride = blockDim.x;
   io.E = p.E;
   io.actions = p.actions;
+  io.aE = p.E;
+  io.ae0 = 0;
   io.obs = p.obs;
   io.sd = p.sd;
   io.si = p.si;
@@ -108,9 +110,9 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
 
   // Persistent CTA: the tables are staged once, then the CTA walks env blocks of its agent.
   bool first = true;
-  for (int e = wk.j * blockDim.x + threadIdx.x; e - (int)threadIdx.x < p.E;
+  for (int e = p.e_lo + wk.j * blockDim.x + threadIdx.x; e - (int)threadIdx.x < p.e_hi;
        e += wk.n * blockDim.x) {
-    if (e < p.E && p.event_mode != 0) {
+    if (e < p.e_hi && p.event_mode != 0) {
       // pull this thread's action and (small) state rows towards the SM early
       for (int ci = ag.comp_begin; ci < ag.comp_end; ++ci) {
         const pgw_component c = comps[ci];
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
       first = false;
       C_STAMP(5);
     }
-    if (e < p.E) {
+    if (e < p.e_hi) {
       const size_t ae = (size_t)a * p.E + e;
       if (p.event_mode == 0) {
         if (HOUSE && is_house(ag, comps)) house_reset<TEL>(ag, comps, io, e, p.first_reset != 0);
@@ -153,10 +155,15 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
   C_STAMP(6);
   if (p.pdl_trigger == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (p.advance_clock && threadIdx.x == 0)
-    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, gridDim.x);
+    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, p.tickets);
 #ifdef PGW_PHASE_TIMERS
   if (p.phase_clk != nullptr && threadIdx.x == 0) p.phase_clk[(size_t)blockIdx.x * 8 + 1] = (long long)global_timer_ns();
 #endif
+}
+
+bool is_component_kernel(const void* func) {
+  return func == (const void*)component_kernel<false, false> || func == (const void*)component_kernel<true, false> ||
+         func == (const void*)component_kernel<true, true>;
 }
 
 cudaError_t launch_components(const CompParams& p, int smem_bytes, cudaStream_t s) {

@@ -26,6 +26,9 @@ struct CtaWork {
 
 struct CompParams {
   int E, A;
+  int e_lo, e_hi;          // env range of this launch (pgw_step_host pipelines chunks of envs); E stays
+                           // the row stride of every per-env array
+  unsigned int tickets;    // CTAs of all launches of the step's last kernel (clock advance)
   int event_mode;          // 0 = reset (event row 0), 1 = step (event row clock+1)
   int advance_clock;       // 1 when this kernel is the last one of the step (no feeder)
   int clip_init_soc;       // reset: clip init_soc to each storage's range (PGW_OPT_CLIP_INIT_SOC)
@@ -106,6 +109,8 @@ struct Tc2Params {
 
 struct PfParams {
   int E, A, nb, nn, nl, nbp, nnp, max_iter;
+  int e_lo, e_hi;          // env range of this launch; E stays the row stride
+  unsigned int tickets;    // CTAs of all launches of the step's last kernel (clock advance)
   double tol;
   int event_mode;          // 0 = reset (base load only, event row 0), 1 = step
   int advance_clock;
@@ -156,9 +161,15 @@ struct FusedParams {
   CompParams c;            // component side: tables, event rows, caller buffers, state
   PfParams f;              // power-flow side: tc2 tables and images, voltages, penalty hook
   int C;                   // components per env
+  int act_dim;             // action rows per env
   int e_lo, e_hi;
   int tmem_cols;           // 32 x (1 + Znb chunks), rounded up to a power of two
   unsigned int tickets;    // CTAs of all launches of this step (the last one advances the clock)
+  int stagger_cycles;      // CTA b delays the fetch of its first tile's actions by b x this many SM
+                           // cycles (actions in host memory: requests served in tile order, so that
+                           // the first tiles write their observations while the last ones still read)
+  int pdl_trigger;         // 1: griddepcontrol.launch_dependents once the CTA has consumed the actions of
+                           // its last tile (the next env chunk's launch may start: pgw_step_host)
 };
 
 struct StatsParams {
@@ -178,6 +189,9 @@ cudaError_t launch_powerflow(const PfParams& p, cudaStream_t s);
 cudaError_t launch_powerflow_tc(const PfParams& p, cudaStream_t s);
 cudaError_t launch_powerflow_tc2(const PfParams& p, cudaStream_t s);
 size_t tc2_smem_bytes(const PfParams& p);
+int tc2_grid(const PfParams& p);        // CTAs launch_powerflow_tc2 uses for p's env range
+int fp64_grid(const PfParams& p);       // the same for launch_powerflow
+int tc_grid(const PfParams& p);         // and for launch_powerflow_tc (whole batch only)
 size_t tc2_polish_bytes(const PfParams& p);
 bool tc2_polish_active(const PfParams& p);
 int tc2_padded_chunks(int nch);      // instantiated tile width for nch chunks of 8 branches (0 = none)
@@ -185,8 +199,10 @@ constexpr int kTc2MaxChunks = 11;   // 88 load branches: B and A images fill sha
 constexpr int kTcNb = 16;      // branch slots of the tensor-core kernel (IEEE-13 class feeders)
 constexpr int kTcK3 = 96;      // 3 x 32: [x_hi | x_lo | x_hi] against [B_hi ; B_hi ; B_lo]
 cudaError_t launch_stats(const StatsParams& p, cudaStream_t s);
-cudaError_t launch_step_fused(const FusedParams& P, int grid, cudaStream_t s);
+cudaError_t launch_step_fused(const FusedParams& P, int grid, cudaStream_t s, bool programmatic = false);
 size_t step_fused_smem_bytes(const FusedParams& P);
 int step_fused_tiles(int envs);
+bool is_step_fused_kernel(const void* func);   // graph node identification (api.cu)
+bool is_component_kernel(const void* func);
 
 }  // namespace pgw

@@ -128,11 +128,11 @@ __global__ void __launch_bounds__(256, 2) pf_fixed_point_kernel(const PfParams p
     for (int j = 0; j < TPE; ++j) zr[j] = zbbT[(size_t)j * nbp + lane];
   }
 
-  const int groups = (p.E + EPB - 1) / EPB;
+  const int groups = (p.e_hi - p.e_lo + EPB - 1) / EPB;
   for (int g = blockIdx.x; g < groups; g += gridDim.x) {
-    const int e_raw = g * EPB + le;
-    const bool valid = e_raw < p.E;
-    const int e = valid ? e_raw : p.E - 1;
+    const int e_raw = p.e_lo + g * EPB + le;
+    const bool valid = e_raw < p.e_hi;
+    const int e = valid ? e_raw : p.e_hi - 1;
 
     // ---- per-branch nominal power: base load of the event + the agents on that load
     double2 s[R], u[R], u0[R];
@@ -287,22 +287,22 @@ __global__ void __launch_bounds__(256, 2) pf_fixed_point_kernel(const PfParams p
     __syncthreads();
     for (int idx = threadIdx.x; idx < p.nn * EPB; idx += blockDim.x) {
       const int n = idx / EPB, j = idx % EPB;
-      const int ee = g * EPB + j;
-      if (ee < p.E) p.vmag[(size_t)n * p.E + ee] = stage_all[(size_t)j * p.nn + n];
+      const int ee = p.e_lo + g * EPB + j;
+      if (ee < p.e_hi) p.vmag[(size_t)n * p.E + ee] = stage_all[(size_t)j * p.nn + n];
     }
     __syncthreads();
   }
   if (p.advance_clock && threadIdx.x == 0)
-    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, gridDim.x);
+    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, p.tickets);
 }
+
+int fp64_grid(const PfParams& p);
 
 template <int TPE, int R, bool ZREG>
 static cudaError_t launch_pf_t(const PfParams& p, cudaStream_t s) {
   const int threads = 256;
   const int epb = threads / TPE;
-  const int groups = (p.E + epb - 1) / epb;
-  int grid = groups < 148 * 4 ? groups : 148 * 4;
-  if (grid < 1) grid = 1;
+  const int grid = fp64_grid(p);
   const size_t smem = (size_t)(p.stage_blob ? p.blob_bytes : 0) + (size_t)(2 + 2 * p.nl) * 8 +
                       (size_t)epb * p.nbp * sizeof(double2) + (size_t)epb * p.nn * sizeof(double);
   if (smem > 48 * 1024) {
@@ -312,6 +312,14 @@ static cudaError_t launch_pf_t(const PfParams& p, cudaStream_t s) {
   }
   pf_fixed_point_kernel<TPE, R, ZREG><<<grid, threads, smem, s>>>(p);
   return cudaGetLastError();
+}
+
+int fp64_grid(const PfParams& p) {
+  const int tpe = p.nbp == 16 ? 16 : 32;
+  const int epb = 256 / tpe;
+  const int groups = (p.e_hi - p.e_lo + epb - 1) / epb;
+  const int grid = groups < 148 * 4 ? groups : 148 * 4;
+  return grid < 1 ? 1 : grid;
 }
 
 cudaError_t launch_powerflow(const PfParams& p, cudaStream_t s) {

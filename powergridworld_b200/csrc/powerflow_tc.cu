@@ -355,13 +355,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) pf_tc_kernel(const PfParams p) 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_COLS)
                  : "memory");
   if (p.advance_clock && tid == 0)
-    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, gridDim.x);
+    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, p.tickets);
+}
+
+int tc_grid(const PfParams& p) {
+  const int tiles = (p.E + TC_M - 1) / TC_M;
+  const int grid = tiles < 148 * 2 ? tiles : 148 * 2;
+  return grid < 1 ? 1 : grid;
 }
 
 cudaError_t launch_powerflow_tc(const PfParams& p, cudaStream_t s) {
   const int tiles = (p.E + TC_M - 1) / TC_M;
-  int grid = tiles < 148 * 2 ? tiles : 148 * 2;
-  if (grid < 1) grid = 1;
+  const int grid = tc_grid(p);
   const size_t smem = (size_t)TC_A_BYTES + (size_t)p.tc_blob_bytes + (size_t)(2 + 2 * p.nl) * 8 + 16;
   cudaError_t err = cudaFuncSetAttribute(pf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);

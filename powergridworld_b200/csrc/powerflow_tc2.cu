@@ -127,17 +127,17 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
   // tables, the operand images and the TMEM allocation are in flight: 32-byte sectors of
   // [rows][128 envs], spread over the CTA.
   auto prefetch_tile = [&](int tile) {
-    const size_t e0 = (size_t)tile * T2_M;
+    const size_t e0 = (size_t)p.e_lo + (size_t)tile * T2_M;
     if (p.warm_start)
       for (int i = tid; i < p.nb * 64; i += T2_THREADS) {
         const size_t ee = e0 + (size_t)(i & 63) * 2;
-        if (ee < (size_t)p.E)
+        if (ee < (size_t)p.e_hi)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(p.u_state + (size_t)(i >> 6) * p.E + ee));
       }
     if (!STANDALONE && p.agent_p != nullptr)
       for (int i = tid; i < p.A * 32; i += T2_THREADS) {
         const size_t ee = e0 + (size_t)(i & 31) * 4;
-        if (ee < (size_t)p.E) {
+        if (ee < (size_t)p.e_hi) {
           const size_t off = (size_t)(i >> 5) * p.E + ee;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(p.agent_p + off));
           if (p.reward_hook) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.ep_ret + off));
@@ -220,11 +220,11 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
     tma_bulk_g2s(sB, src, 2 * PB, &mbar_b);
   };
 
-  const int tiles = (p.E + T2_M - 1) / T2_M;
+  const int tiles = (p.e_hi - p.e_lo + T2_M - 1) / T2_M;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int e_raw = tile * T2_M + row;
-    const bool valid = e_raw < p.E;
-    const int e = valid ? e_raw : p.E - 1;
+    const int e_raw = p.e_lo + tile * T2_M + row;
+    const bool valid = e_raw < p.e_hi;
+    const int e = valid ? e_raw : p.e_hi - 1;
     const bool more_tiles = tile + (int)gridDim.x < tiles;
 
     // ---- nominal power (p.u. on 1 MVA, scaled by xs) of my branches; initial drop into D[1].
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
                  "r"((uint32_t)t.tmem_cols)
                  : "memory");
   if (p.advance_clock && tid == 0)
-    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, gridDim.x);
+    clock_advance_if_last(my_ticket, p.ticket, p.clock, clk, p.tickets);
 #ifdef PGW_PHASE_TIMERS
   if (p.phase_clk != nullptr && threadIdx.x == 0) {
     p.phase_clk[(size_t)blockIdx.x * 16 + 10] = clock64();
@@ -743,8 +743,17 @@ static cudaError_t launch_tc2_t(const PfParams& p, int grid, size_t smem, cudaSt
   return cudaLaunchKernelEx(&cfg, kern, p, *p.tc2.consts, 0);
 }
 
+int tc2_grid(const PfParams& p) {
+  const int tiles = (p.e_hi - p.e_lo + T2_M - 1) / T2_M;
+  const bool polish = tc2_polish_active(p);
+  const bool dense = !polish && p.tc2.nch == 2 && tiles > 148 * t2_ctas_per_sm(2) && p.tc2.tmem_cols <= 128;
+  const int per_sm = dense ? 4 : t2_ctas_per_sm(p.tc2.nch);
+  const int grid = tiles < 148 * per_sm ? tiles : 148 * per_sm;
+  return grid < 1 ? 1 : grid;
+}
+
 cudaError_t launch_powerflow_tc2(const PfParams& p, cudaStream_t s) {
-  const int tiles = (p.E + T2_M - 1) / T2_M;
+  const int tiles = (p.e_hi - p.e_lo + T2_M - 1) / T2_M;
   // the dense build pays off when the tiles do not fit one wave of the regular one
   const bool polish = tc2_polish_active(p);
   const bool dense = !polish && p.tc2.nch == 2 && tiles > 148 * t2_ctas_per_sm(2) && p.tc2.tmem_cols <= 128;

@@ -60,7 +60,7 @@ __device__ __forceinline__ void sf_wait_ld() {
 }
 
 struct SfLayout {                                      // byte offsets into dynamic shared memory
-  uint32_t b, a, stage, tab, blob, drow, irow, i64, dmax, part, cp, cr, total;
+  uint32_t b, a, stage, tab, blob, drow, irow, i64, dmax, part, cp, cr, act, total;
 };
 
 __host__ __device__ inline SfLayout sf_layout(const FusedParams& P) {
@@ -83,16 +83,29 @@ __host__ __device__ inline SfLayout sf_layout(const FusedParams& P) {
   L.part = take(2u * 16u * SF_ENVS * 4u);              // per-branch min / max |v| partials
   L.cp = take((uint32_t)P.C * SF_ENVS * 8u);           // component real power
   L.cr = take((uint32_t)P.C * SF_ENVS * 8u);           // component reward
+  L.act = take((uint32_t)P.act_dim * SF_ENVS * 8u);    // the tile's actions, [act_dim][32]
   L.total = o;
   return L;
 }
+
+// Phase stamps of tools/phase_probe.py (instrumented build only, -DPGW_PHASE_TIMERS): thread 0 of
+// every CTA records the SM clock at the phase boundaries of its first tile.
+#ifdef PGW_PHASE_TIMERS
+#define SF_STAMP(k)                                                                  \
+  do {                                                                               \
+    if (pf.phase_clk != nullptr && threadIdx.x == 0 && first_tile)                   \
+      pf.phase_clk[(size_t)(blockIdx.x + P.e_lo / SF_ENVS) * 16 + (k)] = clock64();    \
+  } while (0)
+#else
+#define SF_STAMP(k) do { } while (0)
+#endif
 
 template <bool ANY_M5>
 __global__ void __launch_bounds__(SF_THREADS, 1)
     step_fused_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ Tc2Consts kc,
                       const __grid_constant__ Tc2Polish kp) {
   extern __shared__ __align__(1024) unsigned char sf_smem[];
-  __shared__ __align__(8) uint64_t mbar_tab, mbar_ev, mbar_b, mbar_mma, mbar_a;
+  __shared__ __align__(8) uint64_t mbar_tab, mbar_ev, mbar_b, mbar_mma, mbar_a, mbar_act;
   __shared__ uint32_t tmem_base_s;
   const CompParams& pc = P.c;
   const PfParams& pf = P.f;
@@ -116,8 +129,14 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
   float* sVmx = sVmn + 16 * SF_ENVS;
   double* sCp = reinterpret_cast<double*>(sf_smem + L.cp);         // [C][env]
   double* sCr = reinterpret_cast<double*>(sf_smem + L.cr);
+  double* sAct = reinterpret_cast<double*>(sf_smem + L.act);
 
   // ---- prologue: clock, staging of everything that is shared by the envs, TMEM
+  bool first_tile = true;
+#ifdef PGW_PHASE_TIMERS
+  if (pf.phase_clk != nullptr && threadIdx.x == 0) pf.phase_clk[(size_t)(blockIdx.x + P.e_lo / SF_ENVS) * 16 + 12] = (long long)global_timer_ns();
+#endif
+  SF_STAMP(0);
   const int clk = *pc.clock;
   unsigned int my_ticket = 0u;
   const int event = clk + 1;
@@ -127,6 +146,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     mbar_init(&mbar_b, 1);
     mbar_init(&mbar_mma, 1);
     mbar_init(&mbar_a, 8);                             // one arrival per repacking warp
+    mbar_init(&mbar_act, 1);
     mbar_expect_tx(&mbar_tab, (uint32_t)t.tab_bytes + (uint32_t)pc.blob_bytes);
     tma_bulk_g2s(sBlob, pc.blob, (uint32_t)pc.blob_bytes, &mbar_tab);
     tma_bulk_g2s(sT, t.blob + t.off_tab, (uint32_t)t.tab_bytes, &mbar_tab);
@@ -155,7 +175,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
+  SF_STAMP(1);
   mbar_wait(&mbar_tab, 0);
+  SF_STAMP(2);
 
   const pgw_agent* agents = reinterpret_cast<const pgw_agent*>(sBlob);
   const pgw_component* comps = reinterpret_cast<const pgw_component*>(sBlob + pc.off_comps);
@@ -174,6 +196,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
   io.scr.stride = 0;
   io.E = E;
   io.actions = pc.actions;
+  io.aE = E;
+  io.ae0 = 0;
   io.obs = pc.obs;
   io.sd = pc.sd;
   io.si = pc.si;
@@ -198,7 +222,6 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
   const float4 cst = t2_cst(kc, b);
   const float2 gh = ANY_M5 ? t2_gh(kc, b) : make_float2(1.f, 0.f);
   uint32_t mma_phase = 0, a_phase = 0;
-  bool first_tile = true;
 
   // One accumulation chain D = A_lo B_hi + A_hi B_lo + A_hi B_hi (small terms first) into the
   // accumulator at column d_col against the image pair at byte offset b_off.
@@ -269,6 +292,33 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
 
   const int span = P.e_hi - P.e_lo;
   const int tiles = (span + SF_ENVS - 1) / SF_ENVS;
+  // The actions of a (full) tile are fetched into shared memory by TMA bulk copies, one 256-byte
+  // row segment each, while the prologue / the previous tile's power flow runs: the component
+  // steps then find them on chip.  With actions in HOST memory this is what decouples the PCIe
+  // reads from the component code, and CTA b delays its first fetch by b x stagger_cycles so that
+  // the link serves the tiles in order -- the first tiles write their observations (GPU -> host)
+  // while the last ones still wait for their actions (host -> GPU).
+  auto tile_in_smem = [&](int tile) {
+    const int e0 = P.e_lo + tile * SF_ENVS;
+    return (E % 2 == 0) && (e0 % 2 == 0) && e0 + SF_ENVS <= P.e_hi;
+  };
+  auto fetch_actions = [&](int tile) {                 // warp 0
+    if (tile < tiles && tile_in_smem(tile)) {
+      const int e0 = P.e_lo + tile * SF_ENVS;
+      if (lane == 0) mbar_expect_tx(&mbar_act, (uint32_t)P.act_dim * SF_ENVS * 8u);
+      __syncwarp();
+      for (int r = lane; r < P.act_dim; r += 32)
+        tma_bulk_g2s(sAct + (size_t)r * SF_ENVS, pc.actions + (size_t)r * E + e0, SF_ENVS * 8u, &mbar_act);
+    }
+  };
+  uint32_t act_phase = 0;
+  if (w == 0) {
+    if (P.stagger_cycles > 0) {
+      const long long c0 = clock64(), wait = (long long)blockIdx.x * P.stagger_cycles;
+      while (clock64() - c0 < wait) { }
+    }
+    fetch_actions(blockIdx.x);
+  }
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int e_raw = P.e_lo + tile * SF_ENVS + lane;
     const bool valid = e_raw < P.e_hi;
@@ -282,6 +332,14 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     if (w < 2) sDmax[w * SF_ENVS + lane] = 0;
 
     if (first_tile) mbar_wait(&mbar_ev, 0);            // event row has landed
+    if (tile_in_smem(tile)) {                          // CTA uniform
+      mbar_wait(&mbar_act, act_phase);
+      act_phase ^= 1u;
+      io.actions = sAct; io.aE = SF_ENVS; io.ae0 = P.e_lo + tile * SF_ENVS;
+    } else {
+      io.actions = pc.actions; io.aE = E; io.ae0 = 0;
+    }
+    SF_STAMP(3);
 
     // ---- components: warp w steps components w, w + 16, ... of every env of the tile
     for (int ci = w; ci < P.C; ci += SF_WARPS) {
@@ -300,7 +358,14 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
       sCr[ci * SF_ENVS + lane] = rw;
     }
     if (w == 0 && valid) pc.done[e] = drow[0] != 0.0 ? 1 : 0;
+    SF_STAMP(4);
     __syncthreads();
+    // Host-buffer steps run as a chain of env chunks (programmatic dependent launches): this CTA
+    // has read the actions of its last tile, the next chunk may start reading its own while this
+    // one's observations drain over the other direction of the link.
+    if (P.pdl_trigger && tile + (int)gridDim.x >= tiles) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (w == 0) fetch_actions(tile + (int)gridDim.x);  // the staging area is free again
+    SF_STAMP(5);
 
     // ---- agents: real power (base.py:51-55; summed in component order from 0.0 like the
     //      reference), kept for the power flow; the reward waits for the penalty
@@ -344,6 +409,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     __syncthreads();
     repack();
     issue(false);
+    SF_STAMP(6);
 
     // ---- fixed point
     int it = 0, my_it = 0;
@@ -382,6 +448,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
       if (all_done) break;
     }
 
+    SF_STAMP(7);
+    [[maybe_unused]] const int it_stamp = it;
     // ---- float64 polish of my branch voltage (the expansion chains run meanwhile)
     const bool polish = t.polish > 0 && pf.reward_hook;
     double2 u64 = make_double2(kp.u0[b].x + (double)dprev.x * (double)ds1,
@@ -410,6 +478,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
       pf.u_state[(size_t)b * E + e] = u64;
     }
 
+    SF_STAMP(8);
     // ---- node magnitudes: my branch's wye-load node, then my slots of the expansion
     float vmn = 3.0e38f, vmx = -3.0e38f;
     if (b < pf.nb) {
@@ -454,6 +523,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     sVmx[w * SF_ENVS + lane] = vmx;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                                   // magnitudes (global) and partials visible
+    SF_STAMP(9);
 
     // Penalty node that is not a wye-load node: its row of the last sweep from the currents
     // still in shared memory.
@@ -508,6 +578,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
       }
     }
     __syncthreads();                                   // shared arrays are reused by the next tile
+    SF_STAMP(10);
+#ifdef PGW_PHASE_TIMERS
+    if (pf.phase_clk != nullptr && threadIdx.x == 0 && first_tile) pf.phase_clk[(size_t)(blockIdx.x + P.e_lo / SF_ENVS) * 16 + 11] = it_stamp;
+#endif
     first_tile = false;
   }
 
@@ -517,19 +591,38 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
                  "r"((uint32_t)P.tmem_cols)
                  : "memory");
   if (tid == 0) clock_advance_if_last(my_ticket, pc.ticket, pc.clock, clk, P.tickets);
+#ifdef PGW_PHASE_TIMERS
+  if (pf.phase_clk != nullptr && threadIdx.x == 0) {
+    pf.phase_clk[(size_t)(blockIdx.x + P.e_lo / SF_ENVS) * 16 + 14] = clock64();
+    pf.phase_clk[(size_t)(blockIdx.x + P.e_lo / SF_ENVS) * 16 + 13] = (long long)global_timer_ns();
+  }
+#endif
+}
+
+bool is_step_fused_kernel(const void* func) {
+  return func == (const void*)step_fused_kernel<false> || func == (const void*)step_fused_kernel<true>;
 }
 
 size_t step_fused_smem_bytes(const FusedParams& P) { return sf_layout(P).total; }
 
 int step_fused_tiles(int envs) { return (envs + SF_ENVS - 1) / SF_ENVS; }
 
-cudaError_t launch_step_fused(const FusedParams& P, int grid, cudaStream_t s) {
+cudaError_t launch_step_fused(const FusedParams& P, int grid, cudaStream_t s, bool programmatic) {
   auto kern = P.f.tc2.any_m5 ? step_fused_kernel<true> : step_fused_kernel<false>;
   const size_t smem = step_fused_smem_bytes(P);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  kern<<<grid, SF_THREADS, smem, s>>>(P, *P.f.tc2.consts, *P.f.tc2.pconsts);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(SF_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = programmatic ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, P, *P.f.tc2.consts, *P.f.tc2.pconsts);
 }
 
 }  // namespace pgw

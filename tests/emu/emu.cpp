@@ -35,7 +35,7 @@ static pgw::AgentIO make_io(const EmuArgs* a) {
   pgw::AgentIO io;
   io.scr.p = g_scratch;
   io.scr.stride = 1;
-  io.E = a->E; io.actions = a->actions; io.obs = a->obs; io.sd = a->sd; io.si = a->si;
+  io.E = a->E; io.actions = a->actions; io.aE = a->E; io.ae0 = 0; io.obs = a->obs; io.sd = a->sd; io.si = a->si;
   io.init_soc = a->init_soc; io.clip_init_soc = a->clip_init_soc; io.vmin = a->vmin; io.vmax = a->vmax; io.vbus = a->vbus;
   io.dpar = a->dpar; io.ipar = a->ipar; io.drow = a->drow; io.irow = a->irow;
   return io;

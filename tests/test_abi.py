@@ -60,8 +60,9 @@ def test_constants_of_the_binding_match_the_header():
     for name in ("STORAGE", "PV", "EV", "BUILDING", "HS_BEGIN", "HS_PV", "HS_STORAGE", "HS_EV", "HS_DEVICES",
                  "HS_MAX_COMPONENTS", "F_TELEMETRY", "HS_TEL_ROWS", "F_RESCALE", "F_GRID_AWARE",
                  "F_PV_VOLT_REWARD", "F_STALE_REWARD", "F_BUILDING_FAST", "OPT_PF_KERNEL", "OPT_WARM_START",
-                 "OPT_GRAPHS", "OPT_PDL", "OPT_CLIP_INIT_SOC", "ABI_VERSION", "NUM_STATS"):
+                 "OPT_GRAPHS", "OPT_PDL", "OPT_CLIP_INIT_SOC", "OPT_PF_POLISH", "OPT_PF_TC_TOL_NANO",
+                 "OPT_FUSED", "OPT_HOST_CHUNKS", "OPT_HOST_ZERO_COPY", "ABI_VERSION", "NUM_STATS"):
         assert name in known, f"PGW_{name} not found in pgw.h"
         assert getattr(N, name) == known[name], (name, getattr(N, name), known[name])
         checked += 1
-    assert checked == 24
+    assert checked == 29

@@ -50,14 +50,6 @@ SURVEY_BYTES = {"c1": 3 * (264 + 28 + 40) + 1, "c2": (16 * 100 + 72 + 8 * 4) + 2
 _PF_NAMES = {"fp64": "fp64-simt", "tc": "tcgen05 split-tf32", "tc2": "tcgen05 split-fp16, Z-bus in smem"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of component_kernel per launch, from the committed
-# `ncu --set full` captures (profiles/r1s3_ncu_full_raw_*.csv); keyed by (workload, envs per GPU)
-NCU_TRAFFIC = {("c1", 4096): 1.557e6, ("c1", 262144): 202.3e6, ("c3", 16384): 151.65e6}
-NCU_TRAFFIC_PF = {("c1", 4096): 1.294e6, ("c3", 16384): 49.78e6}     # pf_tc2_kernel, same captures
-# sm__pipe_tensor_cycles_active.max (% of elapsed, busy SMs) of pf_tc2_kernel in the same captures
-NCU_TENSOR_PCT = {("c1", 4096): 2.45, ("c1", 262144): 5.72, ("c3", 16384): 22.47}
-
-
 def _dtype_label(has_pf):
     """The arithmetic the step computes in (not a precision claim)."""
     if not has_pf or PF_KERNEL == "fp64":
@@ -67,7 +59,9 @@ def _dtype_label(has_pf):
     return "f64 components; power flow: split-tf32 operands / fp32 accumulate (tcgen05)"
 
 
-def _config(n_gpus):
+def _config(n_gpus, workload=None, envs=None):
+    WORKLOAD = workload or globals()["WORKLOAD"]
+    ENVS_PER_GPU = envs or globals()["ENVS_PER_GPU"]
     if WORKLOAD == "c2":
         return {"workload": "C2: component-only EV station (100 vehicles) + PV + storage, "
                             f"{ENVS_PER_GPU} envs per GPU, no power flow",
@@ -144,46 +138,77 @@ class _OracleHouse:
 
 # --------------------------------------------------------------------------- CPU arm
 def _cpu_worker(args):
-    """One independent oracle env stepped for `steps` steps (episodes restart as needed)."""
-    seed, steps = args
+    """One independent CPU env stepped for `budget` seconds (episodes restart as needed); returns
+    (steps done, seconds spent stepping) -- building the env is not part of the measurement.
+    kind "port": the oracle's restatement of the reference classes; kind "reference": the
+    UNMODIFIED reference classes (baseline/_ref or $PGW_REFERENCE_ROOT through oracle/ref_harness.py)
+    with the power-flow port plugged into pf_config["cls"] (gridworld/multiagent_env.py:80)."""
+    seed, budget, kind = args
+    import contextlib
+
     import numpy as np
 
     from oracle.flatten import action_layout, unflatten_action
-    from oracle.namespace import ORACLE_NS as NS
-    env = _make_env(NS)
+    quiet = contextlib.nullcontext
+    if kind == "reference":
+        from oracle.powerflow import OracleOpenDSSSolver
+        from oracle.ref_harness import quiet_stdout as quiet, reference_namespace
+        from powergridworld_b200.scenarios import catalog as S
+        ns = reference_namespace()
+        with quiet():
+            env = ns.CoordinatedMultiBuildingControlEnv(
+                **S.buildings_scenario(ns, OracleOpenDSSSolver, LOAD_FACTOR))
+    else:
+        from oracle.namespace import ORACLE_NS as NS
+        env = _make_env(NS)
     rng = np.random.default_rng(seed)
     np.random.seed(seed)
     layout = action_layout(env)
     dim = sum(len(lo) for _, _, lo, _, _ in layout)
-    env.reset()
-    t0 = time.perf_counter()
-    done = 0
-    while done < steps:
-        _, _, dn, _ = env.step(unflatten_action(env, rng.uniform(-1, 1, size=dim)))
-        done += 1
-        if dn["__all__"]:
-            env.reset()
-    return time.perf_counter() - t0
+    with quiet():
+        env.reset()
+        for _ in range(3):                             # warm caches / lazy imports
+            env.step(unflatten_action(env, rng.uniform(-1, 1, size=dim)))
+        t0 = time.perf_counter()
+        done = 0
+        while time.perf_counter() - t0 < budget:
+            _, _, dn, _ = env.step(unflatten_action(env, rng.uniform(-1, 1, size=dim)))
+            done += 1
+            if dn["__all__"]:
+                env.reset()
+        return done, time.perf_counter() - t0
 
 
-def cpu_throughput(total_seconds_target=15.0, steps_per_task=96):
-    """Oracle port on all host cores (multiprocessing, one independent env per task)."""
+def _reference_classes_available():
+    if WORKLOAD != "c1":
+        return False
+    try:
+        from oracle.ref_harness import reference_available
+        return reference_available()
+    except Exception:
+        return False
+
+
+def cpu_throughput(total_seconds_target=15.0, kind="port"):
+    """CPU implementation of the path on all host cores: one independent env per core
+    (multiprocessing), all stepping concurrently for the time budget; value = steps done by all
+    of them / the longest stepping time."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    # single-task probe (steady-state ms/step) to size the sample
-    t_probe = _cpu_worker((0, 30)) / 30.0
-    per_task = steps_per_task
-    rounds = max(1, int(round(total_seconds_target / (per_task * t_probe))))
-    tasks = [(i + 1, per_task) for i in range(cores * rounds)]
+    tasks = [(i + 1, float(total_seconds_target), kind) for i in range(cores)]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_cpu_worker, tasks, chunksize=1)
+        res = pool.map(_cpu_worker, tasks, chunksize=1)
     wall = time.perf_counter() - t0
-    total = len(tasks) * per_task
-    return {"value": total / wall, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(tasks)} independent oracle envs x {per_task} steps "
-                      f"(multiprocessing.Pool({cores})), {wall:.1f} s wall, "
-                      f"{1e3 * t_probe:.2f} ms/step single core"}
+    total = sum(n for n, _ in res)
+    busy = max(t for _, t in res)
+    what = "oracle envs (port of the reference classes + power-flow port)" if kind == "port" else \
+        "envs of the UNMODIFIED reference classes (power-flow port plugged into pf_config['cls'])"
+    return {"value": total / busy, "unit": UNIT, "cores": cores,
+            "kind": "port" if kind == "port" else "reference-classes+pf-port",
+            "sample": f"{cores} independent {what}, one per core (multiprocessing.Pool({cores})), stepping "
+                      f"concurrently for {busy:.1f} s: {total} env-steps, {1e3 * busy * cores / max(total, 1):.2f} "
+                      f"ms/step per core ({wall:.1f} s wall with the env construction)"}
 
 
 def run_reference(args):
@@ -191,7 +216,10 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    cb = cpu_throughput(total_seconds_target=max(10.0, min(60.0, 0.1 * args.steps)))
+    budget = max(10.0, min(60.0, 0.1 * args.steps))
+    port = cpu_throughput(total_seconds_target=budget, kind="port")
+    real = cpu_throughput(total_seconds_target=budget, kind="reference") if _reference_classes_available() else None
+    cb = real or port
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak",
@@ -199,8 +227,14 @@ def run_reference(args):
             "config": _config(args.gpus), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
-            "note": "oracle port of the reference classes + complex128 power-flow restatement; "
-                    "the reference's OpenDSS engine is not installable (no network)",
+            "port": port,
+            "note": ("the reference's own MultiAgentEnv / component classes (unmodified, installed in "
+                     "baseline/_ref) with the complex128 power-flow port plugged into pf_config['cls']; "
+                     "`port` = the oracle's restatement of those classes, ~10x faster per core"
+                     if real else
+                     "oracle port of the reference classes + complex128 power-flow restatement (no "
+                     "reference tree on this box)") +
+                    "; the reference's OpenDSS engine is not installable (no network)",
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)
 
@@ -248,39 +282,102 @@ def _peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def run_ours(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    K, W = args.steps, max(args.warmup, 3)
+def _ncu_capture(workload, E):
+    """dram bytes per launch (read + write) and tensor-pipe activity per kernel, PARSED from the
+    committed `ncu --set full` export of this workload (profiles/r2_ncu_full_raw_<workload>_<E>.csv,
+    `ncu -i ... --page raw --csv`); {} when no capture of this size is committed."""
+    import csv
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r2*_ncu_full_raw_{workload}_{E}.csv")))
+    if not paths:
+        return {}
+    path = paths[-1]
+    with open(path, newline="") as fh:
+        rows = list(csv.reader(fh))
+    hdr, units, body = rows[0], rows[1], rows[2:]
+    col = {n: i for i, n in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
-    cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_throughput()                   # before CUDA is initialised (fork)
+    def val(r, name):
+        if name not in col or r[col[name]] == "":
+            return None
+        return float(r[col[name]].replace(",", "")) * scale.get(units[col[name]], 1.0)
+    out = {}
+    for r in body:
+        k = r[col["Kernel Name"]]
+        for key in ("step_fused_kernel", "component_kernel", "pf_tc2_kernel", "pf_fixed_point_kernel"):
+            if key in k:
+                rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
+                tp = val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+                d = out.setdefault(key, {"traffic": [], "tensor_pct": [], "us": []})
+                if rd is not None and wr is not None:
+                    d["traffic"].append(rd + wr)
+                if tp is not None:
+                    d["tensor_pct"].append(tp)
+                t = val(r, "gpu__time_duration.sum")
+                if t is not None:
+                    d["us"].append(t * {"us": 1.0, "ns": 1e-3, "ms": 1e3}.get(units[col["gpu__time_duration.sum"]], 1.0))
+    mean = lambda v: sum(v) / len(v) if v else None
+    res = {k: {"traffic": mean(d["traffic"]), "tensor_pct": mean(d["tensor_pct"]), "us_under_ncu": mean(d["us"]),
+               "launches_captured": len(d["traffic"])} for k, d in out.items()}
+    res["_source"] = os.path.relpath(path, ROOT) + " (ncu --set full --clock-control none, parsed at run time)"
+    return res
 
+
+def _bind_to_gpu_numa(index):
+    """Run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def _component_bytes(env, workload, E, W, K):
+    """Algorithmic bytes per launch of the component work: SURVEY.md 8(d)'s per-env figure x envs; for
+    the EV station the bytes of the vehicles actually parked in the timed events."""
+    survey = SURVEY_BYTES[workload] * E
+    alg = survey
+    if workload == "c2":
+        ev = [c for c in env._b.comps if c.type == 3][0]
+        rows = env._itab[W + 1:W + 1 + K]
+        n_win = float(rows[:, ev.itab_off].mean())
+        n_left = float(rows[:, ev.itab_off + 1].mean())
+        alg = (16.0 * n_win + 8.0 * n_left + 32.0 + 72.0 + 28.0 + 40.0 + 1.0) * E
+    return alg, survey
+
+
+def measure(workload, E, K, W, dev, world=1, rank=0, headline=False, pdl=1):
+    """One workload on this rank's GPU: K device-timed steps with a cold L2 before each, the
+    per-kernel durations of the same loop, and the rooflines they give."""
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    if world > 1:
-        _init_nccl(dev)
-    E = ENVS_PER_GPU
-    env = _make_env(None, num_envs=E, device=dev)
+    from powergridworld_b200 import _native as N
+
+    env = _make_env(None, workload=workload, num_envs=E, device=dev)
     has_pf = env.pf_solver is not None
     if PF_KERNEL != "fp64" and has_pf:
-        from powergridworld_b200 import _native as N
         env.set_option(N.OPT_PF_KERNEL, {"tc": 1, "tc2": 2}[PF_KERNEL])
-    if not args.pdl:
-        from powergridworld_b200 import _native as N
+    if not pdl:
         env.set_option(N.OPT_PDL, 0)
     A = len(env.agents)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    pool_n = 64 if E * env.act_dim <= 65536 * 24 else 8
-    act_pool = torch.rand((pool_n, env.act_dim, E), generator=gen, device=dev,
-                          dtype=torch.float64) * 2.0 - 1.0
+    # a fresh action tensor every step, as a policy loop hands them in: eight buffers in rotation;
+    # the handle replays ONE step graph and re-points its kernel nodes at each of them
+    pool_n = 8
+    act_pool = [torch.rand((env.act_dim, E), generator=gen, device=dev, dtype=torch.float64) * 2.0 - 1.0
+                for _ in range(pool_n)]
     rng = np.random.default_rng(rank)
     soc = torch.as_tensor(30.0 + 5.0 * rng.uniform(-1, 1, size=(env.num_storage, E))).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -296,13 +393,6 @@ def run_ours(args):
             env.reset_batch(soc)
         env.step_batch(act_pool[i % pool_n])
 
-    # A non-default stream: pgw_step then replays one captured CUDA graph per action buffer.
-    stream = torch.cuda.Stream(dev)
-    torch.cuda.set_stream(stream)
-    env.reset_batch(soc)
-    for i in range(pool_n + 2):                       # captures the step graphs (untimed)
-        one_step(i)
-
     def begin_pass():
         """Every pass starts from a fresh episode + W untimed steps, so that all passes see
         the same events (the EV station's work depends on the time of day)."""
@@ -311,10 +401,13 @@ def run_ours(args):
             one_step(i)
         barrier()
 
+    env.reset_batch(soc)
+    for i in range(3):
+        one_step(i)
     begin_pass()
 
     # ---- timed region: K steps, device-timed one by one, cold L2 before each
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index or 0)
     sampler.start()
     launches0 = env.launch_count
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -325,10 +418,10 @@ def run_ours(args):
         starts[i].record()
         one_step(W + i)
         ends[i].record()
-    stats = env.all_reduce_stats()                    # the only collective of the path
+    launches = env.launch_count - launches0
+    stats = env.all_reduce_stats()                    # the only collective: after the timed steps
     barrier()
     wall = time.perf_counter() - wall0
-    launches = env.launch_count - launches0 - 1       # minus the stats kernel
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(sum(step_ms))
     iters_mean = float(env.get_field(7).abs().double().mean()) if has_pf else 0.0
@@ -342,26 +435,116 @@ def run_ours(args):
     #      launches with CUDA events between the kernels on the launch stream
     begin_pass()
     env.set_kernel_timing(True)
-    k1 = K
-    for i in range(k1):
+    for i in range(K):
         flush.zero_()
         one_step(W + i)
-    t_comp_ms, t_pf_ms, n_timed = env.kernel_timing()
+    t_a_ms, t_pf_ms, n_timed = env.kernel_timing()
     env.set_kernel_timing(False)
     sampler.stop_flag = True
+    fused = bool(has_pf and t_pf_ms == 0.0)           # one kernel does the whole step
+    k_a_ms, pf_ms = t_a_ms / max(n_timed, 1), t_pf_ms / max(n_timed, 1)
+
+    out = {"env": env, "E": E, "A": A, "value": value, "ms_per_step": total_ms / K, "launches": int(launches),
+           "stats": stats, "wall": wall, "clocks": sampler.summary(), "has_pf": has_pf, "fused": fused,
+           "barrier": barrier, "one_step": one_step, "begin_pass": begin_pass, "soc": soc}
+    if rank != 0:
+        return out
+
+    peaks, peak_src = _peaks()
+    hbm = peaks["hbm_gbs"]
+    ncu = _ncu_capture(workload, E)
+    comp_bytes, survey_bytes = _component_bytes(env, workload, E, W, K)
+    f = env.pf_solver.feeder if has_pf else None
+    flops = (8.0 * f.nb * f.nb * iters_mean + 8.0 * f.nn * f.nb) * E if has_pf else 0.0
+    pf_peak = peaks.get("bf16_tflops", 1590.0) * (0.5 if PF_KERNEL == "tc" else 1.0)
+    pf_peak_src = ("measured bf16 (= fp16 dense), " if PF_KERNEL != "tc" else "0.5 x measured bf16 (tf32 dense), ") + peak_src
+    hook = 1 if getattr(env, "_penalty", None) is not None else 0
+
+    def roof(kernel, alg_bytes, ms, extra=None):
+        gbs = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        cap = ncu.get(kernel, {})
+        r = {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+             "traffic": cap.get("traffic"), "traffic_source": ncu.get("_source") if cap else None,
+             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms}
+        if extra:
+            r.update(extra)
+        return r
+
+    def tensor_part(kernel, ms):
+        tfs = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        return {"algorithmic_flops_per_launch": flops, "mean_iterations": iters_mean,
+                "tensor": {"achieved_tflops": tfs, "peak_tflops": pf_peak, "frac": tfs / pf_peak,
+                           "peak_source": pf_peak_src,
+                           "pipe_active_pct_ncu": ncu.get(kernel, {}).get("tensor_pct")}}
+
+    rooflines = {}
+    if fused:
+        # whole step in one kernel: the components' bytes + the power flow's state and results;
+        # the agents' power, the rewards before the penalty and the second read of the episode
+        # returns never leave the chip
+        pf_bytes = (16.0 * f.nb * 2 + 8.0 * f.nn + 16.0 + 8.0 * A + 4.0 + 8.0) * E
+        rooflines["step_fused_kernel"] = roof("step_fused_kernel", comp_bytes + pf_bytes, k_a_ms,
+                                              tensor_part("step_fused_kernel", k_a_ms))
+        dominant = rooflines["step_fused_kernel"]
+        share = {"step_fused_kernel": 1.0}
+    else:
+        rooflines["component_kernel"] = roof("component_kernel", comp_bytes, k_a_ms,
+                                             {"survey_bytes_per_launch": survey_bytes})
+        dominant = rooflines["component_kernel"]
+        share = {"components": k_a_ms / max(k_a_ms + pf_ms, 1e-12), "powerflow": pf_ms / max(k_a_ms + pf_ms, 1e-12)}
+        if has_pf:
+            # per env: agents' power in, warm-start branch voltages in and out, node magnitudes,
+            # min/max, bus voltages, iterations, and -- with the penalty hook -- rewards in/out
+            pf_bytes = (8.0 * A + 16.0 * f.nb * 2 + 16.0 * A * hook + 8.0 * f.nn + 16.0 + 8.0 * A + 4.0) * E
+            kname = {"tc": "pf_tc_kernel", "tc2": "pf_tc2_kernel"}.get(PF_KERNEL, "pf_fixed_point_kernel")
+            rooflines[kname] = roof(kname, pf_bytes, pf_ms, tensor_part(kname, pf_ms))
+            rooflines[kname]["arithmetic_intensity_flop_per_byte"] = flops / pf_bytes
+            rooflines[kname]["ridge_flop_per_byte"] = pf_peak * 1e12 / (hbm * 1e9)
+            if pf_ms > k_a_ms:
+                dominant = rooflines[kname]
+    out.update({"rooflines": rooflines, "dominant": dominant, "kernel_share": share})
+    return out
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 3)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_throughput()                   # before CUDA is initialised (fork)
+        if _reference_classes_available():
+            cpu_base["reference_classes"] = cpu_throughput(total_seconds_target=8.0, kind="reference")
+
+    numa_cpus = _bind_to_gpu_numa(local)
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        _init_nccl(dev)
+    E = ENVS_PER_GPU
+    stream = torch.cuda.Stream(dev)                   # a non-default stream: pgw_step replays its graph
+    torch.cuda.set_stream(stream)
+    m = measure(WORKLOAD, E, K, W, dev, world, rank, headline=True, pdl=args.pdl)
+    env, A, has_pf = m["env"], m["A"], m["has_pf"]
+    barrier, one_step, begin_pass, soc = m["barrier"], m["one_step"], m["begin_pass"], m["soc"]
 
     # ---- same loop with a warm L2 (reported next to the headline, not instead of it)
     begin_pass()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k2 = K
     ev0.record()
-    for i in range(k2):
+    for i in range(K):
         one_step(W + i)
     ev1.record()
     barrier()
-    warm_ms = ev0.elapsed_time(ev1) / k2
+    warm_ms = ev0.elapsed_time(ev1) / K
 
-    # ---- end to end: host buffers in, host buffers out, every step
+    # ---- end to end: host buffers in, host buffers out, every step (the public host-buffer call;
+    #      page-locked buffers are read and written in place by the step's kernels over PCIe)
     host_act = [torch.rand((env.act_dim, E), dtype=torch.float64).mul_(2).sub_(1).pin_memory()
                 for _ in range(4)]
     env.reset_host(soc.cpu().numpy())
@@ -387,104 +570,54 @@ def run_ours(args):
     h2d = env.act_dim * E * 8
     d2h = env.obs_dim * E * 8 + A * E * 8 + E
 
+    # ---- the other single-GPU configurations of BASELINE.json, a few steps each (rank 0, N = 1)
+    extra = {}
+    if rank == 0 and world == 1 and WORKLOAD == "c1" and not args.no_extra:
+        env.close()
+        del m["env"]
+        for name, wl, e_n in (("c1x64", "c1", 262144), ("c2", "c2", 65536), ("c3", "c3", 16384)):
+            try:
+                x = measure(wl, e_n, 20, 5, dev)
+                extra[name] = {"workload": _config(1, wl, e_n)["workload"], "envs": e_n, "value": x["value"],
+                               "unit": UNIT, "ms_per_step": x["ms_per_step"], "steps": 20, "warmup": 5,
+                               "gpu_launches": x["launches"], "roofline": x["dominant"],
+                               "rooflines": x["rooflines"], "kernel_share": x["kernel_share"]}
+                x["env"].close()
+            except Exception as exc:                  # a leg that fails must not take the headline down
+                extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
-        peaks, peak_src = _peaks()
-        comp_ms = t_comp_ms / max(n_timed, 1)
-        pf_ms = t_pf_ms / max(n_timed, 1)
-        alg_bytes = SURVEY_BYTES[WORKLOAD] * E
-        survey_bytes = alg_bytes
-        if WORKLOAD == "c2":
-            # The EV kernel only touches the vehicles parked at the event's minute (a static
-            # per-event list), not all n: count what it really moves.  Per parked vehicle one
-            # 8 B read and (at most) one 8 B write, 8 B per just-departed vehicle, the 4-word
-            # charging-set mask (cleared + written), plus the fixed action/obs/reward traffic.
-            ev = [c for c in env._b.comps if c.type == 3][0]
-            rows = env._itab[W + 1:W + 1 + K]
-            n_win = float(rows[:, ev.itab_off].mean())
-            n_left = float(rows[:, ev.itab_off + 1].mean())
-            per_env = 16.0 * n_win + 8.0 * n_left + 32.0 + 72.0 + 28.0 + 40.0 + 1.0
-            alg_bytes = per_env * E
-        achieved = alg_bytes / (comp_ms * 1e-3) / 1e9 if comp_ms > 0 else 0.0
-        f = env.pf_solver.feeder if has_pf else None
-        flops = (8.0 * f.nb * f.nb * iters_mean + 8.0 * f.nn * f.nb) * E if has_pf else 0.0
-        if PF_KERNEL == "tc":      # dense TF32 = half the measured bf16 rate; flops counted once
-            pf_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
-            pf_peak_src = "0.5 x measured bf16 (tf32 dense), " + peak_src
-        elif PF_KERNEL == "tc2":   # dense FP16 = the measured bf16 rate; flops counted once
-            pf_peak = peaks.get("bf16_tflops", 1590.0)
-            pf_peak_src = "measured bf16 (= fp16 dense), " + peak_src
-        else:
-            pf_peak, pf_peak_src = 37.0, "nominal B200 FP64 (no measured FP64 peak)"
-        rf_comp = {"kernel": "component_kernel", "bound": "hbm", "achieved": achieved,
-                   "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                   "frac": achieved / peaks["hbm_gbs"],
-                   "traffic": NCU_TRAFFIC.get((WORKLOAD, E)),
-                   "traffic_source": "profiles/r1s4_ncu_full_raw_c1.csv / _c3.csv, r1s3_..._c1x64.csv "
-                                     "(ncu --set full, one capture)" if (WORKLOAD, E) in NCU_TRAFFIC else None,
-                   "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                   "survey_bytes_per_launch": survey_bytes,
-                   "frac_survey_bytes": (survey_bytes / (comp_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
-                   if comp_ms > 0 else 0.0,
-                   "avg_launch_ms": comp_ms}
-        rf_pf = None
-        if has_pf:
-            # Power-flow kernel, both roofs: per env it reads the agents'
-            # power (A x 8 B), the warm-start branch voltages (nb x 16 B) and -- with a reward
-            # hook -- the rewards (A x 8 B); it writes the branch voltages (nb x 16 B), the node
-            # magnitudes (nn x 8 B), min/max (16 B), the agents' bus voltages (A x 8 B), the
-            # rewards (A x 8 B, hook only) and the iteration count (4 B).  Shared tables (Z-bus
-            # images, event row) are staged in shared memory and not counted.  The roof that
-            # binds is the one with the larger time at peak.
-            hook = 1 if getattr(env, "_penalty", None) is not None else 0
-            pf_bytes = (8.0 * A + 16.0 * f.nb + 8.0 * A * hook + 16.0 * f.nb + 8.0 * f.nn + 16.0 +
-                        8.0 * A + 8.0 * A * hook + 4.0) * E
-            t_hbm = pf_bytes / (peaks["hbm_gbs"] * 1e9)
-            t_tensor = flops / (pf_peak * 1e12)
-            gbs = pf_bytes / (pf_ms * 1e-3) / 1e9 if pf_ms > 0 else 0.0
-            tfs = flops / (pf_ms * 1e-3) / 1e12 if pf_ms > 0 else 0.0
-            hbm_bound = t_hbm >= t_tensor
-            rf_pf = {"kernel": {"tc": "pf_tc_kernel", "tc2": "pf_tc2_kernel"}.get(
-                         PF_KERNEL, "pf_fixed_point_kernel"),
-                     "bound": "hbm" if hbm_bound else ("tensor" if PF_KERNEL != "fp64" else "fp64-fma"),
-                     "achieved": gbs if hbm_bound else tfs,
-                     "peak": peaks["hbm_gbs"] if hbm_bound else pf_peak,
-                     "unit": "GB/s" if hbm_bound else "TFLOP/s",
-                     "frac": (gbs / peaks["hbm_gbs"]) if hbm_bound else (tfs / pf_peak),
-                     "traffic": NCU_TRAFFIC_PF.get((WORKLOAD, E)) if PF_KERNEL == "tc2" else None,
-                     "peak_source": peak_src if hbm_bound else pf_peak_src,
-                     "algorithmic_bytes_per_launch": pf_bytes,
-                     "algorithmic_flops_per_launch": flops,
-                     "arithmetic_intensity_flop_per_byte": flops / pf_bytes,
-                     "ridge_flop_per_byte": pf_peak * 1e12 / (peaks["hbm_gbs"] * 1e9),
-                     "hbm": {"achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"]},
-                     "tensor": {"achieved_tflops": tfs, "peak_tflops": pf_peak, "frac": tfs / pf_peak,
-                                "peak_source": pf_peak_src,
-                                "pipe_active_pct_ncu": NCU_TENSOR_PCT.get((WORKLOAD, E))
-                                if PF_KERNEL == "tc2" else None},
-                     "avg_launch_ms": pf_ms, "mean_iterations": iters_mean}
-        dominant = rf_pf if (rf_pf is not None and pf_ms > comp_ms) else rf_comp
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": _dtype_label(has_pf), "data": "synthetic",
             "config": _config(world),
-            "agent_steps_per_s": value * A,
-            "clocks": sampler.summary(),
+            "agent_steps_per_s": m["value"] * A,
+            "clocks": m["clocks"],
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / ke, "steps": ke},
-            "gpu_launches": int(launches),
-            # `roofline` = the kernel with the larger share of the step; both are always listed
-            "roofline": dominant,
-            "roofline_components": rf_comp,
-            "roofline_pf": rf_pf,
-            "kernel_share": {"components": comp_ms / max(comp_ms + pf_ms, 1e-12),
-                             "powerflow": pf_ms / max(comp_ms + pf_ms, 1e-12)},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / ke, "steps": ke,
+                    "path": "pgw_step_host on page-locked buffers: the kernels read the actions and write "
+                            "observations / rewards / done flags in host memory (zero-copy over PCIe)"},
+            "gpu_launches": m["launches"],
+            # `roofline` = the kernel with the largest share of the step; all of them under `rooflines`
+            "roofline": m["dominant"],
+            "rooflines": m["rooflines"],
+            "kernel_share": m["kernel_share"],
+            "step_kernels": list(m["rooflines"].keys()),
+            "collective_in_timed_region": False,
+            "scaling_note": "value times each step on the device (CUDA events, max over ranks): the env shards "
+                            "never exchange data, the statistics all-reduce runs after the timed steps; e2e "
+                            "(host buffers, wall clock, max over ranks) is the figure that sees the host",
             "warm_l2": {"ms_per_step": warm_ms, "value": E * world / (warm_ms * 1e-3)},
-            "stats": [float(x) for x in stats.cpu()],
-            "wall_s_timed_region": wall,
+            "stats": [float(x) for x in m["stats"].cpu()],
+            "wall_s_timed_region": m["wall"],
+            "parity": {"voltages_pu": 1e-6, "rewards": "rtol 1e-5, atol 2e-5 (float64 polish of the tcgen05 solve)",
+                       "components": "bit-identical to the two-kernel path; <= 6e-14 relative to the oracle",
+                       "tests": "tests/test_gpu_parity.py, tests/test_gpu_api.py"},
+            "numa_cpus_bound": numa_cpus,
         }
-        if not has_pf:
-            del line["roofline_pf"]
+        if extra:
+            line["extra"] = {"workloads": extra}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
@@ -667,6 +800,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1x64 / C2 / C3 legs after the headline")
     ap.add_argument("--pdl", type=int, default=1, choices=[0, 1],
                     help="power flow as a programmatic dependent launch of the component kernel "
                          "(library default 1; applies to feeders whose solver CTA leaves room on the SM)")

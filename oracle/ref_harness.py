@@ -30,7 +30,18 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("PGW_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """$PGW_REFERENCE_ROOT, the authoring container's mount, or the git-ignored install that
+    oracle/install_reference.py leaves in baseline/_ref (the only one present on a GPU box)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("PGW_REFERENCE_ROOT"), "/root/reference",
+                 os.path.join(here, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "gridworld")):
+            return cand
+    return os.environ.get("PGW_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
@@ -184,6 +195,41 @@ def load_reference():
     ns.root = REFERENCE_ROOT
     _REF = ns
     return ns
+
+
+def reference_namespace(ref=None):
+    """The reference's classes as a plugin namespace for the scenario catalog, plus the two
+    subclasses its own example scripts define outside the package."""
+    ref = ref or load_reference()
+
+    class ThisPVEnv(ref.PVEnv):                       # scenarios/heterogeneous.py:46-52
+        def step_reward(self, **kwargs):
+            v = kwargs["min_voltage"]
+            viol = min(0, v - 0.95) + min(0, 1.05 - v)
+            return -(1000 * viol) ** 2, {}
+
+    class Coordinated(ref.MultiAgentEnv):             # examples/marl/openai/train.py:37-88
+        VOLTAGE_LIMITS = [0.95, 1.05]
+        VV_UNIT_PENALTY = 1e4
+
+        def reward_transform(self, rew_dict):
+            pen = self.get_voltage_violation() * self.VV_UNIT_PENALTY
+            n = len(rew_dict)
+            for k in rew_dict.keys():
+                rew_dict[k] -= (pen / n)
+            return rew_dict
+
+        def get_voltage_violation(self):
+            bus_id = list(set(self.agent_name_bus_map.values()))[0]
+            v = self.pf_solver.get_bus_voltage_by_name(bus_id)
+            return max([0.0, self.VOLTAGE_LIMITS[0] - v, v - self.VOLTAGE_LIMITS[1]])
+
+    return types.SimpleNamespace(
+        MultiComponentEnv=ref.MultiComponentEnv,
+        FiveZoneROMThermalEnergyEnv=ref.FiveZoneROMThermalEnergyEnv,
+        PVEnv=ref.PVEnv, GridAwarePVEnv=ThisPVEnv, EnergyStorageEnv=ref.EnergyStorageEnv,
+        EVChargingEnv=ref.EVChargingEnv, MultiAgentEnv=ref.MultiAgentEnv,
+        CoordinatedMultiBuildingControlEnv=Coordinated)
 
 
 class quiet_stdout:

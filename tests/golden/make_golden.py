@@ -33,39 +33,8 @@ sys.path.insert(0, ROOT)
 
 from tests import scenarios as S  # noqa: E402
 from tests.flatten import flat_obs, unflatten_action, action_layout  # noqa: E402
-from oracle.ref_harness import load_reference, quiet_stdout  # noqa: E402
+from oracle.ref_harness import load_reference, quiet_stdout, reference_namespace  # noqa: E402
 from oracle.powerflow import OracleOpenDSSSolver  # noqa: E402
-
-
-def reference_namespace(ref):
-    class ThisPVEnv(ref.PVEnv):                       # scenarios/heterogeneous.py:46-52
-        def step_reward(self, **kwargs):
-            v = kwargs["min_voltage"]
-            viol = min(0, v - 0.95) + min(0, 1.05 - v)
-            return -(1000 * viol) ** 2, {}
-
-    class Coordinated(ref.MultiAgentEnv):             # examples/marl/openai/train.py:37-88
-        VOLTAGE_LIMITS = [0.95, 1.05]
-        VV_UNIT_PENALTY = 1e4
-
-        def reward_transform(self, rew_dict):
-            pen = self.get_voltage_violation() * self.VV_UNIT_PENALTY
-            n = len(rew_dict)
-            for k in rew_dict.keys():
-                rew_dict[k] -= (pen / n)
-            return rew_dict
-
-        def get_voltage_violation(self):
-            bus_id = list(set(self.agent_name_bus_map.values()))[0]
-            v = self.pf_solver.get_bus_voltage_by_name(bus_id)
-            return max([0.0, self.VOLTAGE_LIMITS[0] - v, v - self.VOLTAGE_LIMITS[1]])
-
-    return types.SimpleNamespace(
-        MultiComponentEnv=ref.MultiComponentEnv,
-        FiveZoneROMThermalEnergyEnv=ref.FiveZoneROMThermalEnergyEnv,
-        PVEnv=ref.PVEnv, GridAwarePVEnv=ThisPVEnv, EnergyStorageEnv=ref.EnergyStorageEnv,
-        EVChargingEnv=ref.EVChargingEnv, MultiAgentEnv=ref.MultiAgentEnv,
-        CoordinatedMultiBuildingControlEnv=Coordinated)
 
 
 def storage_socs(ref, env):

@@ -290,6 +290,14 @@ int pgw_stats(pgw_env* env, double* out, void* cuda_stream);
 int pgw_clock(const pgw_env* env);
 /* Number of kernels this handle has launched since creation (bench accounting). */
 long long pgw_launch_count(const pgw_env* env);
+/* CUDA graphs captured and instantiated since creation: pgw_step keeps ONE per handle however many
+ * different caller buffers it sees; pgw_step_host one per set of host buffers (at most 8). */
+long long pgw_graph_captures(const pgw_env* env);
+/* Resets taken so far.  The first reset of a handle initialises the state that the reference keeps
+ * across episodes (Home-Steward meta state and storage cost, gridworld/base_hs.py:53-61); a
+ * checkpoint carries the count so that a resumed handle does not repeat that (pgw_set_reset_count). */
+long long pgw_reset_count(const pgw_env* env);
+int pgw_set_reset_count(pgw_env* env, long long resets);
 /* Runtime options (pgw_set_option): */
 #define PGW_OPT_PF_KERNEL 0   /* 0 = FP64 SIMT fixed point (default); 1 = tcgen05 tensor-core
                                  fixed point (split-TF32 operands, FP32 accumulate in TMEM),

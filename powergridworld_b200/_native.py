@@ -82,6 +82,9 @@ SYMBOLS = {
     "pgw_stats": (C.c_int, [_vp, _vp, _vp]),
     "pgw_clock": (C.c_int, [_vp]),
     "pgw_launch_count": (C.c_longlong, [_vp]),
+    "pgw_graph_captures": (C.c_longlong, [_vp]),
+    "pgw_reset_count": (C.c_longlong, [_vp]),
+    "pgw_set_reset_count": (C.c_int, [_vp, C.c_longlong]),
     "pgw_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "pgw_pf_solve": (C.c_int, [_vp, _vp, _vp, _vp]),
     "pgw_set_timing": (C.c_int, [_vp, C.c_int]),

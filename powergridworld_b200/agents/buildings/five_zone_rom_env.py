@@ -57,6 +57,37 @@ class FiveZoneROMEnv(ComponentEnv):
     def _terminal_after(self):
         return self.max_episode_steps - 1           # time_index == max_episode_steps - 1 (:301)
 
+    def _meta(self, ctx) -> dict:
+        """The state dict get_obs builds and step returns as meta (:223, :256-271): zone
+        temperatures C x + mean from the device state, comfort margins against the event's
+        bounds, exogenous entries of the event row, the lagged grid variables the step saw."""
+        from collections import OrderedDict
+        Cm, mean = assets.array("building/ss_C"), assets.array("building/mean_output")
+        s0, d0 = self._slot["sd"][0], self._slot["dtab"][0]
+        T = [Cm[z] * ctx.sd(s0 + z) + mean[z] for z in range(5)]
+        lb, ub = ctx.dtab(d0 + 12), ctx.dtab(d0 + 13)
+        st = OrderedDict()
+        for z in range(5):
+            st[f"zone_temp_{z}"] = T[z]
+        for z in range(5):
+            st[f"zone_upper_viol_{z}"] = T[z] - ub
+        for z in range(5):
+            st[f"zone_lower_viol_{z}"] = lb - T[z]
+        st["comfort_lower"], st["comfort_upper"] = ctx.scalar(lb), ctx.scalar(ub)
+        st["outdoor_temp"] = ctx.scalar(ctx.dtab(d0 + 11))
+        st["p_consumed"] = ctx.sd(s0 + 5)
+        st["time_of_day"] = ctx.scalar(ctx.dtab(d0 + 14))
+        # nominal 1.0 unless delivered; min / max default to the BUS voltage (sic, :265-267),
+        # then the delivered grid variables overwrite their keys (:271)
+        bv = ctx.grid("bus_voltage") if "bus_voltage" in self._obs_labels else None
+        for key in ("bus_voltage", "min_voltage", "max_voltage"):
+            st[key] = bv if bv is not None else 1.0
+        st["p_setpoint"] = np.inf
+        for key in ("min_voltage", "max_voltage"):
+            if key in self._obs_labels:
+                st[key] = ctx.grid(key)
+        return st
+
     def _emit(self, b, agent_index, standalone):
         if not self._thermal_energy_reward:
             raise NotImplementedError(

@@ -47,6 +47,10 @@ class EnergyStorageEnv(ComponentEnv):
     def _terminal_after(self):
         return self.max_episode_steps - 1           # simulation_step + 1 == max (:155-157, :181)
 
+    def _meta(self, ctx) -> dict:
+        soc = ctx.sd(self._slot["sd"][0])
+        return {"state_of_charge": ctx.vector([soc])}         # raw_obs, a 1-vector (:178)
+
     def _emit(self, b, agent_index, standalone):
         dpar = [self.storage_range[0], self.storage_range[1], self.charge_efficiency,
                 self.discharge_efficiency, self.max_power, self.control_interval_in_hr,

@@ -62,6 +62,10 @@ class PVEnv(ComponentEnv):
     def _terminal_after(self):
         return self.episode_length - 1              # index == episode_length - 1 (:117-119)
 
+    def _meta(self, ctx) -> dict:
+        # raw available power of the row the step acted on (obs_meta of get_obs, :113, :143)
+        return {"real_power": ctx.scalar(-ctx.dtab(self._slot["dtab"][0]))}
+
     def _emit(self, b, agent_index, standalone):
         flags = (N.F_RESCALE if self.rescale_spaces else 0) | \
                 (N.F_GRID_AWARE if self.grid_aware else 0)

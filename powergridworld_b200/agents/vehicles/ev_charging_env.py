@@ -83,6 +83,24 @@ class EVChargingEnv(ComponentEnv):
         # reset leaves time_index == 1 (hidden step, :163); terminal at max_episode_steps - 1
         return self.max_episode_steps - 2
 
+    def _meta(self, ctx) -> dict:
+        """The station's state dict (get_obs returns it as meta, :121-128; step_reward adds
+        nothing, :135-142).  Raw values: the delivered observation, un-scaled when the spaces are
+        rescaled (the inverse map reproduces the raw value to an ulp or two)."""
+        o0 = self._slot["obs"][0]
+        hi = self._observation_space.high
+        out = OrderedDict()
+        for j, key in enumerate(self._obs_labels):
+            v = ctx.obs(o0 + j)
+            out[key] = (v + 1.0) * (0.5 * hi[j]) if self.rescale_spaces else v
+        # meta.update(rew_meta) (:259-262): the unserved-energy REWARD TERM replaces the state
+        # entry of the same name, and the peak term is added
+        over = out["real_power_consumed"] - self.peak_threshold
+        over = over * (over > 0)
+        out["peak_reward"] = -self.peak_penalty * over ** 2
+        out["real_power_unserved"] = -self.unserved_penalty * out["real_power_unserved"] ** 2
+        return out
+
     _rows = None
 
     def _draw_roster(self):

@@ -94,6 +94,11 @@ class ComponentEnv(ABC):
     def obs_labels(self) -> list:
         return self._obs_labels
 
+    # ---- meta of a step, rebuilt from the device state (the 4th return value of
+    # gridworld's step(); ctx: see MultiAgentEnv._meta_context)
+    def _meta(self, ctx) -> dict:
+        return {}
+
     # ---- spec compiler hooks
     @abstractmethod
     def _emit(self, builder, agent_index: int, standalone: bool) -> None:
@@ -138,6 +143,9 @@ class MultiComponentEnv(ComponentEnv):
 
     def _terminal_after(self):
         return min(e._terminal_after() for e in self.envs)
+
+    def _meta(self, ctx) -> dict:
+        return {e.name: e._meta(ctx) for e in self.envs}     # base.py:127-130
 
     @property
     def obs_labels_dict(self) -> Dict[str, list]:

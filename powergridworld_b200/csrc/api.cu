@@ -72,6 +72,7 @@ struct pgw_env {
   long long resets = 0;
   int has_house = 0;          // 1 = houses, 2 = houses with step_meta telemetry
   long long launches = 0;
+  long long graph_captures = 0;        // graphs captured + instantiated since creation
   // device tables
   unsigned char* comp_blob = nullptr;   // [agents | comps | dpar | ipar]
   int comp_blob_bytes = 0, off_comps = 0, off_dpar = 0, off_ipar = 0, dpar_len = 0;
@@ -214,6 +215,44 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
         k.act_off >= spec->act_dim || k.dpar_off < 0 || k.dpar_off > spec->dpar_len ||
         k.ipar_off < 0 || k.ipar_off > spec->ipar_len)
       return fail(PGW_ERR_INVALID, "component offsets out of range");
+    {
+      // rows each component kind reads and writes (layouts in include/pgw.h): a spec that is off
+      // by a row must come back as PGW_ERR_INVALID, not as an out-of-bounds access on the device
+      auto ip = [&](int i) { return k.ipar_off + i < spec->ipar_len ? spec->ipar[k.ipar_off + i] : -1; };
+      const bool tel = (k.flags & PGW_F_TELEMETRY) != 0;
+      int act = 1, obs_min = 1, sd = 0, si = 0, dw = 0, iw = 0;
+      switch (k.type) {
+        case PGW_STORAGE: sd = 1; break;
+        case PGW_PV: obs_min = (k.flags & PGW_F_GRID_AWARE) ? 2 : 1; dw = 1; break;
+        case PGW_EV: case PGW_HS_EV: {
+          const int n = ip(0), words = ip(1), cap = ip(2);
+          if (n <= 0 || words != (n + 31) / 32 || cap <= 0)
+            return fail(PGW_ERR_INVALID, "EV station: ipar must hold n, ceil(n/32), list capacity");
+          obs_min = k.type == PGW_EV ? 6 : 7;
+          sd = n + (k.type == PGW_HS_EV ? 1 : 0); si = words; dw = 2 + 2 * cap; iw = 2 + 2 * cap;
+          break;
+        }
+        case PGW_BUILDING: act = 6; sd = 6; dw = 17; break;
+        case PGW_HS_BEGIN: act = 0; obs_min = 0; sd = 5; dw = 1; break;
+        case PGW_HS_PV: dw = 1; break;
+        case PGW_HS_STORAGE: obs_min = 2; sd = 2; break;
+        case PGW_HS_DEVICES: {
+          const int cols = ip(0);
+          if (cols <= 0) return fail(PGW_ERR_INVALID, "devices: ipar must hold the column count");
+          obs_min = cols; dw = 2 * cols;
+          break;
+        }
+        default: break;
+      }
+      if (tel && k.type >= PGW_HS_PV) sd += PGW_HS_TEL_ROWS;
+      if (k.act_off + act > spec->act_dim) return fail(PGW_ERR_INVALID, "component action rows out of range");
+      if (k.obs_dim < obs_min) return fail(PGW_ERR_INVALID, "component observation rows: fewer than the kind writes");
+      if (k.sd_off < 0 || k.sd_off + sd > spec->sd_rows || k.si_off < 0 || k.si_off + si > spec->si_rows)
+        return fail(PGW_ERR_INVALID, "component state rows out of range");
+      if (k.dtab_off < 0 || k.dtab_off + dw > spec->dtab_stride || k.itab_off < 0 ||
+          k.itab_off + iw > spec->itab_stride)
+        return fail(PGW_ERR_INVALID, "component event-row block out of range");
+    }
     if (!spec->feeder && (k.flags & (PGW_F_GRID_AWARE | PGW_F_PV_VOLT_REWARD)))
       return fail(PGW_ERR_INVALID, "grid-aware component without a feeder");
     if (k.type == PGW_BUILDING && (k.flags & PGW_F_BUILDING_FAST) && k.obs_dim != 15)
@@ -928,7 +967,7 @@ static pgw::FusedParams step_fused_params(pgw_env* env, const double* actions, d
   pgw::FusedParams P{};
   P.c = step_comp_params(env, actions, obs, rew, done, e_lo, e_hi, 1, 0);
   P.f = step_pf_params(env, rew, e_lo, e_hi, 1u, false);
-  P.C = env->C; P.act_dim = env->act_dim; P.e_lo = e_lo; P.e_hi = e_hi; P.tmem_cols = env->fused_tmem_cols;
+  P.C = env->C; P.act_dim = env->act_dim; P.sd_rows = env->sd_rows; P.e_lo = e_lo; P.e_hi = e_hi; P.tmem_cols = env->fused_tmem_cols;
   P.tickets = tickets ? tickets : (unsigned int)fused_grid(e_hi - e_lo);
   P.stagger_cycles = stagger;
   return P;
@@ -1045,6 +1084,7 @@ static int capture_step_graph(pgw_env* env, const double* actions, double* obs, 
     else { g.kind[q] = 2; g.nargs[q] = env->pf_kernel == 2 ? 3 : 1; }
   }
   g.actions = actions; g.obs = obs; g.rew = rew; g.done = done;
+  ++env->graph_captures;
   return PGW_OK;
 }
 
@@ -1229,6 +1269,7 @@ static int zero_copy_step(pgw_env* env, const double* actions, double* obs, doub
       cudaGraphDestroy(graph);
       if (ce != cudaSuccess) return fail(PGW_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
       env->host_graphs.push_back({actions, obs, rew, done, exec});
+      ++env->graph_captures;
     }
   }
   if (exec) {
@@ -1295,6 +1336,7 @@ int pgw_step_host(pgw_env* env, const double* actions, double* obs, double* rew,
       cudaGraphDestroy(graph);
       if (ce != cudaSuccess) return fail(PGW_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
       env->host_graphs.push_back({actions, obs, rew, done, exec});
+      ++env->graph_captures;
     }
   }
   if (exec) {
@@ -1465,6 +1507,13 @@ int pgw_debug_comp_span(pgw_env* env, long long* host_out, int ctas) {
 int pgw_debug_num_comp_ctas(pgw_env* env) { return env ? env->num_ctas : 0; }
 #endif
 long long pgw_launch_count(const pgw_env* env) { return env ? env->launches : 0; }
+long long pgw_graph_captures(const pgw_env* env) { return env ? env->graph_captures : 0; }
+long long pgw_reset_count(const pgw_env* env) { return env ? env->resets : 0; }
+int pgw_set_reset_count(pgw_env* env, long long resets) {
+  if (!env || resets < 0) return fail(PGW_ERR_INVALID, "invalid argument");
+  env->resets = resets;
+  return PGW_OK;
+}
 
 int pgw_set_option(pgw_env* env, int option, int value) {
   if (env && option == PGW_OPT_CLIP_INIT_SOC) {      // a reset parameter: the step graphs stay valid

@@ -162,6 +162,7 @@ struct FusedParams {
   PfParams f;              // power-flow side: tc2 tables and images, voltages, penalty hook
   int C;                   // components per env
   int act_dim;             // action rows per env
+  int sd_rows;             // double state rows per env
   int e_lo, e_hi;
   int tmem_cols;           // 32 x (1 + Znb chunks), rounded up to a power of two
   unsigned int tickets;    // CTAs of all launches of this step (the last one advances the clock)

@@ -137,6 +137,28 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
   if (pf.phase_clk != nullptr && threadIdx.x == 0) pf.phase_clk[(size_t)(blockIdx.x + P.e_lo / SF_ENVS) * 16 + 12] = (long long)global_timer_ns();
 #endif
   SF_STAMP(0);
+  const int tiles0 = (P.e_hi - P.e_lo + SF_ENVS - 1) / SF_ENVS;
+  // Pull the first tile's state rows (double state, warm-start voltages, episode returns, lagged
+  // grid variables) towards L2 while the clock, the tables and the operand images are in flight:
+  // eight 32-byte sectors per 256-byte row segment, rows spread over the warps.
+  if ((int)blockIdx.x < tiles0 && lane < 16 && pf.warm_start && w < pf.nb) {   // 16-byte elements
+    const size_t e0 = (size_t)P.e_lo + (size_t)blockIdx.x * SF_ENVS + (size_t)lane * 2;
+    if (e0 < (size_t)P.e_hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf.u_state + (size_t)w * E + e0));
+  }
+  if ((int)blockIdx.x < tiles0 && lane < 8) {
+    const size_t e0 = (size_t)P.e_lo + (size_t)blockIdx.x * SF_ENVS + (size_t)lane * 4;
+    if (e0 < (size_t)P.e_hi) {
+      for (int r = w; r < P.sd_rows; r += SF_WARPS) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc.sd + (size_t)r * E + e0));
+      for (int a = w; a < pc.A; a += SF_WARPS) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf.ep_ret + (size_t)a * E + e0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pc.vbus + (size_t)a * E + e0));
+      }
+      if (w == 0) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pc.vmin + e0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pc.vmax + e0));
+      }
+    }
+  }
   const int clk = *pc.clock;
   unsigned int my_ticket = 0u;
   const int event = clk + 1;

@@ -49,7 +49,8 @@ class ZBusSolver(PowerFlowSolver):
         self.base_load = np.stack([f.load_kw[pq], f.load_kvar[pq]], axis=1)
         self._pq_mask = pq
         self.bus_voltages = {}
-        self._env = None           # owning MultiAgentEnv (set by it) or a private 1-env handle
+        self._env = None           # the MultiAgentEnv that owns this solver (set by it), if any
+        self._host_env = None      # private one-env handle behind a stand-alone calculate_power_flow
 
     # ---- table compilation used by MultiAgentEnv
     def base_load_at(self, current_time):
@@ -67,19 +68,25 @@ class ZBusSolver(PowerFlowSolver):
     def calculate_power_flow(self, p_controllable_consumed: dict = None,
                              q_controllable_consumed: dict = None, current_time: str = None):
         from powergridworld_b200.multiagent_env import _standalone_solver_env
-        if self._env is None or not getattr(self._env, "_is_solver_host", False):
-            self._env = _standalone_solver_env(self)
+        if self._env is not None:
+            # the owning env solves on the device inside reset / step; a second, private solve
+            # here would leave two sets of voltages behind one accessor
+            raise RuntimeError("this solver belongs to a MultiAgentEnv: its power flow runs inside "
+                               "env.reset() / env.step(); build a separate OpenDSSSolver for "
+                               "stand-alone solves")
+        if self._host_env is None:
+            self._host_env = _standalone_solver_env(self)
         kw, kvar = self.base_load_at(current_time)
         if p_controllable_consumed is not None:
             for name in self.load_bus_name:                                  # :115-129
                 i = self.feeder.load_index(name)
                 kw[i] += p_controllable_consumed.get(name, 0.0)
                 kvar[i] += (q_controllable_consumed or {}).get(name, 0.0)
-        self._env._solve_loads(kw, kvar)
-        self.bus_voltages = self._env._voltage_dict()
+        self._host_env._solve_loads(kw, kvar)
+        self.bus_voltages = self._host_env._voltage_dict()
 
     def get_bus_voltages(self) -> dict:
-        if self._env is not None and not getattr(self._env, "_is_solver_host", False):
+        if self._env is not None:
             self.bus_voltages = self._env._voltage_dict()
         return self.bus_voltages
 

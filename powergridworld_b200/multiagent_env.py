@@ -14,9 +14,10 @@ handle.  ``reset``/``step`` then run entirely on the GPU:
     pinned host arrays (the end-to-end path).
 
 Deviations from the reference, all deliberate: ``history`` is only recorded when
-``record_history=True``; ``meta`` dicts carry the grid-level entries only;
-overriding ``get_external_obs_vars`` is rejected (the grid variables are assembled
-on the device with the reference's one-step lag).
+``record_history=True``; overriding ``get_external_obs_vars`` is rejected (the grid
+variables are assembled on the device with the reference's one-step lag).  The
+``meta`` dicts of ``step`` are rebuilt from the device state (``_step_meta``; the
+batched form is ``meta_batch``).
 """
 from __future__ import annotations
 
@@ -90,6 +91,39 @@ class SpecBuilder:
         self.objs.append(obj)
 
 
+class _MetaCtx:
+    """What a component's ``_meta`` hook reads to rebuild the reference's step meta: rows of the
+    double state and of the delivered observation (NumPy scalars for one env, ``[E]`` tensors
+    for a batch), the host copy of the step's event row, and the lagged grid variables the
+    step's observations were built from."""
+
+    def __init__(self, env, agent_index, sd, obs, event, lag, batch):
+        self.env, self.agent, self._sd, self._obs = env, agent_index, sd, obs
+        self.event, self.lag, self.batch = event, lag, batch
+
+    def sd(self, row):
+        return self._sd[row]
+
+    def obs(self, row):
+        return self._obs[row]
+
+    def dtab(self, col):
+        return float(self.env._dtab[self.event, col])
+
+    def scalar(self, v):
+        return v if self.batch else np.float64(v)
+
+    def vector(self, items):
+        return _torch().stack(list(items)) if self.batch else np.array(items, dtype=np.float64)
+
+    def grid(self, key):
+        if self.lag is None:
+            return None
+        if key == "bus_voltage":
+            return self.lag["vbus"][self.agent]
+        return self.lag["vmin" if key == "min_voltage" else "vmax"]
+
+
 class MultiAgentEnv:
     """gridworld/multiagent_env.py:20-230 over ``num_envs`` instances on one GPU."""
 
@@ -143,7 +177,8 @@ class MultiAgentEnv:
                 solver.tol = pf_tol
             if pf_max_iter is not None:
                 solver.max_iter = pf_max_iter
-            solver._env = self
+            if not getattr(self, "_is_solver_host", False):
+                solver._env = self
             self.pf_solver = solver
 
         self.observation_space = {a.name: a.observation_space for a in self.agents}
@@ -259,14 +294,8 @@ class MultiAgentEnv:
                 self.act_slices[ag.name] = ag._slot["act"]
                 self.obs_slices[ag.name] = ag._slot["obs"]
 
-    def _open(self, device):
-        torch = _torch()
-        if not torch.cuda.is_available():
-            raise N.NativeError("powergridworld_b200 needs a CUDA device (B200, sm_100a); "
-                                "there is no CPU fallback")
-        self.device = torch.device(device if device is not None else
-                                   f"cuda:{torch.cuda.current_device()}")
-        lib = N.lib()
+    def _build_spec(self):
+        """The pgw_spec of the compiled scenario + the objects that keep its pointers alive."""
         b = self._b
         spec = N.Spec()
         spec.abi_version = N.ABI_VERSION
@@ -316,6 +345,17 @@ class MultiAgentEnv:
                 fd.penalty_vlo, fd.penalty_vhi, fd.penalty_unit = self._penalty
             spec.feeder = C.pointer(fd)
             keep += [fd, arrs]
+        return spec, keep
+
+    def _open(self, device):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise N.NativeError("powergridworld_b200 needs a CUDA device (B200, sm_100a); "
+                                "there is no CPU fallback")
+        self.device = torch.device(device if device is not None else
+                                   f"cuda:{torch.cuda.current_device()}")
+        lib = N.lib()
+        spec, keep = self._build_spec()
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             N.check(lib.pgw_create(C.byref(spec), C.byref(handle)))
@@ -333,6 +373,8 @@ class MultiAgentEnv:
         self._pin = None
         self._host_step = None
         self._needs_reset = True
+        self._lag = None
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -455,6 +497,7 @@ class MultiAgentEnv:
                                         self._stream()))
         self.episode_step = 0
         self._needs_reset = False
+        self._lag = None
         if self.record_history:
             self.history = {"timestamp": [], "voltage": [], "agent_power_p": []}
         return self.obs
@@ -469,8 +512,14 @@ class MultiAgentEnv:
                 or not actions.is_contiguous() or actions.device != self.device:
             raise ValueError(f"actions must be a contiguous float64 [{self.act_dim}, "
                              f"{self.num_envs}] tensor on {self.device}")
-        rc = self._lib.pgw_step(self._h, actions.data_ptr(), self._obs_ptr, self._rew_ptr,
-                                self._done_ptr, torch.cuda.current_stream(self.device).cuda_stream)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if torch.cuda.current_device() == self._dev_index:
+            rc = self._lib.pgw_step(self._h, actions.data_ptr(), self._obs_ptr, self._rew_ptr,
+                                    self._done_ptr, stream)
+        else:                                       # the caller's current device is another GPU
+            with torch.cuda.device(self.device):
+                rc = self._lib.pgw_step(self._h, actions.data_ptr(), self._obs_ptr, self._rew_ptr,
+                                        self._done_ptr, stream)
         if rc:
             N.check(rc)
         self.episode_step += 1
@@ -592,7 +641,11 @@ class MultiAgentEnv:
                 continue
             fields[f] = self.get_field(f).clone()
         state = {"fields": fields, "episode_step": self.episode_step, "obs": self.obs.clone(),
-                 "needs_reset": self._needs_reset}
+                 "needs_reset": self._needs_reset,
+                 # resets taken so far: the first reset of a handle gives the state that the
+                 # reference keeps across episodes its constructor value (house meta state,
+                 # storage cost), later ones must not
+                 "resets": int(self._lib.pgw_reset_count(self._h))}
         rand = self._randomised()
         if rand:                                    # the rosters drawn at the last reset
             state["rosters"] = [None if o._rows is None else np.array(o._rows) for o in rand]
@@ -613,10 +666,15 @@ class MultiAgentEnv:
             if t.numel():
                 N.check(self._lib.pgw_set(self._h, int(f), C.c_void_p(t.data_ptr()),
                                           t.numel() * t.element_size(), self._stream()))
-        N.check(self._lib.pgw_set_clock(self._h, int(state["episode_step"]), self._stream()))
-        self.episode_step = int(state["episode_step"])
+        N.check(self._lib.pgw_set_reset_count(self._h, int(state.get("resets", 1))))
+        if state["episode_step"] is None:           # checkpoint taken before the first reset
+            self.episode_step, self._needs_reset = None, True
+        else:
+            N.check(self._lib.pgw_set_clock(self._h, int(state["episode_step"]), self._stream()))
+            self.episode_step = int(state["episode_step"])
+            self._needs_reset = bool(state["needs_reset"])
         self.obs.copy_(state["obs"])
-        self._needs_reset = bool(state["needs_reset"])
+        self._lag = None
 
     def stats(self):
         """Episode statistics reduced on the device: tensor[8], see include/pgw.h."""
@@ -705,7 +763,39 @@ class MultiAgentEnv:
         if init_storage is not None:
             init_storage = np.asarray(init_storage, dtype=np.float64).reshape(self.num_storage, 1)
         obs = self.reset_batch(init_storage)
+        self._lag = self._grid_snapshot()
         return self._obs_dict(obs[:, 0].cpu().numpy())
+
+    # ---- step meta (the 4th return value of gridworld's step, multiagent_env.py:168, :210)
+    def _grid_snapshot(self, batch=False):
+        """The grid variables of the last solve, i.e. what the NEXT step's observations (and
+        the building's state dict) are built from (multiagent_env.py:90-115, :167)."""
+        if self.pf_solver is None:
+            return None
+        vb, mn, mx = (self.get_field(f) for f in (N.FIELD_VBUS, N.FIELD_VMIN, N.FIELD_VMAX))
+        if batch:
+            return {"vbus": vb, "vmin": mn, "vmax": mx}
+        vb, mn, mx = vb[:, 0].cpu().numpy(), mn.cpu().numpy(), mx.cpu().numpy()
+        return {"vbus": [np.float64(x) for x in vb], "vmin": np.float64(mn[0]), "vmax": np.float64(mx[0])}
+
+    def _step_meta(self, flat_obs: np.ndarray) -> dict:
+        """{agent: meta} of the step just taken, one env: every stock component's meta as the
+        reference returns it (storage ``state_of_charge``, PV ``real_power``, the EV station's
+        and the building's state dicts), rebuilt from the device state."""
+        sd = self.get_field(N.FIELD_STATE_D)[:, 0].cpu().numpy() if self._b.sd_rows else np.zeros(0)
+        meta = {}
+        for i, a in enumerate(self.agents):
+            meta[a.name] = a._meta(_MetaCtx(self, i, sd, flat_obs, self.episode_step, self._lag, False))
+        self._lag = self._grid_snapshot()
+        return meta
+
+    def meta_batch(self, lag=None) -> dict:
+        """The same metas for the whole batch: {agent: {component: {key: tensor[E] or float}}}
+        from the current device state.  The building's grid entries need the grid variables the
+        step OBSERVED: pass ``lag=env._grid_snapshot(batch=True)`` taken before the step."""
+        sd = self.get_field(N.FIELD_STATE_D)
+        return {a.name: a._meta(_MetaCtx(self, i, sd, self.obs, self.episode_step, lag, True))
+                for i, a in enumerate(self.agents)}
 
     def get_obs(self) -> Dict[str, any]:
         self._require_single()
@@ -722,8 +812,7 @@ class MultiAgentEnv:
         rew_d = {a.name: float(host[self.obs_dim + i]) for i, a in enumerate(self.agents)}
         dones = {a.name: bool(all_done) for a in self.agents}
         dones["__all__"] = bool(all_done)
-        meta = {a.name: ({e.name: {} for e in a.envs} if isinstance(a, MultiComponentEnv) else {})
-                for a in self.agents}
+        meta = self._step_meta(host[:self.obs_dim])
         p = self.get_field(N.FIELD_AGENT_P)[:, 0].cpu().numpy()
         for i, a in enumerate(self.agents):
             a._real_power = float(p[i])             # agent.real_power (base.py:51-55)
@@ -735,18 +824,23 @@ class MultiAgentEnv:
 
 
 def reduce_stats(s, group=None):
-    """All-reduce of a ``pgw_stats`` vector: SUM on the additive entries 0-5 (env-steps,
-    reward sum, episode returns, violation sum, non-converged count, iterations), MIN on
-    entry 6 (min voltage), MAX on entry 7.  One NCCL call for the sums, two scalar ones for
-    the extrema; identity when no process group is initialised."""
+    """All-reduce of a ``pgw_stats`` vector in ONE collective: SUM on the additive entries 0-5
+    (env-steps, reward sum, episode returns, violation sum, non-converged count, iterations),
+    MIN on entry 6 (min voltage), MAX on entry 7.  The extrema travel in rank-owned slots of the
+    summed vector (every other rank contributes 0 there) and are reduced locally afterwards;
+    identity when no process group is initialised."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return s
-    add, lo, hi = s[:6].clone(), s[6:7].clone(), s[7:8].clone()
-    dist.all_reduce(add, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
-    return _torch().cat([add, lo, hi])
+    torch = _torch()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    packed = torch.zeros(6 + 2 * world, dtype=s.dtype, device=s.device)
+    packed[:6] = s[:6]
+    packed[6 + rank] = s[6]
+    packed[6 + world + rank] = s[7]
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return torch.cat([packed[:6], packed[6:6 + world].min().reshape(1),
+                      packed[6 + world:].max().reshape(1)])
 
 
 def shard_envs(total_envs: int, rank: int, world_size: int):

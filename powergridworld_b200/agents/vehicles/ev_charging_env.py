@@ -20,6 +20,17 @@ from powergridworld_b200.base import ComponentEnv
 from powergridworld_b200.utils import maybe_rescale_box_space
 
 
+def _popcount(word):
+    """Set bits of a 32-bit state word: a NumPy scalar (one env) or an int32 tensor [E]."""
+    if isinstance(word, (int, np.integer)):
+        return np.float64(bin(int(word) & 0xFFFFFFFF).count("1"))
+    x = word.long() & 0xFFFFFFFF
+    x = x - ((x >> 1) & 0x55555555)
+    x = (x & 0x33333333) + ((x >> 2) & 0x33333333)
+    x = (x + (x >> 4)) & 0x0F0F0F0F
+    return ((x * 0x01010101) & 0xFFFFFFFF).__rshift__(24).double()
+
+
 def _read_vehicle_csv(path):
     import pandas as pd
     df = pd.read_csv(path)
@@ -93,6 +104,16 @@ class EVChargingEnv(ComponentEnv):
         for j, key in enumerate(self._obs_labels):
             v = ctx.obs(o0 + j)
             out[key] = (v + 1.0) * (0.5 * hi[j]) if self.rescale_spaces else v
+        # the state dict is NOT clipped to the observation bounds (:121-128 copies self.state), the
+        # scaled observation is: with vehicle_multiplier > 1 the vehicle count exceeds its bound
+        # num_vehicles (:81, :247), so it is counted from the charging-set words instead
+        s0, words = self._slot["si"]
+        count = None
+        for w in range(words):
+            word = ctx.si(s0 + w)
+            c = _popcount(word)
+            count = c if count is None else count + c
+        out["num_active_vehicles"] = self.vehicle_multiplier * count
         # meta.update(rew_meta) (:259-262): the unserved-energy REWARD TERM replaces the state
         # entry of the same name, and the peak term is added
         over = out["real_power_consumed"] - self.peak_threshold

@@ -100,6 +100,14 @@ class _MetaCtx:
     def __init__(self, env, agent_index, sd, obs, event, lag, batch):
         self.env, self.agent, self._sd, self._obs = env, agent_index, sd, obs
         self.event, self.lag, self.batch = event, lag, batch
+        self._si = None
+
+    def si(self, row):
+        """Row of the uint32 state (fetched on first use: only the EV station's meta reads it)."""
+        if self._si is None:
+            si = self.env.get_field(N.FIELD_STATE_I)
+            self._si = si if self.batch else si[:, 0].cpu().numpy()
+        return self._si[row]
 
     def sd(self, row):
         return self._sd[row]

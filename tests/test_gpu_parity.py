@@ -614,7 +614,7 @@ def test_tc2_every_tile_width_standalone_and_in_env(tmp_path, n_loads):
     assert a.feeder.nb == n_loads
     for s_, k in ((a, 0), (b, 2)):
         s_.calculate_power_flow(current_time="08-12-2021 12:00:00")
-        s_._env.set_option(N.OPT_PF_KERNEL, k)
+        s_._host_env.set_option(N.OPT_PF_KERNEL, k)
     names = a.feeder.load_names
     ctrl = {names[0]: 150.0, names[3]: -80.0, names[n_loads - 1]: 40.0}
     for s_ in (a, b):

@@ -39,7 +39,7 @@ with warnings.catch_warnings():
     run(PNS.MultiAgentEnv(**S.der123_scenario(PNS, PNS.OpenDSSSolver), num_envs=130), 2, 2)
 s = PNS.OpenDSSSolver(**dict(S.IEEE13, system_load_rescale_factor=0.7))
 s.calculate_power_flow(current_time="01-01-2021 05:00:00")
-s._env.set_option(N.OPT_PF_KERNEL, 2)
+s._host_env.set_option(N.OPT_PF_KERNEL, 2)
 s.calculate_power_flow(current_time="01-01-2021 05:00:00")
 cfg = SH.two_vehicles(HNS)
 run(PNS.MultiAgentEnv(

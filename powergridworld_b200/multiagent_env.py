@@ -132,7 +132,13 @@ class _MetaCtx:
         return self.lag["vmin" if key == "min_voltage" else "vmax"]
 
 
-class MultiAgentEnv:
+try:                                                   # multiagent_env.py:13-17: an RLlib env when ray is there
+    from ray.rllib.env.multi_agent_env import MultiAgentEnv as _Env
+except ImportError:
+    _Env = object
+
+
+class MultiAgentEnv(_Env):
     """gridworld/multiagent_env.py:20-230 over ``num_envs`` instances on one GPU."""
 
     # grid-level reward hook; subclasses set these (see CoordinatedMultiBuildingControlEnv)
@@ -147,6 +153,8 @@ class MultiAgentEnv:
             raise NotImplementedError(
                 "overriding get_external_obs_vars is not supported: grid variables are "
                 "assembled on the device (no CPU fallback)")
+        if _Env is not object:
+            super().__init__()
         self.common_config = common_config
         self.rescale_spaces = rescale_spaces
         assert agents is not None and len(agents) > 0, "need at least one agent!"

@@ -278,3 +278,57 @@ def test_standalone_solve_on_an_owned_solver_is_refused():
     solo.calculate_power_flow(current_time="08-12-2021 00:00:00")
     v = solo.get_bus_voltages()
     assert len(v) == 38 and 0.9 < min(v.values()) < max(v.values()) < 1.1
+
+
+def test_rllib_style_adapter_speaks_the_gymnasium_multi_agent_protocol():
+    """examples/marl/rllib/heterogeneous/train.py:12-17 hands RLlib `MultiAgentEnv(**config)`; the
+    adapter is the same env behind reset -> (obs, infos) / step -> 5-tuple."""
+    from powergridworld_b200.adapters import RLlibMultiAgentEnv
+    cfg = S.heterogeneous_scenario(PNS, PNS.OpenDSSSolver, 0.65)
+    ad = RLlibMultiAgentEnv(dict(cfg, max_episode_steps=6))
+    ref = PNS.MultiAgentEnv(**dict(cfg, max_episode_steps=6))
+    np.random.seed(3)
+    obs, infos = ad.reset(seed=3)
+    np.random.seed(3)
+    want = ref.reset()
+    assert set(obs) == set(ad.possible_agents) == set(infos) == set(ref.agent_names)
+    np.testing.assert_array_equal(flat_obs(ad.env, obs), flat_obs(ref, want))
+    rng = np.random.default_rng(0)
+    for t in range(ad.max_episode_steps):
+        flat = rng.uniform(-1, 1, size=ref.act_dim)
+        o, r, term, trunc, info = ad.step(unflatten_action(ad.env, flat))
+        o2, r2, d2, m2 = ref.step(unflatten_action(ref, flat))
+        np.testing.assert_array_equal(flat_obs(ad.env, o), flat_obs(ref, o2))
+        assert r == r2 and term == d2 and not any(trunc.values())
+        assert set(info) <= set(ref.agent_names) | {"__common__"}
+        assert info["pv"]["real_power"] == m2["pv"]["real_power"]
+    assert term["__all__"]
+
+
+def test_batched_joint_vector_env_autoresets_and_matches_step_host():
+    from powergridworld_b200.adapters import BatchedJointVectorEnv
+    E = 96
+    cfg = dict(S.buildings_scenario(PNS, PNS.OpenDSSSolver, 1.2), max_episode_steps=5,
+               env_cls=PNS.CoordinatedMultiBuildingControlEnv, pf_kernel="tc2")
+    vec = BatchedJointVectorEnv(cfg, num_envs=E)
+    ref = PNS.CoordinatedMultiBuildingControlEnv(
+        **{k: v for k, v in cfg.items() if k != "env_cls"}, num_envs=E)
+    soc = np.random.default_rng(1).uniform(10, 40, size=(ref.num_storage, E))
+    obs, _ = vec.reset(options={"init_storage": soc})
+    want = ref.reset_host(soc)
+    assert obs.shape == (E, ref.obs_dim) == vec.observation_space.shape
+    np.testing.assert_array_equal(obs, want.T)
+    rng = np.random.default_rng(2)
+    steps = vec.env.episode_length
+    for t in range(steps):
+        a = rng.uniform(-1, 1, size=(E, ref.act_dim))
+        o, r, term, trunc, info = vec.step(a)
+        o2, r2, d2 = ref.step_host(np.ascontiguousarray(a.T))
+        np.testing.assert_array_equal(info["agent_rewards"], r2)
+        np.testing.assert_array_equal(r, r2.sum(axis=0))
+        last = t == steps - 1
+        assert term.all() == last and not trunc.any()
+        np.testing.assert_array_equal(info["final_observation"] if last else o, o2.T)
+    assert vec.episodes == 1 and o.shape == (E, ref.obs_dim)   # o is the next episode's first observation
+    sl = vec.agent_obs_slices["building-1"]
+    assert sl.stop - sl.start == sum(s.shape[0] for s in ref.observation_space["building-1"].values())

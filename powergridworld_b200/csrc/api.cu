@@ -105,6 +105,7 @@ struct pgw_env {
     cudaGraphNode_t nodes[2] = {nullptr, nullptr};
     cudaKernelNodeParams params[2] = {};
     int kind[2] = {0, 0}, nargs[2] = {1, 1}, num_nodes = 0, pdl = 0;
+    bool has_event = false;             // the fused node's parameters carry a host-side event index
     const void *actions = nullptr, *obs = nullptr, *rew = nullptr, *done = nullptr;
     void destroy() {
       if (exec) cudaGraphExecDestroy(exec);
@@ -776,6 +777,33 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
       }
       blob.resize((blob.size() + 15) / 16 * 16, 0);
       t.tab_bytes = (int)(blob.size() - (size_t)t.off_tab);
+      t.off_ftab = (int)blob.size(); t.ftab_bytes = 0; t.pen_slot = -1;
+      if (t.polish_ok) {                               // the fused step kernel's own section
+        auto putf = [&blob, &t](const void* src, size_t bytes) {
+          const size_t off = (blob.size() + 15) / 16 * 16;
+          blob.resize(off + bytes, 0);
+          if (bytes) memcpy(blob.data() + off, src, bytes);
+          return (int)(off - (size_t)t.off_ftab);
+        };
+        std::vector<int32_t> aslot(std::max(env->A, 1), -1);
+        for (int a = 0; a < env->A; ++a)
+          for (int k = 0; k < nb; ++k)
+            if (node[a] >= 0 && dnode[k] == node[a]) aslot[a] = k;
+        for (int k = 0; k < nb; ++k)
+          if (env->punit != 0.0 && dnode[k] == env->penalty_node) t.pen_slot = k;
+        t.f_kc = putf(&env->tc2c, sizeof(env->tc2c));
+        t.f_kp = putf(&env->tc2p, sizeof(env->tc2p));
+        t.f_aslot = putf(aslot.data(), aslot.size() * 4);
+        std::vector<float> z32(2 * 16 * 16, 0.f);     // float32 pre-sweep: Zbb^T / xscale, [j][k]
+        for (int j = 0; j < nb; ++j)
+          for (int k = 0; k < nb; ++k) {
+            const double2 z = Z(k, j);
+            z32[2 * (j * 16 + k)] = (float)(z.x / xs); z32[2 * (j * 16 + k) + 1] = (float)(z.y / xs);
+          }
+        t.f_z32 = putf(z32.data(), z32.size() * 4);
+        blob.resize((blob.size() + 15) / 16 * 16, 0);
+        t.ftab_bytes = (int)(blob.size() - (size_t)t.off_ftab);
+      }
       pgw::PfParams probe{};
       probe.nl = f.nl; probe.tc2 = t;
       if (pgw::tc2_smem_bytes(probe) + 6 * 1024 <= 227 * 1024) {   // + the kernel's static arrays
@@ -963,8 +991,9 @@ static int fused_grid(int envs) { return std::max(1, std::min(pgw::step_fused_ti
 // advances the clock); 0 = this launch is the whole step.
 static pgw::FusedParams step_fused_params(pgw_env* env, const double* actions, double* obs, double* rew,
                                           uint8_t* done, int e_lo, int e_hi, unsigned int tickets,
-                                          int stagger = 0) {
+                                          int stagger = 0, int event = -1) {
   pgw::FusedParams P{};
+  P.event = event;
   P.c = step_comp_params(env, actions, obs, rew, done, e_lo, e_hi, 1, 0);
   P.f = step_pf_params(env, rew, e_lo, e_hi, 1u, false);
   P.C = env->C; P.act_dim = env->act_dim; P.sd_rows = env->sd_rows; P.e_lo = e_lo; P.e_hi = e_hi; P.tmem_cols = env->fused_tmem_cols;
@@ -993,11 +1022,11 @@ static unsigned int step_pf_tickets(pgw_env* env, const int* bounds, int chunks)
 
 static int enqueue_step(pgw_env* env, const double* actions, double* obs, double* rew,
                         uint8_t* done, cudaStream_t s, bool timed, int e_lo = 0, int e_hi = -1,
-                        int chunks = 1, unsigned int pf_tickets = 0u, int stagger = 0) {
+                        int chunks = 1, unsigned int pf_tickets = 0u, int stagger = 0, int event = -1) {
   if (e_hi < 0) e_hi = env->E;
   if (use_fused(env)) {
     if (timed) PGW_CUDA(cudaEventRecord(env->next_event(), s));
-    const pgw::FusedParams P = step_fused_params(env, actions, obs, rew, done, e_lo, e_hi, pf_tickets, stagger);
+    const pgw::FusedParams P = step_fused_params(env, actions, obs, rew, done, e_lo, e_hi, pf_tickets, stagger, event);
     PGW_CUDA(pgw::launch_step_fused(P, fused_grid(e_hi - e_lo), s));
     if (timed) {                                       // one kernel: reported in the component slot
       PGW_CUDA(cudaEventRecord(env->next_event(), s));
@@ -1022,7 +1051,7 @@ static int step_kernels(const pgw_env* env) { return use_fused(env) ? 1 : (env->
 // (cudaGraphExecKernelNodeSetParams: no re-capture, no re-instantiation; a policy loop that
 // hands in a fresh action tensor every step replays the same executable graph).
 static int retarget_step_graph(pgw_env* env, const double* actions, double* obs, double* rew,
-                               uint8_t* done) {
+                               uint8_t* done, int event) {
   pgw_env::StepGraph& g = env->step_graph;
   for (int i = 0; i < g.num_nodes; ++i) {
     cudaKernelNodeParams np = g.params[i];
@@ -1032,8 +1061,9 @@ static int retarget_step_graph(pgw_env* env, const double* actions, double* obs,
     pgw::CompParams cp;
     pgw::PfParams pf;
     if (g.kind[i] == 0) {
-      fp = step_fused_params(env, actions, obs, rew, done, 0, env->E, 0u);
+      fp = step_fused_params(env, actions, obs, rew, done, 0, env->E, 0u, 0, event);
       args[0] = &fp;
+      g.has_event = event >= 0;
     } else if (g.kind[i] == 1) {
       cp = step_comp_params(env, actions, obs, rew, done, 0, env->E, 1, g.pdl);
       args[0] = &cp;
@@ -1079,11 +1109,12 @@ static int capture_step_graph(pgw_env* env, const double* actions, double* obs, 
     const int q = g.num_nodes++;
     g.nodes[q] = nodes[i];
     PGW_CUDA(cudaGraphKernelNodeGetParams(nodes[i], &g.params[q]));
-    if (pgw::is_step_fused_kernel(g.params[q].func)) { g.kind[q] = 0; g.nargs[q] = 3; }
+    if (pgw::is_step_fused_kernel(g.params[q].func)) { g.kind[q] = 0; g.nargs[q] = 1; }
     else if (pgw::is_component_kernel(g.params[q].func)) { g.kind[q] = 1; g.nargs[q] = 1; }
     else { g.kind[q] = 2; g.nargs[q] = env->pf_kernel == 2 ? 3 : 1; }
   }
   g.actions = actions; g.obs = obs; g.rew = rew; g.done = done;
+  g.has_event = false;
   ++env->graph_captures;
   return PGW_OK;
 }
@@ -1107,11 +1138,18 @@ int pgw_step(pgw_env* env, const double* actions, double* obs, double* rew, uint
     int rc = PGW_OK;
     if (!g.exec) rc = capture_step_graph(env, actions, obs, rew, done, s);
     else if (g.actions != actions || g.obs != obs || g.rew != rew || g.done != done)
-      rc = retarget_step_graph(env, actions, obs, rew, done);
+      // the node parameters are rewritten anyway: the step's event index rides along and the
+      // fused kernel skips its read of the device clock
+      rc = retarget_step_graph(env, actions, obs, rew, done, env->clock + 1);
+    else if (g.has_event)                              // same buffers again: back to the device clock
+      rc = retarget_step_graph(env, actions, obs, rew, done, -1);
     if (rc != PGW_OK) return rc;
     PGW_CUDA(cudaGraphLaunch(g.exec, s));
   } else {
-    int rc = enqueue_step(env, actions, obs, rew, done, s, env->timing);
+    // direct launches know the event index; a launch recorded into the CALLER's capture is
+    // replayed with frozen parameters and has to read the device clock
+    const int event = cap == cudaStreamCaptureStatusNone ? env->clock + 1 : -1;
+    int rc = enqueue_step(env, actions, obs, rew, done, s, env->timing, 0, -1, 1, 0u, 0, event);
     if (rc != PGW_OK) return rc;
   }
   env->launches += step_kernels(env);

@@ -104,6 +104,12 @@ struct Tc2Params {
   // the rows the reward hook and the agents read (Tc2Polish.rows), so that those voltages meet
   // the float64 tolerance (rewards 1e-5 relative / 2e-5 absolute).  0 = off.
   int polish, polish_ok, polish_row;   // polish_row: penalty node if it is NOT a wye-load node, else -1
+  // Tables of the fused step kernel only (step_fused.cu), a section of their own behind the
+  // shared ones: the Tc2Consts and Tc2Polish records byte for byte (the fused kernel reads them
+  // from shared memory -- warp-uniform broadcasts -- instead of the parameter constant bank, whose
+  // 7 kB are cold in every SM's constant cache at every launch) and, per agent, the load branch
+  // whose wye node is the agent's bus (-1: none).  pen_slot: the same for the penalty node.
+  int off_ftab, ftab_bytes, f_kc, f_kp, f_aslot, f_z32, pen_slot;   // f_z32: float2 Zbb^T / xscale
   float xscale, descale1, descale2, tol;
 };
 
@@ -171,6 +177,10 @@ struct FusedParams {
                            // the first tiles write their observations while the last ones still read)
   int pdl_trigger;         // 1: griddepcontrol.launch_dependents once the CTA has consumed the actions of
                            // its last tile (the next env chunk's launch may start: pgw_step_host)
+  int event;               // >= 0: the step's event row, known to the host (direct launches, and graph
+                           // replays whose node parameters are rewritten for new caller buffers anyway):
+                           // the kernel skips the read of the device clock that the row's address would
+                           // otherwise wait for.  -1: read the device clock (replays of a frozen graph).
 };
 
 struct StatsParams {

@@ -59,8 +59,30 @@ __device__ __forceinline__ void sf_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// The load characteristic in float32 with correctly rounded reciprocals (the hot loop's
+// rsqrt.approx is good to 2^-22.9: squared, 2.6e-7 relative on a current) -- currents SCALED by
+// xscale like t2_current's.
+template <bool ANY_M5>
+__device__ __forceinline__ void sf_current32(float4 c, float2 gh, float dr, float di, float ds, float sr,
+                                             float si, float& x, float& y) {
+  const float ur = fmaf(dr, ds, c.x), ui = fmaf(di, ds, c.y);
+  const float m2 = fmaf(ur, ur, ui * ui);
+  const float cl = fminf(fmaxf(m2, c.z), c.w);
+  float kf = __frcp_rn(cl);
+  if (ANY_M5) kf = fmaf(gh.y, __frsqrt_rn(cl), gh.x * kf);
+  const float tr = ur * kf, ti = ui * kf;
+  x = fmaf(sr, tr, si * ti);                           // conj(s) u k
+  y = fmaf(sr, ti, -(si * tr));
+}
+__device__ __forceinline__ void sf_cmac_sub32(float2& acc, float2 z, float2 i) {
+  acc.x = fmaf(-z.x, i.x, acc.x);
+  acc.x = fmaf(z.y, i.y, acc.x);
+  acc.y = fmaf(-z.x, i.y, acc.y);
+  acc.y = fmaf(-z.y, i.x, acc.y);
+}
+
 struct SfLayout {                                      // byte offsets into dynamic shared memory
-  uint32_t b, a, stage, tab, blob, drow, irow, i64, dmax, part, cp, cr, act, total;
+  uint32_t b, a, stage, tab, ftab, blob, drow, irow, i64, dmax, part, vn, cp, cr, act, total;
 };
 
 __host__ __device__ inline SfLayout sf_layout(const FusedParams& P) {
@@ -75,12 +97,14 @@ __host__ __device__ inline SfLayout sf_layout(const FusedParams& P) {
   L.a = take(2u * SF_APB);
   L.stage = take(2u * 32u * SF_ENVS * 2u);             // hi | lo: [32 k][32 envs] halves
   L.tab = take((uint32_t)P.f.tc2.tab_bytes);
+  L.ftab = take((uint32_t)P.f.tc2.ftab_bytes);
   L.blob = take((uint32_t)P.c.blob_bytes);
   L.drow = take((uint32_t)P.c.dstride * 8u);
   L.irow = take((uint32_t)P.c.istride * 4u + 16u);
   L.i64 = take(16u * SF_ENVS * 16u);                   // currents of a polish sweep
   L.dmax = take(2u * SF_ENVS * 4u);
   L.part = take(2u * 16u * SF_ENVS * 4u);              // per-branch min / max |v| partials
+  L.vn = take(16u * SF_ENVS * 8u);                     // |v| of each branch's wye node (penalty, bus voltages)
   L.cp = take((uint32_t)P.C * SF_ENVS * 8u);           // component real power
   L.cr = take((uint32_t)P.C * SF_ENVS * 8u);           // component reward
   L.act = take((uint32_t)P.act_dim * SF_ENVS * 8u);    // the tile's actions, [act_dim][32]
@@ -102,8 +126,7 @@ __host__ __device__ inline SfLayout sf_layout(const FusedParams& P) {
 
 template <bool ANY_M5>
 __global__ void __launch_bounds__(SF_THREADS, 1)
-    step_fused_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ Tc2Consts kc,
-                      const __grid_constant__ Tc2Polish kp) {
+    step_fused_kernel(const __grid_constant__ FusedParams P) {
   extern __shared__ __align__(1024) unsigned char sf_smem[];
   __shared__ __align__(8) uint64_t mbar_tab, mbar_ev, mbar_b, mbar_mma, mbar_a, mbar_act;
   __shared__ uint32_t tmem_base_s;
@@ -120,6 +143,12 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
   unsigned char* sA = sf_smem + L.a;
   __half* sStage = reinterpret_cast<__half*>(sf_smem + L.stage);   // [part][k][env]
   unsigned char* sT = sf_smem + L.tab;
+  // per-branch constants of the load model and the float64 polish tables: shared memory, every
+  // read a warp-uniform broadcast (as kernel parameters they were 7 kB of cold constant-cache lines)
+  const Tc2Consts& kc = *reinterpret_cast<const Tc2Consts*>(sf_smem + L.ftab + t.f_kc);
+  const Tc2Polish& kp = *reinterpret_cast<const Tc2Polish*>(sf_smem + L.ftab + t.f_kp);
+  const int32_t* aslot = reinterpret_cast<const int32_t*>(sf_smem + L.ftab + t.f_aslot);
+  const float2* z32 = reinterpret_cast<const float2*>(sf_smem + L.ftab + t.f_z32);   // Zbb^T / xscale
   unsigned char* sBlob = sf_smem + L.blob;
   double* drow = reinterpret_cast<double*>(sf_smem + L.drow);
   int32_t* irow = reinterpret_cast<int32_t*>(sf_smem + L.irow);
@@ -127,6 +156,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
   int* sDmax = reinterpret_cast<int*>(sf_smem + L.dmax);           // [2][env] float bits
   float* sVmn = reinterpret_cast<float*>(sf_smem + L.part);        // [16][env]
   float* sVmx = sVmn + 16 * SF_ENVS;
+  double* sVn = reinterpret_cast<double*>(sf_smem + L.vn);         // [16][env]
   double* sCp = reinterpret_cast<double*>(sf_smem + L.cp);         // [C][env]
   double* sCr = reinterpret_cast<double*>(sf_smem + L.cr);
   double* sAct = reinterpret_cast<double*>(sf_smem + L.act);
@@ -159,7 +189,50 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
       }
     }
   }
-  const int clk = *pc.clock;
+  // The parameter block sits in the constant bank and is cold in this SM's constant cache: one
+  // lane per warp touches its 64-byte lines now, in parallel, instead of every first use of a
+  // field paying its own miss later on the critical path.
+  if (lane == 0) {
+    constexpr int kLines = (int)((sizeof(FusedParams) + 63) / 64);
+    for (int l = w; l < kLines; l += SF_WARPS) {
+      const int v = reinterpret_cast<const int*>(&P)[l * 16];
+      asm volatile("" ::"r"(v));
+    }
+  }
+  const int span = P.e_hi - P.e_lo;
+  const int tiles = (span + SF_ENVS - 1) / SF_ENVS;
+  // The actions of a (full) tile are fetched into shared memory by TMA bulk copies, one 256-byte
+  // row segment each, issued by warp 1 at kernel entry / while the previous tile's power flow
+  // runs: the component steps then find them on chip.  (The first fetch used to be issued after
+  // the tables had landed: a second ~1.4 us TMA round trip in front of the component steps.)
+  // With actions in HOST memory this is what decouples the PCIe reads from the component code, and
+  // CTA b delays its first fetch by b x stagger_cycles so that the link serves the tiles in order
+  // -- the first tiles write their observations (GPU -> host) while the last ones still wait for
+  // their actions (host -> GPU).
+  auto tile_in_smem = [&](int tile) {
+    const int e0 = P.e_lo + tile * SF_ENVS;
+    return (E % 2 == 0) && (e0 % 2 == 0) && e0 + SF_ENVS <= P.e_hi;
+  };
+  auto fetch_actions = [&](int tile) {                 // warp 1
+    if (tile < tiles && tile_in_smem(tile)) {
+      const int e0 = P.e_lo + tile * SF_ENVS;
+      if (lane == 0) mbar_expect_tx(&mbar_act, (uint32_t)P.act_dim * SF_ENVS * 8u);
+      __syncwarp();
+      for (int r = lane; r < P.act_dim; r += 32)
+        tma_bulk_g2s(sAct + (size_t)r * SF_ENVS, pc.actions + (size_t)r * E + e0, SF_ENVS * 8u, &mbar_act);
+    }
+  };
+  if (w == 1) {
+    if (lane == 0) mbar_init(&mbar_act, 1);
+    __syncwarp();
+    if (P.stagger_cycles > 0) {
+      const long long c0 = clock64(), wait = (long long)blockIdx.x * P.stagger_cycles;
+      while (clock64() - c0 < wait) { }
+    }
+    fetch_actions(blockIdx.x);
+  }
+  const bool host_event = P.event >= 0;                // CTA uniform
+  const int clk = host_event ? P.event - 1 : *pc.clock;
   unsigned int my_ticket = 0u;
   const int event = clk + 1;
   if (tid == 0) {
@@ -168,10 +241,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     mbar_init(&mbar_b, 1);
     mbar_init(&mbar_mma, 1);
     mbar_init(&mbar_a, 8);                             // one arrival per repacking warp
-    mbar_init(&mbar_act, 1);
-    mbar_expect_tx(&mbar_tab, (uint32_t)t.tab_bytes + (uint32_t)pc.blob_bytes);
+    mbar_expect_tx(&mbar_tab, (uint32_t)t.tab_bytes + (uint32_t)t.ftab_bytes + (uint32_t)pc.blob_bytes);
     tma_bulk_g2s(sBlob, pc.blob, (uint32_t)pc.blob_bytes, &mbar_tab);
     tma_bulk_g2s(sT, t.blob + t.off_tab, (uint32_t)t.tab_bytes, &mbar_tab);
+    tma_bulk_g2s(sf_smem + L.ftab, t.blob + t.off_ftab, (uint32_t)t.ftab_bytes, &mbar_tab);
     const uint32_t img = (uint32_t)(1 + t.ncc) * 2u * SF_PB;
     mbar_expect_tx(&mbar_b, img);
     tma_bulk_g2s(sB, t.blob, img, &mbar_b);            // Zbb images, then the Znb chunks
@@ -180,7 +253,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     mbar_expect_tx(&mbar_ev, dbytes + ibytes);
     tma_bulk_g2s(drow, pc.dtab + (size_t)event * pc.dstride, dbytes, &mbar_ev);
     if (ibytes) tma_bulk_g2s(irow, pc.itab + (size_t)event * pc.istride, ibytes, &mbar_ev);
-    my_ticket = clock_take_ticket(pc.ticket, clk);
+    if (!host_event) my_ticket = clock_take_ticket(pc.ticket, clk);
   }
   if (w == 0) {                                        // one warp owns TMEM alloc / free
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -312,35 +385,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     a_phase ^= 1u;
   };
 
-  const int span = P.e_hi - P.e_lo;
-  const int tiles = (span + SF_ENVS - 1) / SF_ENVS;
-  // The actions of a (full) tile are fetched into shared memory by TMA bulk copies, one 256-byte
-  // row segment each, while the prologue / the previous tile's power flow runs: the component
-  // steps then find them on chip.  With actions in HOST memory this is what decouples the PCIe
-  // reads from the component code, and CTA b delays its first fetch by b x stagger_cycles so that
-  // the link serves the tiles in order -- the first tiles write their observations (GPU -> host)
-  // while the last ones still wait for their actions (host -> GPU).
-  auto tile_in_smem = [&](int tile) {
-    const int e0 = P.e_lo + tile * SF_ENVS;
-    return (E % 2 == 0) && (e0 % 2 == 0) && e0 + SF_ENVS <= P.e_hi;
-  };
-  auto fetch_actions = [&](int tile) {                 // warp 0
-    if (tile < tiles && tile_in_smem(tile)) {
-      const int e0 = P.e_lo + tile * SF_ENVS;
-      if (lane == 0) mbar_expect_tx(&mbar_act, (uint32_t)P.act_dim * SF_ENVS * 8u);
-      __syncwarp();
-      for (int r = lane; r < P.act_dim; r += 32)
-        tma_bulk_g2s(sAct + (size_t)r * SF_ENVS, pc.actions + (size_t)r * E + e0, SF_ENVS * 8u, &mbar_act);
-    }
-  };
   uint32_t act_phase = 0;
-  if (w == 0) {
-    if (P.stagger_cycles > 0) {
-      const long long c0 = clock64(), wait = (long long)blockIdx.x * P.stagger_cycles;
-      while (clock64() - c0 < wait) { }
-    }
-    fetch_actions(blockIdx.x);
-  }
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int e_raw = P.e_lo + tile * SF_ENVS + lane;
     const bool valid = e_raw < P.e_hi;
@@ -386,7 +431,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     // has read the actions of its last tile, the next chunk may start reading its own while this
     // one's observations drain over the other direction of the link.
     if (P.pdl_trigger && tile + (int)gridDim.x >= tiles) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (w == 0) fetch_actions(tile + (int)gridDim.x);  // the staging area is free again
+    if (w == 1) fetch_actions(tile + (int)gridDim.x);  // the staging area is free again
     SF_STAMP(5);
 
     // ---- agents: real power (base.py:51-55; summed in component order from 0.0 like the
@@ -479,9 +524,34 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     const bool my_row = ((kp.rows >> b) & 1u) != 0u;
     if (polish) {
       const int sweeps = t.polish + ((kp.rows != 0u || t.polish_row >= 0) ? 1 : 0);
+      // Sweep 0 in float32.  A full sweep only has to take every branch voltage from the fixed
+      // point's ~1e-7 p.u. to ~1e-8: it feeds the currents of the next sweep, whose rows the rewards
+      // read in float64, and a sweep contracts the error by more than 10x.  Float32 currents are
+      // half the shared-memory traffic of the float64 sweep (every thread reads all currents of
+      // its env: 14 warps x 14 x 512 B was the sweep's bound) and the FMAs run on the FP32 pipe.
+      {
+        float2* sI32 = reinterpret_cast<float2*>(sI64);
+        if (b < pf.nb) {
+          float x, y;
+          sf_current32<ANY_M5>(cst, gh, dprev.x, dprev.y, ds1, sr, si, x, y);
+          sI32[b * SF_ENVS + lane] = make_float2(x, y);
+        }
+        __syncthreads();
+        if (b < pf.nb) {
+          float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll 2
+          for (int jj = 0; jj + 1 < pf.nb; jj += 2) {
+            sf_cmac_sub32(a0, z32[jj * 16 + b], sI32[jj * SF_ENVS + lane]);
+            sf_cmac_sub32(a1, z32[(jj + 1) * 16 + b], sI32[(jj + 1) * SF_ENVS + lane]);
+          }
+          if (pf.nb & 1) sf_cmac_sub32(a0, z32[(pf.nb - 1) * 16 + b], sI32[(pf.nb - 1) * SF_ENVS + lane]);
+          u64 = make_double2(kp.u0[b].x + (double)(a0.x + a1.x), kp.u0[b].y + (double)(a0.y + a1.y));
+          if (t.polish == 1 && valid) pf.u_state[(size_t)b * E + e] = u64;
+        }
+      }
 #pragma unroll 1
-      for (int sweep = 0; sweep < sweeps; ++sweep) {
-        if (sweep > 0) __syncthreads();                // everyone has read the previous currents
+      for (int sweep = 1; sweep < sweeps; ++sweep) {
+        __syncthreads();                               // everyone has read the previous currents
         if (b < pf.nb) sI64[b * SF_ENVS + lane] = t2_current64(kp.model[b], s64, u64, kp.vlo2[b], kp.vhi2[b]);
         __syncthreads();
         if (b < pf.nb && (sweep < t.polish || my_row)) {
@@ -515,6 +585,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
           mag = (double)(m2f * t2_rsqrt(fmaxf(m2f, 1e-30f)) * dscale[b]);
         }
         vmn = vmx = (float)mag;
+        sVn[b * SF_ENVS + lane] = mag;
         if (valid) pf.vmag[(size_t)n * E + e] = mag;
       }
     }
@@ -563,7 +634,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     if (valid) {
       double pen_share = 0.0, viol = 0.0;
       if (pf.punit != 0.0) {
-        const double v = have_row ? v_row : pf.vmag[(size_t)pf.penalty_node * E + e];
+        const double v = have_row ? v_row
+                                  : (t.pen_slot >= 0 ? sVn[t.pen_slot * SF_ENVS + lane]
+                                                     : pf.vmag[(size_t)pf.penalty_node * E + e]);
         viol = fmax(0.0, fmax(pf.pvlo - v, v - pf.pvhi));                 // train.py:71-88
         pen_share = (viol * pf.punit) / (double)pf.A;                     // train.py:56-61
       }
@@ -591,7 +664,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
         }
         const int node = anode[a];
         double vb = 1.0;
-        if (node >= 0) vb = (have_row && node == t.polish_row) ? v_row : pf.vmag[(size_t)node * E + e];
+        if (node >= 0)
+          vb = (have_row && node == t.polish_row) ? v_row
+               : (aslot[a] >= 0 ? sVn[aslot[a] * SF_ENVS + lane] : pf.vmag[(size_t)node * E + e]);
         const double r = pf.reward_hook ? ra - pen_share : ra;
         pf.vbus[ae] = vb;
         pc.rew[ae] = r;
@@ -612,7 +687,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
                  "r"((uint32_t)P.tmem_cols)
                  : "memory");
-  if (tid == 0) clock_advance_if_last(my_ticket, pc.ticket, pc.clock, clk, P.tickets);
+  if (tid == 0) {
+    if (!host_event) clock_advance_if_last(my_ticket, pc.ticket, pc.clock, clk, P.tickets);
+    else if (blockIdx.x == 0) *pc.clock = event;       // nobody reads it in this mode: any CTA may publish
+  }
 #ifdef PGW_PHASE_TIMERS
   if (pf.phase_clk != nullptr && threadIdx.x == 0) {
     pf.phase_clk[(size_t)(blockIdx.x + P.e_lo / SF_ENVS) * 16 + 14] = clock64();
@@ -644,7 +722,7 @@ cudaError_t launch_step_fused(const FusedParams& P, int grid, cudaStream_t s, bo
   attr[0].val.programmaticStreamSerializationAllowed = programmatic ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, P, *P.f.tc2.consts, *P.f.tc2.pconsts);
+  return cudaLaunchKernelEx(&cfg, kern, P);
 }
 
 }  // namespace pgw

@@ -38,6 +38,10 @@ def main():
     rng = np.random.default_rng(0)
     soc = rng.uniform(10, 45, size=(env.num_storage, E))
     acts = torch.as_tensor(rng.uniform(-1, 1, size=(env.act_dim, E))).cuda()
+    # PGW_PROBE_ROTATE=1: two action buffers in turn, i.e. the node parameters are rewritten every
+    # step and carry the event index (the kernel skips its clock read), as in bench.py's loop
+    rotate = os.environ.get("PGW_PROBE_ROTATE", "0") == "1"
+    acts2 = acts.clone()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     st = torch.cuda.Stream()
     torch.cuda.set_stream(st)
@@ -49,7 +53,7 @@ def main():
             if cold:
                 flush.fill_(t & 0xFF)
             e0.record()
-            env.step_batch(acts)
+            env.step_batch(acts2 if (rotate and t % 2) else acts)
             e1.record()
             if t >= 20:
                 buf = np.zeros((ctas, 16), dtype=np.int64)
@@ -59,7 +63,7 @@ def main():
         a = np.stack(acc).astype(np.float64)
         d = np.diff(a[:, :, :11], axis=2) / mhz
         span = (a[:, :, 13].max(axis=1) - a[:, :, 12].min(axis=1)) / 1e3
-        print(f"--- fused C1 E={E} ctas={ctas} {'cold' if cold else 'warm'} L2, SM {mhz:.0f} MHz, iterations "
+        print(f"--- fused C1 E={E} ctas={ctas} {'event index from the host' if rotate else 'device clock'}, {'cold' if cold else 'warm'} L2, SM {mhz:.0f} MHz, iterations "
               f"{a[:, :, 11].mean():.2f}; first entry -> last exit {span.mean():.2f} us; step by CUDA events "
               f"{np.mean(ev):.2f} us")
         for k, name in enumerate(PHASES):

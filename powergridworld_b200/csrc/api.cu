@@ -985,7 +985,13 @@ static bool use_fused(const pgw_env* env) {
   return env->fused_mode == 2 || pgw::step_fused_tiles(env->E) <= 2 * 148;
 }
 
-static int fused_grid(int envs) { return std::max(1, std::min(pgw::step_fused_tiles(envs), 148)); }
+static int fused_grid(int envs) {
+  static const int cap = [] {                          // PGW_FUSED_GRID: tuning knob (CTAs of the fused kernel)
+    const char* v = getenv("PGW_FUSED_GRID");
+    return v ? std::max(1, atoi(v)) : 148;
+  }();
+  return std::max(1, std::min(pgw::step_fused_tiles(envs), cap));
+}
 
 // `tickets` = CTAs of all the launches that make up the step (the CTA that takes the last ticket
 // advances the clock); 0 = this launch is the whole step.

@@ -115,9 +115,14 @@ __host__ __device__ inline SfLayout sf_layout(const FusedParams& P) {
 // Phase stamps of tools/phase_probe.py (instrumented build only, -DPGW_PHASE_TIMERS): thread 0 of
 // every CTA records the SM clock at the phase boundaries of its first tile.
 #ifdef PGW_PHASE_TIMERS
+#ifdef PGW_STAMP_SECOND_TILE                           // the CTA's SECOND tile: tables, TMEM, code already there
+#define SF_STAMP_TILE (!first_tile)
+#else
+#define SF_STAMP_TILE first_tile
+#endif
 #define SF_STAMP(k)                                                                  \
   do {                                                                               \
-    if (pf.phase_clk != nullptr && threadIdx.x == 0 && first_tile)                   \
+    if (pf.phase_clk != nullptr && threadIdx.x == 0 && SF_STAMP_TILE)                \
       pf.phase_clk[(size_t)(blockIdx.x + P.e_lo / SF_ENVS) * 16 + (k)] = clock64();    \
   } while (0)
 #else
@@ -677,7 +682,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
     __syncthreads();                                   // shared arrays are reused by the next tile
     SF_STAMP(10);
 #ifdef PGW_PHASE_TIMERS
-    if (pf.phase_clk != nullptr && threadIdx.x == 0 && first_tile) pf.phase_clk[(size_t)(blockIdx.x + P.e_lo / SF_ENVS) * 16 + 11] = it_stamp;
+    if (pf.phase_clk != nullptr && threadIdx.x == 0 && SF_STAMP_TILE) pf.phase_clk[(size_t)(blockIdx.x + P.e_lo / SF_ENVS) * 16 + 11] = it_stamp;
 #endif
     first_tile = false;
   }

@@ -13,7 +13,9 @@ import torch  # noqa: E402
 
 from powergridworld_b200 import _native as N  # noqa: E402
 
-N.LIB_PATH = os.path.join(ROOT, "tools", "_build", "libpgw_b200_phases.so")
+SECOND = os.environ.get("PGW_PROBE_SECOND", "0") == "1"      # stamps of each CTA's second tile (build with
+#                                                               -DPGW_STAMP_SECOND_TILE, run with PGW_FUSED_GRID=64)
+N.LIB_PATH = os.path.join(ROOT, "tools", "_build", "libpgw_b200_phases2.so" if SECOND else "libpgw_b200_phases.so")
 from powergridworld_b200.scenarios import bench as SB  # noqa: E402
 
 PHASES = ["clock read + barrier init + TMA issue + TMEM alloc + zero A", "wait tables / component blob",
@@ -34,7 +36,7 @@ def main():
     lib.pgw_debug_phases.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     mhz = float(subprocess.run(["nvidia-smi", "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits"],
                                capture_output=True, text=True).stdout.split()[0])
-    ctas = min((E + 31) // 32, 148)
+    ctas = min((E + 31) // 32, int(os.environ.get("PGW_FUSED_GRID", "148")))
     rng = np.random.default_rng(0)
     soc = rng.uniform(10, 45, size=(env.num_storage, E))
     acts = torch.as_tensor(rng.uniform(-1, 1, size=(env.act_dim, E))).cuda()
@@ -67,8 +69,10 @@ def main():
               f"{a[:, :, 11].mean():.2f}; first entry -> last exit {span.mean():.2f} us; step by CUDA events "
               f"{np.mean(ev):.2f} us")
         for k, name in enumerate(PHASES):
+            if SECOND and k < 3:
+                continue
             print(f"  {name:64s} mean {d[:, :, k].mean():6.2f} us   max-CTA mean {d[:, :, k].max(axis=1).mean():6.2f} us")
-        tot = (a[:, :, 14] - a[:, :, 0]) / mhz
+        tot = (a[:, :, 10] - a[:, :, 3]) / mhz if SECOND else (a[:, :, 14] - a[:, :, 0]) / mhz
         print(f"  {'entry -> exit':64s} mean {tot.mean():6.2f} us   max-CTA mean {tot.max(axis=1).mean():6.2f} us")
 
 

@@ -73,6 +73,12 @@ typedef enum pgw_component_type {
                                    (cost, reward, raw action, solar / battery / grid power consumed,
                                    device_custom_info entries)                                         */
 #define PGW_HS_TEL_ROWS 13
+#define PGW_F_EV_PER_ENV 64u    /* EVChargingEnv(randomize=True) in a batch: every env instance parks its OWN
+                                   roster sample (ev_charging_env.py:154-157).  ipar = n, ceil(n/32), 0; the
+                                   station's uint32 state is ceil(n/32) charging-set words followed by n
+                                   window words (floor(start) << 16 | floor(end), minutes) per env; the
+                                   window words and the n initial energies are written by the host with
+                                   pgw_set_rows before every pgw_reset; event row = {t, t_next} only        */
 #define PGW_F_STALE_REWARD 8u   /* stand-alone building agent: reward from the pre-step state
                                    (five_zone_rom_env.py:215 precedes :223)                            */
 
@@ -270,6 +276,12 @@ int pgw_get(pgw_env* env, int field, void* dst, size_t bytes, void* cuda_stream)
  * reference has no env-level checkpointing; restoring every field of
  * pgw_get plus the clock reproduces the trajectory bit for bit. */
 int pgw_set(pgw_env* env, int field, const void* src, size_t bytes, void* cuda_stream);
+
+/* The same for `row_count` consecutive rows of a [rows][num_envs] field (PGW_FIELD_STATE_D,
+ * PGW_FIELD_STATE_I), starting at `row_begin`: src is a device buffer of row_count x num_envs
+ * elements.  Per-env rosters of randomised charging stations (PGW_F_EV_PER_ENV) go in this way. */
+int pgw_set_rows(pgw_env* env, int field, int row_begin, int row_count, const void* src, size_t bytes,
+                 void* cuda_stream);
 int pgw_set_clock(pgw_env* env, int steps, void* cuda_stream);
 
 /* Replace the VALUES of the parameter block and of both event tables (host pointers; the

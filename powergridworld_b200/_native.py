@@ -21,6 +21,7 @@ HS_BEGIN, HS_PV, HS_STORAGE, HS_EV, HS_DEVICES = 5, 6, 7, 8, 9
 HS_MAX_COMPONENTS = 8
 F_TELEMETRY, HS_TEL_ROWS = 32, 13
 F_RESCALE, F_GRID_AWARE, F_PV_VOLT_REWARD, F_STALE_REWARD, F_BUILDING_FAST = 1, 2, 4, 8, 16
+F_EV_PER_ENV = 64
 
 OPT_PF_KERNEL, OPT_WARM_START, OPT_GRAPHS, OPT_PDL, OPT_CLIP_INIT_SOC = 0, 1, 2, 3, 4
 OPT_PF_POLISH, OPT_PF_TC_TOL_NANO, OPT_FUSED, OPT_HOST_CHUNKS, OPT_HOST_ZERO_COPY = 5, 6, 7, 8, 9
@@ -77,6 +78,7 @@ SYMBOLS = {
     "pgw_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "pgw_get": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _vp]),
     "pgw_set": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _vp]),
+    "pgw_set_rows": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
     "pgw_set_clock": (C.c_int, [_vp, C.c_int, _vp]),
     "pgw_update_tables": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "pgw_stats": (C.c_int, [_vp, _vp, _vp]),

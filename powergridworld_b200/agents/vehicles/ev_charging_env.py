@@ -107,7 +107,7 @@ class EVChargingEnv(ComponentEnv):
         # the state dict is NOT clipped to the observation bounds (:121-128 copies self.state), the
         # scaled observation is: with vehicle_multiplier > 1 the vehicle count exceeds its bound
         # num_vehicles (:81, :247), so it is counted from the charging-set words instead
-        s0, words = self._slot["si"]
+        s0, words = self._slot["si"][0], (self.num_vehicles + 31) // 32
         count = None
         for w in range(words):
             word = ctx.si(s0 + w)
@@ -123,16 +123,48 @@ class EVChargingEnv(ComponentEnv):
         return out
 
     _rows = None
+    _num_envs = 1            # set by the MultiAgentEnv that compiles this station
+
+    @property
+    def _per_env(self) -> bool:
+        """A randomised station in a batch: every env instance samples its own roster, like every
+        instance of the reference's class does in its own reset (:154-157)."""
+        return bool(self.randomize) and self._num_envs > 1
 
     def _draw_roster(self):
         """df.sample(n) (:155): np.random.choice(len(df), n, replace=False), rows kept in drawn
-        order (the order fixes the index each vehicle gets after reset_index, :157)."""
-        self._rows = np.random.choice(len(self._roster_energy), size=self.num_vehicles,
-                                      replace=False)
+        order (the order fixes the index each vehicle gets after reset_index, :157).  In a batch:
+        one draw per env instance, env 0 first -- ``_rows`` is [num_envs, n]."""
+        draw = lambda: np.random.choice(len(self._roster_energy), size=self.num_vehicles, replace=False)
+        self._rows = np.stack([draw() for _ in range(self._num_envs)]) if self._per_env else draw()
+
+    def _per_env_rows(self):
+        """(window words uint32 [n, E], initial energies float64 [n, E]) of the current per-env
+        draw, as PGW_F_EV_PER_ENV lays them out: floor(start) << 16 | floor(end) in minutes."""
+        rows = self._rows                                   # [E, n]
+        start = np.floor(self._roster_start[rows])
+        end = np.floor(self._roster_end[rows])
+        if not (np.array_equal(end, self._roster_end[rows]) and start.min() >= 0 and end.min() >= 0
+                and max(start.max(), end.max()) < 65535):
+            raise NotImplementedError("per-env rosters need parking times that are whole minutes in "
+                                      "[0, 65535) after rounding to the step (ev_charging_env.py:75-76)")
+        words = (start.astype(np.uint32) << np.uint32(16)) | end.astype(np.uint32)
+        return np.ascontiguousarray(words.T), np.ascontiguousarray(self._roster_energy[rows].T)
+
+    def _static_dpar(self):
+        hi = self._observation_space.high
+        dpar = [self.max_charge_rate_kw, self.minutes_per_step / 60., float(self.vehicle_multiplier),
+                self.unserved_penalty, self.peak_penalty, self.peak_threshold, self.reward_scale]
+        return dpar + list(hi) + list(1.0 / hi) + [1.0 / self.reward_scale, 1.0 / 60.0]
 
     def _retable(self):
         """(dpar, dtab_fn, itab_fn) of the current roster; widths do not depend on the draw."""
         n = self.num_vehicles
+        if self._per_env:                                   # the roster lives in per-env state rows
+            times = self.simulation_times
+            n_ev = len(times) - 1
+            return (self._static_dpar(),
+                    lambda r: [times[min(r, n_ev - 1)], times[min(r, n_ev - 1) + 1]], None)
         rows = self._rows if (self.randomize and self._rows is not None) else np.arange(n)
         start = np.floor(self._roster_start[rows])
         end = np.floor(self._roster_end[rows])
@@ -169,16 +201,22 @@ class EVChargingEnv(ComponentEnv):
             row[2 + cap:2 + cap + len(lefts[k])] = lefts[k]
             return row
 
-        hi = self._observation_space.high
-        dpar = [self.max_charge_rate_kw, self.minutes_per_step / 60., float(self.vehicle_multiplier),
-                self.unserved_penalty, self.peak_penalty, self.peak_threshold, self.reward_scale]
-        dpar += list(hi) + list(1.0 / hi) + [1.0 / self.reward_scale, 1.0 / 60.0]
+        dpar = self._static_dpar()
         dpar += list(self._roster_end[rows]) + list(self._roster_energy[rows])
         return dpar, dtab_fn, itab_fn
 
     def _emit(self, b, agent_index, standalone):
         n = self.num_vehicles
         dpar, dtab_fn, itab_fn = self._retable()
+        if self._per_env:
+            if n > 256:
+                raise NotImplementedError("per-env rosters serve stations of up to 256 vehicles")
+            words = (n + 31) // 32
+            b.add_component(self, N.EV, agent_index,
+                            flags=(N.F_RESCALE if self.rescale_spaces else 0) | N.F_EV_PER_ENV,
+                            dpar=dpar, ipar=[n, words, 0], sd_rows=n, si_rows=words + n,
+                            dtab_width=2, dtab_fn=dtab_fn)
+            return
         cap, words = self._cap, (n + 31) // 32
         b.add_component(self, N.EV, agent_index,
                         flags=N.F_RESCALE if self.rescale_spaces else 0,

@@ -227,6 +227,13 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
         case PGW_PV: obs_min = (k.flags & PGW_F_GRID_AWARE) ? 2 : 1; dw = 1; break;
         case PGW_EV: case PGW_HS_EV: {
           const int n = ip(0), words = ip(1), cap = ip(2);
+          if (k.flags & PGW_F_EV_PER_ENV) {            // per-env rosters: window words behind the mask
+            if (k.type != PGW_EV || n <= 0 || n > 256 || words != (n + 31) / 32)
+              return fail(PGW_ERR_INVALID, "EV station with per-env rosters: stock station, 1..256 vehicles, "
+                                           "ipar = n, ceil(n/32), 0");
+            obs_min = 6; sd = n; si = words + n; dw = 2; iw = 0;
+            break;
+          }
           if (n <= 0 || words != (n + 31) / 32 || cap <= 0)
             return fail(PGW_ERR_INVALID, "EV station: ipar must hold n, ceil(n/32), list capacity");
           obs_min = k.type == PGW_EV ? 6 : 7;
@@ -1443,6 +1450,25 @@ int pgw_set(pgw_env* env, int field, const void* src, size_t bytes, void* cuda_s
   if (!dst) return fail(PGW_ERR_INVALID, "field not available (no feeder)");
   if ((rc = check_size(want, bytes))) return rc;
   PGW_CUDA(cudaMemcpyAsync(dst, src, want, cudaMemcpyDeviceToDevice,
+                           static_cast<cudaStream_t>(cuda_stream)));
+  return PGW_OK;
+}
+
+int pgw_set_rows(pgw_env* env, int field, int row_begin, int row_count, const void* src, size_t bytes,
+                 void* cuda_stream) {
+  if (!env || !src) return fail(PGW_ERR_INVALID, "null argument");
+  if (field != PGW_FIELD_STATE_D && field != PGW_FIELD_STATE_I)
+    return fail(PGW_ERR_INVALID, "pgw_set_rows serves the two state arrays");
+  const int rows = field == PGW_FIELD_STATE_D ? env->sd_rows : env->si_rows;
+  const size_t el = field == PGW_FIELD_STATE_D ? 8 : 4;
+  if (row_begin < 0 || row_count < 0 || row_begin + row_count > rows)
+    return fail(PGW_ERR_INVALID, "row range outside the field");
+  int rc = check_size((size_t)row_count * (size_t)env->E * el, bytes);
+  if (rc) return rc;
+  if (row_count == 0) return PGW_OK;
+  unsigned char* base = field == PGW_FIELD_STATE_D ? reinterpret_cast<unsigned char*>(env->sd)
+                                                   : reinterpret_cast<unsigned char*>(env->si);
+  PGW_CUDA(cudaMemcpyAsync(base + (size_t)row_begin * (size_t)env->E * el, src, bytes, cudaMemcpyDeviceToDevice,
                            static_cast<cudaStream_t>(cuda_stream)));
   return PGW_OK;
 }

@@ -26,8 +26,10 @@
 #define PGW_RESTRICT __restrict__
 #if defined(__CUDA_ARCH__)
 #define PGW_POPC(x) __popc(x)
+#define PGW_CTZ(x) (__ffs((int)(x)) - 1)
 #else
 #define PGW_POPC(x) __builtin_popcount(x)
+#define PGW_CTZ(x) __builtin_ctz(x)
 #endif
 #if defined(__CUDACC__)
 #define PGW_NO_UNROLL _Pragma("unroll 1")
@@ -241,6 +243,73 @@ PGW_HD EvTotals ev_charge_pass(const pgw_component& c, const AgentIO& io, int e,
   return t;
 }
 
+// The same pass for a station whose roster is PER ENV (PGW_F_EV_PER_ENV: every env instance of a
+// randomised station samples its own vehicles, ev_charging_env.py:154-157): slot i of env e parks
+// from floor(start) to floor(end) minutes, packed into the env's window word i; "parked at t" is
+// evaluated per env (:186-190), the departed vehicles are old charging set \ new one (:194).
+PGW_HD EvTotals ev_charge_pass_env(const pgw_component& c, const AgentIO& io, int e, double kwh) {
+  const double* dp = io.dpar + c.dpar_off;
+  const int32_t* ip = io.ipar + c.ipar_off;
+  const int n = ip[0], words = ip[1];
+  const double rate = dp[0], inv60 = dp[20];
+  const double t_now = io.drow[c.dtab_off];
+  double* energy = io.sd + (size_t)c.sd_off * io.E + e;
+  uint32_t* mask = io.si + (size_t)c.si_off * io.E + e;
+  const uint32_t* win = mask + (size_t)words * io.E;
+
+  EvTotals t;
+  t.consumed = 0.0; t.demand = 0.0; t.deficit_sum = 0.0; t.unserved = 0.0;
+  t.active = 0; t.n_deficit = 0;
+  uint32_t old_w[8], new_w[8];
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    old_w[w] = w < words ? mask[(size_t)w * io.E] : 0u;
+    new_w[w] = 0u;
+  }
+  for (int i0 = 0; i0 < n; i0 += kEvBatch) {           // ascending slot index, loads batched
+    uint32_t ww[kEvBatch];
+    double need8[kEvBatch];
+#pragma unroll
+    for (int j = 0; j < kEvBatch; ++j) ww[j] = i0 + j < n ? win[(size_t)(i0 + j) * io.E] : 0xFFFF0000u;
+#pragma unroll
+    for (int j = 0; j < kEvBatch; ++j) {
+      const bool parked = t_now >= (double)(ww[j] >> 16) && t_now <= (double)(ww[j] & 0xFFFFu);
+      need8[j] = parked ? energy[(size_t)(i0 + j) * io.E] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < kEvBatch; ++j) {
+      const int i = i0 + j;
+      const double need = need8[j];
+      if (!(need > 0.0)) continue;                      // not parked, or :191
+#pragma unroll
+      for (int w = 0; w < 8; ++w)                       // (static indices: the words stay in registers)
+        if (w == (i >> 5)) new_w[w] |= 1u << (i & 31);
+      ++t.active;
+      t.demand += need;                                 // :210
+      const double left_h = div_by((double)(ww[j] & 0xFFFFu) - t_now, 60.0, inv60);   // :216
+      if (left_h <= 0.0) continue;                      // :218-220
+      t.deficit_sum += fmax(0.0, rate - need / left_h); // :221-223
+      ++t.n_deficit;
+      const double delta = fmin(kwh, need);             // :226-228
+      energy[(size_t)i * io.E] = need - delta;
+      t.consumed += delta;
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (w < words) {
+      mask[(size_t)w * io.E] = new_w[w];
+      uint32_t gone = old_w[w] & ~new_w[w];             // :240-243, ascending index
+      while (gone) {
+        const int bit = PGW_CTZ(gone);
+        gone &= gone - 1u;
+        t.unserved += energy[(size_t)(32 * w + bit) * io.E];
+      }
+    }
+  }
+  return t;
+}
+
 PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double kwh,
                        double& p_out, double& rew) {
   const double* dp = io.dpar + c.dpar_off;
@@ -248,7 +317,8 @@ PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double 
   const double* obs_high = dp + 7;
   const double* inv_high = dp + 13;
   const double t_now = io.drow[c.dtab_off], t_next = io.drow[c.dtab_off + 1];
-  const EvTotals t = ev_charge_pass(c, io, e, kwh);
+  const EvTotals t = (c.flags & PGW_F_EV_PER_ENV) ? ev_charge_pass_env(c, io, e, kwh)
+                                                  : ev_charge_pass(c, io, e, kwh);
   const double unserved = t.unserved;
 
   const double s_consumed = mult * t.consumed;
@@ -275,9 +345,16 @@ PGW_HD void ev_step(const pgw_component& c, const AgentIO& io, int e, double& p_
 PGW_HD void ev_reset(const pgw_component& c, const AgentIO& io, int e) {
   const double* dp = io.dpar + c.dpar_off;
   const int n = io.ipar[c.ipar_off];
-  const double* e0 = dp + 21 + n;
-  double* energy = io.sd + (size_t)c.sd_off * io.E + e;
-  for (int i = 0; i < n; ++i) energy[(size_t)i * io.E] = e0[i];
+  if (c.flags & PGW_F_EV_PER_ENV) {
+    // the host has written this env's window words and initial energies (pgw_set_rows); the
+    // charging set starts empty (:149)
+    uint32_t* mask = io.si + (size_t)c.si_off * io.E + e;
+    for (int w = 0; w < io.ipar[c.ipar_off + 1]; ++w) mask[(size_t)w * io.E] = 0u;
+  } else {
+    const double* e0 = dp + 21 + n;
+    double* energy = io.sd + (size_t)c.sd_off * io.E + e;
+    for (int i = 0; i < n; ++i) energy[(size_t)i * io.E] = e0[i];
+  }
   // Hidden step with action=None -> _action_space.low = 0 (:163, :178).  With
   // rescale_spaces the reference still pushes that 0 through to_raw, i.e. 0.5.
   double a = 0.0, p, r;

@@ -238,6 +238,8 @@ class MultiAgentEnv(_Env):
         agent_recs = (N.Agent * len(self.agents))()
         for ai, ag in enumerate(self.agents):
             begin = len(b.comps)
+            for comp in getattr(ag, "envs", [ag]):
+                comp._num_envs = self.num_envs          # randomised stations: one roster per env instance
             ag._emit(b, ai, standalone=not isinstance(ag, MultiComponentEnv))
             rec = agent_recs[ai]
             rec.comp_begin, rec.comp_end = begin, len(b.comps)
@@ -446,7 +448,8 @@ class MultiAgentEnv(_Env):
             ioff, iw = o._slot["itab"]
             for r in range(n_events):
                 self._dtab[r, doff:doff + dw] = dtab_fn(r)
-                self._itab[r, ioff:ioff + iw] = itab_fn(r)
+                if iw:
+                    self._itab[r, ioff:ioff + iw] = itab_fn(r)
 
     def _reset_draws(self, init_storage):
         """Host-side randomness of a reset in the reference's order -- agents in turn, their
@@ -475,8 +478,29 @@ class MultiAgentEnv(_Env):
         self._push_roster_tables()
         return np.stack(soc) if draw_soc else init_storage
 
+    def _per_env_roster_rows(self):
+        """[(field, first row, array [rows, E])] of the per-env rosters just drawn: window words into
+        the uint32 state behind each station's charging-set words, initial energies into its
+        double state (PGW_F_EV_PER_ENV)."""
+        out = []
+        for o in self._randomised():
+            if getattr(o, "_per_env", False) and o._rows is not None:
+                words, energy = o._per_env_rows()
+                out.append((N.FIELD_STATE_I, o._slot["si"][0] + (o.num_vehicles + 31) // 32, words))
+                out.append((N.FIELD_STATE_D, o._slot["sd"][0], energy))
+        return out
+
     def _push_roster_tables(self):
         self._rebuild_roster_tables()
+        if self._h is not None:
+            torch = _torch()
+            for field, row0, arr in self._per_env_roster_rows():
+                t = torch.from_numpy(arr.view(np.int32) if arr.dtype == np.uint32 else arr).to(self.device)
+                with torch.cuda.device(self.device):
+                    N.check(self._lib.pgw_set_rows(self._h, field, row0, arr.shape[0],
+                                                   C.c_void_p(t.data_ptr()), t.numel() * t.element_size(),
+                                                   self._stream()))
+                self._keep_rows = getattr(self, "_keep_rows", [])[-8:] + [t]   # alive until the copy ran
         if self._h is not None:
             dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
             with _torch().cuda.device(self.device):

@@ -116,6 +116,9 @@ class EmulatedEnv:
         """``drawn``: the SOCs are the reference's own (unclipped) draw, not an explicit
         init_storage (PGW_OPT_CLIP_INIT_SOC = 0)."""
         self._powerflow(0, controllable=False)
+        for field, row0, arr in self.env._per_env_roster_rows():   # what pgw_set_rows does on the device
+            dst = self.sd if field == N.FIELD_STATE_D else self.si
+            dst[row0:row0 + arr.shape[0]] = arr
         soc = np.ascontiguousarray(init_soc, dtype=np.float64) if init_soc is not None else None
         self.lib.emu_set_first_reset(1 if self.resets == 0 else 0)
         self.resets += 1

@@ -830,9 +830,10 @@ def test_randomized_rosters_replay_reference_trace_on_gpu():
 
 
 def test_randomized_station_standalone_and_batched_vs_oracle():
-    """Per-object protocol and a ragged batch: the roster drawn at reset is shared by all envs
-    of the batch, every env replays the oracle station that drew the same roster; the host-
-    buffer entry points go through the same draw."""
+    """Per-object protocol and a ragged batch: every env of the batch draws its OWN roster at
+    reset (one np.random.choice per env instance, env 0 first -- ev_charging_env.py:154-157 is per
+    instance), every env replays the oracle station that drew the same roster; the host-buffer
+    entry points go through the same draws."""
     torch = _torch()
     cfg = dict(num_vehicles=37, minutes_per_step=5, max_charge_rate_kw=7., peak_threshold=40.,
                vehicle_multiplier=2., rescale_spaces=True, randomize=True)
@@ -859,13 +860,16 @@ def test_randomized_station_standalone_and_batched_vs_oracle():
     for ep, host in enumerate([False, True, False]):
         np.random.seed(30 + ep)
         obs0 = env.reset_host() if host else env.reset_batch().cpu().numpy()
-        np.random.seed(30 + ep)
         refs = [ONS.EVChargingEnv(**cfg) for _ in range(3)]
-        state = np.random.get_state()
-        for r in refs:                               # same draw for every replica
-            np.random.set_state(state)
+        n_all = len(dev._roster_energy)
+        for r, e in zip(refs, [0, 33, 69]):          # env e's draw is the (e + 1)-th of the stream
+            np.random.seed(30 + ep)
+            for _ in range(e):
+                np.random.choice(n_all, size=cfg["num_vehicles"], replace=False)
             o, _ = r.reset()
-            np.testing.assert_allclose(obs0[:, 0], o, rtol=0, atol=1e-12)
+            np.testing.assert_allclose(obs0[:, e], o, rtol=0, atol=1e-12)
+        station = env.agents[0]
+        assert station._rows.shape == (E, cfg["num_vehicles"]) and len({tuple(x) for x in station._rows}) == E
         acts = rng.uniform(-1.1, 1.1, size=(100, 1, E))
         for t in range(100):
             if host:

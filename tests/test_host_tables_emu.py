@@ -9,6 +9,7 @@ import pytest
 
 from tests import scenarios as S
 from tests.emu.harness import EmulatedEnv
+from powergridworld_b200 import _native as N
 from tests.product_ns import PRODUCT_NS as NS
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -243,14 +244,18 @@ def test_three_consecutive_episodes_on_one_env_vs_reference_trace():
         assert bool(d)
 
 
-def test_randomised_rosters_in_a_batch_are_shared_and_match_the_oracle_per_env():
-    """A batch of three envs with randomised stations: one roster draw per station and reset,
-    shared by the envs; with explicit per-env storage SOCs and per-env actions every env replays
-    an oracle env that was handed the same rosters (two resets = two draws)."""
+def test_randomised_rosters_in_a_batch_are_per_env_and_match_the_oracle_per_env():
+    """A batch of three envs with randomised stations: every env instance draws its OWN roster at
+    every reset, like every instance of the reference's class (ev_charging_env.py:154-157); with
+    explicit per-env storage SOCs and per-env actions every env replays an oracle env that was
+    handed the same roster (two resets = two draws per env)."""
     from tests.flatten import flat_obs, unflatten_action
     from tests.oracle_ns import ORACLE_NS as ONS, storage_socs_to_dict
     E = 3
     env = NS.MultiAgentEnv(**S.randomized_ev_scenario(NS, NS.OpenDSSSolver), num_envs=E, _dry_run=True)
+    stations = [o for o in env._b.objs if getattr(o, "randomize", False)]
+    assert all(o._per_env for o in stations)
+    assert all(c.flags & N.F_EV_PER_ENV for c in env._b.comps if c.type == N.EV)
     emu = EmulatedEnv(env)
     refs = [ONS.MultiAgentEnv(**S.randomized_ev_scenario(ONS, ONS.OpenDSSSolver)) for _ in range(E)]
     rng = np.random.default_rng(0)
@@ -260,18 +265,20 @@ def test_randomised_rosters_in_a_batch_are_shared_and_match_the_oracle_per_env()
         np.random.seed(40 + ep)
         assert env._reset_draws(soc) is soc          # explicit SOCs: only the rosters are drawn
         o0 = emu.reset(soc)
-        rosters = [np.array(o._rows) for o in env._b.objs if getattr(o, "randomize", False)]
+        rosters = [np.array(o._rows) for o in stations]            # [E, n] each
+        assert all(r.shape == (E, o.num_vehicles) for r, o in zip(rosters, stations))
+        assert not np.array_equal(rosters[0][0], rosters[0][1])    # env 0 and env 1 park different vehicles
         seen.append(rosters)
         orig = np.random.choice
         for e, r in enumerate(refs):
-            q = list(rosters)
+            q = [x[e] for x in rosters]
             np.random.choice = lambda n, size=None, replace=True: q.pop(0)
             try:
                 r0 = r.reset(init_storage=storage_socs_to_dict(r, soc[:, e]))
             finally:
                 np.random.choice = orig
             np.testing.assert_allclose(o0[:, e], flat_obs(r, r0), rtol=0, atol=OBS_ATOL)
-        for t in range(150):
+        for t in range(285):
             a = rng.uniform(-1, 1, size=(env.act_dim, E))
             o, rew, _ = emu.step(a)
             for e, r in enumerate(refs):

@@ -741,7 +741,10 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
         pgw::Tc2Polish& kp = env->tc2p;
         for (int j = 0; j < 16; ++j)
           for (int k = 0; k < 16; ++k)
+          {
             kp.zT[j * 16 + k] = (j < nb && k < nb) ? Z(k, j) : make_double2(0.0, 0.0);
+            kp.z32[j * 16 + k] = make_float2((float)(kp.zT[j * 16 + k].x / xs), (float)(kp.zT[j * 16 + k].y / xs));
+          }
         for (int k = 0; k < 16; ++k) {
           const bool real = k < nb;
           kp.u0[k] = real ? make_double2(f.u0[2 * k], f.u0[2 * k + 1]) : make_double2(1.0, 0.0);
@@ -801,13 +804,6 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
         t.f_kc = putf(&env->tc2c, sizeof(env->tc2c));
         t.f_kp = putf(&env->tc2p, sizeof(env->tc2p));
         t.f_aslot = putf(aslot.data(), aslot.size() * 4);
-        std::vector<float> z32(2 * 16 * 16, 0.f);     // float32 pre-sweep: Zbb^T / xscale, [j][k]
-        for (int j = 0; j < nb; ++j)
-          for (int k = 0; k < nb; ++k) {
-            const double2 z = Z(k, j);
-            z32[2 * (j * 16 + k)] = (float)(z.x / xs); z32[2 * (j * 16 + k) + 1] = (float)(z.y / xs);
-          }
-        t.f_z32 = putf(z32.data(), z32.size() * 4);
         blob.resize((blob.size() + 15) / 16 * 16, 0);
         t.ftab_bytes = (int)(blob.size() - (size_t)t.off_ftab);
       }

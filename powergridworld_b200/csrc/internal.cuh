@@ -82,6 +82,8 @@ struct Tc2Consts {
 // constant-bank operands and shared memory only carries the per-env currents.
 struct Tc2Polish {
   double2 zT[16 * 16];     // zT[j * 16 + k] = Zbb[k][j], zero padded
+  float2 z32[16 * 16];     // the same / xscale in float32: the polish's float32 pre-sweep works on the
+                           // scaled currents of the tensor-core loop
   double2 u0[16];
   double share[16];        // branch share x 1e-3 (kVA -> p.u. on 1 MVA), 0 for the padded branches
   double vlo2[16], vhi2[16];   // clamp band of |u|^2: model 1 [vmin^2, vmax^2], model 2 [1, 1]
@@ -109,7 +111,7 @@ struct Tc2Params {
   // from shared memory -- warp-uniform broadcasts -- instead of the parameter constant bank, whose
   // 7 kB are cold in every SM's constant cache at every launch) and, per agent, the load branch
   // whose wye node is the agent's bus (-1: none).  pen_slot: the same for the penalty node.
-  int off_ftab, ftab_bytes, f_kc, f_kp, f_aslot, f_z32, pen_slot;   // f_z32: float2 Zbb^T / xscale
+  int off_ftab, ftab_bytes, f_kc, f_kp, f_aslot, pen_slot;
   float xscale, descale1, descale2, tol;
 };
 

@@ -433,19 +433,46 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
         const int c = grp;
         double2 u[8];
         {
+          // Sweep 0 in float32 (as in step_fused.cu): the full sweep feeds the currents of the row
+          // sweep below, which contracts its error by > 10x; float32 currents halve the
+          // shared-memory traffic and the 14 x 8 complex MACs per thread run on the FP32 pipe
+          // instead of the FP64 one (262 144 IEEE-13 envs: the float64 form of this sweep was most
+          // of the 78 us the polish added to the 104 us solve).
           float dn[16];
           t2_ld16(t_lane + last * N + 16 * c, dn);
-          const double dsd = (double)ds1;
+          float2* sI32 = reinterpret_cast<float2*>(sI64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = 8 * c + j;
+            float x, y;
+            t2_current32<ANY_M5>(t2_cst(kc, k), ANY_M5 ? t2_gh(kc, k) : make_float2(1.f, 0.f), dn[j], dn[8 + j],
+                                 ds1, sr[0][j], si[0][j], x, y);
+            if (k < p.nb) sI32[(size_t)k * T2_M + row] = make_float2(x, y);
+          }
+          __syncthreads();
+          T2_STAMP(14);
+          float2 acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll 2
+          for (int jj = 0; jj < p.nb; ++jj) {
+            const float2 ij = sI32[(size_t)jj * T2_M + row];
+            const float2* z = kp.z32 + jj * 16 + 8 * c;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t2_cmac_sub32(acc[j], z[j], ij);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const double2 b = kp.u0[8 * c + j];
-            u[j] = make_double2(b.x + (double)dn[j] * dsd, b.y + (double)dn[8 + j] * dsd);
+            u[j] = make_double2(b.x + (double)acc[j].x, b.y + (double)acc[j].y);
+            if (t.polish == 1 && valid && 8 * c + j < p.nb) p.u_state[(size_t)(8 * c + j) * p.E + e] = u[j];
           }
+          T2_STAMP(15);
         }
         const int sweeps = t.polish + ((kp.rows != 0u || t.polish_row >= 0) ? 1 : 0);
 #pragma unroll 1
-        for (int sweep = 0; sweep < sweeps; ++sweep) {
-          if (sweep > 0) __syncthreads();              // everyone has read the previous currents
+        for (int sweep = 1; sweep < sweeps; ++sweep) {
+          __syncthreads();                             // everyone has read the previous currents
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = 8 * c + j;
@@ -454,10 +481,8 @@ __global__ void __launch_bounds__(NCH <= 4 ? 256 : 512, OCC)
                                                           kp.vlo2[k], kp.vhi2[k]);
           }
           __syncthreads();
-          if (sweep == 0) T2_STAMP(14);
           if (sweep < t.polish) {
             t2_sweep64(kp, p.nb, c, sI64, row, u);
-            if (sweep == 0) T2_STAMP(15);
             if (sweep + 1 == t.polish) {               // warm-start state: after the full sweeps
 #pragma unroll
               for (int j = 0; j < 8; ++j)

@@ -59,28 +59,6 @@ __device__ __forceinline__ void sf_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// The load characteristic in float32 with correctly rounded reciprocals (the hot loop's
-// rsqrt.approx is good to 2^-22.9: squared, 2.6e-7 relative on a current) -- currents SCALED by
-// xscale like t2_current's.
-template <bool ANY_M5>
-__device__ __forceinline__ void sf_current32(float4 c, float2 gh, float dr, float di, float ds, float sr,
-                                             float si, float& x, float& y) {
-  const float ur = fmaf(dr, ds, c.x), ui = fmaf(di, ds, c.y);
-  const float m2 = fmaf(ur, ur, ui * ui);
-  const float cl = fminf(fmaxf(m2, c.z), c.w);
-  float kf = __frcp_rn(cl);
-  if (ANY_M5) kf = fmaf(gh.y, __frsqrt_rn(cl), gh.x * kf);
-  const float tr = ur * kf, ti = ui * kf;
-  x = fmaf(sr, tr, si * ti);                           // conj(s) u k
-  y = fmaf(sr, ti, -(si * tr));
-}
-__device__ __forceinline__ void sf_cmac_sub32(float2& acc, float2 z, float2 i) {
-  acc.x = fmaf(-z.x, i.x, acc.x);
-  acc.x = fmaf(z.y, i.y, acc.x);
-  acc.y = fmaf(-z.x, i.y, acc.y);
-  acc.y = fmaf(-z.y, i.x, acc.y);
-}
-
 struct SfLayout {                                      // byte offsets into dynamic shared memory
   uint32_t b, a, stage, tab, ftab, blob, drow, irow, i64, dmax, part, vn, cp, cr, act, total;
 };
@@ -153,7 +131,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
   const Tc2Consts& kc = *reinterpret_cast<const Tc2Consts*>(sf_smem + L.ftab + t.f_kc);
   const Tc2Polish& kp = *reinterpret_cast<const Tc2Polish*>(sf_smem + L.ftab + t.f_kp);
   const int32_t* aslot = reinterpret_cast<const int32_t*>(sf_smem + L.ftab + t.f_aslot);
-  const float2* z32 = reinterpret_cast<const float2*>(sf_smem + L.ftab + t.f_z32);   // Zbb^T / xscale
+  const float2* z32 = kp.z32;                          // Zbb^T / xscale
   unsigned char* sBlob = sf_smem + L.blob;
   double* drow = reinterpret_cast<double*>(sf_smem + L.drow);
   int32_t* irow = reinterpret_cast<int32_t*>(sf_smem + L.irow);
@@ -538,7 +516,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
         float2* sI32 = reinterpret_cast<float2*>(sI64);
         if (b < pf.nb) {
           float x, y;
-          sf_current32<ANY_M5>(cst, gh, dprev.x, dprev.y, ds1, sr, si, x, y);
+          t2_current32<ANY_M5>(cst, gh, dprev.x, dprev.y, ds1, sr, si, x, y);
           sI32[b * SF_ENVS + lane] = make_float2(x, y);
         }
         __syncthreads();
@@ -546,10 +524,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1)
           float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll 2
           for (int jj = 0; jj + 1 < pf.nb; jj += 2) {
-            sf_cmac_sub32(a0, z32[jj * 16 + b], sI32[jj * SF_ENVS + lane]);
-            sf_cmac_sub32(a1, z32[(jj + 1) * 16 + b], sI32[(jj + 1) * SF_ENVS + lane]);
+            t2_cmac_sub32(a0, z32[jj * 16 + b], sI32[jj * SF_ENVS + lane]);
+            t2_cmac_sub32(a1, z32[(jj + 1) * 16 + b], sI32[(jj + 1) * SF_ENVS + lane]);
           }
-          if (pf.nb & 1) sf_cmac_sub32(a0, z32[(pf.nb - 1) * 16 + b], sI32[(pf.nb - 1) * SF_ENVS + lane]);
+          if (pf.nb & 1) t2_cmac_sub32(a0, z32[(pf.nb - 1) * 16 + b], sI32[(pf.nb - 1) * SF_ENVS + lane]);
           u64 = make_double2(kp.u0[b].x + (double)(a0.x + a1.x), kp.u0[b].y + (double)(a0.y + a1.y));
           if (t.polish == 1 && valid) pf.u_state[(size_t)b * E + e] = u64;
         }

@@ -187,6 +187,28 @@ __device__ __forceinline__ float2 t2_gh(const Tc2Consts& kc, int k) {
   return make_float2(c[k & 1], c[2 + (k & 1)]);
 }
 
+// The load characteristic in float32 with correctly rounded reciprocals (the hot loop's
+// rsqrt.approx is good to 2^-22.9: squared, 2.6e-7 relative on a current) -- currents SCALED by
+// xscale like t2_current's.
+template <bool ANY_M5>
+__device__ __forceinline__ void t2_current32(float4 c, float2 gh, float dr, float di, float ds, float sr,
+                                             float si, float& x, float& y) {
+  const float ur = fmaf(dr, ds, c.x), ui = fmaf(di, ds, c.y);
+  const float m2 = fmaf(ur, ur, ui * ui);
+  const float cl = fminf(fmaxf(m2, c.z), c.w);
+  float kf = __frcp_rn(cl);
+  if (ANY_M5) kf = fmaf(gh.y, __frsqrt_rn(cl), gh.x * kf);
+  const float tr = ur * kf, ti = ui * kf;
+  x = fmaf(sr, tr, si * ti);                           // conj(s) u k
+  y = fmaf(sr, ti, -(si * tr));
+}
+__device__ __forceinline__ void t2_cmac_sub32(float2& acc, float2 z, float2 i) {
+  acc.x = fmaf(-z.x, i.x, acc.x);
+  acc.x = fmaf(z.y, i.y, acc.x);
+  acc.y = fmaf(-z.x, i.y, acc.y);
+  acc.y = fmaf(-z.y, i.x, acc.y);
+}
+
 // ---- FP64 polish (POLISH instantiations): the load characteristic and one row of the sweep
 // u <- u0 - Zbb i(u) in float64, same model semantics as branch_current of powerflow.cu
 // (OpenDSS model 1 = constant PQ inside [vmin, vmax], constant Z outside; 2 = constant Z;

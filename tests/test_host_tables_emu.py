@@ -290,6 +290,39 @@ def test_randomised_rosters_in_a_batch_are_per_env_and_match_the_oracle_per_env(
     assert not np.array_equal(seen[0][0], seen[1][0])           # a new draw per reset
 
 
+def test_per_env_roster_path_equals_the_shared_table_path_bit_for_bit():
+    """The two EV code paths -- per-event window lists compiled on the host (one env / shared roster)
+    and per-env window words evaluated on the device (PGW_F_EV_PER_ENV) -- on the SAME roster, SOCs
+    and actions: observations, rewards and states bit for bit, over a whole day."""
+    E = 4
+    batch = NS.MultiAgentEnv(**S.randomized_ev_scenario(NS, NS.OpenDSSSolver), num_envs=E, _dry_run=True)
+    single = NS.MultiAgentEnv(**S.randomized_ev_scenario(NS, NS.OpenDSSSolver), num_envs=1, _dry_run=True)
+    sb = [o for o in batch._b.objs if getattr(o, "randomize", False)]
+    ss = [o for o in single._b.objs if getattr(o, "randomize", False)]
+    assert all(o._per_env for o in sb) and not any(o._per_env for o in ss)
+    rng = np.random.default_rng(11)
+    np.random.seed(123)
+    soc1 = rng.uniform(10, 45, size=(single.num_storage, 1))
+    single._reset_draws(soc1)                         # draws one roster per station
+    for ob, os_ in zip(sb, ss):
+        ob._rows = np.tile(os_._rows, (E, 1))         # every env of the batch parks the same vehicles
+    batch._rebuild_roster_tables()
+    eb, es = EmulatedEnv(batch), EmulatedEnv(single)
+    ob0, os0 = eb.reset(np.tile(soc1, (1, E))), es.reset(soc1)
+    for e in range(E):
+        np.testing.assert_array_equal(ob0[:, e], os0[:, 0])
+    for t in range(285):
+        a = rng.uniform(-1, 1, size=(single.act_dim, 1))
+        o_b, r_b, _ = eb.step(np.tile(a, (1, E)))
+        o_s, r_s, _ = es.step(a)
+        for e in range(E):
+            np.testing.assert_array_equal(o_b[:, e], o_s[:, 0], err_msg=f"t={t} env={e}")
+            np.testing.assert_array_equal(r_b[:, e], r_s[:, 0])
+    for ob, os_ in zip(sb, ss):                       # remaining energy per vehicle
+        np.testing.assert_array_equal(eb.sd[ob._slot["sd"][0]:ob._slot["sd"][0] + ob.num_vehicles, 0],
+                                      es.sd[os_._slot["sd"][0]:os_._slot["sd"][0] + os_.num_vehicles, 0])
+
+
 def test_scenario_factories_read_like_the_reference():
     """gridworld/scenarios/{buildings,heterogeneous}.py: same signatures, same class names inside
     the config dicts (``OpenDSSSolver``, ``ThisPVEnv``, ...), and the configs build."""

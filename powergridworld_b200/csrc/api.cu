@@ -71,6 +71,7 @@ struct pgw_env {
   int clock = -1;             // host mirror
   long long resets = 0;
   int has_house = 0;          // 1 = houses, 2 = houses with step_meta telemetry
+  bool ev_per_env = false;    // some charging station runs on per-env rosters (PGW_F_EV_PER_ENV)
   long long launches = 0;
   long long graph_captures = 0;        // graphs captured + instantiated since creation
   // device tables
@@ -279,8 +280,10 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
   env->sd_rows = spec->sd_rows; env->si_rows = spec->si_rows;
   env->num_storage = spec->num_storage; env->num_events = spec->num_events;
   env->dstride = spec->dtab_stride; env->istride = spec->itab_stride;
-  for (int c = 0; c < spec->num_components; ++c)
+  for (int c = 0; c < spec->num_components; ++c) {
     if (spec->components[c].type == PGW_HS_BEGIN) env->has_house = std::max(env->has_house, 1);
+    if (spec->components[c].flags & PGW_F_EV_PER_ENV) env->ev_per_env = true;
+  }
   for (int c = 0; c < spec->num_components; ++c)
     if (spec->components[c].type >= PGW_HS_PV && (spec->components[c].flags & PGW_F_TELEMETRY))
       env->has_house = 2;
@@ -814,7 +817,7 @@ int pgw_create(const pgw_spec* spec, pgw_env** out) {
         env->tc2.blob = env->tc2_blob;
         // The fused step kernel serves feeders with <= 16 load branches whose Znb chunks stay
         // resident, stock components on their straight-line paths, tables that fit shared memory.
-        bool ok = nch == 2 && t.resident && !env->has_house && !env->need_scratch &&
+        bool ok = nch == 2 && t.resident && !env->has_house && !env->ev_per_env && !env->need_scratch &&
                   32 * (1 + ncc) <= 512;
         for (int c = 0; c < spec->num_components && ok; ++c) {
           const pgw_component& k = spec->components[c];
@@ -867,6 +870,7 @@ static pgw::CompParams comp_params(pgw_env* env) {
   p.agent_p = env->agent_p; p.ep_ret = env->ep_ret;
   p.clock = env->d_clock; p.ticket = env->d_ticket;
   p.has_house = env->has_house;
+  p.ev_per_env = env->ev_per_env ? 1 : 0;
 #ifdef PGW_PHASE_TIMERS
   p.phase_clk = env->phase_clk + (size_t)4096 * 16;
 #endif

@@ -310,6 +310,10 @@ PGW_HD EvTotals ev_charge_pass_env(const pgw_component& c, const AgentIO& io, in
   return t;
 }
 
+// EVENV: the kernel variant that carries the per-env roster path.  It lives in an instantiation of
+// its own (like the Home-Steward house): inlined into the common kernel its register pressure cost
+// every scenario 15-30 % of the component kernel (C3: 61.5 -> 80.2 us, measured).
+template <bool EVENV>
 PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double kwh,
                        double& p_out, double& rew) {
   const double* dp = io.dpar + c.dpar_off;
@@ -317,8 +321,12 @@ PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double 
   const double* obs_high = dp + 7;
   const double* inv_high = dp + 13;
   const double t_now = io.drow[c.dtab_off], t_next = io.drow[c.dtab_off + 1];
-  const EvTotals t = (c.flags & PGW_F_EV_PER_ENV) ? ev_charge_pass_env(c, io, e, kwh)
-                                                  : ev_charge_pass(c, io, e, kwh);
+  EvTotals t;
+  if constexpr (EVENV) {
+    t = (c.flags & PGW_F_EV_PER_ENV) ? ev_charge_pass_env(c, io, e, kwh) : ev_charge_pass(c, io, e, kwh);
+  } else {
+    t = ev_charge_pass(c, io, e, kwh);
+  }
   const double unserved = t.unserved;
 
   const double s_consumed = mult * t.consumed;
@@ -334,18 +342,20 @@ PGW_HD void ev_advance(const pgw_component& c, const AgentIO& io, int e, double 
   rew = div_by(-dp[3] * (unserved * unserved) + -dp[4] * (over * over), dp[6], dp[19]);
 }
 
+template <bool EVENV = false>
 PGW_HD void ev_step(const pgw_component& c, const AgentIO& io, int e, double& p_out,
                     double& rew) {
   const double* dp = io.dpar + c.dpar_off;
   double a = act_in(io, c.act_off, e);
   if (c.flags & PGW_F_RESCALE) a = to_raw(a, 0.0, 1.0);
-  ev_advance(c, io, e, (a * dp[0]) * dp[1], p_out, rew);      // :182-183
+  ev_advance<EVENV>(c, io, e, (a * dp[0]) * dp[1], p_out, rew);      // :182-183
 }
 
+template <bool EVENV = false>
 PGW_HD void ev_reset(const pgw_component& c, const AgentIO& io, int e) {
   const double* dp = io.dpar + c.dpar_off;
   const int n = io.ipar[c.ipar_off];
-  if (c.flags & PGW_F_EV_PER_ENV) {
+  if (EVENV && (c.flags & PGW_F_EV_PER_ENV)) {
     // the host has written this env's window words and initial energies (pgw_set_rows); the
     // charging set starts empty (:149)
     uint32_t* mask = io.si + (size_t)c.si_off * io.E + e;
@@ -359,7 +369,7 @@ PGW_HD void ev_reset(const pgw_component& c, const AgentIO& io, int e) {
   // rescale_spaces the reference still pushes that 0 through to_raw, i.e. 0.5.
   double a = 0.0, p, r;
   if (c.flags & PGW_F_RESCALE) a = to_raw(a, 0.0, 1.0);
-  ev_advance(c, io, e, (a * dp[0]) * dp[1], p, r);
+  ev_advance<EVENV>(c, io, e, (a * dp[0]) * dp[1], p, r);
 }
 
 // ------------------------------------------------------------------ five-zone building
@@ -978,6 +988,7 @@ PGW_HD void house_reset(const pgw_agent& ag, const pgw_component* comps, const A
   }
 }
 
+template <bool EVENV = false>
 PGW_HD void agent_step(const pgw_agent& ag, const pgw_component* comps, const AgentIO& io, int e,
                        double& p_agent, double& r_agent) {
   p_agent = 0.0;
@@ -988,7 +999,7 @@ PGW_HD void agent_step(const pgw_agent& ag, const pgw_component* comps, const Ag
     switch (c.type) {
       case PGW_STORAGE: storage_step(c, io, e, p); break;
       case PGW_PV: pv_step(c, io, e, p, r); break;
-      case PGW_EV: ev_step(c, io, e, p, r); break;
+      case PGW_EV: ev_step<EVENV>(c, io, e, p, r); break;
       case PGW_BUILDING:
         if (c.flags & PGW_F_BUILDING_FAST) building_step_fast(c, io, e, p, r);
         else building_step(c, io, e, p, r);
@@ -1000,13 +1011,14 @@ PGW_HD void agent_step(const pgw_agent& ag, const pgw_component* comps, const Ag
   }
 }
 
+template <bool EVENV = false>
 PGW_HD void agent_reset(const pgw_agent& ag, const pgw_component* comps, const AgentIO& io, int e) {
   for (int ci = ag.comp_begin; ci < ag.comp_end; ++ci) {
     const pgw_component c = comps[ci];
     switch (c.type) {
       case PGW_STORAGE: storage_reset(c, io, e); break;
       case PGW_PV: pv_obs(c, io, e, -io.drow[c.dtab_off]); break;
-      case PGW_EV: ev_reset(c, io, e); break;
+      case PGW_EV: ev_reset<EVENV>(c, io, e); break;
       case PGW_BUILDING: building_reset(c, io, e); break;
       default: break;
     }

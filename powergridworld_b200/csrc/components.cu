@@ -20,7 +20,8 @@ namespace pgw {
 
 // HOUSE: the scenario contains Home-Steward houses (their code stays out of the other kernel);
 // TEL: some of their components record step_meta telemetry.
-template <bool HOUSE, bool TEL>
+// EVENV: some charging station runs on per-env rosters (PGW_F_EV_PER_ENV).
+template <bool HOUSE, bool TEL, bool EVENV = false>
 __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t mbar[2];
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
       const size_t ae = (size_t)a * p.E + e;
       if (p.event_mode == 0) {
         if (HOUSE && is_house(ag, comps)) house_reset<TEL>(ag, comps, io, e, p.first_reset != 0);
-        else agent_reset(ag, comps, io, e);
+        else agent_reset<EVENV>(ag, comps, io, e);
         p.agent_p[ae] = 0.0;
         p.ep_ret[ae] = 0.0;
       } else {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
         if (p.owns_reward)                      // issued early: its latency hides behind the step
           asm volatile("ld.global.f64 %0, [%1];" : "=d"(er) : "l"(p.ep_ret + ae));
         if (HOUSE && is_house(ag, comps)) house_step<TEL>(ag, comps, io, e, pw, rw);
-        else agent_step(ag, comps, io, e, pw, rw);
+        else agent_step<EVENV>(ag, comps, io, e, pw, rw);
         p.agent_p[ae] = pw;
         p.rew[ae] = rw;
         if (p.owns_reward) {                    // no feeder / no penalty hook: the reward is final
@@ -163,7 +164,8 @@ __global__ void __launch_bounds__(64, 10) component_kernel(const CompParams p) {
 
 bool is_component_kernel(const void* func) {
   return func == (const void*)component_kernel<false, false> || func == (const void*)component_kernel<true, false> ||
-         func == (const void*)component_kernel<true, true>;
+         func == (const void*)component_kernel<true, true> || func == (const void*)component_kernel<false, false, true> ||
+         func == (const void*)component_kernel<true, false, true> || func == (const void*)component_kernel<true, true, true>;
 }
 
 cudaError_t launch_components(const CompParams& p, int smem_bytes, cudaStream_t s) {
@@ -171,6 +173,9 @@ cudaError_t launch_components(const CompParams& p, int smem_bytes, cudaStream_t 
   dim3 grid(p.num_ctas);       // the CTA -> (agent, env blocks) table is built in pgw_create
   auto kern = p.has_house ? (p.has_house > 1 ? component_kernel<true, true> : component_kernel<true, false>)
                           : component_kernel<false, false>;
+  if (p.ev_per_env)
+    kern = p.has_house ? (p.has_house > 1 ? component_kernel<true, true, true> : component_kernel<true, false, true>)
+                       : component_kernel<false, false, true>;
   if (smem_bytes > 48 * 1024) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (err != cudaSuccess) return err;

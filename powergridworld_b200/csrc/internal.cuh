@@ -37,6 +37,7 @@ struct CompParams {
   int owns_reward;         // 1 when no later kernel changes the reward (no feeder / no penalty)
   int has_house;           // 1: the scenario contains Home-Steward houses, 2: with telemetry
                            // (kernel variants)
+  int ev_per_env;          // 1: a charging station runs on per-env rosters (kernel variant)
   int first_reset;         // reset only: first reset of the handle (state that the reference keeps
                            // across episodes gets its constructor value)
   // static tables, one contiguous 16-byte aligned blob: [agents | comps | dpar | ipar]

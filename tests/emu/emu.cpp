@@ -51,7 +51,7 @@ void emu_reset(const EmuArgs* a) {
       if (pgw::is_house(a->agents[ag], a->comps))
         pgw::house_reset<true>(a->agents[ag], a->comps, io, e, g_first_reset != 0);
       else
-        pgw::agent_reset(a->agents[ag], a->comps, io, e);
+        pgw::agent_reset<true>(a->agents[ag], a->comps, io, e);
       a->agent_p[(size_t)ag * a->E + e] = 0.0;
     }
 }
@@ -64,7 +64,7 @@ void emu_step(const EmuArgs* a) {
       if (pgw::is_house(a->agents[ag], a->comps))
         pgw::house_step<true>(a->agents[ag], a->comps, io, e, p, r);
       else
-        pgw::agent_step(a->agents[ag], a->comps, io, e, p, r);
+        pgw::agent_step<true>(a->agents[ag], a->comps, io, e, p, r);
       a->agent_p[(size_t)ag * a->E + e] = p;
       a->rew[(size_t)ag * a->E + e] = r;
     }

@@ -750,9 +750,9 @@ class MultiAgentEnv(_Env):
     def _solve_loads(self, kw: np.ndarray, kvar: np.ndarray):
         torch = _torch()
         f = self.pf_solver.feeder
-        mk = lambda a: torch.as_tensor(np.ascontiguousarray(
+        mk = lambda a: torch.as_tensor(np.array(                          # (a writable copy)
             np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(f.nl, -1),
-                            (f.nl, self.num_envs)))).to(self.device)
+                            (f.nl, self.num_envs)), order="C")).to(self.device)
         tkw, tkvar = mk(kw), mk(kvar)
         with torch.cuda.device(self.device):
             N.check(self._lib.pgw_pf_solve(self._h, C.c_void_p(tkw.data_ptr()),

@@ -1,6 +1,9 @@
-"""Small end-to-end run of every kernel variant for compute-sanitizer (memcheck / racecheck):
-IEEE-13 with all three solvers, the 123-bus-class feeder with the tc2 solver (ragged tile),
-the stand-alone solve, a Home-Steward house batch, checkpoint get/set."""
+"""Small end-to-end run of every kernel variant (written for compute-sanitizer memcheck / racecheck; the
+tool is closed on the current GPU pool, the script still serves as a smoke run of all variants):
+IEEE-13 with all three solvers (two-kernel path, the tcgen05 one with its float64 polish) and the
+fused step kernel (device buffers and page-locked host buffers, ragged last tile), the
+123-bus-class feeder with the tc2 solver (ragged tile), the stand-alone solve, a Home-Steward
+house batch, charging stations on shared and on per-env rosters."""
 import os
 import sys
 import warnings
@@ -19,9 +22,18 @@ from powergridworld_b200.base_hs import house_agent_config
 rng = np.random.default_rng(0)
 
 
-def run(env, steps, kernel=None):
+def run(env, steps, kernel=None, fused=None, host=False):
     if kernel is not None:
         env.set_option(N.OPT_PF_KERNEL, kernel)
+    if fused is not None:
+        env.set_option(N.OPT_FUSED, fused)
+    if host:
+        soc = rng.uniform(10, 40, size=(env.num_storage, env.num_envs))
+        env.reset_host(soc)
+        for _ in range(steps):
+            env.step_host(torch.as_tensor(rng.uniform(-1, 1, size=(env.act_dim, env.num_envs))).pin_memory())
+        torch.cuda.synchronize()
+        return
     E = env.num_envs
     soc = rng.uniform(10, 40, size=(env.num_storage, E))
     env.reset_batch(soc)
@@ -33,7 +45,10 @@ def run(env, steps, kernel=None):
 
 for k in (0, 1, 2):
     run(PNS.CoordinatedMultiBuildingControlEnv(
-        **S.buildings_scenario(PNS, PNS.OpenDSSSolver, 1.2), num_envs=130), 3, k)
+        **S.buildings_scenario(PNS, PNS.OpenDSSSolver, 1.2), num_envs=130), 3, k, fused=0)
+for host in (False, True):
+    run(PNS.CoordinatedMultiBuildingControlEnv(
+        **S.buildings_scenario(PNS, PNS.OpenDSSSolver, 1.2), num_envs=130), 3, 2, fused=2, host=host)
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     run(PNS.MultiAgentEnv(**S.der123_scenario(PNS, PNS.OpenDSSSolver), num_envs=130), 2, 2)
@@ -49,4 +64,7 @@ run(PNS.MultiAgentEnv(
     agents=[{"name": "house", "bus": None, "cls": HNS.HSMultiComponentEnv,
              "config": house_agent_config(cfg)}]), 4)
 run(PNS.MultiAgentEnv(**S.ev_pv_storage_scenario(PNS), num_envs=70), 4)
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    run(PNS.MultiAgentEnv(**S.randomized_ev_scenario(PNS, PNS.OpenDSSSolver), num_envs=70), 4)
 print("sanitize_small: done")

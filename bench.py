@@ -639,7 +639,8 @@ def run_ours(args):
     if rank == 0 and world == 1 and WORKLOAD == "c1" and not args.no_extra:
         env.close()
         del m["env"]
-        for name, wl, e_n in (("c1x64", "c1", 262144), ("c2", "c2", 65536), ("c3", "c3", 16384)):
+        for name, wl, e_n in (("c1x64", "c1", 262144), ("c2", "c2", 65536), ("c3", "c3", 16384),
+                                 ("hs", "hs", 262144)):
             try:
                 x = measure(wl, e_n, 20, 5, dev)
                 extra[name] = {"workload": _config(1, wl, e_n)["workload"], "envs": e_n, "value": x["value"],

@@ -13,6 +13,10 @@ adds what a batched simulator needs on top:
   "sub-environment" per env instance, observation / action = the agents' vectors concatenated in
   the list interface's order (gridworld/multiagent_list_interface_env.py:80-111), host NumPy arrays
   in and out through the page-locked host-buffer step (``pgw_step_host``), autoreset at episode end.
+* ``RLlibBatchedBaseEnv``  -- RLlib's vectorised multi-agent protocol (``BaseEnv``: ``poll`` /
+  ``send_actions`` / ``try_reset`` over ``{env_id: {agent_id: value}}`` dicts) for a whole batch: RLlib
+  batches policy inference over all sub-environments of a ``BaseEnv``, so one ``send_actions`` is one
+  ``step_host`` of the batch.
 * ``to_gym_space``          -- the package's ``Box`` / ``Dict`` stand-ins as real ``gymnasium`` (or
   ``gym``) spaces when one of them is importable.
 
@@ -166,4 +170,106 @@ class BatchedJointVectorEnv(_VectorBase):
         return obs_out, rew.sum(axis=0), terminated, np.zeros(self.num_envs, dtype=bool), infos
 
     def close(self, **kwargs):
+        self.env.close()
+
+
+try:
+    from ray.rllib.env.base_env import BaseEnv as _BaseEnvBase
+except ImportError:
+    _BaseEnvBase = object
+
+
+class RLlibBatchedBaseEnv(_BaseEnvBase):
+    """``num_envs`` instances behind RLlib's ``BaseEnv`` protocol (ray/rllib/env/base_env.py): env ids are
+    the env indices 0 .. num_envs-1, agent ids the scenario's agent names, observations / actions the
+    per-agent nested dicts of the single-env API.  ``gymnasium_api=True`` returns the six-tuple of
+    ray >= 2.3 (terminateds, truncateds), else the five-tuple.  All instances of a handle end their
+    episode on the same step; ``try_reset`` of the first env id resets the batch, the others collect
+    their first observation from it."""
+
+    def __init__(self, config: dict = None, num_envs: int = 1, gymnasium_api: bool = True, **kwargs):
+        cfg = dict(config or {}, **kwargs)
+        cls = cfg.pop("env_cls", MultiAgentEnv)
+        self.env = cls(**cfg, num_envs=num_envs)
+        self.num_envs = int(num_envs)
+        self.gymnasium_api = bool(gymnasium_api)
+        e = self.env
+        self.observation_space = to_gym_space(e.observation_space)
+        self.action_space = to_gym_space(e.action_space)
+        # (agent, component or None, first row, rows) of the flat layouts
+        self._obs_items, self._act_items = [], []
+        for ag in e.agents:
+            comps = getattr(ag, "envs", None)
+            for c in (comps if comps is not None else [ag]):
+                name = c.name if comps is not None else None
+                self._obs_items.append((ag.name, name) + tuple(c._slot["obs"]))
+                self._act_items.append((ag.name, name) + tuple(c._slot["act"]))
+        self._act = None
+        self._pending = None          # (obs [obs_dim, E], rew [A, E] or None, done) not yet polled
+        self._reset_obs = None        # first observations of a fresh episode, handed out by try_reset
+        self._reset_left = set()
+
+    # ---- array <-> nested dict
+    def _obs_of(self, obs, i):
+        out = {}
+        for agent, comp, o0, n in self._obs_items:
+            v = obs[o0:o0 + n, i].copy()
+            if comp is None:
+                out[agent] = v
+            else:
+                out.setdefault(agent, {})[comp] = v
+        return out
+
+    def _fill_actions(self, buf, i, action):
+        for agent, comp, a0, n in self._act_items:
+            a = action[agent] if comp is None else action[agent][comp]
+            buf[a0:a0 + n, i] = np.asarray(a, dtype=np.float64).reshape(n)
+
+    # ---- BaseEnv
+    def poll(self):
+        e = self.env
+        if self._pending is None:                         # first poll: start the episode
+            self._pending = (e.reset_host(), None, False)
+        obs_a, rew_a, done = self._pending
+        self._pending = None
+        names = e.agent_names
+        obs, rew, term, trunc, infos = {}, {}, {}, {}, {}
+        for i in range(self.num_envs):
+            obs[i] = self._obs_of(obs_a, i)
+            rew[i] = {a: (0.0 if rew_a is None else float(rew_a[k, i])) for k, a in enumerate(names)}
+            term[i] = dict({a: bool(done) for a in names}, __all__=bool(done))
+            trunc[i] = dict({a: False for a in names}, __all__=False)
+            infos[i] = {a: {} for a in names}
+        if self.gymnasium_api:
+            return obs, rew, term, trunc, infos, {}
+        return obs, rew, term, infos, {}
+
+    def send_actions(self, action_dict):
+        e = self.env
+        if self._act is None:
+            self._act = e._pinned()["act"]
+        buf = self._act.numpy()
+        for i, action in action_dict.items():
+            self._fill_actions(buf, int(i), action)
+        obs, rew, done = e.step_host(self._act)
+        self._pending = (obs, rew, bool(e._needs_reset))
+
+    def try_reset(self, env_id=None, *, seed=None, options=None):
+        if seed is not None:
+            np.random.seed(seed)
+        if not self._reset_left:                          # first request of this episode boundary
+            self._reset_obs = self.env.reset_host(**(options or {})).copy()
+            self._reset_left = set(range(self.num_envs))
+            self._pending = None
+        ids = range(self.num_envs) if env_id is None else [int(env_id)]
+        obs = {i: self._obs_of(self._reset_obs, i) for i in ids}
+        self._reset_left -= set(ids)
+        if self.gymnasium_api:
+            return obs, {i: {a: {} for a in self.env.agent_names} for i in ids}
+        return obs
+
+    def get_sub_environments(self, as_dict: bool = False):
+        return {} if as_dict else []                      # one device handle, no per-env objects
+
+    def stop(self):
         self.env.close()

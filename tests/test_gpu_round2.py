@@ -332,3 +332,36 @@ def test_batched_joint_vector_env_autoresets_and_matches_step_host():
     assert vec.episodes == 1 and o.shape == (E, ref.obs_dim)   # o is the next episode's first observation
     sl = vec.agent_obs_slices["building-1"]
     assert sl.stop - sl.start == sum(s.shape[0] for s in ref.observation_space["building-1"].values())
+
+
+def test_rllib_base_env_adapter_steps_a_batch_like_independent_envs():
+    """RLlib's BaseEnv protocol over a batch: poll / send_actions / try_reset with {env_id: {agent:
+    ...}} dicts; every env id replays a single env driven through the dict API with the same SOC and
+    actions (the heterogeneous scenario: composite, PV and EV-station agents)."""
+    from powergridworld_b200.adapters import RLlibBatchedBaseEnv
+    E, T = 5, 6
+    cfg = dict(S.heterogeneous_scenario(PNS, PNS.OpenDSSSolver, 0.65), max_episode_steps=T + 1)
+    be = RLlibBatchedBaseEnv(cfg, num_envs=E)
+    singles = [PNS.MultiAgentEnv(**cfg) for _ in range(E)]
+    rng = np.random.default_rng(4)
+    soc = rng.uniform(10, 40, size=(be.env.num_storage, E))
+    obs, infos = be.try_reset(options={"init_storage": soc})
+    assert sorted(obs) == list(range(E))
+    for i, s in enumerate(singles):
+        want = s.reset(init_storage=soc[:, i])
+        np.testing.assert_array_equal(flat_obs(be.env, obs[i]), flat_obs(s, want))
+    for t in range(be.env.episode_length):
+        flat = rng.uniform(-1, 1, size=(E, be.env.act_dim))
+        be.send_actions({i: unflatten_action(be.env, flat[i]) for i in range(E)})
+        obs, rew, term, trunc, infos, _ = be.poll()
+        for i, s in enumerate(singles):
+            o, r, d, _ = s.step(unflatten_action(s, flat[i]))
+            np.testing.assert_allclose(flat_obs(be.env, obs[i]), flat_obs(s, o), rtol=0, atol=1e-12)
+            assert rew[i].keys() == r.keys()
+            np.testing.assert_allclose([rew[i][k] for k in r], list(r.values()), rtol=1e-12, atol=1e-12)
+            assert term[i]["__all__"] == d["__all__"] and not trunc[i]["__all__"]
+    assert term[0]["__all__"]
+    first, _ = be.try_reset(0)
+    rest, _ = be.try_reset(3)
+    assert list(first) == [0] and list(rest) == [3]
+    be.stop()

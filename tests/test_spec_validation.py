@@ -3,6 +3,7 @@ passes the validation (the call then stops at the missing device), a spec that i
 is rejected as PGW_ERR_INVALID (out-of-range rows must not reach the kernels)."""
 import ctypes as C
 
+import numpy as np
 import pytest
 import torch
 
@@ -59,3 +60,37 @@ def test_ev_station_tables_are_checked():
     assert rc == INVALID and "event-row" in msg
     rc, msg = _create(SB.c2_env(num_envs=4, _dry_run=True), _bump("si_off", N.EV, 1))
     assert rc == INVALID and "state rows" in msg
+
+
+def test_per_env_rosters_validate_their_inputs(tmp_path):
+    """EVChargingEnv(randomize=True) in a batch: window words hold whole minutes in [0, 65535) and a
+    station holds at most 256 vehicles; anything else is refused loudly on the host."""
+    import pandas as pd
+    from powergridworld_b200.agents.vehicles.ev_charging_env import EVChargingEnv, _popcount
+    assert [_popcount(np.int32(v)) for v in (0, 1, -1, 0x40000001)] == [0.0, 1.0, 32.0, 2.0]
+    st = EVChargingEnv(num_vehicles=5, randomize=True, name="ev")
+    st._num_envs = 3
+    np.random.seed(0)
+    st._draw_roster()
+    assert st._rows.shape == (3, 5)
+    words, energy = st._per_env_rows()
+    assert words.shape == (5, 3) and words.dtype == np.uint32 and energy.shape == (5, 3)
+    start, end = words >> 16, words & 0xFFFF
+    np.testing.assert_array_equal(start.T, np.floor(st._roster_start[st._rows]))
+    np.testing.assert_array_equal(end.T, np.floor(st._roster_end[st._rows]))
+    np.testing.assert_array_equal(energy.T, st._roster_energy[st._rows])
+    # the reference rounds parking times down to the step (ev_charging_env.py:75-76): only a fractional
+    # step leaves fractional minutes
+    csv = tmp_path / "vehicles.csv"
+    pd.DataFrame({"start_time_min": [12.7, 20.0, 30.0], "end_time_park_min": [102.9, 200.0, 300.0],
+                  "energy_required_kwh": [5.0, 6.0, 7.0]}).to_csv(csv)
+    frac = EVChargingEnv(num_vehicles=3, randomize=True, name="ev", vehicle_csv=str(csv), minutes_per_step=2.5)
+    frac._num_envs = 2
+    frac._draw_roster()
+    with pytest.raises(NotImplementedError, match="whole minutes"):
+        frac._per_env_rows()
+    big = EVChargingEnv(num_vehicles=300, randomize=True, name="ev")
+    big._num_envs = 2
+    from powergridworld_b200.multiagent_env import SpecBuilder
+    with pytest.raises(NotImplementedError, match="256"):
+        big._emit(SpecBuilder(0), 0, True)

@@ -336,7 +336,9 @@ int pgw_set_reset_count(pgw_env* env, long long resets);
                                  and agent-bus voltages then agree with the float64 solver to ~1e-9 p.u.,
                                  i.e. rewards within rtol 1e-5 / atol 2e-5.  0 = off (~5e-8 p.u.)       */
 #define PGW_OPT_PF_TC_TOL_NANO 6 /* convergence threshold max|du| of the tcgen05 solvers in units of
-                                 1e-9 p.u. (default 100 = 1e-7, the split-FP16 operands' floor)          */
+                                 1e-9 p.u. (10 .. 100000).  Default: max(solver tol, 1e-7) -- float32 cannot
+                                 resolve less --, and max(solver tol, 1e-6) where the float64 polish follows
+                                 (PGW_OPT_PF_POLISH > 0): the polish contracts what the loop leaves behind */
 #define PGW_OPT_FUSED 7       /* the whole step in one kernel (component steps -> tcgen05 power flow ->
                                  float64 polish -> rewards per 32-env tile), for feeders with <= 16 load
                                  branches, stock components and power-flow kernel 2: 0 = off, 1 (default)

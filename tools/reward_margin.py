@@ -19,6 +19,8 @@ st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
 a = SB.c1_env(num_envs=E, pf_kernel="tc2")          # fused kernel (automatic at this size)
 b = SB.c1_env(num_envs=E, pf_kernel="fp64")
+if os.environ.get("PGW_TOL_NANO"):                   # convergence threshold of the tcgen05 loop, 1e-9 p.u. units
+    a.set_option(N.OPT_PF_TC_TOL_NANO, int(os.environ["PGW_TOL_NANO"]))
 gen = torch.Generator(device="cuda")
 gen.manual_seed(7)
 worst_ratio, worst_abs, worst_v = 0.0, 0.0, 0.0
@@ -34,6 +36,7 @@ for ep in range(2):
         worst_abs = max(worst_abs, float(err.max()))
         if t % 40 == 0:
             worst_v = max(worst_v, float((a.get_field(N.FIELD_VOLTAGES) - b.get_field(N.FIELD_VOLTAGES)).abs().max()))
-print(json.dumps({"envs": E, "episodes": 2, "steps": 2 * a.episode_length, "launches_per_step": a.launch_count / (2 * a.episode_length + 2),
+iters = float(a.get_field(N.FIELD_PF_ITERS).abs().double().mean())
+print(json.dumps({"tol_nano": os.environ.get("PGW_TOL_NANO", "default"), "mean_iterations_last_step": iters, "envs": E, "episodes": 2, "steps": 2 * a.episode_length, "launches_per_step": a.launch_count / (2 * a.episode_length + 2),
                   "worst_error_over_bound": worst_ratio, "worst_abs_reward_error": worst_abs,
                   "worst_voltage_error_pu": worst_v}))

@@ -14,7 +14,7 @@ for spec in c1:4096 c1:262144 c3:16384 c2:65536; do
   ncu -i $O/full_${w}_$e.ncu-rep --page raw --csv > $O/ncu_full_raw_${w}_$e.csv 2>> $O/err.log
   ncu -i $O/full_${w}_$e.ncu-rep --page source --csv > $O/src_${w}_$e.csv 2>> $O/err.log
   python tools/ncu_walk.py $O/src_${w}_$e.csv 0 15 > $O/ncu_stall_walk_${w}_$e.txt 2>> $O/err.log
-  python tools/ncu_walk.py $O/src_${w}_$e.csv 1 15 >> $O/ncu_stall_walk_${w}_$e.txt 2>> $O/err.log
+  python tools/ncu_walk.py $O/src_${w}_$e.csv 2 15 >> $O/ncu_stall_walk_${w}_$e.txt 2>> $O/err.log   # (the source page lists every launch twice: 0 = first kernel, 2 = second)
   rm -f $O/src_${w}_$e.csv $O/full_${w}_$e.ncu-rep
 done
 tail -5 $O/err.log

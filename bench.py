@@ -651,6 +651,19 @@ def run_ours(args):
             except Exception as exc:                  # a leg that fails must not take the headline down
                 extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
 
+        # C4 (the scenario mix: three handles on three streams) in a process of its own
+        try:
+            import subprocess
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "c4", "--steps", "20",
+                                "--warmup", "5", "--pf-kernel", PF_KERNEL], capture_output=True, text=True,
+                               timeout=300)
+            c4 = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+            extra["c4"] = {k: c4[k] for k in ("config", "value", "unit", "ms_per_step", "steps", "warmup",
+                                             "gpu_launches", "roofline", "e2e", "agent_steps_per_s")}
+            extra["c4"]["envs"] = c4["config"]["envs_per_gpu"]
+        except Exception as exc:
+            extra["c4"] = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K,

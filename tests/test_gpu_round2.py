@@ -365,3 +365,32 @@ def test_rllib_base_env_adapter_steps_a_batch_like_independent_envs():
     rest, _ = be.try_reset(3)
     assert list(first) == [0] and list(rest) == [3]
     be.stop()
+
+
+def test_event_index_and_device_clock_modes_interleave():
+    """The fused step reads its event row through the host-supplied index when the graph's node
+    parameters are rewritten for new caller buffers, and through the device clock when the same buffers
+    come again: any interleaving of the two gives the trajectory of a run on one buffer."""
+    torch = _torch()
+    E, T = 300, 14
+    rng = np.random.default_rng(12)
+    soc = rng.uniform(10, 40, size=(3, E))
+    acts = rng.uniform(-1, 1, size=(T, 24, E))
+    a_env, b_env = (SB.c1_env(num_envs=E, pf_kernel="tc2") for _ in range(2))
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        a_env.reset_batch(soc), b_env.reset_batch(soc)
+        bufs = [torch.empty((24, E), dtype=torch.float64, device="cuda") for _ in range(3)]
+        pattern = [0, 1, 1, 1, 0, 0, 2, 1, 1, 2, 2, 2, 0, 1]          # which buffer each step uses
+        one = torch.empty((24, E), dtype=torch.float64, device="cuda")
+        for t in range(T):
+            x = torch.as_tensor(acts[t]).cuda()
+            bufs[pattern[t]].copy_(x)
+            one.copy_(x)
+            oa, ra, _, _ = a_env.step_batch(bufs[pattern[t]])
+            ob, rb, _, _ = b_env.step_batch(one)
+            assert torch.equal(oa, ob) and torch.equal(ra, rb), t
+        assert a_env._lib.pgw_graph_captures(a_env._h) == 1
+        assert a_env.episode_step == b_env.episode_step == T
+        assert torch.equal(a_env.get_field(N.FIELD_EP_RETURN), b_env.get_field(N.FIELD_EP_RETURN))
+    st.synchronize()
